@@ -1,0 +1,514 @@
+// wah_capi.cu -- the extern "C" boundary of libwah_b200.so (include/wah_b200.h) and the
+// host orchestration behind it.  Mirrors what the reference's host functions do around
+// their kernels (compress.cu:41-209, decompress.cu:18-141) without the per-call
+// cudaMalloc/cudaFree, Thrust scans and 8-byte synchronous copies inside the compute step.
+#include "../../include/wah_b200.h"
+#include "wah_kernels.h"
+
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+
+using namespace wahb200;
+
+// ------------------------------------------------------------------------ errors
+
+static thread_local char g_err[512] = "";
+
+static int fail(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
+#define CUDA_TRY(expr)                                                                             \
+    do {                                                                                           \
+        cudaError_t e__ = (expr);                                                                  \
+        if (e__ != cudaSuccess)                                                                    \
+            return fail(e__ == cudaErrorMemoryAllocation ? WAH_ERR_NOMEM : WAH_ERR_CUDA, "%s: %s", \
+                        #expr, cudaGetErrorString(e__));                                           \
+    } while (0)
+
+extern "C" const char *wah_last_error_string(void) { return g_err; }
+extern "C" int wah_version(void) { return WAH_B200_VERSION; }
+
+// ------------------------------------------------------------------------- sizes
+
+extern "C" uint64_t wah_num_groups(uint64_t n_words)
+{
+    // compress.cu:74-81, in 64-bit safe form: 32 n = 31 q + r
+    return (n_words / 31ull) * 32ull + ((n_words % 31ull) * 32ull + 30ull) / 31ull;
+}
+extern "C" uint64_t wah_max_compressed_words(uint64_t n_words) { return wah_num_groups(n_words); }
+extern "C" uint64_t wah_decoded_words(uint64_t groups)
+{
+    // decompress.cu:84-92
+    return (groups / 32ull) * 31ull + ((groups % 32ull) * 31ull + 31ull) / 32ull;
+}
+
+static inline uint64_t ceil_div(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t>(p) & 15u) == 0; }
+
+// ---------------------------------------------------------------------- compress
+
+// workspace: [0,64) two u64 ping-pong slots chaining launches | [64,128) ticket | descriptors
+static constexpr size_t WS_SLOTS = 0, WS_TICKET = 64, WS_DESC = 128;
+// tiles one launch may cover (descriptor fields are 30/31 bit, wah_kernels.h)
+static constexpr uint64_t MAX_LAUNCH_TILES = MAX_LAUNCH_GROUPS / COMPRESS_TILE_GROUPS;
+
+static uint64_t compress_tiles(uint64_t n_words) { return ceil_div(n_words, COMPRESS_TILE_WORDS); }
+
+extern "C" size_t wah_compress_workspace_bytes(uint64_t n_words)
+{
+    uint64_t tiles = compress_tiles(n_words);
+    if (tiles > MAX_LAUNCH_TILES) tiles = MAX_LAUNCH_TILES;
+    return WS_DESC + (size_t)(tiles + 1) * sizeof(uint64_t);
+}
+
+extern "C" size_t wah_compress_batch_workspace_bytes(uint64_t n_cols, uint64_t words_per_col)
+{
+    uint64_t tiles = compress_tiles(words_per_col) * n_cols;
+    if (tiles > MAX_LAUNCH_TILES) tiles = MAX_LAUNCH_TILES;
+    return WS_DESC + (size_t)(tiles + 1) * sizeof(uint64_t);
+}
+
+static int check_mode(int mode)
+{
+    if (mode != WAH_BLOCK1024 && mode != WAH_CANONICAL) return fail(WAH_ERR_INVALID, "unknown mode %d", mode);
+    return WAH_OK;
+}
+
+extern "C" int wah_compress_batch_device(const uint32_t *d_in, uint64_t n_cols, uint64_t words_per_col,
+                                         uint64_t col_stride_words, int mode, uint32_t *d_out,
+                                         uint64_t out_capacity_words, uint64_t *d_col_offsets,
+                                         void *d_workspace, size_t workspace_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (check_mode(mode)) return WAH_ERR_INVALID;
+    if (!d_col_offsets) return fail(WAH_ERR_INVALID, "d_col_offsets is null");
+    if (n_cols == 0 || words_per_col == 0) {
+        CUDA_TRY(cudaMemsetAsync(d_col_offsets, 0, (size_t)(n_cols + 1) * sizeof(uint64_t), stream));
+        return WAH_OK;
+    }
+    if (!d_in || !d_out || !d_workspace) return fail(WAH_ERR_INVALID, "null device pointer");
+    if (!aligned16(d_workspace)) return fail(WAH_ERR_INVALID, "workspace must be 16-byte aligned");
+    if (n_cols > 1 && col_stride_words < words_per_col)
+        return fail(WAH_ERR_INVALID, "col_stride_words < words_per_col");
+    if (workspace_bytes < wah_compress_batch_workspace_bytes(n_cols, words_per_col))
+        return fail(WAH_ERR_CAPACITY, "workspace too small: %zu < %zu", workspace_bytes,
+                    wah_compress_batch_workspace_bytes(n_cols, words_per_col));
+    const uint64_t tiles_per_col = compress_tiles(words_per_col);
+    if (tiles_per_col > MAX_LAUNCH_TILES)
+        return fail(WAH_ERR_INVALID, "a batch column may hold at most %llu words",
+                    (unsigned long long)(MAX_LAUNCH_TILES * COMPRESS_TILE_WORDS));
+    const uint64_t cols_per_launch = MAX_LAUNCH_TILES / tiles_per_col;
+
+    char *ws = static_cast<char *>(d_workspace);
+    uint64_t *slots = reinterpret_cast<uint64_t *>(ws + WS_SLOTS);
+    int launch = 0;
+    for (uint64_t c0 = 0; c0 < n_cols; c0 += cols_per_launch, launch++) {
+        const uint64_t nc = (n_cols - c0) < cols_per_launch ? (n_cols - c0) : cols_per_launch;
+        CompressParams p;
+        memset(&p, 0, sizeof(p));
+        p.in = d_in + c0 * col_stride_words;
+        p.n_words = words_per_col;
+        p.groups = wah_num_groups(words_per_col);
+        p.col_stride = col_stride_words;
+        p.tiles_per_col = (uint32_t)tiles_per_col;
+        p.n_tiles = (uint32_t)(tiles_per_col * nc);
+        p.n_cols = (uint32_t)nc;
+        p.merge_prev = 0;
+        p.out = d_out;
+        p.out_cap = out_capacity_words;
+        p.ticket = reinterpret_cast<uint32_t *>(ws + WS_TICKET);
+        p.desc = reinterpret_cast<uint64_t *>(ws + WS_DESC);
+        p.base_in = launch == 0 ? nullptr : slots + (launch & 1);
+        p.total_out = slots + ((launch + 1) & 1);
+        p.col_offsets = d_col_offsets + c0;
+        CUDA_TRY(cudaMemsetAsync(ws + WS_TICKET, 0, (WS_DESC - WS_TICKET) + (size_t)p.n_tiles * sizeof(uint64_t),
+                                 stream));
+        CUDA_TRY(launch_compress(p, mode, stream));
+    }
+    return WAH_OK;
+}
+
+extern "C" int wah_compress_device(const uint32_t *d_in, uint64_t n_words, int mode, uint32_t *d_out,
+                                   uint64_t out_capacity_words, uint64_t *d_out_words, void *d_workspace,
+                                   size_t workspace_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (check_mode(mode)) return WAH_ERR_INVALID;
+    if (!d_out_words) return fail(WAH_ERR_INVALID, "d_out_words is null");
+    if (n_words == 0) {
+        CUDA_TRY(cudaMemsetAsync(d_out_words, 0, sizeof(uint64_t), stream));
+        return WAH_OK;
+    }
+    if (!d_in || !d_out || !d_workspace) return fail(WAH_ERR_INVALID, "null device pointer");
+    if (!aligned16(d_workspace)) return fail(WAH_ERR_INVALID, "workspace must be 16-byte aligned");
+    if (workspace_bytes < wah_compress_workspace_bytes(n_words))
+        return fail(WAH_ERR_CAPACITY, "workspace too small: %zu < %zu", workspace_bytes,
+                    wah_compress_workspace_bytes(n_words));
+
+    // A stream longer than one launch can describe is cut into segments at tile boundaries
+    // (multiples of 992 words); each launch appends to the output of the previous one and, in
+    // CANONICAL mode, folds its first run into the previous launch's last word.
+    const uint64_t seg_words = MAX_LAUNCH_TILES * COMPRESS_TILE_WORDS;
+    char *ws = static_cast<char *>(d_workspace);
+    uint64_t *slots = reinterpret_cast<uint64_t *>(ws + WS_SLOTS);
+    int launch = 0;
+    for (uint64_t w0 = 0; w0 < n_words; w0 += seg_words, launch++) {
+        const uint64_t nw = (n_words - w0) < seg_words ? (n_words - w0) : seg_words;
+        const bool last = w0 + nw >= n_words;
+        CompressParams p;
+        memset(&p, 0, sizeof(p));
+        p.in = d_in + w0;
+        p.n_words = nw;
+        p.groups = wah_num_groups(nw);
+        p.col_stride = 0;
+        p.tiles_per_col = (uint32_t)compress_tiles(nw);
+        p.n_tiles = p.tiles_per_col;
+        p.n_cols = 1;
+        p.merge_prev = (launch > 0 && mode == WAH_CANONICAL) ? 1 : 0;
+        p.out = d_out;
+        p.out_cap = out_capacity_words;
+        p.ticket = reinterpret_cast<uint32_t *>(ws + WS_TICKET);
+        p.desc = reinterpret_cast<uint64_t *>(ws + WS_DESC);
+        p.base_in = launch == 0 ? nullptr : slots + (launch & 1);
+        p.total_out = last ? d_out_words : slots + ((launch + 1) & 1);
+        p.col_offsets = nullptr;
+        CUDA_TRY(cudaMemsetAsync(ws + WS_TICKET, 0, (WS_DESC - WS_TICKET) + (size_t)p.n_tiles * sizeof(uint64_t),
+                                 stream));
+        CUDA_TRY(launch_compress(p, mode, stream));
+    }
+    return WAH_OK;
+}
+
+// -------------------------------------------------------------------- decompress
+
+static uint64_t scan_tiles(uint64_t c_words) { return ceil_div(c_words, SCAN_TILE_WORDS); }
+static uint64_t max_out_tiles(uint64_t out_capacity_words) { return ceil_div(out_capacity_words, EXPAND_TILE_WORDS); }
+static size_t ws_desc_off() { return sizeof(DecodeHeader); }
+static size_t ws_starts_off(uint64_t c_words)
+{
+    size_t o = ws_desc_off() + (size_t)scan_tiles(c_words) * sizeof(uint64_t);
+    return (o + 15) & ~(size_t)15;
+}
+
+extern "C" size_t wah_decompress_workspace_bytes(uint64_t c_words, uint64_t out_capacity_words)
+{
+    return ws_starts_off(c_words) + (size_t)(max_out_tiles(out_capacity_words) + 2) * sizeof(ulonglong2);
+}
+
+static int expand_grid()
+{
+    static int grid = 0;
+    if (grid == 0) {
+        int dev = 0, sms = 148;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        grid = sms * 3;
+    }
+    return grid;
+}
+
+static int decompress_common(const uint32_t *d_in, uint64_t c_words, uint32_t *d_out, uint64_t out_cap,
+                             uint64_t *d_out_info, void *d_workspace, size_t workspace_bytes, bool expand,
+                             cudaStream_t stream)
+{
+    if (!d_out_info) return fail(WAH_ERR_INVALID, "d_out_info is null");
+    if (c_words == 0) {
+        CUDA_TRY(cudaMemsetAsync(d_out_info, 0, 2 * sizeof(uint64_t), stream));
+        return WAH_OK;
+    }
+    if (!d_in || !d_workspace || (expand && !d_out)) return fail(WAH_ERR_INVALID, "null device pointer");
+    if (!aligned16(d_in) || !aligned16(d_workspace) || (expand && !aligned16(d_out)))
+        return fail(WAH_ERR_INVALID, "device buffers must be 16-byte aligned");
+    if (scan_tiles(c_words) > 0x7FFFFFFFull) return fail(WAH_ERR_INVALID, "compressed stream too long");
+    const size_t need = wah_decompress_workspace_bytes(c_words, expand ? out_cap : 0);
+    if (workspace_bytes < need) return fail(WAH_ERR_CAPACITY, "workspace too small: %zu < %zu", workspace_bytes, need);
+
+    char *ws = static_cast<char *>(d_workspace);
+    ScanParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.in = d_in;
+    sp.c_words = c_words;
+    sp.n_tiles = (uint32_t)scan_tiles(c_words);
+    sp.hdr = reinterpret_cast<DecodeHeader *>(ws);
+    sp.desc = reinterpret_cast<uint64_t *>(ws + ws_desc_off());
+    sp.starts = expand ? reinterpret_cast<ulonglong2 *>(ws + ws_starts_off(c_words)) : nullptr;
+    sp.max_out_tiles = expand ? max_out_tiles(out_cap) : 0;
+    sp.out_info = d_out_info;
+    CUDA_TRY(cudaMemsetAsync(ws, 0, ws_desc_off() + (size_t)sp.n_tiles * sizeof(uint64_t), stream));
+    CUDA_TRY(launch_scan(sp, stream));
+    if (expand) {
+        ExpandParams ep;
+        memset(&ep, 0, sizeof(ep));
+        ep.in = d_in;
+        ep.c_words = c_words;
+        ep.hdr = sp.hdr;
+        ep.starts = sp.starts;
+        ep.max_out_tiles = sp.max_out_tiles;
+        ep.out = d_out;
+        ep.out_cap = out_cap;
+        CUDA_TRY(launch_expand(ep, expand_grid(), stream));
+    }
+    return WAH_OK;
+}
+
+extern "C" int wah_decompress_device(const uint32_t *d_in, uint64_t c_words, uint32_t *d_out,
+                                     uint64_t out_capacity_words, uint64_t *d_out_info, void *d_workspace,
+                                     size_t workspace_bytes, void *stream)
+{
+    return decompress_common(d_in, c_words, d_out, out_capacity_words, d_out_info, d_workspace, workspace_bytes,
+                             true, (cudaStream_t)stream);
+}
+
+extern "C" int wah_decoded_size_device(const uint32_t *d_in, uint64_t c_words, uint64_t *d_out_info,
+                                       void *d_workspace, size_t workspace_bytes, void *stream)
+{
+    return decompress_common(d_in, c_words, nullptr, 0, d_out_info, d_workspace, workspace_bytes, false,
+                             (cudaStream_t)stream);
+}
+
+// ---------------------------------------------------------------------- host API
+
+namespace {
+struct DevBuf {
+    void *p = nullptr;
+    ~DevBuf()
+    {
+        if (p) cudaFree(p);
+    }
+    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
+};
+struct Timer {
+    cudaEvent_t a = nullptr, b = nullptr;
+    Timer()
+    {
+        cudaEventCreate(&a);
+        cudaEventCreate(&b);
+    }
+    ~Timer()
+    {
+        if (a) cudaEventDestroy(a);
+        if (b) cudaEventDestroy(b);
+    }
+    void start() { cudaEventRecord(a, 0); }
+    float stop()
+    {
+        float ms = 0.f;
+        cudaEventRecord(b, 0);
+        cudaEventSynchronize(b);
+        cudaEventElapsedTime(&ms, a, b);
+        return ms;
+    }
+};
+}  // namespace
+
+extern "C" void wah_free(void *p) { free(p); }
+
+extern "C" int wah_compress_host(const uint32_t *h_in, uint64_t n_words, int mode, uint32_t **h_out,
+                                 uint64_t *out_words, float *ms_h2d, float *ms_compute, float *ms_d2h)
+{
+    if (check_mode(mode)) return WAH_ERR_INVALID;
+    if (!h_out) return fail(WAH_ERR_INVALID, "h_out is null");
+    if (n_words && !h_in) return fail(WAH_ERR_INVALID, "h_in is null");
+    *h_out = nullptr;
+    Timer t;
+    // -- segment 1: allocation + H2D (compress.cu:57-120)
+    t.start();
+    const uint64_t cap = wah_max_compressed_words(n_words);
+    const size_t ws_bytes = wah_compress_workspace_bytes(n_words);
+    DevBuf d_in, d_out, d_ws, d_cnt;
+    CUDA_TRY(d_in.alloc(n_words * 4));
+    CUDA_TRY(d_out.alloc(cap * 4));
+    CUDA_TRY(d_ws.alloc(ws_bytes));
+    CUDA_TRY(d_cnt.alloc(sizeof(uint64_t)));
+    if (n_words) CUDA_TRY(cudaMemcpy(d_in.p, h_in, n_words * 4, cudaMemcpyHostToDevice));
+    const float t0 = t.stop();
+    // -- segment 2: compute (compress.cu:125-172)
+    t.start();
+    int rc = wah_compress_device((const uint32_t *)d_in.p, n_words, mode, (uint32_t *)d_out.p, cap,
+                                 (uint64_t *)d_cnt.p, d_ws.p, ws_bytes, nullptr);
+    if (rc) return rc;
+    uint64_t c = 0;
+    CUDA_TRY(cudaMemcpy(&c, d_cnt.p, sizeof(c), cudaMemcpyDeviceToHost));
+    const float t1 = t.stop();
+    // -- segment 3: D2H + release (compress.cu:177-202)
+    t.start();
+    uint32_t *host = (uint32_t *)malloc((size_t)(c ? c : 1) * 4);
+    if (!host) return fail(WAH_ERR_NOMEM, "malloc of %llu words failed", (unsigned long long)c);
+    if (c) {
+        cudaError_t e = cudaMemcpy(host, d_out.p, c * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            free(host);
+            return fail(WAH_ERR_CUDA, "D2H copy: %s", cudaGetErrorString(e));
+        }
+    }
+    const float t2 = t.stop();
+    *h_out = host;
+    if (out_words) *out_words = c;
+    if (ms_h2d) *ms_h2d = t0;
+    if (ms_compute) *ms_compute = t1;
+    if (ms_d2h) *ms_d2h = t2;
+    return WAH_OK;
+}
+
+extern "C" int wah_decompress_host(const uint32_t *h_in, uint64_t c_words, uint32_t **h_out,
+                                   uint64_t *out_words, float *ms_h2d, float *ms_compute, float *ms_d2h)
+{
+    if (!h_out) return fail(WAH_ERR_INVALID, "h_out is null");
+    if (c_words && !h_in) return fail(WAH_ERR_INVALID, "h_in is null");
+    *h_out = nullptr;
+    Timer t;
+    // -- segment 1: allocation + H2D (decompress.cu:34-56)
+    t.start();
+    DevBuf d_in, d_ws, d_info, d_out;
+    CUDA_TRY(d_in.alloc(c_words * 4));
+    CUDA_TRY(d_info.alloc(2 * sizeof(uint64_t)));
+    if (c_words) CUDA_TRY(cudaMemcpy(d_in.p, h_in, c_words * 4, cudaMemcpyHostToDevice));
+    const float t0 = t.stop();
+    // -- segment 2: size query, allocation of the exact output, expansion (decompress.cu:66-124)
+    t.start();
+    uint64_t info[2] = {0, 0};
+    {
+        const size_t ws0 = wah_decompress_workspace_bytes(c_words, 0);
+        DevBuf d_ws0;
+        CUDA_TRY(d_ws0.alloc(ws0));
+        int rc = wah_decoded_size_device((const uint32_t *)d_in.p, c_words, (uint64_t *)d_info.p, d_ws0.p, ws0,
+                                         nullptr);
+        if (rc) return rc;
+        CUDA_TRY(cudaMemcpy(info, d_info.p, sizeof(info), cudaMemcpyDeviceToHost));
+    }
+    const uint64_t words = info[0];
+    const size_t ws_bytes = wah_decompress_workspace_bytes(c_words, words);
+    CUDA_TRY(d_ws.alloc(ws_bytes));
+    CUDA_TRY(d_out.alloc(words * 4));
+    int rc = wah_decompress_device((const uint32_t *)d_in.p, c_words, (uint32_t *)d_out.p, words,
+                                   (uint64_t *)d_info.p, d_ws.p, ws_bytes, nullptr);
+    if (rc) return rc;
+    uint32_t bad = 0;
+    CUDA_TRY(cudaMemcpy(&bad, (char *)d_ws.p + offsetof(DecodeHeader, bad_words), sizeof(bad),
+                        cudaMemcpyDeviceToHost));
+    const float t1 = t.stop();
+    if (bad) return fail(WAH_ERR_FORMAT, "%u zero-length fill words in the stream", bad);
+    // -- segment 3: D2H + release (decompress.cu:127-133)
+    t.start();
+    uint32_t *host = (uint32_t *)malloc((size_t)(words ? words : 1) * 4);
+    if (!host) return fail(WAH_ERR_NOMEM, "malloc of %llu words failed", (unsigned long long)words);
+    if (words) {
+        cudaError_t e = cudaMemcpy(host, d_out.p, words * 4, cudaMemcpyDeviceToHost);
+        if (e != cudaSuccess) {
+            free(host);
+            return fail(WAH_ERR_CUDA, "D2H copy: %s", cudaGetErrorString(e));
+        }
+    }
+    const float t2 = t.stop();
+    *h_out = host;
+    if (out_words) *out_words = words;
+    if (ms_h2d) *ms_h2d = t0;
+    if (ms_compute) *ms_compute = t1;
+    if (ms_d2h) *ms_d2h = t2;
+    return WAH_OK;
+}
+
+// ----------------------------------------------------------------- range sharding
+
+extern "C" int wah_shard_record_device(const uint32_t *d_shard, uint64_t words, uint64_t groups,
+                                       wah_shard_record *h_record, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (!h_record) return fail(WAH_ERR_INVALID, "h_record is null");
+    memset(h_record, 0, sizeof(*h_record));
+    h_record->words = words;
+    h_record->groups = groups;
+    if (words == 0) return WAH_OK;
+    if (!d_shard) return fail(WAH_ERR_INVALID, "d_shard is null");
+    DevBuf d_res;
+    CUDA_TRY(d_res.alloc(8 * sizeof(uint64_t)));
+    CUDA_TRY(launch_shard_probe(d_shard, words, (uint64_t *)d_res.p, stream));
+    uint64_t r[5];
+    CUDA_TRY(cudaMemcpyAsync(r, d_res.p, sizeof(r), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaStreamSynchronize(stream));
+    h_record->lead_groups = r[0];
+    h_record->lead_words = r[1];
+    h_record->lead_type = (uint32_t)r[2];
+    h_record->trail_groups = r[3];
+    h_record->trail_type = (uint32_t)r[4];
+    return WAH_OK;
+}
+
+extern "C" int wah_stitch_plan(const wah_shard_record *rec, int n_shards, int mode, uint64_t *skip_words,
+                               uint64_t *dst_offset, uint64_t *seam_offset, uint32_t *seam_count,
+                               uint32_t *seam_words, uint64_t *total_words)
+{
+    if (check_mode(mode)) return WAH_ERR_INVALID;
+    if (n_shards < 0 || (n_shards && (!rec || !skip_words || !dst_offset || !seam_offset || !seam_count || !seam_words)))
+        return fail(WAH_ERR_INVALID, "null argument");
+    const uint64_t M = 0x3FFFFFFFull;
+    uint64_t total = 0;
+    bool open = false;        // the stream so far ends in a fill word ...
+    uint32_t open_type = 0;   // ... of this type
+    uint64_t open_count = 0;  // ... and this length
+    for (int r = 0; r < n_shards; r++) {
+        skip_words[r] = 0;
+        seam_count[r] = 0;
+        seam_offset[r] = total;
+        dst_offset[r] = total;
+        const wah_shard_record &s = rec[r];
+        if (s.words == 0) continue;
+        if (mode == WAH_CANONICAL && open && s.lead_groups > 0 && s.lead_type == open_type) {
+            // the run that ends the stream so far continues into this shard: re-split the sum
+            uint64_t sum = open_count + s.lead_groups;
+            const uint64_t full = sum / M, rest = sum % M;
+            const uint64_t k = full + (rest ? 1 : 0);
+            if (k > WAH_MAX_SEAM_WORDS) return fail(WAH_ERR_INVALID, "seam run too long (%llu words)", (unsigned long long)k);
+            uint32_t *sw = seam_words + (size_t)r * WAH_MAX_SEAM_WORDS;
+            for (uint64_t i = 0; i < full; i++) sw[i] = 0x80000000u | (open_type << 30) | (uint32_t)M;
+            if (rest) sw[full] = 0x80000000u | (open_type << 30) | (uint32_t)rest;
+            seam_count[r] = (uint32_t)k;
+            seam_offset[r] = total - 1;
+            total = total - 1 + k;
+            skip_words[r] = s.lead_words;
+            dst_offset[r] = total;
+            const uint64_t body = s.words - s.lead_words;
+            total += body;
+            if (body > 0) {
+                open = s.trail_groups > 0;
+                open_type = s.trail_type;
+                open_count = s.trail_groups;
+            } else {
+                open = true;   // the whole shard was that run
+                open_count = rest ? rest : M;
+            }
+        } else {
+            total += s.words;
+            open = s.trail_groups > 0;
+            open_type = s.trail_type;
+            open_count = s.trail_groups;
+        }
+    }
+    if (total_words) *total_words = total;
+    return WAH_OK;
+}
+
+// --------------------------------------------------------------------- generators
+
+extern "C" int wah_gen_uniform_device(uint32_t *d_out, uint64_t n_words, double density, uint64_t seed,
+                                      void *stream)
+{
+    if (n_words && !d_out) return fail(WAH_ERR_INVALID, "d_out is null");
+    CUDA_TRY(launch_gen_uniform(d_out, n_words, density, seed, (cudaStream_t)stream));
+    return WAH_OK;
+}
+
+extern "C" int wah_gen_paint_runs_device(uint32_t *d_out, uint64_t n_words, const int64_t *d_start_bits,
+                                         const int64_t *d_len_bits, uint64_t n_runs, void *stream)
+{
+    if (n_runs && (!d_out || !d_start_bits || !d_len_bits)) return fail(WAH_ERR_INVALID, "null device pointer");
+    CUDA_TRY(launch_gen_paint_runs(d_out, n_words, d_start_bits, d_len_bits, n_runs, (cudaStream_t)stream));
+    return WAH_OK;
+}

@@ -1,0 +1,95 @@
+// wah_kernels.h -- internal interface between the C ABI (wah_capi.cu) and the kernels.
+#pragma once
+
+#include <cuda_runtime.h>
+#include <stdint.h>
+
+namespace wahb200 {
+
+// ------------------------------------------------------------------ compress
+
+// One launch covers at most MAX_LAUNCH_GROUPS groups so that a tile descriptor
+// (status:2 | no_tail:1 | open:30 | count:31) fits one 64-bit word.
+constexpr uint64_t MAX_LAUNCH_GROUPS = 0x3FFFFFFFull;
+
+constexpr int COMPRESS_THREADS = 256;                         // 8 warps = 8 reference blocks per tile
+constexpr int COMPRESS_TILE_WORDS = COMPRESS_THREADS * 31;    // 7936 words  (31 744 B)
+constexpr int COMPRESS_TILE_GROUPS = COMPRESS_THREADS * 32;   // 8192 groups
+
+struct CompressParams {
+    const uint32_t *in;      // first column of this launch
+    uint64_t n_words;        // words per column
+    uint64_t groups;         // groups per column = ceil(32 n / 31)
+    uint64_t col_stride;     // words between column starts
+    uint32_t tiles_per_col;
+    uint32_t n_tiles;        // tiles_per_col * n_cols
+    uint32_t n_cols;
+    int merge_prev;          // CANONICAL append: merge the first run into out[base-1]
+    uint32_t *out;
+    uint64_t out_cap;
+    uint64_t *desc;          // [n_tiles] zeroed
+    uint32_t *ticket;        // zeroed
+    const uint64_t *base_in; // words already in `out` (nullptr = 0)
+    uint64_t *total_out;     // receives base + words emitted by this launch
+    uint64_t *col_offsets;   // nullptr or [n_cols + 1] for this launch's columns
+};
+
+size_t compress_smem_bytes();
+cudaError_t launch_compress(const CompressParams &p, int mode, cudaStream_t stream);
+
+// ---------------------------------------------------------------- decompress
+
+constexpr int SCAN_THREADS = 256;
+constexpr int SCAN_ITEMS = 8;                                  // compressed words per thread
+constexpr int SCAN_TILE_WORDS = SCAN_THREADS * SCAN_ITEMS;     // 2048
+
+constexpr int EXPAND_THREADS = 256;
+constexpr int EXPAND_TILE_GROUPS = EXPAND_THREADS * 32;        // 8192 groups per output tile
+constexpr int EXPAND_TILE_WORDS = EXPAND_THREADS * 31;         // 7936 output words
+constexpr int EXPAND_MAX_CWORDS = EXPAND_TILE_GROUPS + 8;      // compressed words one output tile can need
+
+// header written by the scan kernel, read by the expand kernel and the host
+struct DecodeHeader {
+    uint64_t groups;        // G
+    uint64_t words;         // ceil(31 G / 32)
+    uint64_t out_tiles;     // ceil(G / EXPAND_TILE_GROUPS)
+    uint32_t bad_words;     // zero-length fills seen
+    uint32_t ticket;
+    uint64_t pad[4];
+};
+
+struct ScanParams {
+    const uint32_t *in;
+    uint64_t c_words;
+    uint32_t n_tiles;
+    uint64_t *desc;          // [n_tiles] zeroed
+    DecodeHeader *hdr;       // zeroed
+    ulonglong2 *starts;      // nullptr (size query) or [max_out_tiles + 1]: {compressed word index, its group offset}
+    uint64_t max_out_tiles;
+    uint64_t *out_info;      // nullptr or device u64[2] {words, groups}
+};
+
+struct ExpandParams {
+    const uint32_t *in;
+    uint64_t c_words;
+    const DecodeHeader *hdr;
+    const ulonglong2 *starts;
+    uint64_t max_out_tiles;
+    uint32_t *out;
+    uint64_t out_cap;
+};
+
+size_t expand_smem_bytes();
+cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream);
+cudaError_t launch_expand(const ExpandParams &p, int grid, cudaStream_t stream);
+
+// --------------------------------------------------------------------- misc
+
+cudaError_t launch_shard_probe(const uint32_t *d_shard, uint64_t words, uint64_t *d_result /*[6]*/,
+                               cudaStream_t stream);
+cudaError_t launch_gen_uniform(uint32_t *d_out, uint64_t n_words, double density, uint64_t seed,
+                               cudaStream_t stream);
+cudaError_t launch_gen_paint_runs(uint32_t *d_out, uint64_t n_words, const int64_t *d_start,
+                                  const int64_t *d_len, uint64_t n_runs, cudaStream_t stream);
+
+}  // namespace wahb200

@@ -1,0 +1,381 @@
+"""Executable model of the CUDA kernels' tile algorithms (pure Python, tiny inputs only).
+
+There is no GPU on the development box, so the index arithmetic of
+``gpu-wah_b200/csrc/wah_compress.cu`` and ``wah_decompress.cu`` -- tail masks, the
+open-run carry through thread / warp / tile scans, the look-back monoid over packed
+descriptors, output-tile boundary bookkeeping, the binary search + walk of the expander --
+is restated here step for step and checked against the oracle in ``test_kernel_model.py``.
+This is TEST INFRASTRUCTURE: it is not a fallback and nothing in the product imports it.
+"""
+from __future__ import annotations
+
+import random
+
+ONES31 = 0x7FFFFFFF
+BIT31 = 0x80000000
+BIT30 = 0x40000000
+MAX_FILL = 0x3FFFFFFF
+M32 = 0xFFFFFFFF
+
+
+def popc(x):
+    return bin(x & M32).count("1")
+
+
+def clz(x):
+    x &= M32
+    return 32 - x.bit_length()
+
+
+def ffs(x):
+    x &= M32
+    return (x & -x).bit_length()  # 1-based, 0 if none
+
+
+def funnelshift_r(lo, hi, s):
+    return (((hi << 32) | lo) >> (s & 31)) & M32
+
+
+def extract_group(row, g):
+    bit = 31 * g
+    wi, s = bit >> 5, bit & 31
+    return funnelshift_r(row[wi], row[wi + 1], s) & ONES31
+
+
+def fill_word(t, n):
+    return BIT31 | (t << 30) | n
+
+
+def word_groups(w):
+    return (w & MAX_FILL) if (w & BIT31) else 1
+
+
+# ------------------------------------------------------------------ compress model
+
+ST_EMPTY, ST_AGG, ST_INCL = 0, 1, 2
+
+
+def lookback(desc, tile, block_mode, t_in_col, rng):
+    """Mirror of the warp-0 look-back loop.  ``desc[i]`` = (status, no_tail, open, count); to
+    exercise the AGGREGATE path, predecessors are randomly presented in their aggregate form."""
+    excl, carry = 0, 0
+    open_done = block_mode or t_in_col == 0
+    look0 = tile - 1
+    while True:
+        lanes = []
+        for lane in range(32):
+            look = look0 - lane
+            if look < 0:
+                lanes.append((ST_INCL, 0, 0, 0))
+            else:
+                agg, incl = desc[look]
+                lanes.append(agg if (agg is not None and rng.random() < 0.5 and look > 0) else incl)
+        first_incl = next((i for i, d in enumerate(lanes) if d[0] == ST_INCL), 32)
+        part = [lane <= first_incl for lane in range(32)]
+        excl += sum(d[3] for lane, d in enumerate(lanes) if part[lane])
+        if not open_done:
+            first_term = next((i for i, d in enumerate(lanes) if part[i] and (d[0] == ST_INCL or not d[1])), 32)
+            carry += sum(d[2] for lane, d in enumerate(lanes) if part[lane] and lane <= first_term)
+            open_done = first_term < 32
+        if first_incl < 32:
+            break
+        look0 -= 32
+    return excl, carry
+
+
+def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0):
+    """cols: list of equally long word lists (one launch).  mode 0 = BLOCK1024, 1 = CANONICAL.
+    merge_prev_words: existing output to append to (CANONICAL append).  Returns (out, col_offsets)."""
+    rng = random.Random(seed)
+    block_mode = mode == 0
+    NW = threads // 32
+    TW, TG = threads * 31, threads * 32
+    n_words = len(cols[0])
+    groups = (32 * n_words + 30) // 31
+    tiles_per_col = (n_words + TW - 1) // TW
+    n_tiles = tiles_per_col * len(cols)
+    out = list(merge_prev_words) if merge_prev_words else []
+    base = len(out)
+    merge_prev = merge_prev_words is not None and mode == 1
+    desc = [None] * n_tiles
+    col_offsets = [0] * (len(cols) + 1)
+
+    for tile in range(n_tiles):
+        col, t = divmod(tile, tiles_per_col)
+        w0 = t * TW
+        src = cols[col]
+        left = n_words - w0
+        nload = TW + 1 if left > TW else left
+        s_in = [src[w0 + i] if i < nload else 0 for i in range(TW + 4)]
+        s_out = [None] * TG
+        th = []
+        for tid in range(threads):
+            lane = tid & 31
+            row = s_in[31 * tid: 31 * tid + 33]
+            g_thread = t * TG + 32 * tid
+            nvalid = 0
+            if g_thread < groups:
+                nvalid = min(32, groups - g_thread)
+            vmask = M32 if nvalid == 32 else ((1 << nvalid) - 1)
+            Z = O = 0
+            prev = row[0]
+            v = prev & ONES31
+            Z |= 1 if v == 0 else 0
+            O |= 1 if v == ONES31 else 0
+            for j in range(1, 31):
+                cur = row[j]
+                v = funnelshift_r(prev, cur, 32 - j) & ONES31
+                Z |= (1 << j) if v == 0 else 0
+                O |= (1 << j) if v == ONES31 else 0
+                prev = cur
+            v = prev >> 1
+            Z |= BIT31 if v == 0 else 0
+            O |= BIT31 if v == ONES31 else 0
+            Z &= vmask
+            O &= vmask
+            F = Z | O
+            nz = no = 0
+            if not (block_mode and lane == 31) and g_thread + 32 < groups:
+                nx = row[31] & ONES31
+                nz = BIT31 if nx == 0 else 0
+                no = BIT31 if nx == ONES31 else 0
+            T = ((~F) & vmask) | (Z & ~((Z >> 1) | nz)) | (O & ~((O >> 1) | no))
+            T &= M32
+            th.append(dict(Z=Z, O=O, F=F, T=T, cnt=popc(T), my_open=clz(T) if T else 32, row=row))
+        s_wcnt, s_wopen, s_whas = [0] * NW, [0] * NW, [0] * NW
+        for warp in range(NW):
+            lanes = th[32 * warp: 32 * warp + 32]
+            incl = 0
+            tb = 0
+            for lane, d in enumerate(lanes):
+                incl += d["cnt"]
+                d["incl"] = incl
+                if d["T"]:
+                    tb |= 1 << lane
+            for lane, d in enumerate(lanes):
+                below = tb & ((1 << lane) - 1)
+                q = 31 - clz(below) if below else 0
+                open_q = lanes[q]["my_open"]
+                d["below"] = below
+                d["prev_open"] = open_q + 32 * (lane - q - 1) if below else 32 * lane
+            qlast = 31 - clz(tb) if tb else 0
+            s_wcnt[warp] = incl
+            s_whas[warp] = 1 if tb else 0
+            s_wopen[warp] = lanes[qlast]["my_open"] + 32 * (31 - qlast) if tb else 1024
+        # warp 0: aggregate + look-back
+        tile_cnt = tile_open = tile_has = 0
+        for w in range(NW):
+            tile_cnt += s_wcnt[w]
+            if s_whas[w]:
+                tile_has, tile_open = 1, s_wopen[w]
+            else:
+                tile_open += s_wopen[w]
+        if t == tiles_per_col - 1:
+            tile_open, tile_has = 0, 1
+        excl = carry = 0
+        defer = tile == 0 and merge_prev
+        if tile == 0:
+            if not defer:
+                desc[0] = (None, (ST_INCL, 0, tile_open, tile_cnt))
+        else:
+            agg = (ST_AGG, tile_has ^ 1, tile_open, tile_cnt)
+            excl, carry = lookback(desc, tile, block_mode, t, rng)
+            incl_open = tile_open if tile_has else carry + tile_open
+            desc[tile] = (agg, (ST_INCL, 0, incl_open, excl + tile_cnt))
+        s_excl = excl
+        s_carry = 0 if (block_mode or t == 0) else carry
+        # emission
+        for warp in range(NW):
+            wprefix = wcarry = 0
+            found = False
+            for w in range(NW):
+                if w < warp:
+                    wprefix += s_wcnt[w]
+                    if s_whas[w]:
+                        wcarry, found = s_wopen[w], True
+                    else:
+                        wcarry += s_wopen[w]
+            if not found:
+                wcarry += s_carry
+            if block_mode:
+                wcarry = 0
+            lanes = th[32 * warp: 32 * warp + 32]
+            for d in lanes:
+                if not d["below"]:
+                    d["prev_open"] += wcarry
+                d["my_off"] = wprefix + d["incl"] - d["cnt"]
+            wcnt = s_wcnt[warp]
+            wrow = s_in[992 * warp: 992 * warp + 994]
+            all_literal = all(d["T"] == M32 and d["F"] == 0 for d in lanes)
+            if all_literal:
+                for k in range(32):
+                    for lane in range(32):
+                        g = 32 * k + lane
+                        s_out[wprefix + g] = extract_group(wrow, g)
+            elif wcnt > 192:
+                for k in range(32):
+                    Tk = lanes[k]["T"]
+                    if Tk == 0:
+                        continue
+                    Fk, Ok, offk, pok = lanes[k]["F"], lanes[k]["O"], lanes[k]["my_off"], lanes[k]["prev_open"]
+                    for lane in range(32):
+                        bit = 1 << lane
+                        if Tk & bit:
+                            lower = Tk & (bit - 1)
+                            if Fk & bit:
+                                ln = lane - (31 - clz(lower)) if lower else lane + 1 + pok
+                                w = fill_word((Ok >> lane) & 1, ln)
+                            else:
+                                w = extract_group(wrow, 32 * k + lane)
+                            s_out[offk + popc(lower)] = w
+            else:
+                for d in lanes:
+                    m, off, prev, extra = d["T"], d["my_off"], -1, d["prev_open"]
+                    while m:
+                        j = ffs(m) - 1
+                        m &= m - 1
+                        if (d["F"] >> j) & 1:
+                            w = fill_word((d["O"] >> j) & 1, (j - prev) + extra)
+                        else:
+                            w = extract_group(d["row"], j)
+                        s_out[off] = w
+                        off += 1
+                        prev, extra = j, 0
+        drop = 0
+        if tile == 0 and merge_prev:
+            if base > 0 and tile_cnt > 0:
+                pw, fw = out[base - 1], s_out[0]
+                if (pw & BIT31) and (fw & BIT31) and ((pw ^ fw) & BIT30) == 0:
+                    total = (pw & MAX_FILL) + (fw & MAX_FILL)
+                    ty = (fw >> 30) & 1
+                    if total <= MAX_FILL:
+                        out[base - 1] = fill_word(ty, total)
+                        drop = 1
+                    else:
+                        out[base - 1] = fill_word(ty, MAX_FILL)
+                        s_out[0] = fill_word(ty, total - MAX_FILL)
+            desc[0] = (None, (ST_INCL, 0, tile_open, tile_cnt - drop))
+        dst0 = base + s_excl
+        if t == 0:
+            col_offsets[col] = dst0
+        if tile == n_tiles - 1:
+            col_offsets[len(cols)] = dst0 + tile_cnt - drop
+        need = dst0 + tile_cnt - drop
+        if len(out) < need:
+            out.extend([None] * (need - len(out)))
+        for i in range(drop, tile_cnt):
+            assert s_out[i] is not None, (tile, i)
+            out[dst0 + i - drop] = s_out[i]
+    assert all(w is not None for w in out)
+    return out, col_offsets
+
+
+# ---------------------------------------------------------------- decompress model
+
+SCAN_THREADS, SCAN_ITEMS = 256, 8
+SCAN_TILE = SCAN_THREADS * SCAN_ITEMS
+TG, TWO = 8192, 7936
+
+
+def scan_model(cw, max_out_tiles):
+    """Mirror of wah_scan_kernel: returns (G, words, out_tiles, starts)."""
+    c = len(cw)
+    n_tiles = (c + SCAN_TILE - 1) // SCAN_TILE
+    starts = {}
+    base = 0
+    k_limit = max_out_tiles + 1
+    for tile in range(n_tiles):
+        off = base
+        for tid in range(SCAN_THREADS):
+            w_begin = tile * SCAN_TILE + tid * SCAN_ITEMS
+            for i in range(SCAN_ITEMS):
+                w = cw[w_begin + i] if w_begin + i < c else BIT31
+                cnt = word_groups(w)
+                k_first = (off + TG - 1) // TG
+                k_end = (off + cnt + TG - 1) // TG
+                k_end = min(k_end, k_limit)
+                k_first = min(k_first, k_end)
+                for k in range(k_first, k_end):
+                    assert k not in starts
+                    starts[k] = (w_begin + i, off)
+                off += cnt
+        base = off
+    G = base
+    words = (G >> 5) * 31 + (((G & 31) * 31 + 31) >> 5)
+    return G, words, (G + TG - 1) // TG, starts
+
+
+def expand_model(cw, out_cap=None):
+    c = len(cw)
+    CLAMP = 2 * TG
+    G, words, real_tiles, starts = scan_model(cw, 1 << 40 if out_cap is None else (out_cap + TWO - 1) // TWO)
+    total_words = words if out_cap is None else min(words, out_cap)
+    out = [None] * total_words
+    n_tiles = real_tiles if out_cap is None else min(real_tiles, (out_cap + TWO - 1) // TWO)
+    for ot in range(n_tiles):
+        ws, g0 = starts[ot]
+        we = starts[ot + 1][0] if ot + 1 < real_tiles else c - 1
+        nw = we - ws + 1
+        assert nw <= TG + 8
+        g_lo = ot * TG
+        skip = g_lo - g0
+        s_cw = cw[ws: ws + nw]
+        s_off = []
+        run = 0
+        for i in range(nw):
+            cc = word_groups(s_cw[i])
+            if i == 0:
+                cc -= skip
+            s_off.append(run)
+            run += min(cc, CLAMP)
+        stage = [None] * TWO
+        for tid in range(256):
+            rel = 32 * tid
+            if not (g_lo + rel < G):
+                continue
+            lo, hi = 0, nw
+            while hi - lo > 1:
+                mid = (lo + hi) >> 1
+                if s_off[mid] <= rel:
+                    lo = mid
+                else:
+                    hi = mid
+            idx = lo
+            wv = s_cw[idx]
+            cc = word_groups(wv)
+            if idx == 0:
+                cc -= skip
+            cc = min(cc, CLAMP)
+            rem = s_off[idx] + cc - rel
+            assert rem >= 1
+            val = (ONES31 if (wv & BIT30) else 0) if (wv & BIT31) else wv
+            o = [0] * 31
+            if rem >= 32:
+                o = [M32 if val else 0] * 31
+            else:
+                pg = 0
+                for j in range(32):
+                    if rem == 0:
+                        while True:
+                            idx += 1
+                            if idx >= nw:
+                                val, rem = 0, 64
+                                break
+                            wv = s_cw[idx]
+                            rem = word_groups(wv)
+                            val = (ONES31 if (wv & BIT30) else 0) if (wv & BIT31) else wv
+                            if rem != 0:
+                                break
+                    if j > 0:
+                        o[j - 1] = funnelshift_r((pg << 1) & M32, val, j)
+                    pg = val
+                    rem -= 1
+            stage[31 * tid: 31 * tid + 31] = o
+        w_lo = ot * TWO
+        if w_lo < total_words:
+            nout = min(TWO, total_words - w_lo)
+            for i in range(nout):
+                assert stage[i] is not None
+                out[w_lo + i] = stage[i]
+    assert all(w is not None for w in out)
+    return out, words, G

@@ -1,0 +1,84 @@
+"""The step-for-step model of the CUDA tile algorithms (tests/kernel_model.py) against the oracle."""
+import numpy as np
+import pytest
+
+import datagen
+import kernel_model as km
+import oracle_lib as orc
+
+TW = 7936
+
+
+def _cases():
+    yield "zeros", np.zeros(2 * TW + 100, dtype=np.uint32)
+    yield "ones", np.full(TW + 992, 0xFFFFFFFF, dtype=np.uint32)
+    yield "dense", datagen.uniform(TW + 500, 0.5, 1)
+    yield "sparse", datagen.uniform(3 * TW + 17, 0.001, 2)
+    yield "d16", datagen.uniform(2 * TW, 1 / 16, 3)
+    yield "clustered", datagen.clustered(3 * TW + 1, 0.3, 300, 4)
+    yield "clustered_long", datagen.clustered(4 * TW, 0.01, 2000, 5)
+    yield "mix", datagen.group_mix(2 * TW + 31, 0.4, 0.3, 6)
+    yield "mix_runs", datagen.group_mix(3 * TW, 0.45, 0.45, 7, run=40)
+    yield "alternating_fills", datagen.group_mix(TW + 62, 0.5, 0.5, 8)
+    for n in (1, 2, 30, 31, 32, 33, 991, 992, 993, TW - 1, TW, TW + 1):
+        yield f"tail_{n}", datagen.uniform(n, 0.02, 100 + n)
+        yield f"tailz_{n}", np.zeros(n, dtype=np.uint32)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+@pytest.mark.parametrize("name,data", list(_cases()), ids=[c[0] for c in _cases()])
+def test_compress_model_matches_oracle(name, data, mode):
+    want = orc.compress(data, mode)
+    got, _ = km.compress_model([data.tolist()], mode, seed=hash(name) & 0xFFFF)
+    assert len(got) == want.size
+    assert np.array_equal(np.array(got, dtype=np.uint32), want)
+
+
+@pytest.mark.parametrize("mode", [0, 1])
+def test_compress_model_batch(mode):
+    cols = np.stack([
+        datagen.uniform(TW + 40, 0.001, 11), np.zeros(TW + 40, dtype=np.uint32),
+        datagen.clustered(TW + 40, 0.2, 500, 12), np.zeros(TW + 40, dtype=np.uint32),
+        np.full(TW + 40, 0xFFFFFFFF, dtype=np.uint32),
+    ])
+    want, offs = orc.compress_batch(cols, mode)
+    got, got_offs = km.compress_model([c.tolist() for c in cols], mode, seed=5)
+    assert np.array_equal(np.array(got, dtype=np.uint32), want)
+    assert got_offs == offs.tolist()
+
+
+def test_compress_model_append_merges_seam():
+    # CANONICAL stream compressed as two launches: the second folds its first run into the last word
+    a = np.zeros(992 * 3, dtype=np.uint32)
+    b = np.zeros(992 * 2, dtype=np.uint32)
+    b[-1] = 5
+    first, _ = km.compress_model([a.tolist()], 1)
+    both, _ = km.compress_model([b.tolist()], 1, merge_prev_words=first)
+    want = orc.compress(np.concatenate([a, b]), 1)
+    assert np.array_equal(np.array(both, dtype=np.uint32), want)
+    # no merge when types differ
+    a2 = np.full(992, 0xFFFFFFFF, dtype=np.uint32)
+    first, _ = km.compress_model([a2.tolist()], 1)
+    both, _ = km.compress_model([b.tolist()], 1, merge_prev_words=first)
+    assert np.array_equal(np.array(both, dtype=np.uint32), orc.compress(np.concatenate([a2, b]), 1))
+
+
+def _streams():
+    for name, data in _cases():
+        yield name + "_b", orc.compress(data, 0), data
+        yield name + "_c", orc.compress(data, 1), data
+    # long fills: many output tiles per compressed word
+    cw = np.array([0x80000000 | 100000, 5, 0xC0000000 | 70000, 0x80000000 | 1, 7, 0xC0000000 | 8191], dtype=np.uint32)
+    yield "long_fills", cw, None
+    yield "one_fill", np.array([0x80000000 | 0x3FFFFFF], dtype=np.uint32)[:1] * 0 + np.uint32(0x80000000 | 300000), None
+
+
+@pytest.mark.parametrize("name,cw,data", list(_streams()), ids=[c[0] for c in _streams()])
+def test_expand_model_matches_oracle(name, cw, data):
+    want = orc.decompress(cw)
+    got, words, groups = km.expand_model(cw.tolist())
+    assert words == want.size and groups == orc.decoded_groups(cw)
+    assert np.array_equal(np.array(got, dtype=np.uint32), want)
+    if data is not None:
+        assert np.array_equal(want[: data.size], data)
+        assert not want[data.size:].any()

@@ -2,20 +2,23 @@
 //
 // Replaces the reference's getCounts + thrust::exclusive_scan + decompressWords +
 // mergeWords (kernels.cu:291-385, decompress.cu:66-115), which materialise an
-// 8-byte count per compressed word, a one-group-per-int intermediate array and
-// expand every fill with a serial per-thread loop (kernels.cu:346-348).
+// 8-byte count per compressed word and a one-group-per-int intermediate array in
+// HBM and expand every fill with a serial per-thread loop (kernels.cu:346-348).
 //
 // Here:
 //   scan kernel   : one pass over the compressed words; per-tile group sums with a
-//                   decoupled look-back give every tile its group offset, and each
-//                   tile records, for every OUTPUT tile boundary (multiples of 8192
-//                   groups) that falls into it, which compressed word covers it.
-//   expand kernel : output-centric and therefore load balanced whatever the fill
-//                   lengths are: a persistent grid walks output tiles of 8192 groups
-//                   = 7936 words; one thread produces 32 groups = 31 output words
-//                   (binary search for its first source word, then a short walk),
-//                   31->32 repack with funnel shifts (kernels.cu:375), staged through
-//                   shared memory and written as full 128-bit lines.
+//                   decoupled look-back (CTA-wide window) give every tile its group
+//                   offset, and each tile records, for every OUTPUT tile boundary
+//                   (multiples of 8192 groups) that falls into it, which compressed
+//                   word covers it.
+//   expand kernel : output-centric, hence load balanced whatever the fill lengths
+//                   are.  A persistent grid walks output tiles of 8192 groups = 7936
+//                   words.  Per tile the one-group-per-int array of the reference
+//                   lives in SHARED memory: compressed words are read coalesced,
+//                   scanned in registers and scattered (literal = one store, zero
+//                   fill = nothing, one fill = a run of stores); then one thread
+//                   repacks 32 groups into 31 words with compile-time funnel shifts
+//                   (mergeWords, kernels.cu:375) and the tile leaves as 128-bit lines.
 // Output tiles are aligned in group space to multiples of 32 groups = 31 words, so no
 // output word is shared between threads or tiles and nothing needs atomics.
 #include "wah_common.cuh"
@@ -27,259 +30,385 @@ namespace {
 
 constexpr uint64_t ST_EMPTY = 0, ST_AGG = 1, ST_INCL = 2;
 constexpr uint64_t VALUE_MASK = (1ull << 62) - 1ull;
-
-__device__ __forceinline__ uint64_t ceil_div_u64(uint64_t a, uint64_t b) { return (a + b - 1) / b; }
+constexpr uint32_t TG_SHIFT = 13;
+static_assert((1u << TG_SHIFT) == (uint32_t)EXPAND_TILE_GROUPS, "output tile must be 8192 groups");
 
 // ------------------------------------------------------------------ scan kernel
+
+// Group counts of one tile of compressed words, kept in registers while the NEXT tile is summed and
+// published (software pipeline, as in the compressor).
+struct ScanState {
+    uint32_t cnt[SCAN_ITEMS];
+    uint64_t first_off;   // group offset of my first word relative to the tile start
+    uint64_t tile_sum;
+};
 
 __global__ void __launch_bounds__(SCAN_THREADS) wah_scan_kernel(const ScanParams p)
 {
     constexpr int NW = SCAN_THREADS / 32;
-    constexpr uint64_t TG = EXPAND_TILE_GROUPS;
+    constexpr int LB = 3;   // look-back window = LB * SCAN_THREADS tiles per round
+    constexpr uint64_t TGM = (uint64_t)EXPAND_TILE_GROUPS - 1ull;
     __shared__ uint64_t s_wsum[NW];
-    __shared__ uint64_t s_base;
-    __shared__ uint32_t s_tile;
+    __shared__ uint64_t s_lb_sum[LB * NW];
+    __shared__ uint32_t s_lb_incl[LB * NW];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    if (tid == 0) s_tile = atomicAdd(&p.hdr->ticket, 1u);
-    __syncthreads();
-    const uint32_t tile = s_tile;
+    const uint32_t stride = gridDim.x;
 
     // blocked arrangement: thread owns SCAN_ITEMS consecutive compressed words
-    const uint64_t w_begin = (uint64_t)tile * SCAN_TILE_WORDS + (uint64_t)tid * SCAN_ITEMS;
-    uint32_t w[SCAN_ITEMS];
-    if (w_begin + SCAN_ITEMS <= p.c_words) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.in + w_begin);
+    auto load = [&](uint32_t tile, uint32_t (&w)[SCAN_ITEMS]) {
+        const uint64_t w_begin = (uint64_t)tile * SCAN_TILE_WORDS + (uint64_t)tid * SCAN_ITEMS;
+        if (tile < p.n_tiles && w_begin + SCAN_ITEMS <= p.c_words) {
+            const uint4 *src = reinterpret_cast<const uint4 *>(p.in + w_begin);
 #pragma unroll
-        for (int v = 0; v < SCAN_ITEMS / 4; v++) {
-            const uint4 x = ld_stream_v4(src + v);
-            w[4 * v + 0] = x.x;
-            w[4 * v + 1] = x.y;
-            w[4 * v + 2] = x.z;
-            w[4 * v + 3] = x.w;
-        }
-    } else {
-#pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++)
-            w[i] = (w_begin + i < p.c_words) ? ld_stream_u32(p.in + w_begin + i) : BIT31;   // fill of 0 groups
-    }
-
-    uint32_t cnt[SCAN_ITEMS];
-    uint64_t tsum = 0;
-    uint32_t bad = 0;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        cnt[i] = word_groups(w[i]);   // getCounts, kernels.cu:298-304
-        tsum += cnt[i];
-        bad += (cnt[i] == 0u && w_begin + i < p.c_words) ? 1u : 0u;
-    }
-    bad = warp_sum(bad);
-    if (lane == 0 && bad) atomicAdd(&p.hdr->bad_words, bad);
-
-    const uint64_t incl = warp_incl_scan_u64(tsum);
-    if (lane == 31) s_wsum[warp] = incl;
-    __syncthreads();
-
-    // ---- tile total + decoupled look-back (status:2 | value:62)
-    if (warp == 0) {
-        uint64_t tile_sum = 0;
-#pragma unroll
-        for (int k = 0; k < NW; k++) tile_sum += s_wsum[k];
-        uint64_t excl = 0;
-        if (tile == 0u) {
-            if (lane == 0) st_relaxed_u64(p.desc, (ST_INCL << 62) | tile_sum);
+            for (int v = 0; v < SCAN_ITEMS / 4; v++) {
+                const uint4 x = ld_stream_v4(src + v);
+                w[4 * v + 0] = x.x;
+                w[4 * v + 1] = x.y;
+                w[4 * v + 2] = x.z;
+                w[4 * v + 3] = x.w;
+            }
         } else {
-            if (lane == 0) st_relaxed_u64(p.desc + tile, (ST_AGG << 62) | tile_sum);
-            int64_t look = (int64_t)tile - 1 - (int64_t)lane;
+#pragma unroll
+            for (int i = 0; i < SCAN_ITEMS; i++)
+                w[i] = (tile < p.n_tiles && w_begin + i < p.c_words) ? ld_stream_u32(p.in + w_begin + i)
+                                                                      : BIT31;   // fill of 0 groups
+        }
+    };
+
+    // counts, block scan, publish the tile's aggregate
+    auto summarize = [&](uint32_t tile, const uint32_t (&w)[SCAN_ITEMS]) -> ScanState {
+        ScanState st;
+        const uint64_t w_begin = (uint64_t)tile * SCAN_TILE_WORDS + (uint64_t)tid * SCAN_ITEMS;
+        uint64_t tsum = 0;
+        uint32_t bad = 0;
+#pragma unroll
+        for (int i = 0; i < SCAN_ITEMS; i++) {
+            st.cnt[i] = word_groups(w[i]);   // getCounts, kernels.cu:298-304
+            tsum += st.cnt[i];
+            bad += (st.cnt[i] == 0u && w_begin + i < p.c_words) ? 1u : 0u;
+        }
+        if (__any_sync(0xffffffffu, bad != 0u)) {
+            bad = warp_sum(bad);
+            if (lane == 0) atomicAdd(&p.hdr->bad_words, bad);
+        }
+        const uint64_t incl = warp_incl_scan_u64(tsum);
+        __syncthreads();   // the previous tile's warp sums have been consumed
+        if (lane == 31) s_wsum[warp] = incl;
+        __syncthreads();
+        uint64_t tile_sum = 0, wprefix = 0;
+#pragma unroll
+        for (int k = 0; k < NW; k++) {
+            const uint64_t s = s_wsum[k];
+            if (k < (int)warp) wprefix += s;
+            tile_sum += s;
+        }
+        st.first_off = wprefix + incl - tsum;
+        st.tile_sum = tile_sum;
+        if (tid == 0) st_relaxed_u64(p.desc + tile, ((tile == 0u ? ST_INCL : ST_AGG) << 62) | tile_sum);
+        return st;
+    };
+
+    uint32_t tile = blockIdx.x;
+    uint32_t raw[SCAN_ITEMS];
+    load(tile, raw);
+    ScanState cur = summarize(tile, raw);
+    load(tile + stride, raw);
+
+    while (tile < p.n_tiles) {
+        const uint32_t next = tile + stride;
+        ScanState nxt;
+        if (next < p.n_tiles) {
+            nxt = summarize(next, raw);   // published before this tile's look-back (see wah_compress.cu)
+            load(next + stride, raw);
+        }
+
+        // ---- decoupled look-back (status:2 | value:62), LB 32-tile windows per warp and round
+        uint64_t excl = 0;
+        if (tile != 0u) {
+            int64_t look = (int64_t)tile - 1 - (int64_t)tid;
             while (true) {
-                uint64_t d;
-                do {
-                    d = look >= 0 ? ld_relaxed_u64(p.desc + look) : (ST_INCL << 62);
-                } while (__any_sync(0xffffffffu, (d >> 62) == ST_EMPTY));
-                const uint32_t incl_mask = __ballot_sync(0xffffffffu, (d >> 62) == ST_INCL);
-                const uint32_t first_incl = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 32u;
-                excl += warp_sum_u64(lane <= first_incl ? (d & VALUE_MASK) : 0ull);
-                if (first_incl < 32u) break;
-                look -= 32;
-            }
-            if (lane == 0) st_relaxed_u64(p.desc + tile, (ST_INCL << 62) | (excl + tile_sum));
-        }
-        if (lane == 0) {
-            s_base = excl;
-            if (tile == p.n_tiles - 1u) {
-                // decompress.cu:82-93: G = last offset + last count, realSize = ceil(31 G / 32)
-                const uint64_t G = excl + tile_sum;
-                const uint64_t words = (G >> 5) * 31ull + (((G & 31ull) * 31ull + 31ull) >> 5);
-                p.hdr->groups = G;
-                p.hdr->words = words;
-                p.hdr->out_tiles = ceil_div_u64(G, TG);
-                if (p.out_info) {
-                    p.out_info[0] = words;
-                    p.out_info[1] = G;
+#pragma unroll
+                for (int r = 0; r < LB; r++) {
+                    const int64_t lk = look - (int64_t)r * SCAN_THREADS;
+                    uint64_t d;
+                    if (lk >= 0) {
+                        do {
+                            d = ld_relaxed_u64(p.desc + lk);
+                        } while ((d >> 62) == ST_EMPTY);
+                    } else {
+                        d = ST_INCL << 62;
+                    }
+                    const uint32_t incl_mask = __ballot_sync(0xffffffffu, (d >> 62) == ST_INCL);
+                    const uint32_t first_incl = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 32u;
+                    const uint64_t sm = warp_sum_u64(lane <= first_incl ? (d & VALUE_MASK) : 0ull);
+                    if (lane == 0) {
+                        s_lb_sum[r * NW + warp] = sm;
+                        s_lb_incl[r * NW + warp] = first_incl < 32u;
+                    }
                 }
+                __syncthreads();
+                bool done = false;
+#pragma unroll
+                for (int k = 0; k < LB * NW; k++) {
+                    if (!done) {
+                        excl += s_lb_sum[k];
+                        done = s_lb_incl[k] != 0u;
+                    }
+                }
+                if (done) break;
+                look -= LB * SCAN_THREADS;
+                __syncthreads();
+            }
+            if (tid == 0) st_relaxed_u64(p.desc + tile, (ST_INCL << 62) | (excl + cur.tile_sum));
+        }
+        if (tid == 0 && tile == p.n_tiles - 1u) {
+            // decompress.cu:82-93: G = last offset + last count, realSize = ceil(31 G / 32)
+            const uint64_t G = excl + cur.tile_sum;
+            const uint64_t words = (G >> 5) * 31ull + (((G & 31ull) * 31ull + 31ull) >> 5);
+            p.hdr->groups = G;
+            p.hdr->words = words;
+            p.hdr->out_tiles = (G + TGM) >> TG_SHIFT;
+            if (p.out_info) {
+                p.out_info[0] = words;
+                p.out_info[1] = G;
             }
         }
-    }
-    __syncthreads();
 
-    if (p.starts == nullptr) return;
-
-    // ---- which compressed word covers each output-tile boundary k*TG ?
-    uint64_t wprefix = 0;
+        // ---- which compressed word covers each output-tile boundary k * 8192 ?
+        if (p.starts != nullptr) {
+            const uint64_t w_begin = (uint64_t)tile * SCAN_TILE_WORDS + (uint64_t)tid * SCAN_ITEMS;
+            uint64_t off = excl + cur.first_off;   // group offset of my first word
+            const uint64_t k_limit = p.max_out_tiles + 1ull;
 #pragma unroll
-    for (int k = 0; k < NW; k++)
-        if (k < (int)warp) wprefix += s_wsum[k];
-    uint64_t off = s_base + wprefix + incl - tsum;   // group offset of my first word
-    const uint64_t k_limit = p.max_out_tiles + 1ull;
-#pragma unroll
-    for (int i = 0; i < SCAN_ITEMS; i++) {
-        // boundaries with off <= k*TG < off + cnt
-        uint64_t k_first = ceil_div_u64(off, TG);
-        uint64_t k_end = ceil_div_u64(off + cnt[i], TG);
-        if (k_end > k_limit) k_end = k_limit;
-        if (k_first > k_end) k_first = k_end;
-        const bool heavy = (k_end - k_first) > 4ull;
-        uint32_t hm = __ballot_sync(0xffffffffu, heavy);
-        while (hm) {
-            // a long fill spans many output tiles: the whole warp writes its boundaries
-            const int srcl = __ffs(hm) - 1;
-            hm &= hm - 1u;
-            const uint64_t kf = __shfl_sync(0xffffffffu, k_first, srcl);
-            const uint64_t ke = __shfl_sync(0xffffffffu, k_end, srcl);
-            const uint64_t o = __shfl_sync(0xffffffffu, off, srcl);
-            const uint64_t wi = __shfl_sync(0xffffffffu, w_begin, srcl) + (uint64_t)i;
-            for (uint64_t k = kf + lane; k < ke; k += 32) p.starts[k] = make_ulonglong2(wi, o);
+            for (int i = 0; i < SCAN_ITEMS; i++) {
+                // boundaries with off <= k * 8192 < off + cnt
+                uint64_t k_first = (off + TGM) >> TG_SHIFT;
+                uint64_t k_end = (off + cur.cnt[i] + TGM) >> TG_SHIFT;
+                if (k_end > k_limit) k_end = k_limit;
+                if (k_first > k_end) k_first = k_end;
+                const bool heavy = (k_end - k_first) > 4ull;
+                uint32_t hm = __ballot_sync(0xffffffffu, heavy);
+                while (hm) {
+                    // a long fill spans many output tiles: the whole warp writes its boundaries
+                    const int srcl = __ffs(hm) - 1;
+                    hm &= hm - 1u;
+                    const uint64_t kf = __shfl_sync(0xffffffffu, k_first, srcl);
+                    const uint64_t ke = __shfl_sync(0xffffffffu, k_end, srcl);
+                    const uint64_t o = __shfl_sync(0xffffffffu, off, srcl);
+                    const uint64_t wi = __shfl_sync(0xffffffffu, w_begin, srcl) + (uint64_t)i;
+                    for (uint64_t k = kf + lane; k < ke; k += 32) p.starts[k] = make_ulonglong2(wi, o);
+                }
+                if (!heavy)
+                    for (uint64_t k = k_first; k < k_end; k++) p.starts[k] = make_ulonglong2(w_begin + i, off);
+                off += cur.cnt[i];
+            }
         }
-        if (!heavy)
-            for (uint64_t k = k_first; k < k_end; k++) p.starts[k] = make_ulonglong2(w_begin + i, off);
-        off += cnt[i];
+        __syncthreads();   // look-back partials are rewritten by the next tile
+        tile = next;
+        cur = nxt;
     }
 }
 
 // ---------------------------------------------------------------- expand kernel
 
+constexpr int EXP_CHUNK = EXPAND_THREADS * 8;          // compressed words scanned per round
+constexpr int GRP_WORDS = EXPAND_TILE_GROUPS + EXPAND_TILE_GROUPS / 32;   // rows of 32 groups padded to 33
+constexpr int EXP_LIST = 512;                          // long one-fills deferred to a warp-wide store loop
+constexpr uint32_t EXP_CLAMP = 2u * EXPAND_TILE_GROUPS;   // any count >= the tile span behaves the same
+
+__device__ __forceinline__ uint32_t grp_pos(uint32_t g) { return g + (g >> 5); }
+
+__device__ __forceinline__ void load8(const ExpandParams &p, uint64_t i0, uint32_t (&w)[8])
+{
+    if (i0 + 8 <= p.c_words) {
+        const uint4 *src = reinterpret_cast<const uint4 *>(p.in + i0);
+        const uint4 a = ld_stream_v4(src), b = ld_stream_v4(src + 1);
+        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
+        w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
+    } else {
+#pragma unroll
+        for (int i = 0; i < 8; i++) w[i] = (i0 + i < p.c_words) ? ld_stream_u32(p.in + i0 + i) : BIT31;
+    }
+}
+
 __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const ExpandParams p)
 {
     constexpr int NW = EXPAND_THREADS / 32;
-    constexpr uint32_t CLAMP = 2u * EXPAND_TILE_GROUPS;   // any count >= tile span behaves the same
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *s_cw = smem;                         // EXPAND_MAX_CWORDS compressed words
-    uint32_t *s_off = smem + EXPAND_MAX_CWORDS;    // their group offsets relative to the tile start
-    uint32_t *s_stage = smem;                      // EXPAND_TILE_WORDS output words (aliases the above)
+    uint32_t *s_grp = smem;                  // GRP_WORDS: one group per int, rows of 32 padded to 33
+    uint32_t *s_stage = smem + GRP_WORDS;    // EXPAND_TILE_WORDS output words
     __shared__ uint32_t s_wsum[NW];
+    __shared__ uint2 s_list[EXP_LIST];
+    __shared__ uint32_t s_nlist;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t G = p.hdr->groups;
     uint64_t total_words = p.hdr->words;
     if (total_words > p.out_cap) total_words = p.out_cap;
     const uint64_t real_tiles = p.hdr->out_tiles;
-    const uint64_t n_tiles = real_tiles < p.max_out_tiles ? real_tiles : p.max_out_tiles;
+    uint64_t n_tiles = real_tiles < p.max_out_tiles ? real_tiles : p.max_out_tiles;
+    {
+        const uint64_t need = (total_words + EXPAND_TILE_WORDS - 1) / EXPAND_TILE_WORDS;   // tiles with room
+        if (n_tiles > need) n_tiles = need;
+    }
 
-    for (uint64_t ot = blockIdx.x; ot < n_tiles; ot += gridDim.x) {
-        const ulonglong2 st = p.starts[ot];
-        const uint64_t ws = st.x;
-        const uint64_t we = (ot + 1 < real_tiles) ? p.starts[ot + 1].x : p.c_words - 1;
-        uint32_t nw = (uint32_t)(we - ws + 1);            // <= EXPAND_TILE_GROUPS + 1 for a well-formed stream
-        if (nw > (uint32_t)EXPAND_MAX_CWORDS) nw = EXPAND_MAX_CWORDS;   // zero-length fills: flagged by the scan
-        const uint64_t g_lo = ot * (uint64_t)EXPAND_TILE_GROUPS;
-        const uint32_t skip = (uint32_t)(g_lo - st.y);    // groups of word ws that belong to earlier tiles
-
-        for (uint32_t i = tid; i < nw; i += EXPAND_THREADS) s_cw[i] = ld_stream_u32(p.in + ws + i);
-        __syncthreads();
-
-        // ---- block scan of the (clamped) group counts -> s_off
-        const uint32_t ipt = (nw + EXPAND_THREADS - 1) / EXPAND_THREADS;
-        const uint32_t i0 = tid * ipt;
-        uint32_t tsum = 0;
-        for (uint32_t i = i0; i < i0 + ipt && i < nw; i++) {
-            uint32_t c = word_groups(s_cw[i]);
-            if (i == 0) c -= skip;
-            tsum += c > CLAMP ? CLAMP : c;
+    // where a tile's compressed words start / end (written by the scan kernel)
+    auto tile_info = [&](uint64_t ot, uint64_t &ws, uint64_t &we, uint32_t &skip, uint32_t &first) {
+        if (ot < n_tiles) {
+            const ulonglong2 st = p.starts[ot];
+            ws = st.x;
+            we = (ot + 1 < real_tiles) ? p.starts[ot + 1].x : p.c_words - 1;
+            skip = (uint32_t)((ot << TG_SHIFT) - st.y);   // groups of word ws that belong to earlier tiles
+            first = (ws == we) ? p.in[ws] : 0u;           // a tile inside ONE word is written without decoding
+        } else {
+            ws = we = 0;
+            skip = first = 0;
         }
-        const uint32_t incl = warp_incl_scan(tsum);
-        if (lane == 31) s_wsum[warp] = incl;
-        __syncthreads();
-        uint32_t run = incl - tsum;
-#pragma unroll
-        for (int k = 0; k < NW; k++)
-            if (k < (int)warp) run += s_wsum[k];
-        for (uint32_t i = i0; i < i0 + ipt && i < nw; i++) {
-            uint32_t c = word_groups(s_cw[i]);
-            if (i == 0) c -= skip;
-            s_off[i] = run;
-            run += c > CLAMP ? CLAMP : c;
-        }
-        __syncthreads();
+    };
 
-        // ---- my 32 groups -> 31 output words
-        const uint32_t rel = 32u * tid;
-        const bool active = g_lo + rel < G;
-        uint32_t o[31];
-        if (active) {
-            // last word whose offset is <= rel
-            uint32_t lo = 0, hi = nw;   // invariant: s_off[lo] <= rel, answer in [lo, hi)
-            while (hi - lo > 1u) {
-                const uint32_t mid = (lo + hi) >> 1;
-                if (s_off[mid] <= rel) lo = mid;
-                else hi = mid;
-            }
-            uint32_t idx = lo;
-            uint32_t wv = s_cw[idx];
-            uint32_t c = word_groups(wv);
-            if (idx == 0) c -= skip;
-            if (c > CLAMP) c = CLAMP;
-            uint32_t rem = s_off[idx] + c - rel;                                   // groups of word idx left at rel
-            uint32_t val = is_fill(wv) ? ((wv & BIT30) ? ONES31 : 0u) : wv;       // kernels.cu:337-354
-            if (rem >= 32u) {
-                // whole chunk inside one fill
-                const uint32_t f = val ? 0xFFFFFFFFu : 0u;
-#pragma unroll
-                for (int j = 0; j < 31; j++) o[j] = f;
-            } else {
-                uint32_t pg = 0;
-#pragma unroll
-                for (int j = 0; j < 32; j++) {
-                    if (rem == 0u) {
-                        do {
-                            idx++;
-                            if (idx >= nw) {   // past the end of the stream: zero padding
-                                val = 0u;
-                                rem = 64u;
-                                break;
-                            }
-                            wv = s_cw[idx];
-                            rem = word_groups(wv);
-                            val = is_fill(wv) ? ((wv & BIT30) ? ONES31 : 0u) : wv;
-                        } while (rem == 0u);
-                    }
-                    // 31 -> 32 repack (mergeWords, kernels.cu:375):
-                    // word j-1 = group[j-1] >> (j-1) | group[j] << (32-j)
-                    if (j > 0) o[j - 1] = __funnelshift_r(pg << 1, val, j);
-                    pg = val;
-                    rem--;
-                }
-            }
-        }
-        __syncthreads();   // everyone is done with s_cw / s_off
-        if (active) {
-#pragma unroll
-            for (int j = 0; j < 31; j++) s_stage[31u * tid + j] = o[j];
-        }
-        __syncthreads();
+    uint64_t ot = blockIdx.x;
+    uint64_t ws, we, ws_n, we_n;
+    uint32_t skip, skip_n, first, first_n;
+    uint32_t w[8];
+    tile_info(ot, ws, we, skip, first);
+    if (ot < n_tiles) load8(p, (ws & ~3ull) + 8ull * tid, w);
 
-        // ---- coalesced write of the tile
+    for (; ot < n_tiles; ot += gridDim.x) {
+        // the next tile's bookkeeping is fetched now and its first words after the scatter below, so
+        // neither load latency sits on the next iteration's critical path
+        tile_info(ot + gridDim.x, ws_n, we_n, skip_n, first_n);
+
+        const uint64_t g_lo = ot << TG_SHIFT;
         const uint64_t w_lo = ot * (uint64_t)EXPAND_TILE_WORDS;
-        if (w_lo < total_words) {
-            const uint64_t avail = total_words - w_lo;
-            const uint32_t nout = avail < (uint64_t)EXPAND_TILE_WORDS ? (uint32_t)avail : (uint32_t)EXPAND_TILE_WORDS;
-            uint32_t *dst = p.out + w_lo;
-            const uint32_t nvec = nout >> 2;
-            uint4 *dst4 = reinterpret_cast<uint4 *>(dst);
+        const uint64_t avail = total_words - w_lo;
+        const uint32_t nout = avail < (uint64_t)EXPAND_TILE_WORDS ? (uint32_t)avail : (uint32_t)EXPAND_TILE_WORDS;
+        uint32_t *dst = p.out + w_lo;
+        uint4 *dst4 = reinterpret_cast<uint4 *>(dst);
+        const uint32_t nvec = nout >> 2;
+        const uint64_t wa = ws & ~3ull;   // 16-byte aligned start; words before ws are ignored
+
+        bool fast = false;
+        if (ws == we && is_fill(first) && (ot + 1 < real_tiles || !(first & BIT30))) {
+            // the whole tile lies inside one fill word (the stream's last tile may end in a partly
+            // padded word: a one-fill there takes the general path)
+            fast = true;
+            const uint32_t f = (first & BIT30) ? 0xFFFFFFFFu : 0u;
+            const uint4 v = make_uint4(f, f, f, f);
+            for (uint32_t i = tid; i < nvec; i += EXPAND_THREADS) st_stream_v4(dst4 + i, v);
+            for (uint32_t i = (nvec << 2) + tid; i < nout; i += EXPAND_THREADS) dst[i] = f;
+        }
+        if (fast) {
+            ws = ws_n;
+            we = we_n;
+            skip = skip_n;
+            first = first_n;
+            if (ot + gridDim.x < n_tiles) load8(p, (ws & ~3ull) + 8ull * tid, w);
+            continue;
+        }
+
+        // ---- 1. clear the group array
+        {
+            uint4 *z = reinterpret_cast<uint4 *>(s_grp);
+            for (uint32_t i = tid; i < GRP_WORDS / 4; i += EXPAND_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+            if (tid == 0) s_nlist = 0;
+        }
+        __syncthreads();   // also: the previous tile's staging area has been written out
+
+        // ---- 2. scan the compressed words of the tile in rounds of EXP_CHUNK and scatter them
+        const uint32_t nw = (uint32_t)(we - wa + 1);    // words wa .. we
+        int32_t running = 0;                            // group offset (tile relative) of the round's first word
+        for (uint32_t c0 = 0; c0 < nw; c0 += EXP_CHUNK) {
+            const uint64_t i0 = wa + c0 + 8ull * tid;   // my 8 consecutive words
+            if (c0 != 0) load8(p, i0, w);
+            uint32_t c[8];
+            uint32_t tsum = 0;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                const uint64_t gi = i0 + i;
+                uint32_t x = word_groups(w[i]);
+                if (gi < ws || gi > we) x = 0;           // outside this tile's word range
+                else if (gi == ws) x -= skip;            // part of the first word belongs to earlier tiles
+                c[i] = x > EXP_CLAMP ? EXP_CLAMP : x;
+                tsum += c[i];
+            }
+            const uint32_t incl = warp_incl_scan(tsum);
+            if (c0 != 0) __syncthreads();   // previous round's s_wsum consumed
+            if (lane == 31) s_wsum[warp] = incl;
+            __syncthreads();
+            int32_t off = running + (int32_t)(incl - tsum);
+            uint32_t round_sum = 0;
+#pragma unroll
+            for (int k = 0; k < NW; k++) {
+                const uint32_t sv = s_wsum[k];
+                if (k < (int)warp) off += (int32_t)sv;
+                round_sum += sv;
+            }
+            running += (int32_t)round_sum;
+#pragma unroll
+            for (int i = 0; i < 8; i++) {
+                if (c[i] != 0u && off < EXPAND_TILE_GROUPS) {
+                    const uint32_t wv = w[i];
+                    if (!is_fill(wv)) {
+                        s_grp[grp_pos((uint32_t)off)] = wv;                      // kernels.cu:351-354
+                    } else if (wv & BIT30) {                                      // one-fill, kernels.cu:337-348
+                        const uint32_t lo = (uint32_t)off;
+                        uint32_t hi = lo + c[i];
+                        if (hi > (uint32_t)EXPAND_TILE_GROUPS) hi = EXPAND_TILE_GROUPS;
+                        if (hi - lo <= 8u) {
+                            for (uint32_t g = lo; g < hi; g++) s_grp[grp_pos(g)] = ONES31;
+                        } else {
+                            const uint32_t e = atomicAdd(&s_nlist, 1u);
+                            if (e < EXP_LIST) s_list[e] = make_uint2(lo, hi);
+                            else for (uint32_t g = lo; g < hi; g++) s_grp[grp_pos(g)] = ONES31;
+                        }
+                    }
+                }
+                off += (int32_t)c[i];
+            }
+            if (running >= EXPAND_TILE_GROUPS) break;   // uniform: the tile is covered
+        }
+        // start fetching the next tile's first words; they are consumed one iteration from now
+        ws = ws_n;
+        we = we_n;
+        skip = skip_n;
+        first = first_n;
+        if (ot + gridDim.x < n_tiles) load8(p, (ws & ~3ull) + 8ull * tid, w);
+        __syncthreads();
+
+        // ---- 3. long one-fills: a warp per run
+        {
+            const uint32_t nl = s_nlist < (uint32_t)EXP_LIST ? s_nlist : (uint32_t)EXP_LIST;
+            for (uint32_t e = warp; e < nl; e += NW) {
+                const uint2 r = s_list[e];
+                for (uint32_t g = r.x + lane; g < r.y; g += 32) s_grp[grp_pos(g)] = ONES31;
+            }
+            if (nl) __syncthreads();
+        }
+
+        // ---- 4. my 32 groups -> 31 output words (mergeWords, kernels.cu:375:
+        //         word j = group[j] >> j | group[j+1] << (31-j)); rows padded to 33 = conflict free
+        if (g_lo + 32ull * tid < G) {
+            const uint32_t *r = s_grp + 33u * tid;
+            uint32_t *o = s_stage + 31u * tid;
+            uint32_t a = r[0];
+#pragma unroll
+            for (int j = 0; j < 31; j++) {
+                const uint32_t b = r[j + 1];
+                o[j] = __funnelshift_r(a << 1, b, j + 1);
+                a = b;
+            }
+        }
+        __syncthreads();
+
+        // ---- 5. coalesced 128-bit write of the tile
+        {
             const uint4 *src4 = reinterpret_cast<const uint4 *>(s_stage);
             for (uint32_t i = tid; i < nvec; i += EXPAND_THREADS) st_stream_v4(dst4 + i, src4[i]);
             for (uint32_t i = (nvec << 2) + tid; i < nout; i += EXPAND_THREADS) dst[i] = s_stage[i];
         }
-        __syncthreads();   // staging is reused as s_cw by the next tile
+        // no barrier here: the next tile's clear touches s_grp only, and its first barrier orders this
+        // tile's staging reads before the next repack writes
     }
 }
 
@@ -287,20 +416,41 @@ __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const Exp
 
 size_t expand_smem_bytes()
 {
-    return (size_t)(2 * EXPAND_MAX_CWORDS) * sizeof(uint32_t);
+    return (size_t)(GRP_WORDS + EXPAND_TILE_WORDS) * sizeof(uint32_t);
 }
 
 cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream)
 {
-    wah_scan_kernel<<<p.n_tiles, SCAN_THREADS, 0, stream>>>(p);
-    return cudaGetLastError();
+    // persistent + cooperative: the look-back spins on tiles owned by other CTAs, all must be resident
+    static int max_grid = 0;
+    if (max_grid == 0) {
+        int dev = 0, sms = 0, per_sm = 0;
+        cudaError_t e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wah_scan_kernel, SCAN_THREADS, 0);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        if (per_sm > 4) per_sm = 4;
+        max_grid = sms * per_sm;
+    }
+    int grid = max_grid;
+    if ((uint32_t)grid > p.n_tiles) grid = (int)p.n_tiles;
+    ScanParams params = p;
+    void *args[] = {&params};
+    return cudaLaunchCooperativeKernel((const void *)wah_scan_kernel, dim3(grid), dim3(SCAN_THREADS), args, 0, stream);
 }
 
 cudaError_t launch_expand(const ExpandParams &p, int grid, cudaStream_t stream)
 {
     const size_t smem = expand_smem_bytes();
-    cudaError_t e = cudaFuncSetAttribute(wah_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-    if (e != cudaSuccess) return e;
+    static bool configured = false;
+    if (!configured) {
+        cudaError_t e = cudaFuncSetAttribute(wah_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        configured = true;
+    }
     wah_expand_kernel<<<grid, EXPAND_THREADS, smem, stream>>>(p);
     return cudaGetLastError();
 }

@@ -55,31 +55,45 @@ def word_groups(w):
 ST_EMPTY, ST_AGG, ST_INCL = 0, 1, 2
 
 
-def lookback(desc, tile, block_mode, t_in_col, rng):
-    """Mirror of the warp-0 look-back loop.  ``desc[i]`` = (status, no_tail, open, count); to
-    exercise the AGGREGATE path, predecessors are randomly presented in their aggregate form."""
+def lookback(desc, tile, block_mode, t_in_col, rng, threads=256):
+    """Mirror of the CTA-wide look-back: every warp reduces its own 32-tile window, the partials are
+    combined in warp order.  ``desc[i]`` = (aggregate form, inclusive form); to exercise the AGGREGATE
+    path, predecessors are randomly presented in their aggregate form."""
+    NW = threads // 32
     excl, carry = 0, 0
     open_done = block_mode or t_in_col == 0
     look0 = tile - 1
     while True:
-        lanes = []
-        for lane in range(32):
-            look = look0 - lane
-            if look < 0:
-                lanes.append((ST_INCL, 0, 0, 0))
-            else:
-                agg, incl = desc[look]
-                lanes.append(agg if (agg is not None and rng.random() < 0.5 and look > 0) else incl)
-        first_incl = next((i for i, d in enumerate(lanes) if d[0] == ST_INCL), 32)
-        part = [lane <= first_incl for lane in range(32)]
-        excl += sum(d[3] for lane, d in enumerate(lanes) if part[lane])
-        if not open_done:
-            first_term = next((i for i, d in enumerate(lanes) if part[i] and (d[0] == ST_INCL or not d[1])), 32)
-            carry += sum(d[2] for lane, d in enumerate(lanes) if part[lane] and lane <= first_term)
-            open_done = first_term < 32
-        if first_incl < 32:
+        parts = []
+        for warp in range(NW):
+            lanes = []
+            for lane in range(32):
+                look = look0 - (32 * warp + lane)
+                if look < 0:
+                    lanes.append((ST_INCL, 0, 0, 0))
+                else:
+                    agg, incl = desc[look]
+                    lanes.append(agg if (agg is not None and rng.random() < 0.6 and look > 0) else incl)
+            first_incl = next((i for i, d in enumerate(lanes) if d[0] == ST_INCL), 32)
+            part = [lane <= first_incl for lane in range(32)]
+            csum = sum(d[3] for lane, d in enumerate(lanes) if part[lane])
+            osum, flags = 0, (1 if first_incl < 32 else 0)
+            if not block_mode:
+                first_term = next((i for i, d in enumerate(lanes) if part[i] and (d[0] == ST_INCL or not d[1])), 32)
+                osum = sum(d[2] for lane, d in enumerate(lanes) if part[lane] and lane <= first_term)
+                flags |= 2 if first_term < 32 else 0
+            parts.append((csum, osum, flags))
+        done = False
+        for csum, osum, flags in parts:
+            if not done:
+                excl += csum
+                if not open_done:
+                    carry += osum
+                    open_done = bool(flags & 2)
+                done = bool(flags & 1)
+        if done:
             break
-        look0 -= 32
+        look0 -= threads
     return excl, carry
 
 
@@ -119,18 +133,18 @@ def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0):
             vmask = M32 if nvalid == 32 else ((1 << nvalid) - 1)
             Z = O = 0
             prev = row[0]
-            v = prev & ONES31
-            Z |= 1 if v == 0 else 0
-            O |= 1 if v == ONES31 else 0
+            u = (prev << 1) & M32          # u = group << 1 | one junk bit
+            Z |= 1 if (u & 0xFFFFFFFE) == 0 else 0
+            O |= 1 if (~u & 0xFFFFFFFE) == 0 else 0
             for j in range(1, 31):
                 cur = row[j]
-                v = funnelshift_r(prev, cur, 32 - j) & ONES31
-                Z |= (1 << j) if v == 0 else 0
-                O |= (1 << j) if v == ONES31 else 0
+                u = funnelshift_r(prev, cur, 31 - j)
+                Z |= (1 << j) if (u & 0xFFFFFFFE) == 0 else 0
+                O |= (1 << j) if (~u & 0xFFFFFFFE) == 0 else 0
                 prev = cur
-            v = prev >> 1
-            Z |= BIT31 if v == 0 else 0
-            O |= BIT31 if v == ONES31 else 0
+            u = prev
+            Z |= BIT31 if (u & 0xFFFFFFFE) == 0 else 0
+            O |= BIT31 if (~u & 0xFFFFFFFE) == 0 else 0
             Z &= vmask
             O &= vmask
             F = Z | O
@@ -179,7 +193,7 @@ def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0):
                 desc[0] = (None, (ST_INCL, 0, tile_open, tile_cnt))
         else:
             agg = (ST_AGG, tile_has ^ 1, tile_open, tile_cnt)
-            excl, carry = lookback(desc, tile, block_mode, t, rng)
+            excl, carry = lookback(desc, tile, block_mode, t, rng, threads)
             incl_open = tile_open if tile_has else carry + tile_open
             desc[tile] = (agg, (ST_INCL, 0, incl_open, excl + tile_cnt))
         s_excl = excl
@@ -305,9 +319,16 @@ def scan_model(cw, max_out_tiles):
     return G, words, (G + TG - 1) // TG, starts
 
 
+def grp_pos(g):
+    return g + (g >> 5)
+
+
 def expand_model(cw, out_cap=None):
+    """Mirror of wah_expand_kernel: per output tile, scatter the compressed words into a padded
+    one-group-per-int array, then repack rows of 32 groups into 31 words."""
     c = len(cw)
     CLAMP = 2 * TG
+    CHUNK = 2048
     G, words, real_tiles, starts = scan_model(cw, 1 << 40 if out_cap is None else (out_cap + TWO - 1) // TWO)
     total_words = words if out_cap is None else min(words, out_cap)
     out = [None] * total_words
@@ -315,67 +336,66 @@ def expand_model(cw, out_cap=None):
     for ot in range(n_tiles):
         ws, g0 = starts[ot]
         we = starts[ot + 1][0] if ot + 1 < real_tiles else c - 1
-        nw = we - ws + 1
-        assert nw <= TG + 8
         g_lo = ot * TG
         skip = g_lo - g0
-        s_cw = cw[ws: ws + nw]
-        s_off = []
-        run = 0
-        for i in range(nw):
-            cc = word_groups(s_cw[i])
-            if i == 0:
-                cc -= skip
-            s_off.append(run)
-            run += min(cc, CLAMP)
+        w_lo = ot * TWO
+        if w_lo >= total_words:
+            continue
+        nout = min(TWO, total_words - w_lo)
+        first = cw[ws]
+        if ws == we and (first & BIT31) and (ot + 1 < real_tiles or not (first & BIT30)):
+            f = M32 if (first & BIT30) else 0
+            for i in range(nout):
+                out[w_lo + i] = f
+            continue
+        grp = [0] * (TG + TG // 32)
+        wa = ws & ~3
+        nw = we - wa + 1
+        running = 0
+        long_list = []
+        for c0 in range(0, nw, CHUNK):
+            offs = running
+            for tid in range(256):
+                i0 = wa + c0 + 8 * tid
+                for i in range(8):
+                    gi = i0 + i
+                    w = cw[gi] if gi < c else BIT31
+                    x = word_groups(w)
+                    if gi < ws or gi > we:
+                        x = 0
+                    elif gi == ws:
+                        x -= skip
+                    x = min(x, CLAMP)
+                    off = offs
+                    if x != 0 and off < TG:
+                        if not (w & BIT31):
+                            grp[grp_pos(off)] = w
+                        elif w & BIT30:
+                            lo, hi = off, min(off + x, TG)
+                            if hi - lo <= 8:
+                                for g in range(lo, hi):
+                                    grp[grp_pos(g)] = ONES31
+                            else:
+                                long_list.append((lo, hi))
+                    offs += x
+            running = offs
+            if running >= TG:
+                break
+        for lo, hi in long_list:
+            for g in range(lo, hi):
+                grp[grp_pos(g)] = ONES31
         stage = [None] * TWO
         for tid in range(256):
-            rel = 32 * tid
-            if not (g_lo + rel < G):
+            if not (g_lo + 32 * tid < G):
                 continue
-            lo, hi = 0, nw
-            while hi - lo > 1:
-                mid = (lo + hi) >> 1
-                if s_off[mid] <= rel:
-                    lo = mid
-                else:
-                    hi = mid
-            idx = lo
-            wv = s_cw[idx]
-            cc = word_groups(wv)
-            if idx == 0:
-                cc -= skip
-            cc = min(cc, CLAMP)
-            rem = s_off[idx] + cc - rel
-            assert rem >= 1
-            val = (ONES31 if (wv & BIT30) else 0) if (wv & BIT31) else wv
-            o = [0] * 31
-            if rem >= 32:
-                o = [M32 if val else 0] * 31
-            else:
-                pg = 0
-                for j in range(32):
-                    if rem == 0:
-                        while True:
-                            idx += 1
-                            if idx >= nw:
-                                val, rem = 0, 64
-                                break
-                            wv = s_cw[idx]
-                            rem = word_groups(wv)
-                            val = (ONES31 if (wv & BIT30) else 0) if (wv & BIT31) else wv
-                            if rem != 0:
-                                break
-                    if j > 0:
-                        o[j - 1] = funnelshift_r((pg << 1) & M32, val, j)
-                    pg = val
-                    rem -= 1
-            stage[31 * tid: 31 * tid + 31] = o
-        w_lo = ot * TWO
-        if w_lo < total_words:
-            nout = min(TWO, total_words - w_lo)
-            for i in range(nout):
-                assert stage[i] is not None
-                out[w_lo + i] = stage[i]
+            r = grp[33 * tid: 33 * tid + 32]
+            a = r[0]
+            for j in range(31):
+                b = r[j + 1]
+                stage[31 * tid + j] = funnelshift_r((a << 1) & M32, b, j + 1)
+                a = b
+        for i in range(nout):
+            assert stage[i] is not None
+            out[w_lo + i] = stage[i]
     assert all(w is not None for w in out)
     return out, words, G

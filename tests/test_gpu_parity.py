@@ -1,0 +1,271 @@
+"""Parity of the CUDA path (through the C ABI) with the oracle.  Needs a B200."""
+import ctypes
+import json
+import os
+import subprocess
+
+import numpy as np
+import pytest
+import torch
+
+import datagen
+import gpu_wah_b200 as wah
+import oracle_lib as orc
+
+pytestmark = pytest.mark.gpu
+ROOT = os.path.dirname(os.path.dirname(os.path.abspath(__file__)))
+KATS = json.load(open(os.path.join(ROOT, "tests", "golden", "kat.json")))
+TW = 7936
+MODES = [wah.WAH_BLOCK1024, wah.WAH_CANONICAL]
+
+
+def to_dev(a):
+    return torch.from_numpy(np.ascontiguousarray(a).view(np.int32)).cuda()
+
+
+def to_host(t):
+    return t.cpu().numpy().view(np.uint32)
+
+
+def gpu_compress(data, mode, cap=None):
+    n = data.size
+    d_in = to_dev(data) if n else torch.empty(0, dtype=torch.int32, device="cuda")
+    cap = wah.max_compressed_words(n) if cap is None else cap
+    d_out = torch.full((max(cap, 1),), -1, dtype=torch.int32, device="cuda")
+    d_cnt = torch.full((1,), -1, dtype=torch.int64, device="cuda")
+    ws = wah.Workspace.for_compress(n)
+    wah.compress_device(d_in, n, d_out, cap, d_cnt, ws, mode)
+    c = int(d_cnt.item())
+    return to_host(d_out[: min(c, cap)]), c
+
+
+def gpu_decompress(cw, cap=None):
+    c = cw.size
+    d_in = to_dev(cw) if c else torch.empty(0, dtype=torch.int32, device="cuda")
+    words = orc.decoded_words(orc.decoded_groups(cw))
+    cap = words if cap is None else cap
+    d_out = torch.full((max(cap, 1),), -1, dtype=torch.int32, device="cuda")
+    d_info = torch.full((2,), -1, dtype=torch.int64, device="cuda")
+    ws = wah.Workspace.for_decompress(c, cap)
+    wah.decompress_device(d_in, c, d_out, cap, d_info, ws)
+    info = d_info.cpu().tolist()
+    return to_host(d_out[: min(info[0], cap)]), info
+
+
+def _cases():
+    yield "zeros", lambda: np.zeros(2 * TW + 100, dtype=np.uint32)
+    yield "ones", lambda: np.full(5 * TW + 992, 0xFFFFFFFF, dtype=np.uint32)
+    yield "dense", lambda: datagen.uniform(40 * TW + 500, 0.5, 1)
+    yield "sparse", lambda: datagen.uniform(300 * TW + 17, 0.001, 2)
+    yield "sparse_1e-4", lambda: datagen.uniform(300 * TW + 5, 0.0001, 12)
+    yield "d16", lambda: datagen.uniform(64 * TW, 1 / 16, 3)
+    yield "d0.01", lambda: datagen.uniform(64 * TW + 3, 0.01, 13)
+    yield "clustered", lambda: datagen.clustered(100 * TW + 1, 0.3, 300, 4)
+    yield "clustered_long", lambda: datagen.clustered(400 * TW, 0.01, 2000, 5)
+    yield "clustered_1e-4", lambda: datagen.clustered(500 * TW, 0.0001, 1000, 15)
+    yield "mix", lambda: datagen.group_mix(20 * TW + 31, 0.4, 0.3, 6)
+    yield "mix_runs", lambda: datagen.group_mix(30 * TW, 0.45, 0.45, 7, run=40)
+    yield "alternating_fills", lambda: datagen.group_mix(3 * TW + 62, 0.5, 0.5, 8)
+    for n in (1, 2, 30, 31, 32, 33, 991, 992, 993, TW - 1, TW, TW + 1, 2 * TW + 4):
+        yield f"tail_{n}", (lambda n=n: datagen.uniform(n, 0.02, 100 + n))
+        yield f"tailz_{n}", (lambda n=n: np.zeros(n, dtype=np.uint32))
+
+
+CASES = list(_cases())
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name,gen", CASES, ids=[c[0] for c in CASES])
+def test_compress_bit_exact(name, gen, mode):
+    data = gen()
+    want = orc.compress(data, mode)
+    got, c = gpu_compress(data, mode)
+    assert c == want.size
+    assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name,gen", CASES, ids=[c[0] for c in CASES])
+def test_decompress_bit_exact(name, gen, mode):
+    data = gen()
+    cw = orc.compress(data, mode)
+    want = orc.decompress(cw)
+    got, info = gpu_decompress(cw)
+    assert info == [want.size, orc.num_groups(data.size)]
+    assert np.array_equal(got, want)
+    assert np.array_equal(got[: data.size], data)
+
+
+@pytest.mark.parametrize("kat", KATS, ids=[k["kat"] for k in KATS])
+def test_golden_vectors(kat):
+    data = np.array(kat["input_words"], dtype=np.uint32)
+    want = np.array(kat["compressed_words"], dtype=np.uint32)
+    got, c = gpu_compress(data, wah.WAH_BLOCK1024)
+    assert c == want.size and np.array_equal(got, want)
+    dec, _ = gpu_decompress(got)
+    assert np.array_equal(dec, data)
+
+
+def test_empty_input():
+    got, c = gpu_compress(np.empty(0, dtype=np.uint32), wah.WAH_BLOCK1024)
+    assert c == 0 and got.size == 0
+    dec, info = gpu_decompress(np.empty(0, dtype=np.uint32))
+    assert info == [0, 0]
+
+
+def test_decode_long_fills_and_any_valid_stream():
+    f = lambda t, n: 0x80000000 | (t << 30) | n
+    cw = np.array([f(0, 100000), 5, f(1, 70000), f(0, 1), 7, f(1, 8191), f(0, 3_000_000), 0x7FFFFFFE,
+                   f(1, 1), f(1, 2), f(0, 31), f(0, 33)], dtype=np.uint32)
+    want = orc.decompress(cw)
+    got, info = gpu_decompress(cw)
+    assert info[0] == want.size and np.array_equal(got, want)
+    # streams that END inside a one-fill: the last output word is only partly covered
+    for tail in ([f(1, 100000)], [f(1, 8192 * 3 + 5)], [7, f(1, 8192 - 1)], [f(0, 5), f(1, 8192 * 2)], [f(1, 1)],
+                 [f(0, 8192), f(1, 17)], [f(1, 8191), 3, f(1, 40)]):
+        cw = np.array(tail, dtype=np.uint32)
+        want = orc.decompress(cw)
+        got, info = gpu_decompress(cw)
+        assert info[0] == want.size and np.array_equal(got, want), tail
+
+
+def test_output_capacity_is_respected():
+    data = datagen.uniform(10 * TW, 0.3, 5)
+    want = orc.compress(data, wah.WAH_BLOCK1024)
+    cap = want.size // 2
+    n = data.size
+    d_out = torch.full((cap + 64,), -1, dtype=torch.int32, device="cuda")
+    d_cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    wah.compress_device(to_dev(data), n, d_out, cap, d_cnt, wah.Workspace.for_compress(n))
+    assert int(d_cnt.item()) == want.size                      # true length is still reported
+    assert np.array_equal(to_host(d_out[:cap]), want[:cap])
+    assert (d_out[cap:] == -1).all()                           # nothing past the capacity
+    dec_cap = 3 * TW + 11
+    d_dec = torch.full((dec_cap + 64,), -1, dtype=torch.int32, device="cuda")
+    d_info = torch.zeros(2, dtype=torch.int64, device="cuda")
+    wah.decompress_device(to_dev(want), want.size, d_dec, dec_cap, d_info, wah.Workspace.for_decompress(want.size, dec_cap))
+    assert d_info.cpu().tolist()[0] == n
+    assert np.array_equal(to_host(d_dec[:dec_cap]), data[:dec_cap])
+    assert (d_dec[dec_cap:] == -1).all()
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_batch_columns(mode):
+    wpc = 2 * TW + 64
+    cols = np.stack([
+        datagen.uniform(wpc, 0.001, 11), np.zeros(wpc, dtype=np.uint32), datagen.clustered(wpc, 0.2, 500, 12),
+        np.zeros(wpc, dtype=np.uint32), np.full(wpc, 0xFFFFFFFF, dtype=np.uint32), datagen.uniform(wpc, 0.5, 13),
+        np.zeros(wpc, dtype=np.uint32),
+    ])
+    want, offs = orc.compress_batch(cols, mode)
+    n_cols = cols.shape[0]
+    cap = wah.max_compressed_words(wpc) * n_cols
+    d_out = torch.empty(cap, dtype=torch.int32, device="cuda")
+    d_offs = torch.full((n_cols + 1,), -1, dtype=torch.int64, device="cuda")
+    ws = wah.Workspace.for_compress_batch(n_cols, wpc)
+    wah.compress_batch_device(to_dev(cols.reshape(-1)), n_cols, wpc, wpc, d_out, cap, d_offs, ws, mode)
+    got_offs = d_offs.cpu().numpy().astype(np.uint64)
+    assert np.array_equal(got_offs, offs)
+    assert np.array_equal(to_host(d_out[: int(offs[-1])]), want)
+
+
+def test_host_entry_points_mirror_the_reference():
+    # compress()/decompress() semantics: host in, host out, optional ms timers (compress.h:12-18)
+    data = datagen.uniform(992 * 300, 1 / 16, 21)
+    t = {}
+    cw = wah.compress(data, timings=t)
+    assert np.array_equal(cw, orc.compress(data, orc.BLOCK1024))
+    assert set(t) == {"h2d_ms", "compute_ms", "d2h_ms"} and all(v >= 0 for v in t.values())
+    back = wah.decompress(cw)
+    assert back.size == data.size and np.array_equal(back, data)
+    cwc = wah.compress(data, wah.WAH_CANONICAL)
+    assert np.array_equal(cwc, orc.compress(data, orc.CANONICAL))
+    assert np.array_equal(wah.decompress(cwc), data)
+
+
+def test_mangled_dropin_symbols_work():
+    # call the C++-mangled compress()/decompress() the way tests.o / source.o do
+    lib = wah.lib
+    comp, dec = lib._Z8compressPjyPyPfS1_S1_, lib._Z10decompressPjyPyPfS1_S1_
+    comp.restype = dec.restype = ctypes.c_void_p
+    pf = ctypes.POINTER(ctypes.c_float)
+    comp.argtypes = dec.argtypes = [ctypes.c_void_p, ctypes.c_ulonglong, ctypes.POINTER(ctypes.c_ulonglong), pf, pf, pf]
+    data = np.zeros(992, dtype=np.uint32)
+    c = ctypes.c_ulonglong()
+    p = comp(data.ctypes.data, 992, ctypes.byref(c), None, None, None)
+    assert p and c.value == 1
+    assert ctypes.cast(p, ctypes.POINTER(ctypes.c_uint32))[0] == 0x80000400       # tests.cpp:169
+    n = ctypes.c_ulonglong()
+    q = dec(p, 1, ctypes.byref(n), None, None, None)
+    assert q and n.value == 992
+    lib.wah_free(p)
+    lib.wah_free(q)
+
+
+@pytest.mark.skipif(not os.path.exists(os.path.join(ROOT, "oracle", "_ref", "ref_tests_b200")),
+                    reason="oracle/_ref/ref_tests_b200 not built")
+def test_reference_tests_cpp_against_the_product():
+    """The reference's own unmodified tests.cpp, linked against libwah_b200.so."""
+    r = subprocess.run([os.path.join(ROOT, "oracle", "_ref", "ref_tests_b200"), "--big"], capture_output=True,
+                       text=True, timeout=900)
+    res = dict(line.split()[1:3] for line in r.stdout.splitlines() if line.startswith("RESULT"))
+    for name in ["warpCompressionTest", "blockCompressionTest", "blockMergeTest", "blockMergeWithOnesStartsTest",
+                 "blockMergeAlternatingTest", "blockMergeFinalLiterals", "zerosTest", "compressAndDecompressTest",
+                 "randomDataTest"]:
+        assert res.get(name) == "1", (name, r.stdout[-2000:])
+    # stale goldens: bit compare fails for any correct encoder, the reference's included
+    assert res.get("blockMergeWanderingLiterals") == "0" and res.get("multiBlockTest") == "0"
+
+
+REF_LIB = os.path.join(ROOT, "oracle", "_ref", "libgpuwah_ref.so")
+
+
+def _ref_call(what, data, tmp_path):
+    """the reference's own CUDA implementation, in a process of its own (tests/ref_runner.py)"""
+    import sys
+
+    if not os.path.exists(REF_LIB):
+        pytest.skip("oracle/_ref/libgpuwah_ref.so not built")
+    fin, fout = str(tmp_path / f"{what}_in.npy"), str(tmp_path / f"{what}_out.npy")
+    np.save(fin, data)
+    subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_runner.py"), REF_LIB, what, fin, fout],
+                   check=True, timeout=600)
+    return np.load(fout)
+
+
+REF_CASES = [
+    ("kat_all", lambda: np.concatenate([np.array(k["input_words"], dtype=np.uint32) for k in KATS[1:]])),
+    ("sparse", lambda: datagen.uniform(992 * 2000, 0.001, 31)),
+    ("d16", lambda: datagen.uniform(992 * 500, 1 / 16, 32)),
+    ("dense", lambda: datagen.uniform(992 * 300, 0.5, 33)),
+    ("clustered", lambda: datagen.clustered(992 * 3000, 0.05, 1000, 34)),
+    ("zeros", lambda: np.zeros(992 * 64, dtype=np.uint32)),
+    ("mix_runs", lambda: datagen.group_mix(992 * 200, 0.45, 0.45, 35, run=40)),
+]
+
+
+@pytest.mark.parametrize("name,gen", REF_CASES, ids=[c[0] for c in REF_CASES])
+def test_oracle_and_product_against_the_reference_kernels(name, gen, tmp_path):
+    """Pins the oracle (and the product) on the output of the reference's own CUDA kernels,
+    built untouched for sm_100a (oracle/Makefile), on its defined domain n % 992 == 0."""
+    data = gen()
+    assert data.size % 992 == 0
+    ref = _ref_call("compress", data, tmp_path)
+    want = orc.compress(data, orc.BLOCK1024)
+    # Known reference defect (kernels.cu:252-254): in the last block, lane 30
+    # (owner of input word n-1) and lane 31 both store blockCounts[blk]; when the last two groups are
+    # two different output words and lane 30's store lands last, the reference drops its final word.
+    # Everything before that word must be identical.
+    assert ref.size in (want.size, want.size - 1), (ref.size, want.size)
+    assert np.array_equal(ref, want[: ref.size]), "oracle differs from the reference encoder"
+    if ref.size != want.size:
+        last2 = [orc._lib.wah_oracle_group(data.ctypes.data, data.size, orc.num_groups(data.size) - k) for k in (2, 1)]
+        kinds = [0 if g == 0 else 1 if g == 0x7FFFFFFF else 2 for g in last2]
+        assert kinds[0] != kinds[1] or kinds[0] == 2, "reference dropped a word outside its known race"
+        print(f"[{name}] reference dropped its last word (blockCounts race); prefix of {ref.size} words identical")
+    got, _ = gpu_compress(data, wah.WAH_BLOCK1024)
+    assert np.array_equal(got, want)
+    # the reference DEcoder must accept our CANONICAL stream too (any valid stream decodes)
+    canon, _ = gpu_compress(data, wah.WAH_CANONICAL)
+    back = _ref_call("decompress", canon, tmp_path)
+    assert np.array_equal(back[: data.size], data)

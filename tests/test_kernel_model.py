@@ -70,6 +70,10 @@ def _streams():
     # long fills: many output tiles per compressed word
     cw = np.array([0x80000000 | 100000, 5, 0xC0000000 | 70000, 0x80000000 | 1, 7, 0xC0000000 | 8191], dtype=np.uint32)
     yield "long_fills", cw, None
+    f = lambda t, n: 0x80000000 | (t << 30) | n
+    for k, tail in enumerate(([f(1, 100000)], [f(1, 8192 * 3 + 5)], [7, f(1, 8192 - 1)], [f(0, 5), f(1, 8192 * 2)], [f(1, 1)],
+                              [f(0, 8192), f(1, 17)], [f(1, 8191), 3, f(1, 40)])):
+        yield f"ones_tail_{k}", np.array(tail, dtype=np.uint32), None
     yield "one_fill", np.array([0x80000000 | 0x3FFFFFF], dtype=np.uint32)[:1] * 0 + np.uint32(0x80000000 | 300000), None
 
 

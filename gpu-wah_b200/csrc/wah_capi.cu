@@ -55,10 +55,23 @@ static inline bool aligned16(const void *p) { return (reinterpret_cast<uintptr_t
 
 // ---------------------------------------------------------------------- compress
 
-// workspace: [0,64) two u64 ping-pong slots chaining launches | [64,128) ticket | descriptors
-static constexpr size_t WS_SLOTS = 0, WS_TICKET = 64, WS_DESC = 128;
+// workspace: [0,64) two u64 ping-pong slots chaining launches | [64,128) seam scratch (lead bits u64,
+// adjust i32) | descriptors
+static constexpr size_t WS_SLOTS = 0, WS_SEAM = 64, WS_DESC = 128;
 // tiles one launch may cover (descriptor fields are 30/31 bit, wah_kernels.h)
-static constexpr uint64_t MAX_LAUNCH_TILES = MAX_LAUNCH_GROUPS / COMPRESS_TILE_GROUPS;
+static constexpr uint64_t HW_MAX_LAUNCH_TILES = MAX_LAUNCH_GROUPS / COMPRESS_TILE_GROUPS;
+static uint64_t g_max_launch_tiles = HW_MAX_LAUNCH_TILES;
+#define MAX_LAUNCH_TILES g_max_launch_tiles
+
+// test hook: shrink the segment one launch covers so that the multi-launch path (and its CANONICAL
+// seam) can be exercised with small inputs; 0 restores the default
+static uint64_t *g_trace = nullptr;
+extern "C" void wah_test_set_trace(uint64_t *d_trace) { g_trace = d_trace; }
+
+extern "C" void wah_test_set_max_launch_tiles(uint64_t tiles)
+{
+    g_max_launch_tiles = (tiles == 0 || tiles > HW_MAX_LAUNCH_TILES) ? HW_MAX_LAUNCH_TILES : tiles;
+}
 
 static uint64_t compress_tiles(uint64_t n_words) { return ceil_div(n_words, COMPRESS_TILE_WORDS); }
 
@@ -121,16 +134,14 @@ extern "C" int wah_compress_batch_device(const uint32_t *d_in, uint64_t n_cols, 
         p.tiles_per_col = (uint32_t)tiles_per_col;
         p.n_tiles = (uint32_t)(tiles_per_col * nc);
         p.n_cols = (uint32_t)nc;
-        p.merge_prev = 0;
+        p.lead_adjust = nullptr;
         p.out = d_out;
         p.out_cap = out_capacity_words;
-        p.ticket = reinterpret_cast<uint32_t *>(ws + WS_TICKET);
         p.desc = reinterpret_cast<uint64_t *>(ws + WS_DESC);
         p.base_in = launch == 0 ? nullptr : slots + (launch & 1);
         p.total_out = slots + ((launch + 1) & 1);
         p.col_offsets = d_col_offsets + c0;
-        CUDA_TRY(cudaMemsetAsync(ws + WS_TICKET, 0, (WS_DESC - WS_TICKET) + (size_t)p.n_tiles * sizeof(uint64_t),
-                                 stream));
+        CUDA_TRY(cudaMemsetAsync(ws + WS_DESC, 0, (size_t)p.n_tiles * sizeof(uint64_t), stream));
         CUDA_TRY(launch_compress(p, mode, stream));
     }
     return WAH_OK;
@@ -155,7 +166,7 @@ extern "C" int wah_compress_device(const uint32_t *d_in, uint64_t n_words, int m
 
     // A stream longer than one launch can describe is cut into segments at tile boundaries
     // (multiples of 992 words); each launch appends to the output of the previous one and, in
-    // CANONICAL mode, folds its first run into the previous launch's last word.
+    // CANONICAL mode, its leading run is joined with the previous launch's last word (launch_seam).
     const uint64_t seg_words = MAX_LAUNCH_TILES * COMPRESS_TILE_WORDS;
     char *ws = static_cast<char *>(d_workspace);
     uint64_t *slots = reinterpret_cast<uint64_t *>(ws + WS_SLOTS);
@@ -172,16 +183,22 @@ extern "C" int wah_compress_device(const uint32_t *d_in, uint64_t n_words, int m
         p.tiles_per_col = (uint32_t)compress_tiles(nw);
         p.n_tiles = p.tiles_per_col;
         p.n_cols = 1;
-        p.merge_prev = (launch > 0 && mode == WAH_CANONICAL) ? 1 : 0;
+        p.lead_adjust = nullptr;
+        if (launch > 0 && mode == WAH_CANONICAL) {
+            // the segment's leading run may continue the last word written so far
+            p.lead_adjust = reinterpret_cast<int32_t *>(ws + WS_SEAM + 8);
+            CUDA_TRY(launch_seam(p.in, nw, p.groups, d_out, out_capacity_words, slots + (launch & 1),
+                                 reinterpret_cast<unsigned long long *>(ws + WS_SEAM),
+                                 reinterpret_cast<int32_t *>(ws + WS_SEAM + 8), stream));
+        }
         p.out = d_out;
         p.out_cap = out_capacity_words;
-        p.ticket = reinterpret_cast<uint32_t *>(ws + WS_TICKET);
         p.desc = reinterpret_cast<uint64_t *>(ws + WS_DESC);
         p.base_in = launch == 0 ? nullptr : slots + (launch & 1);
         p.total_out = last ? d_out_words : slots + ((launch + 1) & 1);
         p.col_offsets = nullptr;
-        CUDA_TRY(cudaMemsetAsync(ws + WS_TICKET, 0, (WS_DESC - WS_TICKET) + (size_t)p.n_tiles * sizeof(uint64_t),
-                                 stream));
+        p.trace = g_trace;
+        CUDA_TRY(cudaMemsetAsync(ws + WS_DESC, 0, (size_t)p.n_tiles * sizeof(uint64_t), stream));
         CUDA_TRY(launch_compress(p, mode, stream));
     }
     return WAH_OK;

@@ -10,24 +10,23 @@
 //   warp    = 1024 groups = 992 words = one reference block, so in BLOCK1024 mode
 //             (bit-exact to the reference: runs never cross a block, kernels.cu:256)
 //             no run state ever leaves a warp
-//   CTA     = persistent, launched cooperatively (all CTAs co-resident), walks tiles
-//             blockIdx + k * gridDim of THREADS*31 words.  The next tile's input is
-//             already in flight (cp.async, triple-buffered shared memory) while the
-//             current one is classified from shared memory (stride 31 words per
-//             thread = bank-conflict free)
-//   grid    = SMs x resident CTAs; tile prefix (words emitted so far, length of the
-//             fill run still open at the tile's end) by decoupled look-back over one
-//             64-bit descriptor per tile, with the WHOLE CTA reading a 512-tile
-//             window per round (lock-stepped persistent CTAs would otherwise walk a
-//             dozen 32-tile windows, one L2 round trip each).  The loop is software
-//             pipelined: tile k+1 is classified and published before the look-back
-//             of tile k, so a look-back never waits for a neighbour's classification.
+//   tile    = NWORK reference blocks, one per WORKER warp
+//   CTA     = persistent and warp specialised (cooperative launch: all CTAs co-resident):
+//               NWORK worker warps   classify a tile from shared memory, compact its words
+//                                    into a per-warp staging area and copy them out coalesced
+//               1 control warp       tile aggregate -> decoupled look-back over one 64-bit
+//                                    descriptor per tile -> hands the workers their offsets
+//               1 producer warp      cp.async.bulk (TMA) of tile blockIdx + k * gridDim into a
+//                                    ring of STAGES shared-memory buffers, mbarrier signalled
+//             The roles talk through mbarriers only; there is no __syncthreads in the loop.
+//             Workers are software pipelined: tile k+1 is classified and its aggregate handed
+//             to the control warp BEFORE tile k is emitted, so the look-back latency of tile k
+//             is covered by useful work.
 //
 // A run is emitted where it ENDS ("tail"): group k is a tail if it is a literal,
 // or the next group has another type, or it is the last group of the stream /
 // block.  The k-th tail is the k-th output word; a fill's length is the distance
-// to the previous tail, which flows forward through the scans.  Output words go
-// straight to global memory: a warp's words are one contiguous span.
+// to the previous tail, which flows forward through the scans.
 #include "wah_common.cuh"
 #include "wah_kernels.h"
 
@@ -47,482 +46,654 @@ __device__ __forceinline__ uint32_t desc_no_tail(uint64_t d) { return (uint32_t)
 __device__ __forceinline__ uint32_t desc_open(uint64_t d) { return (uint32_t)(d >> 31) & MAX_FILL; }
 __device__ __forceinline__ uint32_t desc_count(uint64_t d) { return (uint32_t)d & 0x7FFFFFFFu; }
 
-__device__ __forceinline__ void cp_async_16(uint32_t smem_addr, const void *gptr)
+// ---- mbarrier / bulk-copy primitives (PTX) -----------------------------------------
+
+__device__ __forceinline__ void mbar_init(uint32_t bar, uint32_t count)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16;" ::"r"(smem_addr), "l"(gptr) : "memory");
+    asm volatile("mbarrier.init.shared::cta.b64 [%0], %1;" ::"r"(bar), "r"(count) : "memory");
 }
-__device__ __forceinline__ void cp_async_16_zfill(uint32_t smem_addr, const void *gptr, uint32_t src_bytes)
+__device__ __forceinline__ void mbar_arrive(uint32_t bar)
 {
-    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(smem_addr), "l"(gptr), "r"(src_bytes)
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.shared::cta.b64 st, [%0];\n\t}" ::"r"(bar) : "memory");
+}
+__device__ __forceinline__ void mbar_arrive_expect_tx(uint32_t bar, uint32_t bytes)
+{
+    asm volatile("{\n\t.reg .b64 st;\n\tmbarrier.arrive.expect_tx.shared::cta.b64 st, [%0], %1;\n\t}" ::"r"(bar),
+                 "r"(bytes)
                  : "memory");
 }
-__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
-template <int N>
-__device__ __forceinline__ void cp_async_wait()
+__device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
 {
-    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+    asm volatile(
+        "{\n\t"
+        ".reg .pred p;\n\t"
+        "WAIT_LOOP:\n\t"
+        "mbarrier.try_wait.parity.shared::cta.b64 p, [%0], %1;\n\t"
+        "@p bra DONE;\n\t"
+        "bra WAIT_LOOP;\n\t"
+        "DONE:\n\t"
+        "}" ::"r"(bar),
+        "r"(parity)
+        : "memory");
+}
+// global -> shared bulk copy (TMA engine), completion counted in bytes on an mbarrier
+__device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
+{
+    asm volatile("cp.async.bulk.shared::cluster.global.mbarrier::complete_tx::bytes [%0], [%1], %2, [%3];" ::"r"(dst),
+                 "l"(src), "r"(bytes), "r"(bar)
+                 : "memory");
 }
 
-template <int THREADS>
-struct TileGeom {
-    static constexpr int NW = THREADS / 32;
-    static constexpr int TILE_WORDS = THREADS * WORDS_PER_THREAD;
-    static constexpr int TILE_GROUPS = THREADS * GROUPS_PER_THREAD;
-    static constexpr int BUF_WORDS = TILE_WORDS + 4;   // + look-ahead word, padded to 16 B
-    static constexpr int NVEC = TILE_WORDS / 4;
-    static_assert(TILE_WORDS % 4 == 0, "tile must be a whole number of 16-byte vectors");
+__device__ __forceinline__ uint32_t smem_u32(const void *p) { return (uint32_t)__cvta_generic_to_shared(p); }
+
+// ---- optional phase trace (compile with -DWAH_TRACE; p.trace = [n_ctas][iters][8] u64) ----------
+#ifdef WAH_TRACE
+#define TRACE(i, slot, val)                                                                                  \
+    do {                                                                                                     \
+        if (p.trace && (i) < 64u) p.trace[((uint64_t)blockIdx.x * 64u + (i)) * 8u + (slot)] = (uint64_t)(val); \
+    } while (0)
+__device__ __forceinline__ uint64_t gtime()
+{
+    uint64_t t;
+    asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(t));
+    return t;
+}
+#else
+#define TRACE(i, slot, val) \
+    do {                    \
+    } while (0)
+#endif
+
+// ---- kernel geometry ------------------------------------------------------------------
+
+constexpr int WARP_RING = 512;    // staged output words per worker warp (the CTA's ring is NWORK times this)
+constexpr int QDEPTH = 8;         // tiles a CTA may have between classification and copy-out
+constexpr uint32_t MODE_RING = 0, MODE_DIRECT = 1;
+
+template <int NWORK, int STAGES>
+struct Geom {
+    static constexpr int TILE_WORDS = NWORK * 992;
+    static constexpr int TILE_GROUPS = NWORK * 1024;
+    static constexpr int PAD_FRONT = 4;                       // row[-1] of the tile's first thread
+    static constexpr int STAGE_WORDS = TILE_WORDS + 8;        // + 4 in front, + look-ahead word (16 B) behind
+    static constexpr int THREADS = (NWORK + 2) * 32;
+    static constexpr int RING_WORDS = NWORK * WARP_RING;      // power of two for NWORK = 4, 8
+    static_assert((RING_WORDS & (RING_WORDS - 1)) == 0, "ring size must be a power of two");
+    static_assert(TILE_WORDS == COMPRESS_TILE_WORDS, "the C ABI sizes its descriptor array from COMPRESS_TILE_WORDS");
 };
 
-// Start the asynchronous copy of one tile (+1 look-ahead word) into a shared-memory buffer,
-// zero filled past the end of the column.  Always commits exactly one cp.async group.
-template <int THREADS>
-__device__ __forceinline__ void stage_tile(const CompressParams &p, uint32_t tile, uint32_t *buf, uint32_t tid)
-{
-    using G = TileGeom<THREADS>;
-    if (tile < p.n_tiles) {
-        const uint32_t col = tile / p.tiles_per_col;
-        const uint32_t t = tile - col * p.tiles_per_col;
-        const uint64_t w0 = (uint64_t)t * G::TILE_WORDS;
-        const uint32_t *src = p.in + (uint64_t)col * p.col_stride + w0;
-        const uint64_t left = p.n_words - w0;   // words from the tile start to the column end
-        const uint32_t s_base = (uint32_t)__cvta_generic_to_shared(buf);
-        const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
-        if (aligned && left > (uint64_t)G::TILE_WORDS) {
-            // full tile followed by at least one more word: plain 16-byte copies
-            const uint4 *src4 = reinterpret_cast<const uint4 *>(src);
-#pragma unroll
-            for (int k = 0; k < (G::NVEC + THREADS - 1) / THREADS; k++) {
-                const uint32_t i = tid + k * THREADS;
-                if (i < G::NVEC) cp_async_16(s_base + 16u * i, src4 + i);
-            }
-            if (tid == 0) cp_async_16_zfill(s_base + 16u * G::NVEC, src + G::TILE_WORDS, 4u);
-        } else if (aligned) {
-            const uint32_t nload = left > (uint64_t)G::TILE_WORDS ? (uint32_t)G::TILE_WORDS + 1u : (uint32_t)left;
-            for (uint32_t i = tid; i < G::BUF_WORDS / 4; i += THREADS) {
-                const uint32_t b = 4u * i;
-                const uint32_t bytes = b >= nload ? 0u : (nload - b >= 4u ? 16u : (nload - b) * 4u);
-                cp_async_16_zfill(s_base + 16u * i, bytes ? (const void *)(src + b) : (const void *)src, bytes);
-            }
-        } else {
-            // column start not 16-byte aligned: scalar staging
-            const uint32_t nload = left > (uint64_t)G::TILE_WORDS ? (uint32_t)G::TILE_WORDS + 1u : (uint32_t)left;
-            for (uint32_t i = tid; i < G::BUF_WORDS; i += THREADS) buf[i] = i < nload ? ld_stream_u32(src + i) : 0u;
-        }
-    }
-    cp_async_commit();
-}
+// producer -> workers, one per input stage
+struct StageInfo {
+    uint32_t gvalid;     // groups of the tile that exist (0 .. TILE_GROUPS)
+    uint32_t has_next;   // a group of the same column follows the tile (CANONICAL look-ahead)
+    uint32_t tile;       // global tile index
+    uint32_t pad;
+};
 
-// Everything emission needs from classification, kept in registers while the NEXT tile is
-// classified (the loop is software pipelined, see the kernel).
-struct TileState {
-    uint32_t T, F, O;       // tail / fill / one-fill masks of my 32 groups
-    uint32_t my_off;        // tile-relative index of my first output word
-    uint32_t prev_open;     // length of the run open at my chunk's start (without the tile's carry-in)
-    uint32_t wcnt;          // words my warp emits
-    uint32_t flags;         // bit0: a lower lane of my warp has a tail, bit1: a lower warp has a tail
+// workers -> workers, one per input stage: warp aggregates exchanged at the workers' barrier
+template <int NWORK>
+struct WarpAgg {
+    uint32_t wcnt[NWORK];      // words emitted by each warp
+    uint32_t wopen[NWORK];     // groups after the warp's last tail (1024 if it has none)
+    uint32_t whas[NWORK];      // warp has at least one tail
+};
+
+// one per tile in flight between the workers and the control warp (slot = CTA-local tile index % QDEPTH)
+template <int NWORK>
+struct TileMeta {
+    // workers -> control
+    uint32_t wprefix[NWORK];   // words emitted by the lower warps of the tile
+    uint32_t wopen[NWORK];
+    uint32_t whas[NWORK];
     uint32_t tile_cnt, tile_open, tile_has;
+    uint32_t ring_base;        // ring position of the tile's first staged word
+    uint32_t mode;             // MODE_RING: words staged in the ring, MODE_DIRECT: the workers write them
+    // control -> workers in MODE_DIRECT
+    int32_t lead_adjust;       // added to the launch's very first word (seam with an earlier launch)
+    uint64_t dst;              // output word index of the tile's first word
+    uint32_t wcarry[NWORK];    // groups of a run still open where the warp starts (CANONICAL)
 };
 
-template <int THREADS, bool BLOCK_MODE>
-__global__ void __launch_bounds__(THREADS, 2) wah_compress_kernel(const CompressParams p)
+template <int NWORK, int STAGES>
+struct Smem {
+    using G = Geom<NWORK, STAGES>;
+    uint32_t stage[STAGES][G::STAGE_WORDS];
+    uint32_t ring[G::RING_WORDS];
+    TileMeta<NWORK> meta[QDEPTH];
+    WarpAgg<NWORK> wagg[STAGES];
+    StageInfo info[STAGES];
+    uint64_t full[STAGES], empty[STAGES];              // input ring: producer <-> workers
+    uint64_t agg[QDEPTH], pref[QDEPTH], done[QDEPTH];  // tile queue: workers <-> control
+};
+
+// literal group j (0..31) of the row that starts at `row`: stream bits [31 j, 31 j + 31), LSB first
+// (kernels.cu:79).  Reads row[j-1] and row[j]; for j = 0 the clamped shift by 32 drops row[-1].
+__device__ __forceinline__ uint32_t row_group(const uint32_t *row, uint32_t j)
 {
-    using G = TileGeom<THREADS>;
-    constexpr int NW = G::NW;
-    constexpr int LB = 2;   // descriptors each thread reads per look-back round (window = LB * THREADS tiles)
+    const uint32_t *q = row + j;
+    return __funnelshift_rc(q[-1], q[0], 32u - j) & ONES31;
+}
 
-    extern __shared__ __align__(16) uint32_t smem[];   // three input buffers of BUF_WORDS
-
-    __shared__ uint32_t s_wcnt[NW];      // words emitted by each warp
-    __shared__ uint32_t s_wopen[NW];     // groups after the warp's last tail (1024 if it has none)
-    __shared__ uint32_t s_whas[NW];      // warp has at least one tail
-    __shared__ uint32_t s_lb_cnt[LB * NW];    // look-back partials of each warp's 32-tile windows
-    __shared__ uint32_t s_lb_open[LB * NW];
-    __shared__ uint32_t s_lb_flags[LB * NW];  // bit0: window holds an INCLUSIVE descriptor, bit1: open run resolved
-    __shared__ uint32_t s_drop;
+template <int NWORK, int STAGES, bool BLOCK_MODE>
+__global__ void __launch_bounds__((NWORK + 2) * 32, 2) wah_compress_kernel(const CompressParams p)
+{
+    using G = Geom<NWORK, STAGES>;
+    using SM = Smem<NWORK, STAGES>;
+    extern __shared__ __align__(128) unsigned char smem_raw[];
+    SM &sm = *reinterpret_cast<SM *>(smem_raw);
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t stride = gridDim.x;
-    if (tid == 0) s_drop = 0;
-    const uint64_t base = p.base_in ? *p.base_in : 0ull;
+    const uint32_t n_my = blockIdx.x < p.n_tiles ? (p.n_tiles - blockIdx.x + stride - 1u) / stride : 0u;
 
-    // classify tile `tile` from buffer s_in, publish its aggregate, return the per-thread state
-    auto classify = [&](uint32_t tile, const uint32_t *s_in) -> TileState {
-        const uint32_t col = tile / p.tiles_per_col;
-        const uint32_t t = tile - col * p.tiles_per_col;   // tile index inside the column
-
-        // ---- my 32 groups (kernels.cu:79 regroup, :93-112 classification)
-        const uint32_t *row = s_in + WORDS_PER_THREAD * tid;
-        const uint64_t g_thread = (uint64_t)t * G::TILE_GROUPS + 32u * tid;   // first group, column relative
-        uint32_t nvalid = 0;
-        if (g_thread < p.groups) nvalid = (p.groups - g_thread) >= 32u ? 32u : (uint32_t)(p.groups - g_thread);
-        const uint32_t vmask = nvalid == 32u ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
-
-        uint32_t Z = 0, O = 0;
-        {
-            // u = group << 1 | (one junk bit): zero / all-ones tests on the top 31 bits
-            uint32_t prev = row[0];
-            uint32_t u = prev << 1;
-            if ((u & 0xFFFFFFFEu) == 0u) Z |= 1u;
-            if ((~u & 0xFFFFFFFEu) == 0u) O |= 1u;
-#pragma unroll
-            for (int j = 1; j < 31; j++) {
-                const uint32_t cur_w = row[j];
-                u = __funnelshift_r(prev, cur_w, 31 - j);
-                if ((u & 0xFFFFFFFEu) == 0u) Z |= (1u << j);
-                if ((~u & 0xFFFFFFFEu) == 0u) O |= (1u << j);
-                prev = cur_w;
-            }
-            u = prev;
-            if ((u & 0xFFFFFFFEu) == 0u) Z |= BIT31;
-            if ((~u & 0xFFFFFFFEu) == 0u) O |= BIT31;
+    if (tid == 0) {
+        for (int s = 0; s < STAGES; s++) {
+            mbar_init(smem_u32(&sm.full[s]), 1);
+            mbar_init(smem_u32(&sm.empty[s]), NWORK);
         }
-        Z &= vmask;
-        O &= vmask;
-        const uint32_t F = Z | O;
-
-        // type of the group after my chunk (first group of the next thread)
-        uint32_t nz = 0, no = 0;
-        if (!(BLOCK_MODE && lane == 31u) && g_thread + 32u < p.groups) {
-            const uint32_t nx = row[31] & ONES31;
-            nz = (nx == 0u) ? BIT31 : 0u;
-            no = (nx == ONES31) ? BIT31 : 0u;
+        for (int q = 0; q < QDEPTH; q++) {
+            mbar_init(smem_u32(&sm.agg[q]), NWORK);
+            mbar_init(smem_u32(&sm.pref[q]), 1);
+            mbar_init(smem_u32(&sm.done[q]), 1);
         }
-        // tail = literal, or fill whose successor differs (run-end rule, kernels.cu:126-141);
-        // the last group of the stream, and of every 1024-group block in BLOCK mode, has no successor
-        const uint32_t T = ((~F) & vmask) | (Z & ~((Z >> 1) | nz)) | (O & ~((O >> 1) | no));
-        const uint32_t cnt = __popc(T);
-        const uint32_t my_open = T ? (uint32_t)__clz(T) : 32u;   // groups after my last tail
-
-        // ---- warp scan: output offset and length of the run open at my chunk's start
-        const uint32_t incl = warp_incl_scan(cnt);
-        const uint32_t tb = __ballot_sync(0xffffffffu, T != 0u);
-        const uint32_t below = tb & lanemask_lt();
-        const uint32_t q = below ? 31u - (uint32_t)__clz(below) : 0u;
-        const uint32_t open_q = __shfl_sync(0xffffffffu, my_open, q);
-        uint32_t prev_open = below ? open_q + 32u * (lane - q - 1u) : 32u * lane;   // + carries if !below
-        const uint32_t qlast = tb ? 31u - (uint32_t)__clz(tb) : 0u;
-        const uint32_t open_last = __shfl_sync(0xffffffffu, my_open, qlast);
-        const uint32_t wcnt = __shfl_sync(0xffffffffu, incl, 31);
-        __syncthreads();   // the previous tile's warp aggregates have been consumed by everyone
-        if (lane == 0) {
-            s_wcnt[warp] = wcnt;
-            s_whas[warp] = tb != 0u;
-            s_wopen[warp] = tb ? open_last + 32u * (31u - qlast) : 1024u;
-        }
-        __syncthreads();
-
-        // ---- tile aggregate (every thread; NW is small) and my warp's prefix
-        TileState st;
-        uint32_t tile_cnt = 0, tile_open = 0, tile_has = 0;
-        uint32_t wprefix = 0, wcarry = 0;
-        bool wfound = false;
-#pragma unroll
-        for (int w = 0; w < NW; w++) {
-            const uint32_t c = s_wcnt[w], h = s_whas[w], o = s_wopen[w];
-            if (w < (int)warp) {
-                wprefix += c;
-                if (h) {
-                    wcarry = o;
-                    wfound = true;
-                } else {
-                    wcarry += o;
-                }
-            }
-            tile_cnt += c;
-            if (h) {
-                tile_has = 1;
-                tile_open = o;
-            } else {
-                tile_open += o;
-            }
-        }
-        // the end of a column is always a tail (lanes past the end hold no groups)
-        if (t == p.tiles_per_col - 1u) {
-            tile_open = 0;
-            tile_has = 1;
-        }
-        if (!BLOCK_MODE && !below) prev_open += wcarry;
-        st.T = T;
-        st.F = F;
-        st.O = O;
-        st.my_off = wprefix + incl - cnt;
-        st.prev_open = prev_open;
-        st.wcnt = wcnt;
-        st.flags = (below ? 1u : 0u) | (wfound ? 2u : 0u);
-        st.tile_cnt = tile_cnt;
-        st.tile_open = tile_open;
-        st.tile_has = tile_has;
-
-        // publish: tile 0 has no predecessor (unless it still has to merge with an earlier launch)
-        if (tid == 0) {
-            if (tile == 0u) {
-                if (!p.merge_prev) st_relaxed_u64(p.desc, desc_pack(ST_INCL, 0, tile_open, tile_cnt));
-            } else {
-                st_relaxed_u64(p.desc + tile, desc_pack(ST_AGG, tile_has ^ 1u, tile_open, tile_cnt));
-            }
-        }
-        return st;
-    };
-
-    // ---- prologue: two tiles in flight, the first one classified and published
-    uint32_t tile = blockIdx.x;
-    stage_tile<THREADS>(p, tile, smem, tid);
-    stage_tile<THREADS>(p, tile + stride, smem + G::BUF_WORDS, tid);
-    TileState cur_st;
-    if (tile < p.n_tiles) {
-        cp_async_wait<1>();
-        __syncthreads();
-        cur_st = classify(tile, smem);
+        asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
-    int cur = 0;   // buffer of `tile`
+    __syncthreads();
 
-    // Software pipeline: tile k+1 is classified and its aggregate published BEFORE the look-back of
-    // tile k.  CTAs of a round-robin grid run in step; without the skew every look-back would wait for
-    // the slowest of its same-round predecessors to finish classifying.
-    while (tile < p.n_tiles) {
-        const uint32_t next = tile + stride;
-        const int nxt = cur == 2 ? 0 : cur + 1, nn = nxt == 2 ? 0 : nxt + 1;
-        const uint32_t *s_in = smem + cur * G::BUF_WORDS;
-        // third buffer: last read by the emission of the tile before `tile`, which ended with barrier (C)
-        stage_tile<THREADS>(p, next + stride, smem + nn * G::BUF_WORDS, tid);
-        TileState next_st;
-        if (next < p.n_tiles) {
-            cp_async_wait<1>();
-            __syncthreads();   // (A) `next` is staged
-            next_st = classify(next, smem + nxt * G::BUF_WORDS);
-        }
-
-        const TileState st = cur_st;
-        const uint32_t col = tile / p.tiles_per_col;
-        const uint32_t t = tile - col * p.tiles_per_col;
-
-        // ---- decoupled look-back, LB 32-tile windows per warp and round
-        uint32_t excl = 0, carry = 0;
-        if (tile != 0u) {
-            // BLOCK mode never carries a run; CANONICAL restarts at every column
-            bool open_done = BLOCK_MODE || (t == 0u);
-            int64_t look = (int64_t)tile - 1 - (int64_t)tid;
-            while (true) {
-#pragma unroll
-                for (int r = 0; r < LB; r++) {
-                    const int64_t lk = look - (int64_t)r * THREADS;
-                    uint64_t d;
-                    if (lk >= 0) {
-                        do {
-                            d = ld_relaxed_u64(p.desc + lk);
-                        } while (desc_status(d) == ST_EMPTY);
+    if (warp == NWORK + 1) {
+        // =========================================================== producer warp
+        for (uint32_t i = 0; i < n_my; i++) {
+            const uint32_t s = i % STAGES, use = i / STAGES;
+            if (use > 0) mbar_wait(smem_u32(&sm.empty[s]), (use - 1u) & 1u);
+            const uint32_t tile = blockIdx.x + i * stride;
+            const uint32_t col = tile / p.tiles_per_col;
+            const uint32_t t = tile - col * p.tiles_per_col;
+            const uint64_t w0 = (uint64_t)t * G::TILE_WORDS;
+            const uint32_t *src = p.in + (uint64_t)col * p.col_stride + w0;
+            const uint64_t left = p.n_words - w0;                  // words from the tile start to the column end
+            const uint64_t g0 = (uint64_t)t * G::TILE_GROUPS;
+            const uint64_t gleft = p.groups - g0;
+            uint32_t *buf = &sm.stage[s][G::PAD_FRONT];
+            const uint32_t bar = smem_u32(&sm.full[s]);
+            // words to stage: the tile and, if the column goes on, one look-ahead word
+            const uint32_t nload = left > (uint64_t)G::TILE_WORDS ? (uint32_t)G::TILE_WORDS + 1u : (uint32_t)left;
+            if (lane == 0) {
+                sm.info[s].gvalid = gleft >= (uint64_t)G::TILE_GROUPS ? (uint32_t)G::TILE_GROUPS : (uint32_t)gleft;
+                sm.info[s].has_next = gleft > (uint64_t)G::TILE_GROUPS ? 1u : 0u;
+                sm.info[s].tile = tile;
+            }
+            const bool aligned = (reinterpret_cast<uintptr_t>(src) & 15u) == 0;
+            if (aligned) {
+                // whole 16-byte units by TMA, the ragged end (and zero words behind it) by hand
+                const uint32_t nbulk = left >= (uint64_t)G::TILE_WORDS + 4u ? (uint32_t)G::TILE_WORDS + 4u : (nload & ~3u);
+                if (nbulk < nload + 2u && lane < 8u) {
+                    const uint32_t i0 = nbulk + lane;
+                    if (i0 < (uint32_t)G::TILE_WORDS + 4u) buf[i0] = i0 < nload ? ld_stream_u32(src + i0) : 0u;
+                }
+                __syncwarp();
+                if (lane == 0) {
+                    TRACE(i, 0, clock64());
+                    TRACE(i, 7, gtime());
+                    if (nbulk) {
+                        mbar_arrive_expect_tx(bar, nbulk * 4u);
+                        bulk_g2s(smem_u32(buf), src, nbulk * 4u, bar);
                     } else {
-                        d = desc_pack(ST_INCL, 0, 0, 0);
-                    }
-                    const uint32_t incl_mask = __ballot_sync(0xffffffffu, desc_status(d) == ST_INCL);
-                    const uint32_t first_incl = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 32u;
-                    const bool part = lane <= first_incl;   // first_incl == 32: every lane takes part
-                    const uint32_t csum = warp_sum(part ? desc_count(d) : 0u);
-                    uint32_t osum = 0, flags = first_incl < 32u ? 1u : 0u;
-                    if (!BLOCK_MODE) {
-                        // towards older tiles until one ends a run (or carries a resolved value)
-                        const uint32_t term_mask =
-                            __ballot_sync(0xffffffffu, part && (desc_status(d) == ST_INCL || !desc_no_tail(d)));
-                        const uint32_t first_term = term_mask ? (uint32_t)__ffs(term_mask) - 1u : 32u;
-                        osum = warp_sum((part && lane <= first_term) ? desc_open(d) : 0u);
-                        flags |= first_term < 32u ? 2u : 0u;
-                    }
-                    if (lane == 0) {
-                        s_lb_cnt[r * NW + warp] = csum;
-                        s_lb_open[r * NW + warp] = osum;
-                        s_lb_flags[r * NW + warp] = flags;
+                        mbar_arrive(bar);
                     }
                 }
-                __syncthreads();
+            } else {
+                // column start not 16-byte aligned: plain staging by the producer warp
+                for (uint32_t i0 = lane; i0 < (uint32_t)G::TILE_WORDS + 4u; i0 += 32u)
+                    buf[i0] = i0 < nload ? ld_stream_u32(src + i0) : 0u;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(bar);
+            }
+        }
+    } else if (warp == NWORK) {
+        // ============================================================ control warp
+        constexpr int LBN = 8;   // descriptors per lane and look-back round (window = 32 * LBN tiles)
+        const uint64_t base = p.base_in ? *p.base_in : 0ull;
+        const int32_t lead_adjust = p.lead_adjust ? *p.lead_adjust : 0;
+        for (uint32_t i = 0; i < n_my; i++) {
+            const uint32_t q = i % QDEPTH, use = i / QDEPTH;
+            const uint32_t tile = blockIdx.x + i * stride;
+            const uint32_t col = tile / p.tiles_per_col;
+            const uint32_t t = tile - col * p.tiles_per_col;
+            TileMeta<NWORK> &mt = sm.meta[q];
+
+            mbar_wait(smem_u32(&sm.agg[q]), use & 1u);
+            if (lane == 0) TRACE(i, 3, clock64());
+
+            // ---- tile aggregate (computed and published to the other CTAs by the workers)
+            const uint32_t tile_cnt = mt.tile_cnt, tile_open = mt.tile_open, tile_has = mt.tile_has;
+
+            // ---- decoupled look-back: rounds of 32 * LBN descriptors, nearest tile first
+            uint32_t excl = 0, carry = 0;
+            if (tile != 0u) {
+                bool open_done = BLOCK_MODE || (t == 0u);   // BLOCK mode never carries; CANONICAL restarts per column
+                uint32_t csum = 0, osum = 0;
+                int64_t look = (int64_t)tile - 1 - (int64_t)lane;
                 bool done = false;
+                while (!done) {
+                    uint64_t d[LBN];
 #pragma unroll
-                for (int w = 0; w < LB * NW; w++) {
-                    if (!done) {
-                        const uint32_t f = s_lb_flags[w];
-                        excl += s_lb_cnt[w];
-                        if (!open_done) {
-                            carry += s_lb_open[w];
-                            open_done = (f & 2u) != 0u;
+                    for (int r = 0; r < LBN; r++) {
+                        const int64_t lk = look - 32 * r;
+                        d[r] = lk >= 0 ? ld_relaxed_u64(p.desc + lk) : desc_pack(ST_INCL, 0, 0, 0);
+                    }
+#pragma unroll
+                    for (int r = 0; r < LBN; r++) {
+                        if (!done) {
+                            const int64_t lk = look - 32 * r;
+                            while (__any_sync(0xffffffffu, desc_status(d[r]) == ST_EMPTY)) {
+                                if (desc_status(d[r]) == ST_EMPTY) d[r] = ld_relaxed_u64(p.desc + lk);
+                            }
+                            const uint32_t incl_mask = __ballot_sync(0xffffffffu, desc_status(d[r]) == ST_INCL);
+                            const uint32_t first_incl = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 32u;
+                            const bool part = lane <= first_incl;   // first_incl == 32: every lane takes part
+                            if (part) csum += desc_count(d[r]);
+                            if (!open_done) {
+                                // towards older tiles until one ends a run (or carries a resolved value)
+                                const uint32_t term_mask = __ballot_sync(
+                                    0xffffffffu, part && (desc_status(d[r]) == ST_INCL || !desc_no_tail(d[r])));
+                                const uint32_t first_term = term_mask ? (uint32_t)__ffs(term_mask) - 1u : 32u;
+                                if (part && lane <= first_term) osum += desc_open(d[r]);
+                                open_done = first_term < 32u;
+                            }
+                            done = first_incl < 32u;
                         }
-                        done = (f & 1u) != 0u;
                     }
+                    look -= 32 * LBN;
                 }
-                if (done) break;
-                look -= LB * THREADS;
-                __syncthreads();   // partials are rewritten in the next round
+                excl = warp_sum(csum);
+                if (!BLOCK_MODE) carry = warp_sum(osum);
+                if (BLOCK_MODE || t == 0u) carry = 0;
+                const uint32_t incl_open = tile_has ? tile_open : carry + tile_open;
+                if (lane == 0) st_relaxed_u64(p.desc + tile, desc_pack(ST_INCL, 0, incl_open, excl + tile_cnt));
             }
-            const uint32_t incl_open = st.tile_has ? st.tile_open : carry + st.tile_open;
-            if (tid == 0) st_relaxed_u64(p.desc + tile, desc_pack(ST_INCL, 0, incl_open, excl + st.tile_cnt));
-            if (BLOCK_MODE || t == 0u) carry = 0;
+
+            const uint64_t dst0 = base + excl;
+            const int32_t adjust = (excl == 0u) ? lead_adjust : 0;   // no word of this launch precedes the tile
+            // run still open where each warp starts (CANONICAL): lane w looks at the warps below it
+            uint32_t run = carry;
+            if (!BLOCK_MODE) {
+#pragma unroll
+                for (int w = 0; w < NWORK - 1; w++) {
+                    const uint32_t h = mt.whas[w], o = mt.wopen[w];
+                    if ((int)lane > w) run = h ? o : run + o;
+                }
+            }
+            const uint32_t mode = mt.mode;
+            if (mode == MODE_DIRECT) {
+                // ---- the workers write this tile themselves: hand them their offsets
+                if (lane < NWORK) mt.wcarry[lane] = run;
+                if (lane == 0) {
+                    mt.dst = dst0;
+                    mt.lead_adjust = adjust;
+                }
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sm.pref[q]));
+                if (lane == 0) TRACE(i, 4, clock64());
+            } else {
+                if (lane == 0) TRACE(i, 4, clock64());
+                // ---- the tile's words are staged back to back in the ring: patch the first word of each
+                //      warp (it may close a run that started before the warp), then copy out coalesced
+                const uint32_t rb = mt.ring_base;
+                if (lane < NWORK) {
+                    const uint32_t pre = mt.wprefix[lane];
+                    const uint32_t nxt = lane + 1 < NWORK ? mt.wprefix[lane + 1 < NWORK ? lane + 1 : lane] : tile_cnt;
+                    uint32_t add = BLOCK_MODE ? 0u : run;
+                    if (pre == 0u) add += (uint32_t)adjust;   // the launch's first word
+                    if (nxt > pre && add != 0u) sm.ring[(rb + pre) & (G::RING_WORDS - 1)] += add;
+                }
+                __syncwarp();
+                const uint32_t room =
+                    dst0 >= p.out_cap ? 0u
+                                      : (p.out_cap - dst0 >= (uint64_t)G::TILE_GROUPS ? (uint32_t)G::TILE_GROUPS
+                                                                                       : (uint32_t)(p.out_cap - dst0));
+                const uint32_t ncopy = tile_cnt < room ? tile_cnt : room;
+                uint32_t *dst = p.out + dst0;
+#pragma unroll 4
+                for (uint32_t k = lane; k < ncopy; k += 32u)
+                    st_stream_u32(dst + k, sm.ring[(rb + k) & (G::RING_WORDS - 1)]);
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&sm.done[q]));
+                TRACE(i, 5, clock64());
+                if (p.col_offsets && t == 0u) p.col_offsets[col] = dst0;
+                if (tile == p.n_tiles - 1u) {
+                    const uint64_t total = dst0 + tile_cnt;
+                    *p.total_out = total;
+                    if (p.col_offsets) p.col_offsets[p.n_cols] = total;
+                }
+            }
+            __syncwarp();
         }
+    } else {
+        // ============================================================= worker warps
+        uint32_t head = 0;   // words this CTA has staged so far (ring position, monotonic, same in every warp)
+        uint32_t jd = 0;     // oldest tile of this CTA not yet known to be copied out
 
-        // ---- emit straight to global memory
-        const uint32_t T = st.T, F = st.F, O = st.O;
-        uint32_t prev_open = st.prev_open;
-        if (!BLOCK_MODE && st.flags == 0u) prev_open += carry;   // no tail before me in this tile
-        const uint32_t tile_cnt = st.tile_cnt;
-        const uint64_t dst0 = base + excl;
-        const uint32_t my_off = st.my_off;
-        uint32_t *dst = p.out + dst0;
-        // words of this tile the output buffer still has room for
-        const uint32_t room = dst0 >= p.out_cap ? 0u
-                              : (p.out_cap - dst0 >= (uint64_t)G::TILE_GROUPS ? (uint32_t)G::TILE_GROUPS
-                                                                               : (uint32_t)(p.out_cap - dst0));
-        const uint32_t *row = s_in + WORDS_PER_THREAD * tid;
-        const uint32_t *wrow = s_in + 992u * warp;
-
-        const bool all_literal = __all_sync(0xffffffffu, T == 0xFFFFFFFFu && F == 0u);
-        if (all_literal) {
-            // every group of the warp is a literal: lane-per-output-word, fully coalesced
-            const uint32_t wprefix = __shfl_sync(0xffffffffu, my_off, 0);
-#pragma unroll 8
-            for (uint32_t k = 0; k < 32u; k++) {
-                const uint32_t g = 32u * k + lane;
-                const uint32_t pos = wprefix + g;
-                if (pos < room) st_stream_u32(dst + pos, extract_group(wrow, g));
+        for (uint32_t i = 0; i < n_my; i++) {
+            const uint32_t s = i % STAGES, q = i % QDEPTH;
+            TileMeta<NWORK> &mt = sm.meta[q];
+            // the queue slot is free again once tile i - QDEPTH has been copied out
+            while (jd + QDEPTH <= i) {
+                mbar_wait(smem_u32(&sm.done[jd % QDEPTH]), (jd / QDEPTH) & 1u);
+                jd++;
             }
-        } else if (st.wcnt > 192u) {
-            // dense warp: lanes cooperate on one thread-chunk at a time (contiguous stores)
-            for (uint32_t k = 0; k < 32u; k++) {
-                const uint32_t Tk = __shfl_sync(0xffffffffu, T, k);
-                if (Tk == 0u) continue;
-                const uint32_t Fk = __shfl_sync(0xffffffffu, F, k);
-                const uint32_t Ok = __shfl_sync(0xffffffffu, O, k);
-                const uint32_t offk = __shfl_sync(0xffffffffu, my_off, k);
-                const uint32_t pok = __shfl_sync(0xffffffffu, prev_open, k);
-                const uint32_t bit = 1u << lane;
-                if (Tk & bit) {
-                    const uint32_t lower = Tk & (bit - 1u);
-                    uint32_t w;
-                    if (Fk & bit) {
-                        const uint32_t len = lower ? lane - (31u - (uint32_t)__clz(lower)) : lane + 1u + pok;
-                        w = fill_word((Ok >> lane) & 1u, len);
-                    } else {
-                        w = extract_group(wrow, 32u * k + lane);
-                    }
-                    const uint32_t pos = offk + __popc(lower);
-                    if (pos < room) st_stream_u32(dst + pos, w);
+            mbar_wait(smem_u32(&sm.full[s]), (i / STAGES) & 1u);
+            if (tid == 0) TRACE(i, 1, clock64());
+
+            const uint32_t *stage = &sm.stage[s][G::PAD_FRONT];
+            const uint32_t *row = stage + WORDS_PER_THREAD * tid;
+            const uint32_t gvalid = sm.info[s].gvalid;
+            const uint32_t has_next = sm.info[s].has_next;
+            const uint32_t g_thread = 32u * tid;
+            uint32_t nvalid = gvalid > g_thread ? gvalid - g_thread : 0u;
+            if (nvalid > 32u) nvalid = 32u;
+            const uint32_t vmask = nvalid == 32u ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+
+            // ---- regroup 32 -> 31 bit (kernels.cu:79) and classify (kernels.cu:93-112)
+            uint32_t Z = 0, O = 0;
+            {
+                // u = group << 1 | (one junk bit): zero / all-ones tests on the top 31 bits
+                uint32_t prev = row[0];
+                uint32_t u = prev << 1;
+                if ((u & 0xFFFFFFFEu) == 0u) Z |= 1u;
+                if ((~u & 0xFFFFFFFEu) == 0u) O |= 1u;
+#pragma unroll
+                for (int j = 1; j < 31; j++) {
+                    const uint32_t cur_w = row[j];
+                    u = __funnelshift_r(prev, cur_w, 31 - j);
+                    if ((u & 0xFFFFFFFEu) == 0u) Z |= (1u << j);
+                    if ((~u & 0xFFFFFFFEu) == 0u) O |= (1u << j);
+                    prev = cur_w;
                 }
+                u = prev;
+                if ((u & 0xFFFFFFFEu) == 0u) Z |= BIT31;
+                if ((~u & 0xFFFFFFFEu) == 0u) O |= BIT31;
             }
-        } else {
-            // sparse warp: every thread walks its own few tails
-            uint32_t m = T, off = my_off;
-            int prev = -1;
-            uint32_t extra = prev_open;
-            while (m) {
-                const int j = __ffs(m) - 1;
-                m &= m - 1u;
-                uint32_t w;
-                if ((F >> j) & 1u) {
-                    w = fill_word((O >> j) & 1u, (uint32_t)(j - prev) + extra);
+            Z &= vmask;
+            O &= vmask;
+            const uint32_t F = Z | O;
+
+            // type of the group after my chunk (first group of the next thread / tile)
+            uint32_t nz = 0, no = 0;
+            const bool succ = BLOCK_MODE ? (lane != 31u && g_thread + 32u < gvalid)
+                                         : (g_thread + 32u < gvalid || (tid == NWORK * 32u - 1u && has_next));
+            if (succ) {
+                const uint32_t nx = row[31] & ONES31;
+                nz = (nx == 0u) ? BIT31 : 0u;
+                no = (nx == ONES31) ? BIT31 : 0u;
+            }
+            // tail = literal, or fill whose successor differs (run-end rule, kernels.cu:126-141);
+            // the last group of the stream, and of every 1024-group block in BLOCK mode, has no successor
+            const uint32_t T = ((~F) & vmask) | (Z & ~((Z >> 1) | nz)) | (O & ~((O >> 1) | no));
+            const uint32_t cnt = __popc(T);
+            const uint32_t my_open = T ? (uint32_t)__clz(T) : 32u;   // groups after my last tail
+
+            // ---- warp scan: output offset and length of the run open at my chunk's start
+            const uint32_t incl = warp_incl_scan(cnt);
+            const uint32_t tb = __ballot_sync(0xffffffffu, T != 0u);
+            const uint32_t below = tb & lanemask_lt();
+            const uint32_t qb = below ? 31u - (uint32_t)__clz(below) : 0u;
+            const uint32_t open_q = __shfl_sync(0xffffffffu, my_open, qb);
+            // (the run open where the WARP starts is added to the warp's first word at copy-out)
+            const uint32_t prev_open = below ? open_q + 32u * (lane - qb - 1u) : 32u * lane;
+            const uint32_t off = incl - cnt;
+            const uint32_t wcnt = __shfl_sync(0xffffffffu, incl, 31);
+            const uint32_t qlast = tb ? 31u - (uint32_t)__clz(tb) : 0u;
+            const uint32_t open_last = __shfl_sync(0xffffffffu, my_open, qlast);
+            const bool all_literal = __all_sync(0xffffffffu, T == 0xFFFFFFFFu && F == 0u);
+
+            // ---- exchange the warp aggregates (workers' named barrier), derive the tile's
+            WarpAgg<NWORK> &wa = sm.wagg[s];
+            if (lane == 31u) {
+                wa.wcnt[warp] = wcnt;
+                wa.whas[warp] = tb != 0u;
+                wa.wopen[warp] = tb ? open_last + 32u * (31u - qlast) : 1024u;
+            }
+            asm volatile("bar.sync 1, %0;" ::"n"(NWORK * 32) : "memory");
+            uint32_t tile_cnt = 0, tile_open = 0, tile_has = 0, wprefix = 0;
+#pragma unroll
+            for (int w = 0; w < NWORK; w++) {
+                const uint32_t cw = wa.wcnt[w], h = wa.whas[w], o = wa.wopen[w];
+                if (w < (int)warp) wprefix += cw;
+                tile_cnt += cw;
+                if (h) {
+                    tile_has = 1;
+                    tile_open = o;
                 } else {
-                    w = extract_group(row, (uint32_t)j);
+                    tile_open += o;
                 }
-                if (off < room) st_stream_u32(dst + off, w);
-                off++;
-                prev = j;
-                extra = 0;
             }
-        }
+            if (BLOCK_MODE || has_next == 0u) {   // the end of a column is always a tail
+                tile_open = 0;
+                tile_has = 1;
+            }
+            const bool ring_mode = tile_cnt <= (uint32_t)G::RING_WORDS;
+            if (warp == 0 && lane == 0) {
+                // publish the aggregate to the other CTAs at once: their look-backs never wait for this
+                // CTA's control warp
+                const uint32_t tile = sm.info[s].tile;
+                st_relaxed_u64(p.desc + tile, tile == 0u ? desc_pack(ST_INCL, 0, tile_open, tile_cnt)
+                                                         : desc_pack(ST_AGG, tile_has ^ 1u, tile_open, tile_cnt));
+                mt.tile_cnt = tile_cnt;
+                mt.tile_open = tile_open;
+                mt.tile_has = tile_has;
+                mt.ring_base = head;
+                mt.mode = ring_mode ? MODE_RING : MODE_DIRECT;
+            }
+            if (lane == 31u) {
+                mt.wprefix[warp] = wprefix;
+                mt.wopen[warp] = wa.wopen[warp];
+                mt.whas[warp] = wa.whas[warp];
+            }
+            if (tid == 0) TRACE(i, 2, clock64());
 
-        // ---- seam with an earlier launch (CANONICAL append): fold my first run into its last word
-        if (tile == 0u && p.merge_prev) {
-            __syncthreads();   // the tile's words are in global memory, visible to the whole CTA
-            if (tid == 0) {
-                uint32_t drop = 0;
-                if (base > 0 && tile_cnt > 0 && base < p.out_cap) {
-                    const uint32_t pw = p.out[base - 1], fw = p.out[base];
-                    if (is_fill(pw) && is_fill(fw) && ((pw ^ fw) & BIT30) == 0u) {
-                        const uint64_t total = (uint64_t)fill_count(pw) + fill_count(fw);
-                        const uint32_t ty = (fw >> 30) & 1u;
-                        if (total <= MAX_FILL) {
-                            p.out[base - 1] = fill_word(ty, (uint32_t)total);
-                            drop = 1;
-                        } else {
-                            p.out[base - 1] = fill_word(ty, MAX_FILL);
-                            p.out[base] = fill_word(ty, (uint32_t)(total - MAX_FILL));
+            // compaction of my words into the ring at `origin`: those with warp-relative index in
+            // [lo, lo + WARP_RING) when `windowed`, else all of them
+            auto compact = [&](uint32_t origin, uint32_t lo, bool windowed) {
+                // literals: the group itself (kernels.cu:107-112,256)
+                uint32_t m = T & ~F;
+                while (m) {
+                    const uint32_t j = 31u - (uint32_t)__clz(m);
+                    m ^= 1u << j;
+                    const uint32_t idx = off + __popc(T & ((1u << j) - 1u)) - lo;
+                    if (!windowed || idx < (uint32_t)WARP_RING)
+                        sm.ring[(origin + idx) & (G::RING_WORDS - 1)] = row_group(row, j);
+                }
+                // fills: BIT31 | type << 30 | length (kernels.cu:244-248)
+                m = T & F;
+                while (m) {
+                    const uint32_t j = 31u - (uint32_t)__clz(m);
+                    m ^= 1u << j;
+                    const uint32_t lower = T & ((1u << j) - 1u);
+                    const uint32_t len = lower ? j - (31u - (uint32_t)__clz(lower)) : j + 1u + prev_open;
+                    const uint32_t idx = off + __popc(lower) - lo;
+                    if (!windowed || idx < (uint32_t)WARP_RING)
+                        sm.ring[(origin + idx) & (G::RING_WORDS - 1)] = fill_word((O >> j) & 1u, len);
+                }
+            };
+
+            if (ring_mode) {
+                // ---- stage the tile's words back to back in the ring; the control warp copies them out
+                //      once the tile's offset is known.  Wait until the ring has room for them.
+                while (jd < i && head - sm.meta[jd % QDEPTH].ring_base + tile_cnt > (uint32_t)G::RING_WORDS) {
+                    mbar_wait(smem_u32(&sm.done[jd % QDEPTH]), (jd / QDEPTH) & 1u);
+                    jd++;
+                }
+                compact(head + wprefix, 0u, false);
+                head += tile_cnt;
+                __syncwarp();
+                if (lane == 0) {
+                    mbar_arrive(smem_u32(&sm.empty[s]));
+                    mbar_arrive(smem_u32(&sm.agg[q]));
+                }
+            } else {
+                // ---- too many words for the ring (dense data): wait for the tile's offset and write them here
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sm.agg[q]));
+                while (jd < i) {   // ring drained: my slice of it serves as staging area below
+                    mbar_wait(smem_u32(&sm.done[jd % QDEPTH]), (jd / QDEPTH) & 1u);
+                    jd++;
+                }
+                mbar_wait(smem_u32(&sm.pref[q]), (i / QDEPTH) & 1u);
+                const uint64_t dstw = mt.dst + wprefix;
+                const uint32_t room =
+                    dstw >= p.out_cap ? 0u : (p.out_cap - dstw >= 1024ull ? 1024u : (uint32_t)(p.out_cap - dstw));
+                uint32_t *dst = p.out + dstw;
+                if (all_literal) {
+                    // every group of the warp is a literal: lane-per-output-word, fully coalesced
+                    const uint32_t *wrow = stage + 992u * warp;
+#pragma unroll 8
+                    for (uint32_t k = 0; k < 32u; k++) {
+                        const uint32_t g = 32u * k + lane;
+                        if (g < room) st_stream_u32(dst + g, extract_group(wrow, g));
+                    }
+                } else {
+                    uint32_t first_add = BLOCK_MODE ? 0u : mt.wcarry[warp];
+                    if (wprefix == 0u) first_add += (uint32_t)mt.lead_adjust;   // the launch's first word
+                    const uint32_t mine = warp * WARP_RING;
+                    for (uint32_t lo = 0; lo < wcnt; lo += WARP_RING) {
+                        compact(mine, lo, true);
+                        __syncwarp();
+                        const uint32_t nround = wcnt - lo < (uint32_t)WARP_RING ? wcnt - lo : (uint32_t)WARP_RING;
+                        for (uint32_t k = lane; k < nround; k += 32u) {
+                            uint32_t v = sm.ring[mine + k];
+                            if (lo + k == 0u) v += first_add;
+                            if (lo + k < room) st_stream_u32(dst + lo + k, v);
                         }
+                        __syncwarp();
                     }
                 }
-                s_drop = drop;
+                __syncwarp();
+                if (lane == 0) mbar_arrive(smem_u32(&sm.empty[s]));
             }
-            __syncthreads();
-            if (s_drop) {
-                // close the one-word gap: slide the tile's remaining words down (tile 0 of a continuation only)
-                const uint32_t nmove = (tile_cnt < room ? tile_cnt : room);
-                for (uint32_t i0 = 1; i0 < nmove; i0 += THREADS) {
-                    const uint32_t i = i0 + tid;
-                    uint32_t v = 0;
-                    if (i < nmove) v = p.out[base + i];
-                    __syncthreads();
-                    if (i < nmove) p.out[base + i - 1] = v;
-                    __syncthreads();
-                }
-            }
-            if (tid == 0) st_relaxed_u64(p.desc, desc_pack(ST_INCL, 0, st.tile_open, tile_cnt - s_drop));
+            if (tid == 0) TRACE(i, 6, clock64());
         }
-        if (tid == 0) {
-            const uint32_t drop = (tile == 0u) ? s_drop : 0u;
-            if (p.col_offsets && t == 0u) p.col_offsets[col] = dst0;
-            if (tile == p.n_tiles - 1u) {
-                const uint64_t total = dst0 + tile_cnt - drop;
-                *p.total_out = total;
-                if (p.col_offsets) p.col_offsets[p.n_cols] = total;
-            }
-        }
-
-        __syncthreads();   // (C) everyone is done with s_in and the look-back partials
-        tile = next;
-        cur = nxt;
-        cur_st = next_st;
     }
-    cp_async_wait<0>();
 }
+
+// ---- seam between two launches of one CANONICAL stream (inputs beyond MAX_LAUNCH_GROUPS) ----------
+//
+// The next segment may start with a fill run that continues the last word written so far.  The
+// probe measures that leading run straight from the input; the seam kernel then either takes the
+// previous word back (the next launch re-emits it, lengthened by lead_adjust) or, if the sum does
+// not fit the 30-bit counter, saturates the previous word and shortens the next one.
+
+// result[0] = leading bits of the segment that equal its first bit (atomicMin over CTAs)
+__global__ void wah_lead_probe_kernel(const uint32_t *in, uint64_t n_words, unsigned long long *result)
+{
+    constexpr uint64_t CHUNK = 8192;   // words per CTA step
+    __shared__ unsigned long long s_best;
+    const uint32_t pattern = (in[0] & 1u) ? 0xFFFFFFFFu : 0u;
+    for (uint64_t c0 = (uint64_t)blockIdx.x * CHUNK; c0 < n_words; c0 += (uint64_t)gridDim.x * CHUNK) {
+        if (threadIdx.x == 0) s_best = *((volatile unsigned long long *)result);
+        __syncthreads();
+        const unsigned long long best = s_best;
+        __syncthreads();
+        if (best < c0 * 32ull) return;   // an earlier chunk already ended the run
+        unsigned long long mine = ~0ull;
+        for (uint64_t i = c0 + threadIdx.x; i < c0 + CHUNK && i < n_words; i += blockDim.x) {
+            const uint32_t x = in[i] ^ pattern;
+            if (x) {
+                mine = i * 32ull + (uint64_t)(__ffs(x) - 1);
+                break;
+            }
+        }
+        if (mine != ~0ull) atomicMin(result, mine);
+    }
+}
+
+// slot: words written so far (rewritten if the last word is taken back); adjust: for the next launch
+__global__ void wah_seam_kernel(const uint32_t *in, uint64_t n_words, uint64_t groups, uint32_t *out, uint64_t out_cap,
+                                uint64_t *slot, const unsigned long long *lead_bits, int32_t *adjust)
+{
+    if (threadIdx.x != 0 || blockIdx.x != 0) return;
+    const uint64_t base = *slot;
+    int32_t adj = 0;
+    if (base > 0 && base <= out_cap) {
+        const uint32_t type = in[0] & 1u;
+        unsigned long long bits = *lead_bits;
+        if (bits > n_words * 32ull) bits = n_words * 32ull;
+        // the zero padded last group continues a zero run; a one run ends at the last whole group
+        uint64_t lead = (bits == n_words * 32ull && type == 0u) ? groups : bits / 31ull;
+        const uint32_t pw = out[base - 1];
+        if (lead > 0 && is_fill(pw) && ((pw >> 30) & 1u) == type) {
+            const uint64_t c1 = fill_count(pw);
+            if (c1 + lead <= (uint64_t)MAX_FILL) {
+                *slot = base - 1;          // the next launch overwrites the word with the merged run
+                adj = (int32_t)c1;
+            } else {
+                out[base - 1] = fill_word(type, MAX_FILL);
+                adj = (int32_t)c1 - (int32_t)MAX_FILL;
+            }
+        }
+    }
+    *adjust = adj;
+}
+
+template <int NWORK, int STAGES>
+size_t smem_bytes_t()
+{
+    return sizeof(Smem<NWORK, STAGES>) + 128;
+}
+
+constexpr int CFG_NWORK = COMPRESS_TILE_WORDS / 992;
+constexpr int CFG_STAGES = 3;
+// two CTAs per SM: 228 KB of shared memory per SM, 1 KB reserved per CTA
+static_assert(sizeof(Smem<CFG_NWORK, CFG_STAGES>) + 128 <= (233472 - 2048) / 2, "two CTAs per SM must fit");
 
 }  // namespace
 
 size_t compress_smem_bytes()
 {
-    return (size_t)(3 * (COMPRESS_TILE_WORDS + 4)) * sizeof(uint32_t);
+    return smem_bytes_t<CFG_NWORK, CFG_STAGES>();
 }
 
-template <typename K>
-static cudaError_t compress_grid(K kernel, size_t smem, int *grid)
+cudaError_t launch_seam(const uint32_t *d_in, uint64_t n_words, uint64_t groups, uint32_t *d_out, uint64_t out_cap,
+                        uint64_t *d_slot, unsigned long long *d_lead_bits, int32_t *d_adjust, cudaStream_t stream)
 {
-    // all CTAs must be resident at once: the look-back spins on tiles owned by other CTAs
-    int dev = 0, sms = 0, per_sm = 0;
-    cudaError_t e = cudaGetDevice(&dev);
+    cudaError_t e = cudaMemsetAsync(d_lead_bits, 0xFF, sizeof(unsigned long long), stream);
     if (e != cudaSuccess) return e;
-    e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-    if (e != cudaSuccess) return e;
-    e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, COMPRESS_THREADS, smem);
-    if (e != cudaSuccess) return e;
-    if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-    *grid = sms * per_sm;
-    return cudaSuccess;
+    const uint64_t chunks = (n_words + 8191) / 8192;
+    const int grid = (int)(chunks < 592 ? chunks : 592);
+    wah_lead_probe_kernel<<<grid, 256, 0, stream>>>(d_in, n_words, d_lead_bits);
+    wah_seam_kernel<<<1, 32, 0, stream>>>(d_in, n_words, groups, d_out, out_cap, d_slot, d_lead_bits, d_adjust);
+    return cudaGetLastError();
 }
 
 cudaError_t launch_compress(const CompressParams &p, int mode, cudaStream_t stream)
 {
+    // all CTAs must be resident at once (the look-back spins on tiles owned by other CTAs):
+    // cooperative launch of SMs x occupancy CTAs
+    constexpr int THREADS = Geom<CFG_NWORK, CFG_STAGES>::THREADS;
     const size_t smem = compress_smem_bytes();
     static int grids[2] = {0, 0};
     const int m = mode == 0 ? 0 : 1;
-    const void *kernel = m == 0 ? (const void *)wah_compress_kernel<COMPRESS_THREADS, true>
-                                : (const void *)wah_compress_kernel<COMPRESS_THREADS, false>;
+    const void *kernel = m == 0 ? (const void *)wah_compress_kernel<CFG_NWORK, CFG_STAGES, true>
+                                : (const void *)wah_compress_kernel<CFG_NWORK, CFG_STAGES, false>;
     if (grids[m] == 0) {
         cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        int g = 0;
-        e = m == 0 ? compress_grid(wah_compress_kernel<COMPRESS_THREADS, true>, smem, &g)
-                   : compress_grid(wah_compress_kernel<COMPRESS_THREADS, false>, smem, &g);
+        int dev = 0, sms = 0, per_sm = 0;
+        e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
-        grids[m] = g;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        grids[m] = sms * per_sm;
     }
     int grid = grids[m];
     if ((uint32_t)grid > p.n_tiles) grid = (int)p.n_tiles;
     CompressParams params = p;
     void *args[] = {&params};
-    return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(COMPRESS_THREADS), args, smem, stream);
+    return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(THREADS), args, smem, stream);
 }
 
 }  // namespace wahb200

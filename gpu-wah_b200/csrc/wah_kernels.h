@@ -24,18 +24,22 @@ struct CompressParams {
     uint32_t tiles_per_col;
     uint32_t n_tiles;        // tiles_per_col * n_cols
     uint32_t n_cols;
-    int merge_prev;          // CANONICAL append: merge the first run into out[base-1]
+    const int32_t *lead_adjust;  // nullptr or device int: added to the launch's first word (launch_seam)
     uint32_t *out;
     uint64_t out_cap;
     uint64_t *desc;          // [n_tiles] zeroed
-    uint32_t *ticket;        // zeroed
     const uint64_t *base_in; // words already in `out` (nullptr = 0)
     uint64_t *total_out;     // receives base + words emitted by this launch
     uint64_t *col_offsets;   // nullptr or [n_cols + 1] for this launch's columns
+    uint64_t *trace;         // nullptr; phase timestamps in -DWAH_TRACE builds (scripts/trace_compress.py)
 };
 
 size_t compress_smem_bytes();
 cudaError_t launch_compress(const CompressParams &p, int mode, cudaStream_t stream);
+// CANONICAL stream continued by another launch: decide how the next segment's leading run joins
+// the last word written so far (*d_slot words); writes *d_slot and *d_adjust for that launch
+cudaError_t launch_seam(const uint32_t *d_in, uint64_t n_words, uint64_t groups, uint32_t *d_out, uint64_t out_cap,
+                        uint64_t *d_slot, unsigned long long *d_lead_bits, int32_t *d_adjust, cudaStream_t stream);
 
 // ---------------------------------------------------------------- decompress
 

@@ -93,6 +93,7 @@ _sig("wah_shard_record_device", ctypes.c_int, _vp, _u64, _u64, ctypes.POINTER(Sh
 _sig("wah_stitch_plan", ctypes.c_int, ctypes.POINTER(ShardRecord), ctypes.c_int, ctypes.c_int,
      ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_uint32),
      ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(_u64))
+_sig("wah_test_set_max_launch_tiles", None, _u64)
 _sig("wah_gen_uniform_device", ctypes.c_int, _vp, _u64, ctypes.c_double, _u64, _vp)
 _sig("wah_gen_paint_runs_device", ctypes.c_int, _vp, _u64, _vp, _vp, _u64, _vp)
 

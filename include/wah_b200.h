@@ -145,6 +145,13 @@ int wah_gen_uniform_device(uint32_t *d_out, uint64_t n_words, double density, ui
 int wah_gen_paint_runs_device(uint32_t *d_out, uint64_t n_words, const int64_t *d_start_bits,
                               const int64_t *d_len_bits, uint64_t n_runs, void *stream);
 
+/* ---- test hook ---------------------------------------------------------------------- */
+
+/* A stream longer than one kernel launch can describe (2^30 - 1 groups) is compressed as several
+ * chained launches.  This shrinks the per-launch segment to `tiles` tiles of 7936 words so that
+ * the tests can drive that path with small inputs; 0 restores the default.  Not thread safe.   */
+void wah_test_set_max_launch_tiles(uint64_t tiles);
+
 #ifdef __cplusplus
 }
 #endif

@@ -1,0 +1,46 @@
+"""Phase timeline of the compress kernel (needs a -DWAH_TRACE build: make -C gpu-wah_b200 TRACE=1)."""
+import ctypes, sys, os
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gpu_wah_b200 as wah
+
+n = 1 << 25
+d = wah.gen_uniform_device(n, 0.001, 1337)
+cap = wah.max_compressed_words(n)
+out = torch.empty(cap, dtype=torch.int32, device="cuda")
+cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+ws = wah.Workspace.for_compress(n)
+NC = 296
+trace = torch.zeros(NC * 64 * 8, dtype=torch.int64, device="cuda")
+wah.lib.wah_test_set_trace.argtypes = [ctypes.c_void_p]
+for it in range(3):
+    trace.zero_()
+    wah.lib.wah_test_set_trace(trace.data_ptr())
+    wah.compress_device(d, n, out, cap, cnt, ws, 0)
+    torch.cuda.synchronize()
+t = trace.cpu().numpy().reshape(NC, 64, 8).astype(np.int64)
+iters = 14
+names = ["tma_issue", "full_done", "classify_done", "agg_seen", "pref_sent", "pref_seen", "emit_done", "gtime"]
+g0 = t[:, 0, 7].min()
+print("gtime of first TMA issue per CTA (us): min %.2f max %.2f" % (0, (t[:, 0, 7].max() - g0) / 1e3))
+for i in range(iters):
+    gi = t[:, i, 7]
+    print(f"iter {i}: tma issue gtime us  min {(gi.min()-g0)/1e3:7.2f} med {(np.median(gi)-g0)/1e3:7.2f} max {(gi.max()-g0)/1e3:7.2f}")
+def rep(label, a):
+    a = a / 1965.0  # us at 1965 MHz
+    print(f"{label:34s} med {np.median(a):6.2f} p10 {np.percentile(a,10):6.2f} p90 {np.percentile(a,90):6.2f} us")
+for i in (3, 6, 9, 12):
+    print("--- iteration", i)
+    x = t[:, i, :]
+    rep("tma issue -> full seen (worker)", x[:, 1] - x[:, 0])
+    rep("classify+scan", x[:, 2] - x[:, 1])
+    rep("compact/emit (worker)", x[:, 6] - x[:, 2])
+    rep("worker iteration", x[:, 6] - t[:, i - 1, 6])
+    rep("worker done -> agg seen (ctl)", x[:, 3] - x[:, 6])
+    rep("look-back (agg seen -> pref sent)", x[:, 4] - x[:, 3])
+    rep("copy-out (pref sent -> done)", x[:, 5] - x[:, 4])
+    rep("control iteration", x[:, 5] - t[:, i - 1, 5])
+    rep("worker lead over control (tiles)", 1965.0 * np.array([np.searchsorted(t[b, :iters, 6], x[b, 5]) - i for b in range(NC)]))
+last = t[:, :iters, 5].max()
+first = t[:, 0, 0].min()
+print("per-CTA span us: med %.1f" % np.median((t[:, :iters, 5].max(axis=1) - t[:, 0, 0]) / 1965.0))

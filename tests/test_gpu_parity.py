@@ -269,3 +269,32 @@ def test_oracle_and_product_against_the_reference_kernels(name, gen, tmp_path):
     canon, _ = gpu_compress(data, wah.WAH_CANONICAL)
     back = _ref_call("decompress", canon, tmp_path)
     assert np.array_equal(back[: data.size], data)
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_multi_launch_seam(mode):
+    """Streams beyond one launch's descriptor range are compressed as chained launches; in CANONICAL mode
+    the leading run of every segment joins the last word of the previous one (launch_seam)."""
+    TW = 7936
+    rng = np.random.default_rng(7)
+    cases = {
+        "zeros": np.zeros(7 * TW + 100, dtype=np.uint32),
+        "ones": np.full(5 * TW, 0xFFFFFFFF, dtype=np.uint32),
+        "sparse": datagen.uniform(6 * TW + 17, 0.0005, 21),
+        "clustered": datagen.clustered(9 * TW + 1, 0.3, 20000, 22),
+        "literal_at_seams": np.zeros(6 * TW, dtype=np.uint32),
+        "ones_then_zeros": np.concatenate([np.full(2 * TW, 0xFFFFFFFF, dtype=np.uint32), np.zeros(3 * TW + 5, dtype=np.uint32)]),
+    }
+    cases["literal_at_seams"][2 * TW] = 1
+    cases["literal_at_seams"][4 * TW - 1] = 0x80000000
+    del rng
+    try:
+        for tiles in (1, 2, 3):
+            wah.lib.wah_test_set_max_launch_tiles(tiles)
+            for name, data in cases.items():
+                want = orc.compress(data, mode)
+                got, c = gpu_compress(data, mode)
+                assert c == want.size, (name, tiles)
+                assert np.array_equal(got, want), (name, tiles)
+    finally:
+        wah.lib.wah_test_set_max_launch_tiles(0)

@@ -25,6 +25,16 @@ static int fail(int code, const char *fmt, ...)
     return code;
 }
 
+// shared with wah_host.cu
+int wah_set_error(int code, const char *fmt, ...)
+{
+    va_list ap;
+    va_start(ap, fmt);
+    vsnprintf(g_err, sizeof(g_err), fmt, ap);
+    va_end(ap);
+    return code;
+}
+
 #define CUDA_TRY(expr)                                                                             \
     do {                                                                                           \
         cudaError_t e__ = (expr);                                                                  \
@@ -290,7 +300,7 @@ extern "C" int wah_decoded_size_device(const uint32_t *d_in, uint64_t c_words, u
                              (cudaStream_t)stream);
 }
 
-// ---------------------------------------------------------------------- host API
+// ----------------------------------------------------------------- range sharding
 
 namespace {
 struct DevBuf {
@@ -301,138 +311,7 @@ struct DevBuf {
     }
     cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
 };
-struct Timer {
-    cudaEvent_t a = nullptr, b = nullptr;
-    Timer()
-    {
-        cudaEventCreate(&a);
-        cudaEventCreate(&b);
-    }
-    ~Timer()
-    {
-        if (a) cudaEventDestroy(a);
-        if (b) cudaEventDestroy(b);
-    }
-    void start() { cudaEventRecord(a, 0); }
-    float stop()
-    {
-        float ms = 0.f;
-        cudaEventRecord(b, 0);
-        cudaEventSynchronize(b);
-        cudaEventElapsedTime(&ms, a, b);
-        return ms;
-    }
-};
 }  // namespace
-
-extern "C" void wah_free(void *p) { free(p); }
-
-extern "C" int wah_compress_host(const uint32_t *h_in, uint64_t n_words, int mode, uint32_t **h_out,
-                                 uint64_t *out_words, float *ms_h2d, float *ms_compute, float *ms_d2h)
-{
-    if (check_mode(mode)) return WAH_ERR_INVALID;
-    if (!h_out) return fail(WAH_ERR_INVALID, "h_out is null");
-    if (n_words && !h_in) return fail(WAH_ERR_INVALID, "h_in is null");
-    *h_out = nullptr;
-    Timer t;
-    // -- segment 1: allocation + H2D (compress.cu:57-120)
-    t.start();
-    const uint64_t cap = wah_max_compressed_words(n_words);
-    const size_t ws_bytes = wah_compress_workspace_bytes(n_words);
-    DevBuf d_in, d_out, d_ws, d_cnt;
-    CUDA_TRY(d_in.alloc(n_words * 4));
-    CUDA_TRY(d_out.alloc(cap * 4));
-    CUDA_TRY(d_ws.alloc(ws_bytes));
-    CUDA_TRY(d_cnt.alloc(sizeof(uint64_t)));
-    if (n_words) CUDA_TRY(cudaMemcpy(d_in.p, h_in, n_words * 4, cudaMemcpyHostToDevice));
-    const float t0 = t.stop();
-    // -- segment 2: compute (compress.cu:125-172)
-    t.start();
-    int rc = wah_compress_device((const uint32_t *)d_in.p, n_words, mode, (uint32_t *)d_out.p, cap,
-                                 (uint64_t *)d_cnt.p, d_ws.p, ws_bytes, nullptr);
-    if (rc) return rc;
-    uint64_t c = 0;
-    CUDA_TRY(cudaMemcpy(&c, d_cnt.p, sizeof(c), cudaMemcpyDeviceToHost));
-    const float t1 = t.stop();
-    // -- segment 3: D2H + release (compress.cu:177-202)
-    t.start();
-    uint32_t *host = (uint32_t *)malloc((size_t)(c ? c : 1) * 4);
-    if (!host) return fail(WAH_ERR_NOMEM, "malloc of %llu words failed", (unsigned long long)c);
-    if (c) {
-        cudaError_t e = cudaMemcpy(host, d_out.p, c * 4, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) {
-            free(host);
-            return fail(WAH_ERR_CUDA, "D2H copy: %s", cudaGetErrorString(e));
-        }
-    }
-    const float t2 = t.stop();
-    *h_out = host;
-    if (out_words) *out_words = c;
-    if (ms_h2d) *ms_h2d = t0;
-    if (ms_compute) *ms_compute = t1;
-    if (ms_d2h) *ms_d2h = t2;
-    return WAH_OK;
-}
-
-extern "C" int wah_decompress_host(const uint32_t *h_in, uint64_t c_words, uint32_t **h_out,
-                                   uint64_t *out_words, float *ms_h2d, float *ms_compute, float *ms_d2h)
-{
-    if (!h_out) return fail(WAH_ERR_INVALID, "h_out is null");
-    if (c_words && !h_in) return fail(WAH_ERR_INVALID, "h_in is null");
-    *h_out = nullptr;
-    Timer t;
-    // -- segment 1: allocation + H2D (decompress.cu:34-56)
-    t.start();
-    DevBuf d_in, d_ws, d_info, d_out;
-    CUDA_TRY(d_in.alloc(c_words * 4));
-    CUDA_TRY(d_info.alloc(2 * sizeof(uint64_t)));
-    if (c_words) CUDA_TRY(cudaMemcpy(d_in.p, h_in, c_words * 4, cudaMemcpyHostToDevice));
-    const float t0 = t.stop();
-    // -- segment 2: size query, allocation of the exact output, expansion (decompress.cu:66-124)
-    t.start();
-    uint64_t info[2] = {0, 0};
-    {
-        const size_t ws0 = wah_decompress_workspace_bytes(c_words, 0);
-        DevBuf d_ws0;
-        CUDA_TRY(d_ws0.alloc(ws0));
-        int rc = wah_decoded_size_device((const uint32_t *)d_in.p, c_words, (uint64_t *)d_info.p, d_ws0.p, ws0,
-                                         nullptr);
-        if (rc) return rc;
-        CUDA_TRY(cudaMemcpy(info, d_info.p, sizeof(info), cudaMemcpyDeviceToHost));
-    }
-    const uint64_t words = info[0];
-    const size_t ws_bytes = wah_decompress_workspace_bytes(c_words, words);
-    CUDA_TRY(d_ws.alloc(ws_bytes));
-    CUDA_TRY(d_out.alloc(words * 4));
-    int rc = wah_decompress_device((const uint32_t *)d_in.p, c_words, (uint32_t *)d_out.p, words,
-                                   (uint64_t *)d_info.p, d_ws.p, ws_bytes, nullptr);
-    if (rc) return rc;
-    uint32_t bad = 0;
-    CUDA_TRY(cudaMemcpy(&bad, (char *)d_ws.p + offsetof(DecodeHeader, bad_words), sizeof(bad),
-                        cudaMemcpyDeviceToHost));
-    const float t1 = t.stop();
-    if (bad) return fail(WAH_ERR_FORMAT, "%u zero-length fill words in the stream", bad);
-    // -- segment 3: D2H + release (decompress.cu:127-133)
-    t.start();
-    uint32_t *host = (uint32_t *)malloc((size_t)(words ? words : 1) * 4);
-    if (!host) return fail(WAH_ERR_NOMEM, "malloc of %llu words failed", (unsigned long long)words);
-    if (words) {
-        cudaError_t e = cudaMemcpy(host, d_out.p, words * 4, cudaMemcpyDeviceToHost);
-        if (e != cudaSuccess) {
-            free(host);
-            return fail(WAH_ERR_CUDA, "D2H copy: %s", cudaGetErrorString(e));
-        }
-    }
-    const float t2 = t.stop();
-    *h_out = host;
-    if (out_words) *out_words = words;
-    if (ms_h2d) *ms_h2d = t0;
-    if (ms_compute) *ms_compute = t1;
-    if (ms_d2h) *ms_d2h = t2;
-    return WAH_OK;
-}
-
-// ----------------------------------------------------------------- range sharding
 
 extern "C" int wah_shard_record_device(const uint32_t *d_shard, uint64_t words, uint64_t groups,
                                        wah_shard_record *h_record, void *stream_)

@@ -34,14 +34,17 @@ namespace wahb200 {
 
 namespace {
 
-// ---- tile descriptor: status:2 | no_tail:1 | open:30 | count:31 -------------------
-constexpr uint32_t ST_EMPTY = 0, ST_AGG = 1, ST_INCL = 2;
+// ---- tile descriptor: valid:1 | no_tail:1 | open:30 | count:31 (zero = not published yet) -----
+//   count    words the tile emits
+//   no_tail  the tile holds no run end: its groups all belong to one run that is still open
+//   open     groups after the tile's last run end (the whole tile if no_tail)
+// Written once, by the tile's workers, as soon as the tile is classified.
 
-__device__ __forceinline__ uint64_t desc_pack(uint32_t st, uint32_t no_tail, uint32_t open, uint32_t count)
+__device__ __forceinline__ uint64_t desc_pack(uint32_t no_tail, uint32_t open, uint32_t count)
 {
-    return ((uint64_t)st << 62) | ((uint64_t)no_tail << 61) | ((uint64_t)open << 31) | (uint64_t)count;
+    return (1ull << 63) | ((uint64_t)no_tail << 61) | ((uint64_t)open << 31) | (uint64_t)count;
 }
-__device__ __forceinline__ uint32_t desc_status(uint64_t d) { return (uint32_t)(d >> 62); }
+__device__ __forceinline__ bool desc_empty(uint64_t d) { return (d >> 63) == 0ull; }
 __device__ __forceinline__ uint32_t desc_no_tail(uint64_t d) { return (uint32_t)(d >> 61) & 1u; }
 __device__ __forceinline__ uint32_t desc_open(uint64_t d) { return (uint32_t)(d >> 31) & MAX_FILL; }
 __device__ __forceinline__ uint32_t desc_count(uint64_t d) { return (uint32_t)d & 0x7FFFFFFFu; }
@@ -116,7 +119,7 @@ struct Geom {
     static constexpr int TILE_GROUPS = NWORK * 1024;
     static constexpr int PAD_FRONT = 4;                       // row[-1] of the tile's first thread
     static constexpr int STAGE_WORDS = TILE_WORDS + 8;        // + 4 in front, + look-ahead word (16 B) behind
-    static constexpr int THREADS = (NWORK + 2) * 32;
+    static constexpr int THREADS = (NWORK + 3) * 32;
     static constexpr int RING_WORDS = NWORK * WARP_RING;      // power of two for NWORK = 4, 8
     static_assert((RING_WORDS & (RING_WORDS - 1)) == 0, "ring size must be a power of two");
     static_assert(TILE_WORDS == COMPRESS_TILE_WORDS, "the C ABI sizes its descriptor array from COMPRESS_TILE_WORDS");
@@ -175,7 +178,7 @@ __device__ __forceinline__ uint32_t row_group(const uint32_t *row, uint32_t j)
 }
 
 template <int NWORK, int STAGES, bool BLOCK_MODE>
-__global__ void __launch_bounds__((NWORK + 2) * 32, 2) wah_compress_kernel(const CompressParams p)
+__global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const CompressParams p)
 {
     using G = Geom<NWORK, STAGES>;
     using SM = Smem<NWORK, STAGES>;
@@ -251,9 +254,24 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 2) wah_compress_kernel(const
         }
     } else if (warp == NWORK) {
         // ============================================================ control warp
-        constexpr int LBN = 8;   // descriptors per lane and look-back round (window = 32 * LBN tiles)
+        // Offsets by a chained sum instead of a status-polling look-back: this CTA owns tiles b, b + G,
+        // b + 2G, ... (G = gridDim), so the words before tile k are the words before its previous tile
+        // k - G, plus that tile's, plus the aggregates of the G - 1 tiles in between.  Those are published
+        // by the workers of the other CTAs (which run ahead of their control warps), so a control warp
+        // never waits for another control warp.
+        constexpr int LBN = 10;   // descriptors per lane and round (32 * LBN = 320 >= 2 CTAs x 148 SMs)
         const uint64_t base = p.base_in ? *p.base_in : 0ull;
         const int32_t lead_adjust = p.lead_adjust ? *p.lead_adjust : 0;
+        uint32_t own_cnt = 0, own_open = 0;   // words of this launch up to / run open at the end of my previous tile
+        uint64_t d[LBN];                      // first window of the next tile, requested one tile ahead
+        auto request = [&](int64_t hi, int64_t lo) {
+#pragma unroll
+            for (int r = 0; r < LBN; r++) {
+                const int64_t lk = hi - (int64_t)lane - 32 * r;
+                d[r] = lk >= lo ? ld_relaxed_u64(p.desc + lk) : 0ull;
+            }
+        };
+        if (n_my > 0) request((int64_t)blockIdx.x - 1, 0);
         for (uint32_t i = 0; i < n_my; i++) {
             const uint32_t q = i % QDEPTH, use = i / QDEPTH;
             const uint32_t tile = blockIdx.x + i * stride;
@@ -267,53 +285,47 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 2) wah_compress_kernel(const
             // ---- tile aggregate (computed and published to the other CTAs by the workers)
             const uint32_t tile_cnt = mt.tile_cnt, tile_open = mt.tile_open, tile_has = mt.tile_has;
 
-            // ---- decoupled look-back: rounds of 32 * LBN descriptors, nearest tile first
-            uint32_t excl = 0, carry = 0;
-            if (tile != 0u) {
+            // ---- sum the aggregates of tiles [lo, hi], nearest first
+            uint32_t excl = own_cnt, carry = 0;
+            {
+                const int64_t lo = i == 0 ? 0 : (int64_t)tile - (int64_t)stride + 1;
+                int64_t hi = (int64_t)tile - 1;
                 bool open_done = BLOCK_MODE || (t == 0u);   // BLOCK mode never carries; CANONICAL restarts per column
                 uint32_t csum = 0, osum = 0;
-                int64_t look = (int64_t)tile - 1 - (int64_t)lane;
-                bool done = false;
-                while (!done) {
-                    uint64_t d[LBN];
+                bool fresh = true;
+                while (hi >= lo) {
+                    if (!fresh) request(hi, lo);
+                    fresh = false;
 #pragma unroll
                     for (int r = 0; r < LBN; r++) {
-                        const int64_t lk = look - 32 * r;
-                        d[r] = lk >= 0 ? ld_relaxed_u64(p.desc + lk) : desc_pack(ST_INCL, 0, 0, 0);
-                    }
-#pragma unroll
-                    for (int r = 0; r < LBN; r++) {
-                        if (!done) {
-                            const int64_t lk = look - 32 * r;
-                            while (__any_sync(0xffffffffu, desc_status(d[r]) == ST_EMPTY)) {
-                                if (desc_status(d[r]) == ST_EMPTY) d[r] = ld_relaxed_u64(p.desc + lk);
-                            }
-                            const uint32_t incl_mask = __ballot_sync(0xffffffffu, desc_status(d[r]) == ST_INCL);
-                            const uint32_t first_incl = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 32u;
-                            const bool part = lane <= first_incl;   // first_incl == 32: every lane takes part
-                            if (part) csum += desc_count(d[r]);
-                            if (!open_done) {
-                                // towards older tiles until one ends a run (or carries a resolved value)
-                                const uint32_t term_mask = __ballot_sync(
-                                    0xffffffffu, part && (desc_status(d[r]) == ST_INCL || !desc_no_tail(d[r])));
-                                const uint32_t first_term = term_mask ? (uint32_t)__ffs(term_mask) - 1u : 32u;
-                                if (part && lane <= first_term) osum += desc_open(d[r]);
-                                open_done = first_term < 32u;
-                            }
-                            done = first_incl < 32u;
+                        const int64_t lk = hi - (int64_t)lane - 32 * r;
+                        const bool in = lk >= lo;
+                        while (__any_sync(0xffffffffu, in && desc_empty(d[r]))) {
+                            if (in && desc_empty(d[r])) d[r] = ld_relaxed_u64(p.desc + lk);
+                        }
+                        if (in) csum += desc_count(d[r]);
+                        if (!open_done) {
+                            // towards older tiles until one ends a run
+                            const uint32_t term_mask = __ballot_sync(0xffffffffu, in && !desc_no_tail(d[r]));
+                            const uint32_t first_term = term_mask ? (uint32_t)__ffs(term_mask) - 1u : 32u;
+                            if (in && lane <= first_term) osum += desc_open(d[r]);
+                            open_done = first_term < 32u;
                         }
                     }
-                    look -= 32 * LBN;
+                    hi -= 32 * LBN;
                 }
-                excl = warp_sum(csum);
+                // no run end between my previous tile and this one: the run open at its end goes on
+                if (!open_done && lane == 0) osum += own_open;
+                excl += warp_sum(csum);
                 if (!BLOCK_MODE) carry = warp_sum(osum);
                 if (BLOCK_MODE || t == 0u) carry = 0;
-                const uint32_t incl_open = tile_has ? tile_open : carry + tile_open;
-                if (lane == 0) st_relaxed_u64(p.desc + tile, desc_pack(ST_INCL, 0, incl_open, excl + tile_cnt));
             }
+            // my own running totals, for the next tile of this CTA
+            own_cnt = excl + tile_cnt;
+            own_open = tile_has ? tile_open : carry + tile_open;
 
+            // ---- hand the offsets to the writer warp (and to the workers, if they write this tile themselves)
             const uint64_t dst0 = base + excl;
-            const int32_t adjust = (excl == 0u) ? lead_adjust : 0;   // no word of this launch precedes the tile
             // run still open where each warp starts (CANONICAL): lane w looks at the warps below it
             uint32_t run = carry;
             if (!BLOCK_MODE) {
@@ -323,27 +335,44 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 2) wah_compress_kernel(const
                     if ((int)lane > w) run = h ? o : run + o;
                 }
             }
-            const uint32_t mode = mt.mode;
-            if (mode == MODE_DIRECT) {
-                // ---- the workers write this tile themselves: hand them their offsets
-                if (lane < NWORK) mt.wcarry[lane] = run;
-                if (lane == 0) {
-                    mt.dst = dst0;
-                    mt.lead_adjust = adjust;
+            if (lane < NWORK) mt.wcarry[lane] = run;
+            if (lane == 0) {
+                mt.dst = dst0;
+                mt.lead_adjust = (excl == 0u) ? lead_adjust : 0;   // no word of this launch precedes the tile
+            }
+            __syncwarp();
+            if (lane == 0) {
+                mbar_arrive(smem_u32(&sm.pref[q]));
+                TRACE(i, 4, clock64());
+            }
+            // request the next tile's first window now: it is in flight while the workers finish that tile
+            if (i + 1u < n_my) request((int64_t)(tile + stride) - 1, (int64_t)tile + 1);
+            if (lane == 0) {
+                if (p.col_offsets && t == 0u) p.col_offsets[col] = dst0;
+                if (tile == p.n_tiles - 1u) {
+                    const uint64_t total = dst0 + tile_cnt;
+                    *p.total_out = total;
+                    if (p.col_offsets) p.col_offsets[p.n_cols] = total;
                 }
-                __syncwarp();
-                if (lane == 0) mbar_arrive(smem_u32(&sm.pref[q]));
-                if (lane == 0) TRACE(i, 4, clock64());
-            } else {
-                if (lane == 0) TRACE(i, 4, clock64());
-                // ---- the tile's words are staged back to back in the ring: patch the first word of each
-                //      warp (it may close a run that started before the warp), then copy out coalesced
+            }
+        }
+    } else if (warp == NWORK + 2) {
+        // ============================================================= writer warp
+        // copies the words the workers staged in the ring to their place in the output, coalesced
+        for (uint32_t i = 0; i < n_my; i++) {
+            const uint32_t q = i % QDEPTH;
+            TileMeta<NWORK> &mt = sm.meta[q];
+            mbar_wait(smem_u32(&sm.pref[q]), (i / QDEPTH) & 1u);
+            if (mt.mode == MODE_RING) {
+                const uint32_t tile_cnt = mt.tile_cnt;
+                const uint64_t dst0 = mt.dst;
                 const uint32_t rb = mt.ring_base;
+                // the first word of each warp may close a run that started before the warp
                 if (lane < NWORK) {
                     const uint32_t pre = mt.wprefix[lane];
                     const uint32_t nxt = lane + 1 < NWORK ? mt.wprefix[lane + 1 < NWORK ? lane + 1 : lane] : tile_cnt;
-                    uint32_t add = BLOCK_MODE ? 0u : run;
-                    if (pre == 0u) add += (uint32_t)adjust;   // the launch's first word
+                    uint32_t add = BLOCK_MODE ? 0u : mt.wcarry[lane];
+                    if (pre == 0u) add += (uint32_t)mt.lead_adjust;   // the launch's first word
                     if (nxt > pre && add != 0u) sm.ring[(rb + pre) & (G::RING_WORDS - 1)] += add;
                 }
                 __syncwarp();
@@ -361,14 +390,7 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 2) wah_compress_kernel(const
             if (lane == 0) {
                 mbar_arrive(smem_u32(&sm.done[q]));
                 TRACE(i, 5, clock64());
-                if (p.col_offsets && t == 0u) p.col_offsets[col] = dst0;
-                if (tile == p.n_tiles - 1u) {
-                    const uint64_t total = dst0 + tile_cnt;
-                    *p.total_out = total;
-                    if (p.col_offsets) p.col_offsets[p.n_cols] = total;
-                }
             }
-            __syncwarp();
         }
     } else {
         // ============================================================= worker warps
@@ -477,9 +499,7 @@ __global__ void __launch_bounds__((NWORK + 2) * 32, 2) wah_compress_kernel(const
             if (warp == 0 && lane == 0) {
                 // publish the aggregate to the other CTAs at once: their look-backs never wait for this
                 // CTA's control warp
-                const uint32_t tile = sm.info[s].tile;
-                st_relaxed_u64(p.desc + tile, tile == 0u ? desc_pack(ST_INCL, 0, tile_open, tile_cnt)
-                                                         : desc_pack(ST_AGG, tile_has ^ 1u, tile_open, tile_cnt));
+                st_relaxed_u64(p.desc + sm.info[s].tile, desc_pack(tile_has ^ 1u, tile_open, tile_cnt));
                 mt.tile_cnt = tile_cnt;
                 mt.tile_open = tile_open;
                 mt.tile_has = tile_has;

@@ -1,0 +1,465 @@
+// wah_host.cu -- the host-buffer entry points of the C ABI (wah_compress_host / wah_decompress_host):
+// what the reference's compress() / decompress() do around their kernels (compress.cu:41-209,
+// decompress.cu:18-141), rebuilt for a PCIe-attached B200.
+//
+// The reference allocates and frees every device buffer inside each call and copies pageable memory
+// synchronously.  Here a process-wide context keeps the device buffers, a ring of pinned bounce
+// buffers and a small pool of copy threads alive between calls:
+//   * a host buffer that is already page locked is DMAed directly;
+//   * a pageable buffer moves in 4 MiB chunks through the pinned ring, the copy threads moving
+//     chunk k+1 between user memory and the ring while the DMA engine moves chunk k;
+//   * the result is malloc()ed because the reference's callers free() it (compress.cu:181,208);
+//     the copy threads touch it in parallel, so its first-touch page faults are spread over cores.
+#include "../../include/wah_b200.h"
+#include "wah_kernels.h"
+
+#include <sys/mman.h>
+
+#include <algorithm>
+#include <condition_variable>
+#include <cstdarg>
+#include <cstdio>
+#include <cstdlib>
+#include <cstring>
+#include <functional>
+#include <mutex>
+#include <thread>
+#include <vector>
+
+using namespace wahb200;
+
+int wah_set_error(int code, const char *fmt, ...);   // wah_capi.cu
+
+#define CUDA_TRY(expr)                                                                                  \
+    do {                                                                                                \
+        cudaError_t e__ = (expr);                                                                       \
+        if (e__ != cudaSuccess)                                                                         \
+            return wah_set_error(e__ == cudaErrorMemoryAllocation ? WAH_ERR_NOMEM : WAH_ERR_CUDA, "%s: %s", \
+                                 #expr, cudaGetErrorString(e__));                                       \
+    } while (0)
+
+namespace {
+
+constexpr size_t CHUNK = 4u << 20;   // bytes per pinned bounce buffer
+constexpr int NSLOT = 8;             // bounce buffers in the ring
+
+// ------------------------------------------------------------------ copy threads
+
+class CopyPool {
+   public:
+    explicit CopyPool(int n) : n_(n)
+    {
+        for (int i = 1; i < n_; i++) threads_.emplace_back([this, i] { loop(i); });
+    }
+    ~CopyPool()
+    {
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            stop_ = true;
+            gen_++;
+        }
+        cv_.notify_all();
+        for (auto &t : threads_) t.join();
+    }
+    int size() const { return n_; }
+    // run job(i) for i in [0, size()) on the pool; the calling thread takes i = 0
+    void parallel(const std::function<void(int)> &job)
+    {
+        if (n_ == 1) {
+            job(0);
+            return;
+        }
+        {
+            std::lock_guard<std::mutex> g(mu_);
+            job_ = &job;
+            pending_ = n_ - 1;
+            gen_++;
+        }
+        cv_.notify_all();
+        job(0);
+        std::unique_lock<std::mutex> g(mu_);
+        done_.wait(g, [this] { return pending_ == 0; });
+    }
+    // memcpy split over the pool in page-aligned slices
+    void copy(void *dst, const void *src, size_t bytes)
+    {
+        if (bytes < (256u << 10) || n_ == 1) {
+            memcpy(dst, src, bytes);
+            return;
+        }
+        const size_t per = ((bytes + n_ - 1) / n_ + 4095) & ~(size_t)4095;
+        parallel([&](int i) {
+            const size_t a = std::min(bytes, per * i), b = std::min(bytes, per * (i + 1));
+            if (b > a) memcpy((char *)dst + a, (const char *)src + a, b - a);
+        });
+    }
+    // first touch of a freshly allocated buffer, every thread faulting in its own contiguous part
+    // (page faults on one 2 MiB huge page serialise, so the parts are 2 MiB aligned)
+    void prefault(void *p, size_t bytes)
+    {
+        constexpr size_t HP = 2u << 20;
+        const size_t per = ((bytes + n_ - 1) / n_ + HP - 1) & ~(HP - 1);
+        parallel([&](int i) {
+            const size_t a = std::min(bytes, per * i), b = std::min(bytes, per * (i + 1));
+            volatile char *q = (volatile char *)p;
+            for (size_t o = a; o < b; o += 4096) q[o] = 0;
+        });
+    }
+
+   private:
+    void loop(int i)
+    {
+        uint64_t seen = 0;
+        for (;;) {
+            const std::function<void(int)> *job;
+            {
+                std::unique_lock<std::mutex> g(mu_);
+                cv_.wait(g, [&] { return gen_ != seen; });
+                seen = gen_;
+                if (stop_) return;
+                job = job_;
+            }
+            (*job)(i);
+            {
+                std::lock_guard<std::mutex> g(mu_);
+                if (--pending_ == 0) done_.notify_one();
+            }
+        }
+    }
+    int n_;
+    std::vector<std::thread> threads_;
+    std::mutex mu_;
+    std::condition_variable cv_, done_;
+    uint64_t gen_ = 0;
+    bool stop_ = false;
+    int pending_ = 0;
+    const std::function<void(int)> *job_ = nullptr;
+};
+
+// ------------------------------------------------------------------ context
+
+struct DevBuf {
+    void *p = nullptr;
+    size_t cap = 0;
+    cudaError_t reserve(size_t bytes)
+    {
+        if (bytes <= cap) return cudaSuccess;
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+        // grow in 2 MiB steps so that slightly different sizes reuse the buffer
+        const size_t want = (bytes + (2u << 20) - 1) & ~(size_t)((2u << 20) - 1);
+        cudaError_t e = cudaMalloc(&p, want);
+        if (e == cudaSuccess) cap = want;
+        return e;
+    }
+    void release()
+    {
+        if (p) cudaFree(p);
+        p = nullptr;
+        cap = 0;
+    }
+};
+
+struct HostCtx {
+    std::mutex mu;
+    int device = -1;
+    DevBuf a, b, ws, small;          // input, output, workspace, 64 B of scalars
+    char *pin = nullptr;             // NSLOT * CHUNK bytes, page locked
+    cudaStream_t stream = nullptr;   // everything is ordered on this stream
+    cudaEvent_t slot_ev[NSLOT] = {};
+    cudaEvent_t t0 = nullptr, t1 = nullptr;
+    CopyPool *pool = nullptr;
+
+    int init()
+    {
+        int dev = 0;
+        CUDA_TRY(cudaGetDevice(&dev));
+        if (device == dev && stream) return WAH_OK;
+        release();
+        CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
+        CUDA_TRY(cudaHostAlloc((void **)&pin, NSLOT * CHUNK, cudaHostAllocDefault));
+        for (int i = 0; i < NSLOT; i++) CUDA_TRY(cudaEventCreateWithFlags(&slot_ev[i], cudaEventDisableTiming));
+        CUDA_TRY(cudaEventCreate(&t0));
+        CUDA_TRY(cudaEventCreate(&t1));
+        CUDA_TRY(small.reserve(64));
+        if (!pool) {
+            int n = (int)std::thread::hardware_concurrency();
+            if (const char *e = getenv("WAH_B200_COPY_THREADS")) n = atoi(e);
+            pool = new CopyPool(std::max(1, std::min(n, 8)));
+        }
+        device = dev;
+        return WAH_OK;
+    }
+    void release()
+    {
+        a.release();
+        b.release();
+        ws.release();
+        small.release();
+        if (pin) cudaFreeHost(pin);
+        pin = nullptr;
+        for (auto &e : slot_ev) {
+            if (e) cudaEventDestroy(e);
+            e = nullptr;
+        }
+        if (t0) cudaEventDestroy(t0);
+        if (t1) cudaEventDestroy(t1);
+        t0 = t1 = nullptr;
+        if (stream) cudaStreamDestroy(stream);
+        stream = nullptr;
+        device = -1;
+    }
+    float lap()   // milliseconds since the previous lap (stream drained)
+    {
+        float ms = 0.f;
+        cudaEventRecord(t1, stream);
+        cudaEventSynchronize(t1);
+        cudaEventElapsedTime(&ms, t0, t1);
+        cudaEventRecord(t0, stream);
+        return ms;
+    }
+};
+
+HostCtx g_ctx;
+
+bool is_pinned(const void *p)
+{
+    cudaPointerAttributes at;
+    if (cudaPointerGetAttributes(&at, p) != cudaSuccess) {
+        cudaGetLastError();
+        return false;
+    }
+    return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
+}
+
+// host -> device, asynchronous on ctx.stream for pinned memory, pipelined through the ring otherwise
+int upload(HostCtx &c, void *d_dst, const void *h_src, size_t bytes)
+{
+    if (bytes == 0) return WAH_OK;
+    if (is_pinned(h_src)) {
+        CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c.stream));
+        return WAH_OK;
+    }
+    const size_t n = (bytes + CHUNK - 1) / CHUNK;
+    for (size_t k = 0; k < n; k++) {
+        const int s = (int)(k % NSLOT);
+        const size_t off = k * CHUNK, len = std::min(CHUNK, bytes - off);
+        if (k >= NSLOT) CUDA_TRY(cudaEventSynchronize(c.slot_ev[s]));   // the DMA out of this slot is done
+        c.pool->copy(c.pin + s * CHUNK, (const char *)h_src + off, len);
+        CUDA_TRY(cudaMemcpyAsync((char *)d_dst + off, c.pin + s * CHUNK, len, cudaMemcpyHostToDevice, c.stream));
+        CUDA_TRY(cudaEventRecord(c.slot_ev[s], c.stream));
+    }
+    return WAH_OK;
+}
+
+// device -> host; returns with the data in place
+int download(HostCtx &c, void *h_dst, const void *d_src, size_t bytes, bool fresh)
+{
+    if (bytes == 0) return WAH_OK;
+    if (is_pinned(h_dst)) {
+        CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c.stream));
+        CUDA_TRY(cudaStreamSynchronize(c.stream));
+        return WAH_OK;
+    }
+    const size_t n = (bytes + CHUNK - 1) / CHUNK;
+    auto issue = [&](size_t k) -> cudaError_t {
+        const int s = (int)(k % NSLOT);
+        const size_t off = k * CHUNK, len = std::min(CHUNK, bytes - off);
+        cudaError_t e = cudaMemcpyAsync(c.pin + s * CHUNK, (const char *)d_src + off, len, cudaMemcpyDeviceToHost, c.stream);
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(c.slot_ev[s], c.stream);
+    };
+    for (size_t k = 0; k < n && k < NSLOT; k++) CUDA_TRY(issue(k));
+    // the result buffer is fresh from malloc(): fault it in on all copy threads while the first chunks fly
+    if (fresh && bytes >= (1u << 20)) c.pool->prefault(h_dst, bytes);
+    for (size_t k = 0; k < n; k++) {
+        const int s = (int)(k % NSLOT);
+        const size_t off = k * CHUNK, len = std::min(CHUNK, bytes - off);
+        CUDA_TRY(cudaEventSynchronize(c.slot_ev[s]));
+        c.pool->copy((char *)h_dst + off, c.pin + s * CHUNK, len);
+        if (k + NSLOT < n) CUDA_TRY(issue(k + NSLOT));
+    }
+    return WAH_OK;
+}
+
+// malloc for a result the caller will free(); large blocks are advised towards huge pages so that
+// their first touch costs one fault per 2 MiB where the kernel allows it
+uint32_t *alloc_result(uint64_t words)
+{
+    const size_t bytes = (size_t)(words ? words : 1) * 4;
+    char *p = (char *)malloc(bytes);
+    if (p && bytes >= (8u << 20)) {
+        const uintptr_t lo = ((uintptr_t)p + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1);
+        const uintptr_t hi = ((uintptr_t)p + bytes) & ~(uintptr_t)((2u << 20) - 1);
+        if (hi > lo) madvise((void *)lo, hi - lo, MADV_HUGEPAGE);
+    }
+    return (uint32_t *)p;
+}
+
+}  // namespace
+
+extern "C" void wah_free(void *p) { free(p); }
+
+extern "C" void wah_host_release(void)
+{
+    std::lock_guard<std::mutex> g(g_ctx.mu);
+    g_ctx.release();
+}
+
+extern "C" int wah_compress_host(const uint32_t *h_in, uint64_t n_words, int mode, uint32_t **h_out,
+                                 uint64_t *out_words, float *ms_h2d, float *ms_compute, float *ms_d2h)
+{
+    if (mode != WAH_BLOCK1024 && mode != WAH_CANONICAL) return wah_set_error(WAH_ERR_INVALID, "unknown mode %d", mode);
+    if (!h_out) return wah_set_error(WAH_ERR_INVALID, "h_out is null");
+    if (n_words && !h_in) return wah_set_error(WAH_ERR_INVALID, "h_in is null");
+    *h_out = nullptr;
+    std::lock_guard<std::mutex> g(g_ctx.mu);
+    HostCtx &c = g_ctx;
+    if (int rc = c.init()) return rc;
+    CUDA_TRY(cudaEventRecord(c.t0, c.stream));
+    // -- segment 1: buffers (kept between calls) + H2D (compress.cu:57-120)
+    const uint64_t cap = wah_max_compressed_words(n_words);
+    const size_t ws_bytes = wah_compress_workspace_bytes(n_words);
+    CUDA_TRY(c.a.reserve(n_words * 4 + 16));
+    CUDA_TRY(c.b.reserve(cap * 4 + 16));
+    CUDA_TRY(c.ws.reserve(ws_bytes));
+    if (int rc = upload(c, c.a.p, h_in, n_words * 4)) return rc;
+    const float t_h2d = c.lap();
+    // -- segment 2: compute (compress.cu:125-172)
+    uint64_t *d_cnt = (uint64_t *)c.small.p;
+    if (int rc = wah_compress_device((const uint32_t *)c.a.p, n_words, mode, (uint32_t *)c.b.p, cap, d_cnt, c.ws.p,
+                                     ws_bytes, c.stream))
+        return rc;
+    uint64_t cw = 0;
+    CUDA_TRY(cudaMemcpyAsync(&cw, d_cnt, sizeof(cw), cudaMemcpyDeviceToHost, c.stream));
+    const float t_compute = c.lap();   // drains the stream: cw is valid
+    // -- segment 3: D2H into a malloc()ed buffer (compress.cu:177-202)
+    uint32_t *host = alloc_result(cw);
+    if (!host) return wah_set_error(WAH_ERR_NOMEM, "malloc of %llu words failed", (unsigned long long)cw);
+    if (int rc = download(c, host, c.b.p, cw * 4, true)) {
+        free(host);
+        return rc;
+    }
+    const float t_d2h = c.lap();
+    *h_out = host;
+    if (out_words) *out_words = cw;
+    if (ms_h2d) *ms_h2d = t_h2d;
+    if (ms_compute) *ms_compute = t_compute;
+    if (ms_d2h) *ms_d2h = t_d2h;
+    return WAH_OK;
+}
+
+extern "C" int wah_decompress_host(const uint32_t *h_in, uint64_t c_words, uint32_t **h_out,
+                                   uint64_t *out_words, float *ms_h2d, float *ms_compute, float *ms_d2h)
+{
+    if (!h_out) return wah_set_error(WAH_ERR_INVALID, "h_out is null");
+    if (c_words && !h_in) return wah_set_error(WAH_ERR_INVALID, "h_in is null");
+    *h_out = nullptr;
+    std::lock_guard<std::mutex> g(g_ctx.mu);
+    HostCtx &c = g_ctx;
+    if (int rc = c.init()) return rc;
+    CUDA_TRY(cudaEventRecord(c.t0, c.stream));
+    // -- segment 1: buffers + H2D (decompress.cu:34-56)
+    CUDA_TRY(c.a.reserve(c_words * 4 + 16));
+    if (int rc = upload(c, c.a.p, h_in, c_words * 4)) return rc;
+    const float t_h2d = c.lap();
+    // -- segment 2: size query, output buffer, expansion (decompress.cu:66-124)
+    uint64_t *d_info = (uint64_t *)c.small.p;
+    uint64_t info[2] = {0, 0};
+    {
+        const size_t ws0 = wah_decompress_workspace_bytes(c_words, 0);
+        CUDA_TRY(c.ws.reserve(ws0));
+        if (int rc = wah_decoded_size_device((const uint32_t *)c.a.p, c_words, d_info, c.ws.p, ws0, c.stream)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(info, d_info, sizeof(info), cudaMemcpyDeviceToHost, c.stream));
+        CUDA_TRY(cudaStreamSynchronize(c.stream));
+    }
+    const uint64_t words = info[0];
+    const size_t ws_bytes = wah_decompress_workspace_bytes(c_words, words);
+    CUDA_TRY(c.ws.reserve(ws_bytes));
+    CUDA_TRY(c.b.reserve(words * 4 + 16));
+    if (int rc = wah_decompress_device((const uint32_t *)c.a.p, c_words, (uint32_t *)c.b.p, words, d_info, c.ws.p,
+                                       ws_bytes, c.stream))
+        return rc;
+    uint32_t bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(&bad, (char *)c.ws.p + offsetof(DecodeHeader, bad_words), sizeof(bad),
+                             cudaMemcpyDeviceToHost, c.stream));
+    const float t_compute = c.lap();
+    if (bad) return wah_set_error(WAH_ERR_FORMAT, "%u zero-length fill words in the stream", bad);
+    // -- segment 3: D2H into a malloc()ed buffer (decompress.cu:127-133)
+    uint32_t *host = alloc_result(words);
+    if (!host) return wah_set_error(WAH_ERR_NOMEM, "malloc of %llu words failed", (unsigned long long)words);
+    if (int rc = download(c, host, c.b.p, words * 4, true)) {
+        free(host);
+        return rc;
+    }
+    const float t_d2h = c.lap();
+    *h_out = host;
+    if (out_words) *out_words = words;
+    if (ms_h2d) *ms_h2d = t_h2d;
+    if (ms_compute) *ms_compute = t_compute;
+    if (ms_d2h) *ms_d2h = t_d2h;
+    return WAH_OK;
+}
+
+// caller-provided result buffers (page-locked ones are written by DMA directly)
+extern "C" int wah_compress_host_into(const uint32_t *h_in, uint64_t n_words, int mode, uint32_t *h_out,
+                                      uint64_t out_capacity_words, uint64_t *out_words)
+{
+    if (mode != WAH_BLOCK1024 && mode != WAH_CANONICAL) return wah_set_error(WAH_ERR_INVALID, "unknown mode %d", mode);
+    if (!out_words || (out_capacity_words && !h_out)) return wah_set_error(WAH_ERR_INVALID, "null output");
+    if (n_words && !h_in) return wah_set_error(WAH_ERR_INVALID, "h_in is null");
+    std::lock_guard<std::mutex> g(g_ctx.mu);
+    HostCtx &c = g_ctx;
+    if (int rc = c.init()) return rc;
+    const uint64_t cap = wah_max_compressed_words(n_words);
+    const size_t ws_bytes = wah_compress_workspace_bytes(n_words);
+    CUDA_TRY(c.a.reserve(n_words * 4 + 16));
+    CUDA_TRY(c.b.reserve(cap * 4 + 16));
+    CUDA_TRY(c.ws.reserve(ws_bytes));
+    if (int rc = upload(c, c.a.p, h_in, n_words * 4)) return rc;
+    uint64_t *d_cnt = (uint64_t *)c.small.p;
+    if (int rc = wah_compress_device((const uint32_t *)c.a.p, n_words, mode, (uint32_t *)c.b.p, cap, d_cnt, c.ws.p,
+                                     ws_bytes, c.stream))
+        return rc;
+    uint64_t cw = 0;
+    CUDA_TRY(cudaMemcpyAsync(&cw, d_cnt, sizeof(cw), cudaMemcpyDeviceToHost, c.stream));
+    CUDA_TRY(cudaStreamSynchronize(c.stream));
+    *out_words = cw;
+    if (cw > out_capacity_words)
+        return wah_set_error(WAH_ERR_CAPACITY, "result needs %llu words, buffer holds %llu", (unsigned long long)cw,
+                             (unsigned long long)out_capacity_words);
+    return download(c, h_out, c.b.p, cw * 4, false);
+}
+
+extern "C" int wah_decompress_host_into(const uint32_t *h_in, uint64_t c_words, uint32_t *h_out,
+                                        uint64_t out_capacity_words, uint64_t *out_words)
+{
+    if (!out_words || (out_capacity_words && !h_out)) return wah_set_error(WAH_ERR_INVALID, "null output");
+    if (c_words && !h_in) return wah_set_error(WAH_ERR_INVALID, "h_in is null");
+    std::lock_guard<std::mutex> g(g_ctx.mu);
+    HostCtx &c = g_ctx;
+    if (int rc = c.init()) return rc;
+    CUDA_TRY(c.a.reserve(c_words * 4 + 16));
+    if (int rc = upload(c, c.a.p, h_in, c_words * 4)) return rc;
+    // the caller's capacity bounds the output, so one pass does both the size and the expansion
+    uint64_t *d_info = (uint64_t *)c.small.p;
+    const size_t ws_bytes = wah_decompress_workspace_bytes(c_words, out_capacity_words);
+    CUDA_TRY(c.ws.reserve(ws_bytes));
+    CUDA_TRY(c.b.reserve(out_capacity_words * 4 + 16));
+    if (int rc = wah_decompress_device((const uint32_t *)c.a.p, c_words, (uint32_t *)c.b.p, out_capacity_words, d_info,
+                                       c.ws.p, ws_bytes, c.stream))
+        return rc;
+    uint64_t info[2] = {0, 0};
+    uint32_t bad = 0;
+    CUDA_TRY(cudaMemcpyAsync(info, d_info, sizeof(info), cudaMemcpyDeviceToHost, c.stream));
+    CUDA_TRY(cudaMemcpyAsync(&bad, (char *)c.ws.p + offsetof(DecodeHeader, bad_words), sizeof(bad),
+                             cudaMemcpyDeviceToHost, c.stream));
+    CUDA_TRY(cudaStreamSynchronize(c.stream));
+    if (bad) return wah_set_error(WAH_ERR_FORMAT, "%u zero-length fill words in the stream", bad);
+    *out_words = info[0];
+    if (info[0] > out_capacity_words)
+        return wah_set_error(WAH_ERR_CAPACITY, "result needs %llu words, buffer holds %llu",
+                             (unsigned long long)info[0], (unsigned long long)out_capacity_words);
+    return download(c, h_out, c.b.p, info[0] * 4, false);
+}

@@ -89,6 +89,9 @@ _sig("wah_decoded_size_device", ctypes.c_int, _vp, _u64, _vp, _vp, _sz, _vp)
 _sig("wah_compress_host", ctypes.c_int, _vp, _u64, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_u64), _pf, _pf, _pf)
 _sig("wah_decompress_host", ctypes.c_int, _vp, _u64, ctypes.POINTER(_vp), ctypes.POINTER(_u64), _pf, _pf, _pf)
 _sig("wah_free", None, _vp)
+_sig("wah_compress_host_into", ctypes.c_int, _vp, _u64, ctypes.c_int, _vp, _u64, ctypes.POINTER(_u64))
+_sig("wah_decompress_host_into", ctypes.c_int, _vp, _u64, _vp, _u64, ctypes.POINTER(_u64))
+_sig("wah_host_release", None)
 _sig("wah_shard_record_device", ctypes.c_int, _vp, _u64, _u64, ctypes.POINTER(ShardRecord), _vp)
 _sig("wah_stitch_plan", ctypes.c_int, ctypes.POINTER(ShardRecord), ctypes.c_int, ctypes.c_int,
      ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_uint32),

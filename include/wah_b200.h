@@ -97,7 +97,9 @@ int wah_decoded_size_device(const uint32_t *d_in, uint64_t c_words, uint64_t *d_
 /* H2D copy, kernels, D2H copy on the current device; *h_out is malloc()ed, release it with
  * wah_free() (or free()).  The three optional floats receive milliseconds for
  * H2D(+allocation) / compute / D2H(+release), like the reference's out-params
- * (compress.cu:205-207, decompress.cu:136-138).                                            */
+ * (compress.cu:205-207, decompress.cu:136-138).  Page-locked inputs are DMAed directly; pageable
+ * memory moves through a ring of pinned bounce buffers filled by a few copy threads
+ * (WAH_B200_COPY_THREADS, default min(8, cores)).  Calls are serialised by a process-wide lock. */
 int wah_compress_host(const uint32_t *h_in, uint64_t n_words, int mode,
                       uint32_t **h_out, uint64_t *out_words,
                       float *ms_h2d, float *ms_compute, float *ms_d2h);
@@ -105,6 +107,17 @@ int wah_decompress_host(const uint32_t *h_in, uint64_t c_words,
                         uint32_t **h_out, uint64_t *out_words,
                         float *ms_h2d, float *ms_compute, float *ms_d2h);
 void wah_free(void *p);
+
+/* Same work with caller-provided result buffers (no malloc; a page-locked buffer is written by DMA
+ * directly).  *out_words receives the true length; WAH_ERR_CAPACITY if it exceeds the capacity.   */
+int wah_compress_host_into(const uint32_t *h_in, uint64_t n_words, int mode,
+                           uint32_t *h_out, uint64_t out_capacity_words, uint64_t *out_words);
+int wah_decompress_host_into(const uint32_t *h_in, uint64_t c_words,
+                             uint32_t *h_out, uint64_t out_capacity_words, uint64_t *out_words);
+
+/* The host entry points keep their device buffers, pinned bounce buffers and copy threads between
+ * calls (the reference allocates and frees everything per call); this releases them.            */
+void wah_host_release(void);
 
 /* ---- range sharding of one vector across GPUs ------------------------ */
 

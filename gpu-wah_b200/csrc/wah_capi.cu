@@ -145,6 +145,7 @@ extern "C" int wah_compress_batch_device(const uint32_t *d_in, uint64_t n_cols, 
         p.n_tiles = (uint32_t)(tiles_per_col * nc);
         p.n_cols = (uint32_t)nc;
         p.lead_adjust = nullptr;
+        p.one = 1;
         p.out = d_out;
         p.out_cap = out_capacity_words;
         p.desc = reinterpret_cast<uint64_t *>(ws + WS_DESC);
@@ -194,6 +195,7 @@ extern "C" int wah_compress_device(const uint32_t *d_in, uint64_t n_words, int m
         p.n_tiles = p.tiles_per_col;
         p.n_cols = 1;
         p.lead_adjust = nullptr;
+        p.one = 1;
         if (launch > 0 && mode == WAH_CANONICAL) {
             // the segment's leading run may continue the last word written so far
             p.lead_adjust = reinterpret_cast<int32_t *>(ws + WS_SEAM + 8);

@@ -30,6 +30,8 @@
 #include "wah_common.cuh"
 #include "wah_kernels.h"
 
+#include <cstdlib>
+
 namespace wahb200 {
 
 namespace {
@@ -133,7 +135,8 @@ struct StageInfo {
     uint32_t pad;
 };
 
-// workers -> workers, one per input stage: warp aggregates exchanged at the workers' barrier
+// warp aggregates of a tile, exchanged at the workers' barrier and read by the control / writer warps
+// (slot = CTA-local tile index % QDEPTH)
 template <int NWORK>
 struct WarpAgg {
     uint32_t wcnt[NWORK];      // words emitted by each warp
@@ -145,9 +148,6 @@ struct WarpAgg {
 template <int NWORK>
 struct TileMeta {
     // workers -> control
-    uint32_t wprefix[NWORK];   // words emitted by the lower warps of the tile
-    uint32_t wopen[NWORK];
-    uint32_t whas[NWORK];
     uint32_t tile_cnt, tile_open, tile_has;
     uint32_t ring_base;        // ring position of the tile's first staged word
     uint32_t mode;             // MODE_RING: words staged in the ring, MODE_DIRECT: the workers write them
@@ -163,7 +163,7 @@ struct Smem {
     uint32_t stage[STAGES][G::STAGE_WORDS];
     uint32_t ring[G::RING_WORDS];
     TileMeta<NWORK> meta[QDEPTH];
-    WarpAgg<NWORK> wagg[STAGES];
+    WarpAgg<NWORK> wagg[QDEPTH];
     StageInfo info[STAGES];
     uint64_t full[STAGES], empty[STAGES];              // input ring: producer <-> workers
     uint64_t agg[QDEPTH], pref[QDEPTH], done[QDEPTH];  // tile queue: workers <-> control
@@ -175,6 +175,27 @@ __device__ __forceinline__ uint32_t row_group(const uint32_t *row, uint32_t j)
 {
     const uint32_t *q = row + j;
     return __funnelshift_rc(q[-1], q[0], 32u - j) & ONES31;
+}
+
+// Set bit `bit` of Z / O if the group held in the top 31 bits of u is all zeros / all ones.  The bit is
+// added with a predicated multiply-add (`one` is a register holding 1): that is an IMAD, issued to the FMA
+// pipe, which leaves the ALU pipe -- the kernel's bottleneck -- the funnel shift and the two compares.
+__device__ __forceinline__ void classify_group_rt(uint32_t u, uint32_t one, uint32_t bit, uint32_t &Z, uint32_t &O)
+{
+    asm("{\n\t"
+        ".reg .pred pz, po;\n\t"
+        "setp.lt.u32 pz, %2, 2;\n\t"
+        "setp.gt.u32 po, %2, 0xFFFFFFFD;\n\t"
+        "@pz mad.lo.u32 %0, %3, %4, %0;\n\t"
+        "@po mad.lo.u32 %1, %3, %4, %1;\n\t"
+        "}"
+        : "+r"(Z), "+r"(O)
+        : "r"(u), "r"(one), "r"(bit));
+}
+template <int J>
+__device__ __forceinline__ void classify_group(uint32_t u, uint32_t one, uint32_t &Z, uint32_t &O)
+{
+    classify_group_rt(u, one, 1u << J, Z, O);
 }
 
 template <int NWORK, int STAGES, bool BLOCK_MODE>
@@ -236,7 +257,6 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
                 __syncwarp();
                 if (lane == 0) {
                     TRACE(i, 0, clock64());
-                    TRACE(i, 7, gtime());
                     if (nbulk) {
                         mbar_arrive_expect_tx(bar, nbulk * 4u);
                         bulk_g2s(smem_u32(buf), src, nbulk * 4u, bar);
@@ -293,6 +313,9 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
                 bool open_done = BLOCK_MODE || (t == 0u);   // BLOCK mode never carries; CANONICAL restarts per column
                 uint32_t csum = 0, osum = 0;
                 bool fresh = true;
+#ifdef WAH_TRACE
+                uint32_t polls = 0;
+#endif
                 while (hi >= lo) {
                     if (!fresh) request(hi, lo);
                     fresh = false;
@@ -302,6 +325,9 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
                         const bool in = lk >= lo;
                         while (__any_sync(0xffffffffu, in && desc_empty(d[r]))) {
                             if (in && desc_empty(d[r])) d[r] = ld_relaxed_u64(p.desc + lk);
+#ifdef WAH_TRACE
+                            polls++;
+#endif
                         }
                         if (in) csum += desc_count(d[r]);
                         if (!open_done) {
@@ -314,6 +340,9 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
                     }
                     hi -= 32 * LBN;
                 }
+#ifdef WAH_TRACE
+                if (lane == 0) TRACE(i, 7, polls);
+#endif
                 // no run end between my previous tile and this one: the run open at its end goes on
                 if (!open_done && lane == 0) osum += own_open;
                 excl += warp_sum(csum);
@@ -331,7 +360,7 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
             if (!BLOCK_MODE) {
 #pragma unroll
                 for (int w = 0; w < NWORK - 1; w++) {
-                    const uint32_t h = mt.whas[w], o = mt.wopen[w];
+                    const uint32_t h = sm.wagg[q].whas[w], o = sm.wagg[q].wopen[w];
                     if ((int)lane > w) run = h ? o : run + o;
                 }
             }
@@ -368,12 +397,18 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
                 const uint64_t dst0 = mt.dst;
                 const uint32_t rb = mt.ring_base;
                 // the first word of each warp may close a run that started before the warp
-                if (lane < NWORK) {
-                    const uint32_t pre = mt.wprefix[lane];
-                    const uint32_t nxt = lane + 1 < NWORK ? mt.wprefix[lane + 1 < NWORK ? lane + 1 : lane] : tile_cnt;
-                    uint32_t add = BLOCK_MODE ? 0u : mt.wcarry[lane];
+                {
+                    const uint32_t a_cnt = lane < NWORK ? sm.wagg[q].wcnt[lane] : 0u;
+                    uint32_t a_scan = a_cnt;
+#pragma unroll
+                    for (int dd = 1; dd < NWORK; dd <<= 1) {
+                        const uint32_t o = __shfl_up_sync(0xffffffffu, a_scan, dd);
+                        if ((int)lane >= dd) a_scan += o;
+                    }
+                    const uint32_t pre = a_scan - a_cnt;
+                    uint32_t add = (BLOCK_MODE || lane >= NWORK) ? 0u : mt.wcarry[lane < NWORK ? lane : 0];
                     if (pre == 0u) add += (uint32_t)mt.lead_adjust;   // the launch's first word
-                    if (nxt > pre && add != 0u) sm.ring[(rb + pre) & (G::RING_WORDS - 1)] += add;
+                    if (a_cnt != 0u && add != 0u) sm.ring[(rb + pre) & (G::RING_WORDS - 1)] += add;
                 }
                 __syncwarp();
                 const uint32_t room =
@@ -394,6 +429,7 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
         }
     } else {
         // ============================================================= worker warps
+        const uint32_t one = p.one;   // 1, opaque to the compiler (see classify_group_rt)
         uint32_t head = 0;   // words this CTA has staged so far (ring position, monotonic, same in every warp)
         uint32_t jd = 0;     // oldest tile of this CTA not yet known to be copied out
 
@@ -420,22 +456,16 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
             // ---- regroup 32 -> 31 bit (kernels.cu:79) and classify (kernels.cu:93-112)
             uint32_t Z = 0, O = 0;
             {
-                // u = group << 1 | (one junk bit): zero / all-ones tests on the top 31 bits
+                // u = group << 1 | (one junk bit): group == 0 <=> u < 2, group == ONES31 <=> u > 0xFFFFFFFD
                 uint32_t prev = row[0];
-                uint32_t u = prev << 1;
-                if ((u & 0xFFFFFFFEu) == 0u) Z |= 1u;
-                if ((~u & 0xFFFFFFFEu) == 0u) O |= 1u;
+                classify_group<0>(prev << 1, one, Z, O);
 #pragma unroll
                 for (int j = 1; j < 31; j++) {
                     const uint32_t cur_w = row[j];
-                    u = __funnelshift_r(prev, cur_w, 31 - j);
-                    if ((u & 0xFFFFFFFEu) == 0u) Z |= (1u << j);
-                    if ((~u & 0xFFFFFFFEu) == 0u) O |= (1u << j);
+                    classify_group_rt(__funnelshift_r(prev, cur_w, 31 - j), one, 1u << j, Z, O);
                     prev = cur_w;
                 }
-                u = prev;
-                if ((u & 0xFFFFFFFEu) == 0u) Z |= BIT31;
-                if ((~u & 0xFFFFFFFEu) == 0u) O |= BIT31;
+                classify_group_rt(prev, one, BIT31, Z, O);
             }
             Z &= vmask;
             O &= vmask;
@@ -470,46 +500,50 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
             const uint32_t open_last = __shfl_sync(0xffffffffu, my_open, qlast);
             const bool all_literal = __all_sync(0xffffffffu, T == 0xFFFFFFFFu && F == 0u);
 
-            // ---- exchange the warp aggregates (workers' named barrier), derive the tile's
-            WarpAgg<NWORK> &wa = sm.wagg[s];
+            // ---- exchange the warp aggregates (workers' named barrier); lane w then holds warp w's
+            WarpAgg<NWORK> &wa = sm.wagg[q];
             if (lane == 31u) {
                 wa.wcnt[warp] = wcnt;
                 wa.whas[warp] = tb != 0u;
                 wa.wopen[warp] = tb ? open_last + 32u * (31u - qlast) : 1024u;
             }
             asm volatile("bar.sync 1, %0;" ::"n"(NWORK * 32) : "memory");
-            uint32_t tile_cnt = 0, tile_open = 0, tile_has = 0, wprefix = 0;
+            const uint32_t a_cnt = lane < NWORK ? wa.wcnt[lane] : 0u;
+            uint32_t a_scan = a_cnt;
 #pragma unroll
-            for (int w = 0; w < NWORK; w++) {
-                const uint32_t cw = wa.wcnt[w], h = wa.whas[w], o = wa.wopen[w];
-                if (w < (int)warp) wprefix += cw;
-                tile_cnt += cw;
-                if (h) {
-                    tile_has = 1;
-                    tile_open = o;
-                } else {
-                    tile_open += o;
-                }
+            for (int dd = 1; dd < NWORK; dd <<= 1) {
+                const uint32_t o = __shfl_up_sync(0xffffffffu, a_scan, dd);
+                if ((int)lane >= dd) a_scan += o;
             }
-            if (BLOCK_MODE || has_next == 0u) {   // the end of a column is always a tail
-                tile_open = 0;
-                tile_has = 1;
-            }
+            const uint32_t tile_cnt = __shfl_sync(0xffffffffu, a_scan, NWORK - 1);
+            const uint32_t wprefix = __shfl_sync(0xffffffffu, a_scan - a_cnt, warp);
             const bool ring_mode = tile_cnt <= (uint32_t)G::RING_WORDS;
-            if (warp == 0 && lane == 0) {
-                // publish the aggregate to the other CTAs at once: their look-backs never wait for this
+            if (warp == 0) {
+                // publish the aggregate to the other CTAs at once: their offset sums never wait for this
                 // CTA's control warp
-                st_relaxed_u64(p.desc + sm.info[s].tile, desc_pack(tile_has ^ 1u, tile_open, tile_cnt));
-                mt.tile_cnt = tile_cnt;
-                mt.tile_open = tile_open;
-                mt.tile_has = tile_has;
-                mt.ring_base = head;
-                mt.mode = ring_mode ? MODE_RING : MODE_DIRECT;
-            }
-            if (lane == 31u) {
-                mt.wprefix[warp] = wprefix;
-                mt.wopen[warp] = wa.wopen[warp];
-                mt.whas[warp] = wa.whas[warp];
+                uint32_t tile_open = 0, tile_has = 0;
+#pragma unroll
+                for (int w = 0; w < NWORK; w++) {
+                    const uint32_t h = wa.whas[w], o = wa.wopen[w];
+                    if (h) {
+                        tile_has = 1;
+                        tile_open = o;
+                    } else {
+                        tile_open += o;
+                    }
+                }
+                if (BLOCK_MODE || has_next == 0u) {   // the end of a column is always a tail
+                    tile_open = 0;
+                    tile_has = 1;
+                }
+                if (lane == 0) {
+                    st_relaxed_u64(p.desc + sm.info[s].tile, desc_pack(tile_has ^ 1u, tile_open, tile_cnt));
+                    mt.tile_cnt = tile_cnt;
+                    mt.tile_open = tile_open;
+                    mt.tile_has = tile_has;
+                    mt.ring_base = head;
+                    mt.mode = ring_mode ? MODE_RING : MODE_DIRECT;
+                }
             }
             if (tid == 0) TRACE(i, 2, clock64());
 
@@ -688,8 +722,11 @@ cudaError_t launch_seam(const uint32_t *d_in, uint64_t n_words, uint64_t groups,
 
 cudaError_t launch_compress(const CompressParams &p, int mode, cudaStream_t stream)
 {
-    // all CTAs must be resident at once (the look-back spins on tiles owned by other CTAs):
-    // cooperative launch of SMs x occupancy CTAs
+    // A control warp spins on aggregates published by the workers of OTHER CTAs, so every CTA must get
+    // an SM slot without waiting for a CTA of this grid to exit: the grid is capped at SMs x occupancy.
+    // (Tiles are owned statically, tile k only ever waits for tiles < k, so CTAs that are delayed by
+    // foreign work on the GPU merely delay the others.)  WAH_B200_COOPERATIVE=1 makes the launch
+    // cooperative, which has the driver verify co-residency at the price of a slower launch.
     constexpr int THREADS = Geom<CFG_NWORK, CFG_STAGES>::THREADS;
     const size_t smem = compress_smem_bytes();
     static int grids[2] = {0, 0};
@@ -713,7 +750,12 @@ cudaError_t launch_compress(const CompressParams &p, int mode, cudaStream_t stre
     if ((uint32_t)grid > p.n_tiles) grid = (int)p.n_tiles;
     CompressParams params = p;
     void *args[] = {&params};
-    return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(THREADS), args, smem, stream);
+    static const bool cooperative = [] {
+        const char *e = getenv("WAH_B200_COOPERATIVE");
+        return e && e[0] == '1';
+    }();
+    if (cooperative) return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(THREADS), args, smem, stream);
+    return cudaLaunchKernel(kernel, dim3(grid), dim3(THREADS), args, smem, stream);
 }
 
 }  // namespace wahb200

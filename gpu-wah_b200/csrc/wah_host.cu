@@ -40,8 +40,8 @@ int wah_set_error(int code, const char *fmt, ...);   // wah_capi.cu
 
 namespace {
 
-constexpr size_t CHUNK = 4u << 20;   // bytes per pinned bounce buffer
-constexpr int NSLOT = 8;             // bounce buffers in the ring
+constexpr size_t CHUNK = 16u << 20;  // bytes per pinned bounce buffer
+constexpr int NSLOT = 4;             // bounce buffers in the ring
 
 // ------------------------------------------------------------------ copy threads
 
@@ -80,29 +80,22 @@ class CopyPool {
         std::unique_lock<std::mutex> g(mu_);
         done_.wait(g, [this] { return pending_ == 0; });
     }
-    // memcpy split over the pool in page-aligned slices
+    // memcpy split over the pool.  The pieces are the 2 MiB-aligned regions of the destination, dealt
+    // round robin: a freshly malloc()ed destination is faulted in by the copy itself, and page faults on
+    // one (huge) page serialise, so no two threads ever write to the same one.
     void copy(void *dst, const void *src, size_t bytes)
     {
         if (bytes < (256u << 10) || n_ == 1) {
             memcpy(dst, src, bytes);
             return;
         }
-        const size_t per = ((bytes + n_ - 1) / n_ + 4095) & ~(size_t)4095;
+        constexpr uintptr_t HP = 2u << 20;
+        const uintptr_t d0 = (uintptr_t)dst, d1 = d0 + bytes, first = d0 & ~(HP - 1);
         parallel([&](int i) {
-            const size_t a = std::min(bytes, per * i), b = std::min(bytes, per * (i + 1));
-            if (b > a) memcpy((char *)dst + a, (const char *)src + a, b - a);
-        });
-    }
-    // first touch of a freshly allocated buffer, every thread faulting in its own contiguous part
-    // (page faults on one 2 MiB huge page serialise, so the parts are 2 MiB aligned)
-    void prefault(void *p, size_t bytes)
-    {
-        constexpr size_t HP = 2u << 20;
-        const size_t per = ((bytes + n_ - 1) / n_ + HP - 1) & ~(HP - 1);
-        parallel([&](int i) {
-            const size_t a = std::min(bytes, per * i), b = std::min(bytes, per * (i + 1));
-            volatile char *q = (volatile char *)p;
-            for (size_t o = a; o < b; o += 4096) q[o] = 0;
+            for (uintptr_t r = first + (uintptr_t)i * HP; r < d1; r += (uintptr_t)n_ * HP) {
+                const uintptr_t a = std::max(r, d0), b = std::min(r + HP, d1);
+                memcpy((void *)a, (const char *)src + (a - d0), b - a);
+            }
         });
     }
 
@@ -254,7 +247,7 @@ int upload(HostCtx &c, void *d_dst, const void *h_src, size_t bytes)
 }
 
 // device -> host; returns with the data in place
-int download(HostCtx &c, void *h_dst, const void *d_src, size_t bytes, bool fresh)
+int download(HostCtx &c, void *h_dst, const void *d_src, size_t bytes)
 {
     if (bytes == 0) return WAH_OK;
     if (is_pinned(h_dst)) {
@@ -271,8 +264,6 @@ int download(HostCtx &c, void *h_dst, const void *d_src, size_t bytes, bool fres
         return cudaEventRecord(c.slot_ev[s], c.stream);
     };
     for (size_t k = 0; k < n && k < NSLOT; k++) CUDA_TRY(issue(k));
-    // the result buffer is fresh from malloc(): fault it in on all copy threads while the first chunks fly
-    if (fresh && bytes >= (1u << 20)) c.pool->prefault(h_dst, bytes);
     for (size_t k = 0; k < n; k++) {
         const int s = (int)(k % NSLOT);
         const size_t off = k * CHUNK, len = std::min(CHUNK, bytes - off);
@@ -337,7 +328,7 @@ extern "C" int wah_compress_host(const uint32_t *h_in, uint64_t n_words, int mod
     // -- segment 3: D2H into a malloc()ed buffer (compress.cu:177-202)
     uint32_t *host = alloc_result(cw);
     if (!host) return wah_set_error(WAH_ERR_NOMEM, "malloc of %llu words failed", (unsigned long long)cw);
-    if (int rc = download(c, host, c.b.p, cw * 4, true)) {
+    if (int rc = download(c, host, c.b.p, cw * 4)) {
         free(host);
         return rc;
     }
@@ -389,7 +380,7 @@ extern "C" int wah_decompress_host(const uint32_t *h_in, uint64_t c_words, uint3
     // -- segment 3: D2H into a malloc()ed buffer (decompress.cu:127-133)
     uint32_t *host = alloc_result(words);
     if (!host) return wah_set_error(WAH_ERR_NOMEM, "malloc of %llu words failed", (unsigned long long)words);
-    if (int rc = download(c, host, c.b.p, words * 4, true)) {
+    if (int rc = download(c, host, c.b.p, words * 4)) {
         free(host);
         return rc;
     }
@@ -429,7 +420,7 @@ extern "C" int wah_compress_host_into(const uint32_t *h_in, uint64_t n_words, in
     if (cw > out_capacity_words)
         return wah_set_error(WAH_ERR_CAPACITY, "result needs %llu words, buffer holds %llu", (unsigned long long)cw,
                              (unsigned long long)out_capacity_words);
-    return download(c, h_out, c.b.p, cw * 4, false);
+    return download(c, h_out, c.b.p, cw * 4);
 }
 
 extern "C" int wah_decompress_host_into(const uint32_t *h_in, uint64_t c_words, uint32_t *h_out,
@@ -461,5 +452,5 @@ extern "C" int wah_decompress_host_into(const uint32_t *h_in, uint64_t c_words, 
     if (info[0] > out_capacity_words)
         return wah_set_error(WAH_ERR_CAPACITY, "result needs %llu words, buffer holds %llu",
                              (unsigned long long)info[0], (unsigned long long)out_capacity_words);
-    return download(c, h_out, c.b.p, info[0] * 4, false);
+    return download(c, h_out, c.b.p, info[0] * 4);
 }

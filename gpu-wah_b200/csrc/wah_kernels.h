@@ -31,6 +31,7 @@ struct CompressParams {
     const uint64_t *base_in; // words already in `out` (nullptr = 0)
     uint64_t *total_out;     // receives base + words emitted by this launch
     uint64_t *col_offsets;   // nullptr or [n_cols + 1] for this launch's columns
+    uint32_t one;            // always 1 (an opaque multiplier that keeps bit accumulation on the FMA pipe)
     uint64_t *trace;         // nullptr; phase timestamps in -DWAH_TRACE builds (scripts/trace_compress.py)
 };
 

@@ -21,11 +21,6 @@ for it in range(3):
 t = trace.cpu().numpy().reshape(NC, 64, 8).astype(np.int64)
 iters = 14
 names = ["tma_issue", "full_done", "classify_done", "agg_seen", "pref_sent", "pref_seen", "emit_done", "gtime"]
-g0 = t[:, 0, 7].min()
-print("gtime of first TMA issue per CTA (us): min %.2f max %.2f" % (0, (t[:, 0, 7].max() - g0) / 1e3))
-for i in range(iters):
-    gi = t[:, i, 7]
-    print(f"iter {i}: tma issue gtime us  min {(gi.min()-g0)/1e3:7.2f} med {(np.median(gi)-g0)/1e3:7.2f} max {(gi.max()-g0)/1e3:7.2f}")
 def rep(label, a):
     a = a / 1965.0  # us at 1965 MHz
     print(f"{label:34s} med {np.median(a):6.2f} p10 {np.percentile(a,10):6.2f} p90 {np.percentile(a,90):6.2f} us")
@@ -44,3 +39,18 @@ for i in (3, 6, 9, 12):
 last = t[:, :iters, 5].max()
 first = t[:, 0, 0].min()
 print("per-CTA span us: med %.1f" % np.median((t[:, :iters, 5].max(axis=1) - t[:, 0, 0]) / 1965.0))
+print("per-iteration medians (us since the CTA's first TMA issue): full_seen  classify_done  worker_done  agg_seen  pref_sent  copied")
+for i in range(iters + 1):
+    x = t[:, i, :]
+    ok = x[:, 6] > 0
+    if ok.sum() == 0:
+        continue
+    z = lambda col: np.median((x[ok, col] - t[ok, 0, 0]) / 1965.0)
+    print(f"  iter {i:2d} ({ok.sum():3d} CTAs): {z(1):7.2f} {z(2):7.2f} {z(6):7.2f} {z(3):7.2f} {z(4):7.2f} {z(5):7.2f}")
+print("descriptor re-polls per tile: median per iteration", [int(np.median(t[:, i, 7])) for i in range(iters)], "max", [int(t[:, i, 7].max()) for i in range(iters)])
+lb = (t[:, :iters, 4] - t[:, :iters, 3]) / 1965.0
+pl = t[:, :iters, 7]
+for lo_, hi_ in ((0, 0), (1, 2), (3, 10), (11, 10**9)):
+    m = (pl >= lo_) & (pl <= hi_)
+    if m.sum():
+        print(f"  tiles with {lo_}..{hi_} re-polls: {m.sum():5d}  look-back median {np.median(lb[m]):.2f} us")

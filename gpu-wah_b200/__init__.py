@@ -9,6 +9,7 @@ CUDA).  There is no CPU fallback: if the library is missing, import raises.
 from .wah import (  # noqa: F401
     WAH_BLOCK1024,
     WAH_CANONICAL,
+    ShardRecord,
     WahError,
     Workspace,
     compress,

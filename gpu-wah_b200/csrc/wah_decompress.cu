@@ -219,6 +219,39 @@ constexpr uint32_t EXP_CLAMP = 2u * EXPAND_TILE_GROUPS;   // any count >= the ti
 
 __device__ __forceinline__ uint32_t grp_pos(uint32_t g) { return g + (g >> 5); }
 
+// ---- bulk (TMA) store of a finished tile, shared -> global
+__device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t bytes)
+{
+    asm volatile("cp.async.bulk.global.shared::cta.bulk_group [%0], [%1], %2;" ::"l"(dst), "r"(src_smem), "r"(bytes)
+                 : "memory");
+    asm volatile("cp.async.bulk.commit_group;" ::: "memory");
+}
+template <int N>
+__device__ __forceinline__ void bulk_wait_read()
+{
+    asm volatile("cp.async.bulk.wait_group.read %0;" ::"n"(N) : "memory");
+}
+__device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
+
+constexpr int SPARSE_MAX_WORDS = 4096;   // output tiles covered by at most this many compressed words take the bit-scatter path
+constexpr int SP_ROUND = EXPAND_THREADS * 2;   // compressed words per bit-scatter round (two per thread)
+constexpr int SP_LIST = 256;             // long one-fills of a round, finished warp-wide
+
+// OR the stream bits [b0, b1) (tile relative) into the tile image; plain read-modify-write: the caller
+// guarantees that no other thread touches the same words at the same time
+__device__ __forceinline__ void set_bits(uint32_t *img, uint32_t b0, uint32_t b1)
+{
+    const uint32_t w0 = b0 >> 5, w1 = (b1 - 1u) >> 5;
+    const uint32_t m0 = 0xFFFFFFFFu << (b0 & 31u), m1 = 0xFFFFFFFFu >> (31u - ((b1 - 1u) & 31u));
+    if (w0 == w1) {
+        img[w0] |= m0 & m1;
+    } else {
+        img[w0] |= m0;
+        for (uint32_t w = w0 + 1u; w < w1; w++) img[w] = 0xFFFFFFFFu;
+        img[w1] |= m1;
+    }
+}
+
 __device__ __forceinline__ void load8(const ExpandParams &p, uint64_t i0, uint32_t (&w)[8])
 {
     if (i0 + 8 <= p.c_words) {
@@ -241,6 +274,8 @@ __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const Exp
     __shared__ uint32_t s_wsum[NW];
     __shared__ uint2 s_list[EXP_LIST];
     __shared__ uint32_t s_nlist;
+    uint32_t n_sparse = 0;   // bit-scatter tiles so far: they alternate between the two tile images
+    bool have_w = false;     // w[] holds the first words of the current tile (prefetched)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint64_t G = p.hdr->groups;
@@ -272,8 +307,6 @@ __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const Exp
     uint32_t skip, skip_n, first, first_n;
     uint32_t w[8];
     tile_info(ot, ws, we, skip, first);
-    if (ot < n_tiles) load8(p, (ws & ~3ull) + 8ull * tid, w);
-
     for (; ot < n_tiles; ot += gridDim.x) {
         // the next tile's bookkeeping is fetched now and its first words after the scatter below, so
         // neither load latency sits on the next iteration's critical path
@@ -303,8 +336,115 @@ __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const Exp
             we = we_n;
             skip = skip_n;
             first = first_n;
-            if (ot + gridDim.x < n_tiles) load8(p, (ws & ~3ull) + 8ull * tid, w);
+            have_w = false;
             continue;
+        }
+
+        const uint32_t nw_all = (uint32_t)(we - wa + 1);   // words wa .. we
+        if (nw_all <= (uint32_t)SPARSE_MAX_WORDS && nout == (uint32_t)EXPAND_TILE_WORDS) {
+            // ================= bit-scatter path (fill dominated data) =================
+            // The tile image (7936 words) is cleared in shared memory, every literal ORs its 31 bits into
+            // the one or two words it touches, every one-fill sets its bit range, zero fills cost nothing;
+            // the finished image leaves through one bulk (TMA) store while the next tile is assembled in
+            // the other image.  Words 2k and 2k+1 of the compressed stream are handled in separate phases:
+            // two words handled at the same time are then at least two groups (62 bits) apart and never
+            // touch the same 32-bit word, so plain read-modify-writes suffice.
+            uint32_t *img = (n_sparse & 1u) ? s_grp : s_stage;
+            n_sparse++;
+            if (tid == 0) bulk_wait_read<1>();   // the store that last read this image is done
+            __syncthreads();
+            {
+                uint4 *z = reinterpret_cast<uint4 *>(img);
+                for (uint32_t i = tid; i < (uint32_t)EXPAND_TILE_WORDS / 4; i += EXPAND_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+            }
+            int32_t running = 0;   // group offset (tile relative) of the round's first word
+            for (uint32_t c0 = 0; c0 < nw_all; c0 += SP_ROUND) {
+                const uint64_t i0 = wa + c0 + 2ull * tid;   // my two consecutive words
+                uint32_t x[2];
+                if (i0 + 2 <= p.c_words) {
+                    const uint2 v = *reinterpret_cast<const uint2 *>(p.in + i0);
+                    x[0] = v.x;
+                    x[1] = v.y;
+                } else {
+                    x[0] = i0 < p.c_words ? p.in[i0] : BIT31;
+                    x[1] = BIT31;
+                }
+                uint32_t c[2];
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    const uint64_t gi = i0 + i;
+                    uint32_t v = word_groups(x[i]);
+                    if (gi < ws || gi > we) v = 0;   // outside this tile's word range
+                    else if (gi == ws) v -= skip;    // part of the first word belongs to earlier tiles
+                    c[i] = v > EXP_CLAMP ? EXP_CLAMP : v;
+                }
+                const uint32_t tsum = c[0] + c[1];
+                const uint32_t incl = warp_incl_scan(tsum);
+                __syncthreads();   // previous round's s_wsum / list consumed; first round: image cleared
+                if (lane == 31) s_wsum[warp] = incl;
+                if (tid == 0) s_nlist = 0;
+                __syncthreads();
+                int32_t off = running + (int32_t)(incl - tsum);
+                uint32_t round_sum = 0;
+#pragma unroll
+                for (int k = 0; k < NW; k++) {
+                    const uint32_t sv = s_wsum[k];
+                    if (k < (int)warp) off += (int32_t)sv;
+                    round_sum += sv;
+                }
+                running += (int32_t)round_sum;
+#pragma unroll
+                for (int i = 0; i < 2; i++) {
+                    if (c[i] != 0u && off < EXPAND_TILE_GROUPS) {
+                        const uint32_t wv = x[i];
+                        const uint32_t g0 = (uint32_t)off;
+                        if (!is_fill(wv)) {   // kernels.cu:351-354, packed at once (kernels.cu:375)
+                            const uint32_t bit = 31u * g0, w = bit >> 5, sh = bit & 31u;
+                            img[w] |= wv << sh;
+                            if (sh > 1u) img[w + 1] |= wv >> (32u - sh);
+                        } else if (wv & BIT30) {   // one-fill, kernels.cu:337-348
+                            uint32_t g1 = g0 + c[i];
+                            if (g1 > (uint32_t)EXPAND_TILE_GROUPS) g1 = EXPAND_TILE_GROUPS;
+                            const uint32_t b0 = 31u * g0, b1 = 31u * g1;
+                            if (b1 - b0 <= 32u * 48u) {
+                                set_bits(img, b0, b1);
+                            } else {
+                                // long run: its two ragged ends now, the whole words in between warp-wide below
+                                const uint32_t wlo = (b0 + 31u) >> 5, whi = b1 >> 5;
+                                if (b0 & 31u) set_bits(img, b0, wlo << 5);
+                                if (b1 & 31u) set_bits(img, whi << 5, b1);
+                                const uint32_t e = atomicAdd(&s_nlist, 1u);
+                                if (e < (uint32_t)SP_LIST) s_list[e] = make_uint2(wlo, whi);
+                                else for (uint32_t w = wlo; w < whi; w++) img[w] = 0xFFFFFFFFu;
+                            }
+                        }
+                    }
+                    off += (int32_t)c[i];
+                    if (i == 0) __syncthreads();   // even words done before odd words start
+                }
+                __syncthreads();
+                const uint32_t nl = s_nlist < (uint32_t)SP_LIST ? s_nlist : (uint32_t)SP_LIST;
+                for (uint32_t e = warp; e < nl; e += NW) {
+                    const uint2 r = s_list[e];
+                    for (uint32_t w = r.x + lane; w < r.y; w += 32) img[w] = 0xFFFFFFFFu;
+                }
+                if (running >= EXPAND_TILE_GROUPS) break;   // uniform: the tile is covered
+            }
+            // next tile's bookkeeping
+            ws = ws_n;
+            we = we_n;
+            skip = skip_n;
+            first = first_n;
+            have_w = false;
+            fence_async_smem();   // my writes to the image, visible to the bulk copy engine
+            __syncthreads();
+            if (tid == 0) bulk_s2g(dst, (uint32_t)__cvta_generic_to_shared(img), EXPAND_TILE_WORDS * 4u);
+            continue;
+        }
+        // the general path below uses both images as scratch: no bulk store may still be reading them
+        if (n_sparse) {
+            if (tid == 0) bulk_wait_read<0>();
+            __syncthreads();
         }
 
         // ---- 1. clear the group array
@@ -320,7 +460,7 @@ __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const Exp
         int32_t running = 0;                            // group offset (tile relative) of the round's first word
         for (uint32_t c0 = 0; c0 < nw; c0 += EXP_CHUNK) {
             const uint64_t i0 = wa + c0 + 8ull * tid;   // my 8 consecutive words
-            if (c0 != 0) load8(p, i0, w);
+            if (c0 != 0 || !have_w) load8(p, i0, w);
             uint32_t c[8];
             uint32_t tsum = 0;
 #pragma unroll
@@ -373,7 +513,8 @@ __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const Exp
         we = we_n;
         skip = skip_n;
         first = first_n;
-        if (ot + gridDim.x < n_tiles) load8(p, (ws & ~3ull) + 8ull * tid, w);
+        have_w = ot + gridDim.x < n_tiles;
+        if (have_w) load8(p, (ws & ~3ull) + 8ull * tid, w);
         __syncthreads();
 
         // ---- 3. long one-fills: a warp per run
@@ -410,6 +551,7 @@ __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const Exp
         // no barrier here: the next tile's clear touches s_grp only, and its first barrier orders this
         // tile's staging reads before the next repack writes
     }
+    if (tid == 0) bulk_wait_read<0>();   // shared memory must outlive the bulk stores that read it
 }
 
 }  // namespace

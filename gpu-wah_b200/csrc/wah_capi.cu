@@ -232,17 +232,6 @@ extern "C" size_t wah_decompress_workspace_bytes(uint64_t c_words, uint64_t out_
     return ws_starts_off(c_words) + (size_t)(max_out_tiles(out_capacity_words) + 2) * sizeof(ulonglong2);
 }
 
-static int expand_grid()
-{
-    static int grid = 0;
-    if (grid == 0) {
-        int dev = 0, sms = 148;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        grid = sms * 3;
-    }
-    return grid;
-}
-
 static int decompress_common(const uint32_t *d_in, uint64_t c_words, uint32_t *d_out, uint64_t out_cap,
                              uint64_t *d_out_info, void *d_workspace, size_t workspace_bytes, bool expand,
                              cudaStream_t stream)
@@ -271,7 +260,7 @@ static int decompress_common(const uint32_t *d_in, uint64_t c_words, uint32_t *d
     sp.max_out_tiles = expand ? max_out_tiles(out_cap) : 0;
     sp.out_info = d_out_info;
     CUDA_TRY(cudaMemsetAsync(ws, 0, ws_desc_off() + (size_t)sp.n_tiles * sizeof(uint64_t), stream));
-    CUDA_TRY(launch_scan(sp, stream));
+    if (!expand) CUDA_TRY(launch_scan(sp, stream));
     if (expand) {
         ExpandParams ep;
         memset(&ep, 0, sizeof(ep));
@@ -282,7 +271,7 @@ static int decompress_common(const uint32_t *d_in, uint64_t c_words, uint32_t *d
         ep.max_out_tiles = sp.max_out_tiles;
         ep.out = d_out;
         ep.out_cap = out_cap;
-        CUDA_TRY(launch_expand(ep, expand_grid(), stream));
+        CUDA_TRY(launch_decode(sp, ep, stream));
     }
     return WAH_OK;
 }

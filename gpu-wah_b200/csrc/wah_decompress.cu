@@ -43,14 +43,12 @@ struct ScanState {
     uint64_t tile_sum;
 };
 
-__global__ void __launch_bounds__(SCAN_THREADS) wah_scan_kernel(const ScanParams p)
+__device__ __forceinline__ void scan_body(const ScanParams &p)
 {
     constexpr int NW = SCAN_THREADS / 32;
-    constexpr int LB = 3;   // look-back window = LB * SCAN_THREADS tiles per round
     constexpr uint64_t TGM = (uint64_t)EXPAND_TILE_GROUPS - 1ull;
     __shared__ uint64_t s_wsum[NW];
-    __shared__ uint64_t s_lb_sum[LB * NW];
-    __shared__ uint32_t s_lb_incl[LB * NW];
+    __shared__ uint64_t s_lb_sum[NW];
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t stride = gridDim.x;
@@ -105,15 +103,18 @@ __global__ void __launch_bounds__(SCAN_THREADS) wah_scan_kernel(const ScanParams
         }
         st.first_off = wprefix + incl - tsum;
         st.tile_sum = tile_sum;
-        if (tid == 0) st_relaxed_u64(p.desc + tile, ((tile == 0u ? ST_INCL : ST_AGG) << 62) | tile_sum);
+        if (tid == 0) st_relaxed_u64(p.desc + tile, (ST_AGG << 62) | tile_sum);
         return st;
     };
 
     uint32_t tile = blockIdx.x;
+    if (tile >= p.n_tiles) return;   // (uniform) more CTAs than scan tiles
     uint32_t raw[SCAN_ITEMS];
     load(tile, raw);
     ScanState cur = summarize(tile, raw);
     load(tile + stride, raw);
+    uint64_t own_incl = 0;    // groups up to and including my previous tile
+    bool first_tile = true;
 
     while (tile < p.n_tiles) {
         const uint32_t next = tile + stride;
@@ -123,44 +124,29 @@ __global__ void __launch_bounds__(SCAN_THREADS) wah_scan_kernel(const ScanParams
             load(next + stride, raw);
         }
 
-        // ---- decoupled look-back (status:2 | value:62), LB 32-tile windows per warp and round
-        uint64_t excl = 0;
-        if (tile != 0u) {
-            int64_t look = (int64_t)tile - 1 - (int64_t)tid;
-            while (true) {
-#pragma unroll
-                for (int r = 0; r < LB; r++) {
-                    const int64_t lk = look - (int64_t)r * SCAN_THREADS;
-                    uint64_t d;
-                    if (lk >= 0) {
-                        do {
-                            d = ld_relaxed_u64(p.desc + lk);
-                        } while ((d >> 62) == ST_EMPTY);
-                    } else {
-                        d = ST_INCL << 62;
-                    }
-                    const uint32_t incl_mask = __ballot_sync(0xffffffffu, (d >> 62) == ST_INCL);
-                    const uint32_t first_incl = incl_mask ? (uint32_t)__ffs(incl_mask) - 1u : 32u;
-                    const uint64_t sm = warp_sum_u64(lane <= first_incl ? (d & VALUE_MASK) : 0ull);
-                    if (lane == 0) {
-                        s_lb_sum[r * NW + warp] = sm;
-                        s_lb_incl[r * NW + warp] = first_incl < 32u;
-                    }
-                }
-                __syncthreads();
-                bool done = false;
-#pragma unroll
-                for (int k = 0; k < LB * NW; k++) {
-                    if (!done) {
-                        excl += s_lb_sum[k];
-                        done = s_lb_incl[k] != 0u;
-                    }
-                }
-                if (done) break;
-                look -= LB * SCAN_THREADS;
-                __syncthreads();
+        // ---- group offset of the tile by a chained sum (see wah_compress.cu): the groups before my previous
+        //      tile, that tile's, and the aggregates of the tiles in between -- all published by other CTAs
+        //      as soon as they have counted the tile, never waiting for anybody's offset
+        uint64_t excl;
+        {
+            const int64_t lo = first_tile ? 0 : (int64_t)tile - (int64_t)stride + 1;
+            uint64_t acc = 0;
+            for (int64_t lk = (int64_t)tile - 1 - (int64_t)tid; lk >= lo; lk -= SCAN_THREADS) {
+                uint64_t d;
+                do {
+                    d = ld_relaxed_u64(p.desc + lk);
+                } while ((d >> 62) == ST_EMPTY);
+                acc += d & VALUE_MASK;
             }
-            if (tid == 0) st_relaxed_u64(p.desc + tile, (ST_INCL << 62) | (excl + cur.tile_sum));
+            acc = warp_sum_u64(acc);
+            if (lane == 0) s_lb_sum[warp] = acc;
+            __syncthreads();
+            uint64_t total = 0;
+#pragma unroll
+            for (int k = 0; k < NW; k++) total += s_lb_sum[k];
+            excl = own_incl + total;
+            own_incl = excl + cur.tile_sum;
+            first_tile = false;
         }
         if (tid == 0 && tile == p.n_tiles - 1u) {
             // decompress.cu:82-93: G = last offset + last count, realSize = ceil(31 G / 32)
@@ -204,10 +190,19 @@ __global__ void __launch_bounds__(SCAN_THREADS) wah_scan_kernel(const ScanParams
                 off += cur.cnt[i];
             }
         }
-        __syncthreads();   // look-back partials are rewritten by the next tile
+        __syncthreads();   // look-back partials are rewritten by the next tile; this tile's `starts` are written
+        if (tid == 0) {
+            __threadfence();
+            atomicAdd(&p.hdr->scan_done, 1u);   // the expand phase starts when every scan tile has got here
+        }
         tile = next;
         cur = nxt;
     }
+}
+
+__global__ void __launch_bounds__(SCAN_THREADS) wah_scan_kernel(const ScanParams p)
+{
+    scan_body(p);
 }
 
 // ---------------------------------------------------------------- expand kernel
@@ -265,7 +260,7 @@ __device__ __forceinline__ void load8(const ExpandParams &p, uint64_t i0, uint32
     }
 }
 
-__global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const ExpandParams p)
+__device__ __forceinline__ void expand_body(const ExpandParams &p)
 {
     constexpr int NW = EXPAND_THREADS / 32;
     extern __shared__ __align__(16) uint32_t smem[];
@@ -554,6 +549,27 @@ __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const Exp
     if (tid == 0) bulk_wait_read<0>();   // shared memory must outlive the bulk stores that read it
 }
 
+__global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const ExpandParams p)
+{
+    expand_body(p);
+}
+
+// Both phases in one persistent launch: every CTA first takes its share of the scan tiles, then -- once all
+// scan tiles are done, i.e. the decoded size and every output tile's starting point are known -- its share of
+// the output tiles.  Saves a launch and the idle tail / ramp between two kernels.
+static_assert(SCAN_THREADS == EXPAND_THREADS, "the fused kernel runs both phases with one CTA shape");
+__global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_decode_kernel(const ScanParams sp, const ExpandParams ep)
+{
+    scan_body(sp);
+    if (threadIdx.x == 0) {
+        volatile uint32_t *done = &sp.hdr->scan_done;
+        while (*done < sp.n_tiles) __nanosleep(100);
+        __threadfence();
+    }
+    __syncthreads();
+    expand_body(ep);
+}
+
 }  // namespace
 
 size_t expand_smem_bytes()
@@ -582,6 +598,30 @@ cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream)
     ScanParams params = p;
     void *args[] = {&params};
     return cudaLaunchCooperativeKernel((const void *)wah_scan_kernel, dim3(grid), dim3(SCAN_THREADS), args, 0, stream);
+}
+
+cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStream_t stream)
+{
+    // persistent, every CTA resident (both phases spin on results of other CTAs): SMs x occupancy CTAs
+    const size_t smem = expand_smem_bytes();
+    static int grid = 0;
+    if (grid == 0) {
+        cudaError_t e = cudaFuncSetAttribute(wah_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int dev = 0, sms = 0, per_sm = 0;
+        e = cudaGetDevice(&dev);
+        if (e != cudaSuccess) return e;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wah_decode_kernel, EXPAND_THREADS, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        grid = sms * per_sm;
+    }
+    ScanParams a = sp;
+    ExpandParams b = ep;
+    void *args[] = {&a, &b};
+    return cudaLaunchKernel((const void *)wah_decode_kernel, dim3(grid), dim3(EXPAND_THREADS), args, smem, stream);
 }
 
 cudaError_t launch_expand(const ExpandParams &p, int grid, cudaStream_t stream)

@@ -59,7 +59,7 @@ struct DecodeHeader {
     uint64_t words;         // ceil(31 G / 32)
     uint64_t out_tiles;     // ceil(G / EXPAND_TILE_GROUPS)
     uint32_t bad_words;     // zero-length fills seen
-    uint32_t ticket;
+    uint32_t scan_done;     // scan tiles finished (their `starts` entries are written)
     uint64_t pad[4];
 };
 
@@ -87,6 +87,7 @@ struct ExpandParams {
 size_t expand_smem_bytes();
 cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream);
 cudaError_t launch_expand(const ExpandParams &p, int grid, cudaStream_t stream);
+cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStream_t stream);   // scan + expand, one launch
 
 // --------------------------------------------------------------------- misc
 

@@ -253,13 +253,16 @@ static int decompress_common(const uint32_t *d_in, uint64_t c_words, uint32_t *d
     memset(&sp, 0, sizeof(sp));
     sp.in = d_in;
     sp.c_words = c_words;
-    sp.n_tiles = (uint32_t)scan_tiles(c_words);
+    sp.tile_words = scan_tile_words(c_words);
+    sp.n_tiles = (uint32_t)ceil_div(c_words, sp.tile_words);
     sp.hdr = reinterpret_cast<DecodeHeader *>(ws);
     sp.desc = reinterpret_cast<uint64_t *>(ws + ws_desc_off());
     sp.starts = expand ? reinterpret_cast<ulonglong2 *>(ws + ws_starts_off(c_words)) : nullptr;
     sp.max_out_tiles = expand ? max_out_tiles(out_cap) : 0;
     sp.out_info = d_out_info;
-    CUDA_TRY(cudaMemsetAsync(ws, 0, ws_desc_off() + (size_t)sp.n_tiles * sizeof(uint64_t), stream));
+    sp.trace = g_trace;
+    // header, tile descriptors and (their x = 0 means "not recorded yet") the output-tile table
+    CUDA_TRY(cudaMemsetAsync(ws, 0, expand ? need : ws_desc_off() + (size_t)sp.n_tiles * sizeof(uint64_t), stream));
     if (!expand) CUDA_TRY(launch_scan(sp, stream));
     if (expand) {
         ExpandParams ep;
@@ -271,6 +274,7 @@ static int decompress_common(const uint32_t *d_in, uint64_t c_words, uint32_t *d
         ep.max_out_tiles = sp.max_out_tiles;
         ep.out = d_out;
         ep.out_cap = out_cap;
+        ep.trace = g_trace;
         CUDA_TRY(launch_decode(sp, ep, stream));
     }
     return WAH_OK;

@@ -35,13 +35,44 @@ static_assert((1u << TG_SHIFT) == (uint32_t)EXPAND_TILE_GROUPS, "output tile mus
 
 // ------------------------------------------------------------------ scan kernel
 
-// Group counts of one tile of compressed words, kept in registers while the NEXT tile is summed and
-// published (software pipeline, as in the compressor).
-struct ScanState {
-    uint32_t cnt[SCAN_ITEMS];
-    uint64_t first_off;   // group offset of my first word relative to the tile start
-    uint64_t tile_sum;
-};
+// One scan tile = p.tile_words compressed words (a multiple of 1024, at most 8192, chosen by the host so that a
+// short stream is one tile per CTA).  A warp owns a contiguous eighth of the tile and reads it with coalesced
+// 128-bit loads, lane l taking words 4l .. 4l+3 of every 128-word row; the words stay in registers:
+//   pass 1  count the groups of my words (getCounts, kernels.cu:298-304), publish the tile sum;
+//   offset  chained sum over the other CTAs' tile sums (see wah_compress.cu);
+//   pass 2  row by row, a warp scan gives every word its group offset; record, for every output-tile boundary
+//           k * 8192 that falls into a word, which word that is and where it starts.
+constexpr int SCAN_MAXV = 8;   // 128-bit loads per lane and tile
+constexpr int SCAN_HEAVY = 64;  // long fills of a tile queued for the CTA-wide boundary writer
+
+// Four consecutive compressed words, the first at group offset `off`: record every output-tile boundary
+// k * 8192 that falls into one of them (off <= k * 8192 < off + cnt).  A word that covers up to 4 boundaries
+// records them itself; a long fill is queued for the whole CTA.  Out of line: this runs for under 1 % of the
+// words and would otherwise be replicated 8 times in straight-line code that executes once per launch.
+__device__ __noinline__ void record_boundaries(ulonglong2 *starts, uint64_t k_limit, uint64_t wi, uint64_t off, uint4 cnt,
+                                               ulonglong4 *s_heavy, uint32_t *s_nheavy)
+{
+    constexpr uint64_t TGM = (uint64_t)EXPAND_TILE_GROUPS - 1ull;
+    const uint32_t c[4] = {cnt.x, cnt.y, cnt.z, cnt.w};
+#pragma unroll 1
+    for (int j = 0; j < 4; j++) {
+        uint64_t k_first = (off + TGM) >> TG_SHIFT;
+        uint64_t k_end = (off + c[j] + TGM) >> TG_SHIFT;
+        if (k_end != k_first) {
+            if (k_end > k_limit) k_end = k_limit;
+            if (k_first > k_end) k_first = k_end;
+            if (k_end - k_first > 4ull) {
+                const uint32_t e = atomicAdd(s_nheavy, 1u);
+                if (e < (uint32_t)SCAN_HEAVY) {
+                    s_heavy[e] = make_ulonglong4(wi + j, off, k_first, k_end);
+                    k_end = k_first;   // queued
+                }
+            }
+            for (uint64_t k = k_first; k < k_end; k++) starts[k] = make_ulonglong2(wi + j + 1ull, off);
+        }
+        off += c[j];
+    }
+}
 
 __device__ __forceinline__ void scan_body(const ScanParams &p)
 {
@@ -49,108 +80,112 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
     constexpr uint64_t TGM = (uint64_t)EXPAND_TILE_GROUPS - 1ull;
     __shared__ uint64_t s_wsum[NW];
     __shared__ uint64_t s_lb_sum[NW];
+    __shared__ ulonglong4 s_heavy[SCAN_HEAVY];
+    __shared__ uint32_t s_nheavy;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t stride = gridDim.x;
+    const uint32_t nv = p.tile_words / (4u * SCAN_THREADS);   // rows of 128 words per warp
+    const uint32_t seg_words = nv * 128u;
+    uint64_t own_incl = 0;                                     // groups up to and including my previous tile
+    bool first_tile = true;
 
-    // blocked arrangement: thread owns SCAN_ITEMS consecutive compressed words
-    auto load = [&](uint32_t tile, uint32_t (&w)[SCAN_ITEMS]) {
-        const uint64_t w_begin = (uint64_t)tile * SCAN_TILE_WORDS + (uint64_t)tid * SCAN_ITEMS;
-        if (tile < p.n_tiles && w_begin + SCAN_ITEMS <= p.c_words) {
-            const uint4 *src = reinterpret_cast<const uint4 *>(p.in + w_begin);
+    for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += stride) {
+        const uint64_t seg_begin = (uint64_t)tile * p.tile_words + (uint64_t)warp * seg_words;
+
+        // ---- pass 1
+        // (all loads are issued before the first use: a warp executes in order, a use right behind its load
+        //  would put one HBM round trip on every one of them)
+        uint4 x[SCAN_MAXV];
 #pragma unroll
-            for (int v = 0; v < SCAN_ITEMS / 4; v++) {
-                const uint4 x = ld_stream_v4(src + v);
-                w[4 * v + 0] = x.x;
-                w[4 * v + 1] = x.y;
-                w[4 * v + 2] = x.z;
-                w[4 * v + 3] = x.w;
+        for (int v = 0; v < SCAN_MAXV; v++) {
+            const uint64_t i0 = seg_begin + (uint64_t)(v * 32 + (int)lane) * 4u;
+            x[v] = make_uint4(BIT31, BIT31, BIT31, BIT31);   // fills of 0 groups: neutral, see `valid` below
+            if ((uint32_t)v < nv) {
+                if (i0 + 4 <= p.c_words) {
+                    x[v] = ld_stream_v4(reinterpret_cast<const uint4 *>(p.in + i0));
+                } else if (i0 < p.c_words) {
+                    x[v].x = p.in[i0];
+                    if (i0 + 1 < p.c_words) x[v].y = p.in[i0 + 1];
+                    if (i0 + 2 < p.c_words) x[v].z = p.in[i0 + 2];
+                }
             }
-        } else {
-#pragma unroll
-            for (int i = 0; i < SCAN_ITEMS; i++)
-                w[i] = (tile < p.n_tiles && w_begin + i < p.c_words) ? ld_stream_u32(p.in + w_begin + i)
-                                                                      : BIT31;   // fill of 0 groups
         }
-    };
-
-    // counts, block scan, publish the tile's aggregate
-    auto summarize = [&](uint32_t tile, const uint32_t (&w)[SCAN_ITEMS]) -> ScanState {
-        ScanState st;
-        const uint64_t w_begin = (uint64_t)tile * SCAN_TILE_WORDS + (uint64_t)tid * SCAN_ITEMS;
-        uint64_t tsum = 0;
+        uint64_t lsum = 0;
         uint32_t bad = 0;
 #pragma unroll
-        for (int i = 0; i < SCAN_ITEMS; i++) {
-            st.cnt[i] = word_groups(w[i]);   // getCounts, kernels.cu:298-304
-            tsum += st.cnt[i];
-            bad += (st.cnt[i] == 0u && w_begin + i < p.c_words) ? 1u : 0u;
+        for (int v = 0; v < SCAN_MAXV; v++) {
+            const uint64_t i0 = seg_begin + (uint64_t)(v * 32 + (int)lane) * 4u;
+            const uint32_t c0 = word_groups(x[v].x), c1 = word_groups(x[v].y), c2 = word_groups(x[v].z),
+                           c3 = word_groups(x[v].w);
+            lsum += (uint64_t)c0 + c1 + c2 + c3;
+            // zero-length fills inside the stream are malformed (padding words behind its end are not)
+            if ((uint32_t)v < nv)
+                bad += (c0 == 0u && i0 < p.c_words) + (c1 == 0u && i0 + 1 < p.c_words) + (c2 == 0u && i0 + 2 < p.c_words) +
+                       (c3 == 0u && i0 + 3 < p.c_words);
         }
         if (__any_sync(0xffffffffu, bad != 0u)) {
             bad = warp_sum(bad);
             if (lane == 0) atomicAdd(&p.hdr->bad_words, bad);
         }
-        const uint64_t incl = warp_incl_scan_u64(tsum);
-        __syncthreads();   // the previous tile's warp sums have been consumed
-        if (lane == 31) s_wsum[warp] = incl;
+        const uint64_t wtotal = warp_sum_u64(lsum);
+        __syncthreads();   // the previous tile's partial sums have been consumed
+        if (lane == 0) s_wsum[warp] = wtotal;
         __syncthreads();
         uint64_t tile_sum = 0, wprefix = 0;
 #pragma unroll
         for (int k = 0; k < NW; k++) {
-            const uint64_t s = s_wsum[k];
-            if (k < (int)warp) wprefix += s;
-            tile_sum += s;
+            const uint64_t sv = s_wsum[k];
+            if (k < (int)warp) wprefix += sv;
+            tile_sum += sv;
         }
-        st.first_off = wprefix + incl - tsum;
-        st.tile_sum = tile_sum;
         if (tid == 0) st_relaxed_u64(p.desc + tile, (ST_AGG << 62) | tile_sum);
-        return st;
-    };
+#ifdef WAH_TRACE
+        if (p.trace && tid == 0 && first_tile) p.trace[(uint64_t)blockIdx.x * 64u + 4u] = (uint64_t)clock64();
+#endif
 
-    uint32_t tile = blockIdx.x;
-    if (tile >= p.n_tiles) return;   // (uniform) more CTAs than scan tiles
-    uint32_t raw[SCAN_ITEMS];
-    load(tile, raw);
-    ScanState cur = summarize(tile, raw);
-    load(tile + stride, raw);
-    uint64_t own_incl = 0;    // groups up to and including my previous tile
-    bool first_tile = true;
-
-    while (tile < p.n_tiles) {
-        const uint32_t next = tile + stride;
-        ScanState nxt;
-        if (next < p.n_tiles) {
-            nxt = summarize(next, raw);   // published before this tile's look-back (see wah_compress.cu)
-            load(next + stride, raw);
-        }
-
-        // ---- group offset of the tile by a chained sum (see wah_compress.cu): the groups before my previous
-        //      tile, that tile's, and the aggregates of the tiles in between -- all published by other CTAs
-        //      as soon as they have counted the tile, never waiting for anybody's offset
+        // ---- group offset of the tile by a chained sum: the groups before my previous tile, that tile's, and
+        //      the sums of the tiles in between -- published by other CTAs as soon as they have counted them
         uint64_t excl;
         {
             const int64_t lo = first_tile ? 0 : (int64_t)tile - (int64_t)stride + 1;
             uint64_t acc = 0;
-            for (int64_t lk = (int64_t)tile - 1 - (int64_t)tid; lk >= lo; lk -= SCAN_THREADS) {
-                uint64_t d;
-                do {
-                    d = ld_relaxed_u64(p.desc + lk);
-                } while ((d >> 62) == ST_EMPTY);
-                acc += d & VALUE_MASK;
+            // (every thread has at most a few descriptors: request them all, then look at them; sleep between
+            //  polls: a spinning CTA must not take issue slots from the CTAs it waits for)
+            for (int64_t lk0 = (int64_t)tile - 1 - (int64_t)tid; lk0 >= lo; lk0 -= 4 * SCAN_THREADS) {
+                uint64_t d[4];
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int64_t lk = lk0 - (int64_t)r * SCAN_THREADS;
+                    d[r] = lk >= lo ? ld_relaxed_u64(p.desc + lk) : (ST_AGG << 62);
+                }
+#pragma unroll
+                for (int r = 0; r < 4; r++) {
+                    const int64_t lk = lk0 - (int64_t)r * SCAN_THREADS;
+                    while ((d[r] >> 62) == ST_EMPTY) {
+                        __nanosleep(128);
+                        d[r] = ld_relaxed_u64(p.desc + lk);
+                    }
+                    acc += d[r] & VALUE_MASK;
+                }
             }
             acc = warp_sum_u64(acc);
             if (lane == 0) s_lb_sum[warp] = acc;
+            if (tid == 0) s_nheavy = 0;
             __syncthreads();
             uint64_t total = 0;
 #pragma unroll
             for (int k = 0; k < NW; k++) total += s_lb_sum[k];
             excl = own_incl + total;
-            own_incl = excl + cur.tile_sum;
+            own_incl = excl + tile_sum;
+#ifdef WAH_TRACE
+            if (p.trace && tid == 0 && first_tile) p.trace[(uint64_t)blockIdx.x * 64u + 5u] = (uint64_t)clock64();
+#endif
             first_tile = false;
         }
         if (tid == 0 && tile == p.n_tiles - 1u) {
             // decompress.cu:82-93: G = last offset + last count, realSize = ceil(31 G / 32)
-            const uint64_t G = excl + cur.tile_sum;
+            const uint64_t G = excl + tile_sum;
             const uint64_t words = (G >> 5) * 31ull + (((G & 31ull) * 31ull + 31ull) >> 5);
             p.hdr->groups = G;
             p.hdr->words = words;
@@ -159,44 +194,38 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
                 p.out_info[0] = words;
                 p.out_info[1] = G;
             }
+            __threadfence();
+            *reinterpret_cast<volatile uint32_t *>(&p.hdr->valid) = 1u;   // the expand phase polls this
         }
 
-        // ---- which compressed word covers each output-tile boundary k * 8192 ?
+        // ---- pass 2: which compressed word covers each output-tile boundary k * 8192 ?
+        //      A word that covers up to 4 boundaries records them itself; a long fill (it may span a hundred
+        //      thousand output tiles) is queued and written by the whole CTA afterwards.
         if (p.starts != nullptr) {
-            const uint64_t w_begin = (uint64_t)tile * SCAN_TILE_WORDS + (uint64_t)tid * SCAN_ITEMS;
-            uint64_t off = excl + cur.first_off;   // group offset of my first word
             const uint64_t k_limit = p.max_out_tiles + 1ull;
+            uint64_t row_base = excl + wprefix;   // group offset of the row's first word
 #pragma unroll
-            for (int i = 0; i < SCAN_ITEMS; i++) {
-                // boundaries with off <= k * 8192 < off + cnt
-                uint64_t k_first = (off + TGM) >> TG_SHIFT;
-                uint64_t k_end = (off + cur.cnt[i] + TGM) >> TG_SHIFT;
-                if (k_end > k_limit) k_end = k_limit;
-                if (k_first > k_end) k_first = k_end;
-                const bool heavy = (k_end - k_first) > 4ull;
-                uint32_t hm = __ballot_sync(0xffffffffu, heavy);
-                while (hm) {
-                    // a long fill spans many output tiles: the whole warp writes its boundaries
-                    const int srcl = __ffs(hm) - 1;
-                    hm &= hm - 1u;
-                    const uint64_t kf = __shfl_sync(0xffffffffu, k_first, srcl);
-                    const uint64_t ke = __shfl_sync(0xffffffffu, k_end, srcl);
-                    const uint64_t o = __shfl_sync(0xffffffffu, off, srcl);
-                    const uint64_t wi = __shfl_sync(0xffffffffu, w_begin, srcl) + (uint64_t)i;
-                    for (uint64_t k = kf + lane; k < ke; k += 32) p.starts[k] = make_ulonglong2(wi, o);
+            for (int v = 0; v < SCAN_MAXV; v++) {
+                if ((uint32_t)v < nv) {   // uniform
+                    const uint32_t c0 = word_groups(x[v].x), c1 = word_groups(x[v].y), c2 = word_groups(x[v].z),
+                                   c3 = word_groups(x[v].w);
+                    const uint64_t sl = (uint64_t)c0 + c1 + c2 + c3;
+                    const uint64_t incl = warp_incl_scan_u64(sl);
+                    const uint64_t off = row_base + incl - sl;
+                    const uint64_t wi = seg_begin + (uint64_t)(v * 32 + (int)lane) * 4u;
+                    if (((off + TGM) >> TG_SHIFT) != ((off + sl + TGM) >> TG_SHIFT))   // rare: a boundary in my 4 words
+                        record_boundaries(p.starts, k_limit, wi, off, make_uint4(c0, c1, c2, c3), s_heavy, &s_nheavy);
+                    row_base += __shfl_sync(0xffffffffu, incl, 31);
                 }
-                if (!heavy)
-                    for (uint64_t k = k_first; k < k_end; k++) p.starts[k] = make_ulonglong2(w_begin + i, off);
-                off += cur.cnt[i];
+            }
+            __syncthreads();
+            const uint32_t nh = s_nheavy < (uint32_t)SCAN_HEAVY ? s_nheavy : (uint32_t)SCAN_HEAVY;
+            for (uint32_t e = 0; e < nh; e++) {
+                const ulonglong4 h = s_heavy[e];
+                for (uint64_t k = h.z + tid; k < h.w; k += SCAN_THREADS) p.starts[k] = make_ulonglong2(h.x + 1ull, h.y);
             }
         }
-        __syncthreads();   // look-back partials are rewritten by the next tile; this tile's `starts` are written
-        if (tid == 0) {
-            __threadfence();
-            atomicAdd(&p.hdr->scan_done, 1u);   // the expand phase starts when every scan tile has got here
-        }
-        tile = next;
-        cur = nxt;
+        __syncthreads();   // partial sums and the heavy queue are rewritten by the next tile
     }
 }
 
@@ -270,45 +299,96 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     __shared__ uint2 s_list[EXP_LIST];
     __shared__ uint32_t s_nlist;
     uint32_t n_sparse = 0;   // bit-scatter tiles so far: they alternate between the two tile images
-    bool have_w = false;     // w[] holds the first words of the current tile (prefetched)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
-    const uint64_t G = p.hdr->groups;
-    uint64_t total_words = p.hdr->words;
-    if (total_words > p.out_cap) total_words = p.out_cap;
-    const uint64_t real_tiles = p.hdr->out_tiles;
-    uint64_t n_tiles = real_tiles < p.max_out_tiles ? real_tiles : p.max_out_tiles;
-    {
-        const uint64_t need = (total_words + EXPAND_TILE_WORDS - 1) / EXPAND_TILE_WORDS;   // tiles with room
-        if (n_tiles > need) n_tiles = need;
-    }
 
-    // where a tile's compressed words start / end (written by the scan kernel)
-    auto tile_info = [&](uint64_t ot, uint64_t &ws, uint64_t &we, uint32_t &skip, uint32_t &first) {
-        if (ot < n_tiles) {
-            const ulonglong2 st = p.starts[ot];
-            ws = st.x;
-            we = (ot + 1 < real_tiles) ? p.starts[ot + 1].x : p.c_words - 1;
-            skip = (uint32_t)((ot << TG_SHIFT) - st.y);   // groups of word ws that belong to earlier tiles
-            first = (ws == we) ? p.in[ws] : 0u;           // a tile inside ONE word is written without decoding
+    // An output tile can be expanded as soon as the scan has recorded where it starts and where the next one
+    // starts (starts[k].x = word index + 1, 0 = not recorded yet) -- the offsets of the low tiles are known long
+    // before a straggling scan tile at the far end of the stream is done.  The decoded size (the header) is only
+    // needed to recognise the stream's last tile.  Every thread resolves this for itself: the data only ever
+    // goes from "unknown" to its final value, so all threads arrive at the same answer.
+    struct Raw {
+        uint64_t sx, sy, ex;
+    };
+    auto peek = [&](uint64_t ot_, Raw &r) {   // non-blocking
+        r.sx = r.sy = r.ex = 0;
+        if (ot_ < p.max_out_tiles) {
+            // one 16-byte access: x and y of an entry are written (and read) together
+            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(r.sx), "=l"(r.sy) : "l"(p.starts + ot_) : "memory");
+            r.ex = ld_relaxed_u64(reinterpret_cast<const uint64_t *>(p.starts + ot_ + 1));
+        }
+    };
+    auto header_known = [&]() -> bool {
+        if (*reinterpret_cast<const volatile uint32_t *>(&p.hdr->valid) == 0u) return false;
+        __threadfence();
+        return true;
+    };
+    // the first two words a thread handles in the bit-scatter path
+    auto first_words = [&](uint64_t ws_, uint2 &x) {
+        const uint64_t i0 = (ws_ & ~3ull) + 2ull * tid;
+        if (i0 + 2 <= p.c_words) {
+            x = *reinterpret_cast<const uint2 *>(p.in + i0);
         } else {
-            ws = we = 0;
-            skip = first = 0;
+            x.x = i0 < p.c_words ? p.in[i0] : BIT31;
+            x.y = BIT31;
         }
     };
 
-    uint64_t ot = blockIdx.x;
-    uint64_t ws, we, ws_n, we_n;
-    uint32_t skip, skip_n, first, first_n;
+    // Software pipeline over this CTA's tiles: a tile's bookkeeping is requested two tiles ahead and its first
+    // compressed words one tile ahead (if known by then), so their load latencies stay off the critical path.
     uint32_t w[8];
-    tile_info(ot, ws, we, skip, first);
-    for (; ot < n_tiles; ot += gridDim.x) {
-        // the next tile's bookkeeping is fetched now and its first words after the scatter below, so
-        // neither load latency sits on the next iteration's critical path
-        tile_info(ot + gridDim.x, ws_n, we_n, skip_n, first_n);
+    Raw cur, nx1, nx2;
+    uint2 xpre, xpre_n;
+    bool xpre_ok = false, xpre_n_ok = false;
+    uint64_t ot = blockIdx.x;
+    peek(ot, cur);
+    peek(ot + gridDim.x, nx1);
+    for (; ot < p.max_out_tiles; ot += gridDim.x, cur = nx1, nx1 = nx2, xpre = xpre_n, xpre_ok = xpre_n_ok) {
+        peek(ot + 2ull * gridDim.x, nx2);
+        xpre_n_ok = nx1.sx != 0ull;
+        if (xpre_n_ok) first_words(nx1.sx - 1ull, xpre_n);
+
+        // ---- resolve the tile (blocking)
+        bool hdr = false, gone = false, last = false;
+        while (cur.sx == 0ull) {
+            if (!hdr) hdr = header_known();
+            if (hdr && ot >= p.hdr->out_tiles) {
+                gone = true;   // the stream ends before this tile
+                break;
+            }
+            __nanosleep(128);   // polite polling, see scan_body
+            peek(ot, cur);
+        }
+        if (gone) break;
+        while (cur.ex == 0ull) {
+            if (!hdr) hdr = header_known();
+            if (hdr && ot + 1 >= p.hdr->out_tiles) {
+                last = true;   // the stream's last tile: it ends with the last compressed word
+                break;
+            }
+            __nanosleep(128);
+            peek(ot, cur);
+        }
+        const uint64_t w_lo = ot * (uint64_t)EXPAND_TILE_WORDS;
+        if (w_lo >= p.out_cap) break;   // no room for this tile (nor for any later one)
+        const uint64_t ws = cur.sx - 1ull;
+        const uint64_t we = last ? p.c_words - 1 : cur.ex - 1ull;
+        const uint32_t skip = (uint32_t)((ot << TG_SHIFT) - cur.sy);   // groups of word ws that belong to earlier tiles
+        const uint32_t first = (ws == we) ? p.in[ws] : 0u;             // a tile inside ONE word is written without decoding
+        uint64_t G = ~0ull, total_words = p.out_cap;                    // only the last tile is cut short by the stream's end
+        if (last) {
+            G = p.hdr->groups;
+            if (p.hdr->words < total_words) total_words = p.hdr->words;
+        }
+        if (!xpre_ok) first_words(ws, xpre);
+#ifdef WAH_TRACE
+        if (p.trace && tid == 0) {
+            const uint64_t k = (ot - blockIdx.x) / gridDim.x;
+            if (k < 40) p.trace[(uint64_t)blockIdx.x * 64u + 8u + k] = (uint64_t)clock64();
+        }
+#endif
 
         const uint64_t g_lo = ot << TG_SHIFT;
-        const uint64_t w_lo = ot * (uint64_t)EXPAND_TILE_WORDS;
         const uint64_t avail = total_words - w_lo;
         const uint32_t nout = avail < (uint64_t)EXPAND_TILE_WORDS ? (uint32_t)avail : (uint32_t)EXPAND_TILE_WORDS;
         uint32_t *dst = p.out + w_lo;
@@ -317,7 +397,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         const uint64_t wa = ws & ~3ull;   // 16-byte aligned start; words before ws are ignored
 
         bool fast = false;
-        if (ws == we && is_fill(first) && (ot + 1 < real_tiles || !(first & BIT30))) {
+        if (ws == we && is_fill(first) && (!last || !(first & BIT30))) {
             // the whole tile lies inside one fill word (the stream's last tile may end in a partly
             // padded word: a one-fill there takes the general path)
             fast = true;
@@ -326,14 +406,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             for (uint32_t i = tid; i < nvec; i += EXPAND_THREADS) st_stream_v4(dst4 + i, v);
             for (uint32_t i = (nvec << 2) + tid; i < nout; i += EXPAND_THREADS) dst[i] = f;
         }
-        if (fast) {
-            ws = ws_n;
-            we = we_n;
-            skip = skip_n;
-            first = first_n;
-            have_w = false;
-            continue;
-        }
+        if (fast) continue;
 
         const uint32_t nw_all = (uint32_t)(we - wa + 1);   // words wa .. we
         if (nw_all <= (uint32_t)SPARSE_MAX_WORDS && nout == (uint32_t)EXPAND_TILE_WORDS) {
@@ -356,7 +429,10 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             for (uint32_t c0 = 0; c0 < nw_all; c0 += SP_ROUND) {
                 const uint64_t i0 = wa + c0 + 2ull * tid;   // my two consecutive words
                 uint32_t x[2];
-                if (i0 + 2 <= p.c_words) {
+                if (c0 == 0) {
+                    x[0] = xpre.x;
+                    x[1] = xpre.y;
+                } else if (i0 + 2 <= p.c_words) {
                     const uint2 v = *reinterpret_cast<const uint2 *>(p.in + i0);
                     x[0] = v.x;
                     x[1] = v.y;
@@ -425,12 +501,6 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 }
                 if (running >= EXPAND_TILE_GROUPS) break;   // uniform: the tile is covered
             }
-            // next tile's bookkeeping
-            ws = ws_n;
-            we = we_n;
-            skip = skip_n;
-            first = first_n;
-            have_w = false;
             fence_async_smem();   // my writes to the image, visible to the bulk copy engine
             __syncthreads();
             if (tid == 0) bulk_s2g(dst, (uint32_t)__cvta_generic_to_shared(img), EXPAND_TILE_WORDS * 4u);
@@ -455,7 +525,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         int32_t running = 0;                            // group offset (tile relative) of the round's first word
         for (uint32_t c0 = 0; c0 < nw; c0 += EXP_CHUNK) {
             const uint64_t i0 = wa + c0 + 8ull * tid;   // my 8 consecutive words
-            if (c0 != 0 || !have_w) load8(p, i0, w);
+            load8(p, i0, w);
             uint32_t c[8];
             uint32_t tsum = 0;
 #pragma unroll
@@ -503,13 +573,6 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             }
             if (running >= EXPAND_TILE_GROUPS) break;   // uniform: the tile is covered
         }
-        // start fetching the next tile's first words; they are consumed one iteration from now
-        ws = ws_n;
-        we = we_n;
-        skip = skip_n;
-        first = first_n;
-        have_w = ot + gridDim.x < n_tiles;
-        if (have_w) load8(p, (ws & ~3ull) + 8ull * tid, w);
         __syncthreads();
 
         // ---- 3. long one-fills: a warp per run
@@ -554,20 +617,39 @@ __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const Exp
     expand_body(p);
 }
 
-// Both phases in one persistent launch: every CTA first takes its share of the scan tiles, then -- once all
-// scan tiles are done, i.e. the decoded size and every output tile's starting point are known -- its share of
-// the output tiles.  Saves a launch and the idle tail / ramp between two kernels.
+// Both phases in one persistent launch: every CTA first takes its share of the scan tiles, then its share of the
+// output tiles, each of which waits only for its own two `starts` entries.  Saves a launch, the idle tail / ramp
+// between two kernels, and the wait for the slowest scan tile.
 static_assert(SCAN_THREADS == EXPAND_THREADS, "the fused kernel runs both phases with one CTA shape");
+#ifdef WAH_TRACE
+#define DTRACE(slot, val)                                                                      \
+    do {                                                                                       \
+        if (ep.trace && threadIdx.x == 0) ep.trace[(uint64_t)blockIdx.x * 64u + (slot)] = (uint64_t)(val); \
+    } while (0)
+#else
+#define DTRACE(slot, val) \
+    do {                  \
+    } while (0)
+#endif
 __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_decode_kernel(const ScanParams sp, const ExpandParams ep)
 {
-    scan_body(sp);
-    if (threadIdx.x == 0) {
-        volatile uint32_t *done = &sp.hdr->scan_done;
-        while (*done < sp.n_tiles) __nanosleep(100);
-        __threadfence();
+    DTRACE(0, clock64());
+#ifdef WAH_TRACE
+    {
+        uint64_t gt;
+        asm volatile("mov.u64 %0, %%globaltimer;" : "=l"(gt));
+        DTRACE(6, gt);
+        uint32_t smid;
+        asm volatile("mov.u32 %0, %%smid;" : "=r"(smid));
+        DTRACE(7, smid);
     }
+#endif
+    scan_body(sp);
+    DTRACE(1, clock64());
     __syncthreads();
+    DTRACE(2, clock64());
     expand_body(ep);
+    DTRACE(3, clock64());
 }
 
 }  // namespace
@@ -575,6 +657,23 @@ __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_decode_kernel(const Sca
 size_t expand_smem_bytes()
 {
     return (size_t)(GRP_WORDS + EXPAND_TILE_WORDS) * sizeof(uint32_t);
+}
+
+static int decode_grid_cached = 0;
+
+uint32_t scan_tile_words(uint64_t c_words)
+{
+    int sms = 148;
+    if (decode_grid_cached == 0) {
+        int dev = 0;
+        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    }
+    const uint64_t grid = decode_grid_cached ? (uint64_t)decode_grid_cached : (uint64_t)sms * 3;
+    const uint64_t unit = 4ull * SCAN_THREADS;
+    uint64_t tw = ((c_words + grid - 1) / grid + unit - 1) / unit * unit;
+    if (tw < (uint64_t)SCAN_TILE_WORDS) tw = SCAN_TILE_WORDS;
+    if (tw > 8192ull) tw = 8192ull;   // SCAN_MAXV 128-bit loads per lane
+    return (uint32_t)tw;
 }
 
 cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream)
@@ -617,6 +716,7 @@ cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStre
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         grid = sms * per_sm;
+        decode_grid_cached = grid;
     }
     ScanParams a = sp;
     ExpandParams b = ep;

@@ -60,18 +60,22 @@ struct DecodeHeader {
     uint64_t out_tiles;     // ceil(G / EXPAND_TILE_GROUPS)
     uint32_t bad_words;     // zero-length fills seen
     uint32_t scan_done;     // scan tiles finished (their `starts` entries are written)
-    uint64_t pad[4];
+    uint32_t valid;         // groups / words / out_tiles are final
+    uint32_t pad32;
+    uint64_t pad[3];
 };
 
 struct ScanParams {
     const uint32_t *in;
     uint64_t c_words;
-    uint32_t n_tiles;
+    uint32_t n_tiles;        // ceil(c_words / tile_words)
+    uint32_t tile_words;     // words per scan tile: a multiple of 4 * SCAN_THREADS (scan_tile_words())
     uint64_t *desc;          // [n_tiles] zeroed
     DecodeHeader *hdr;       // zeroed
     ulonglong2 *starts;      // nullptr (size query) or [max_out_tiles + 1]: {compressed word index, its group offset}
     uint64_t max_out_tiles;
     uint64_t *out_info;      // nullptr or device u64[2] {words, groups}
+    uint64_t *trace;         // nullptr; -DWAH_TRACE builds only
 };
 
 struct ExpandParams {
@@ -82,9 +86,13 @@ struct ExpandParams {
     uint64_t max_out_tiles;
     uint32_t *out;
     uint64_t out_cap;
+    uint64_t *trace;         // nullptr; phase timestamps in -DWAH_TRACE builds (scripts/trace_decode.py)
 };
 
 size_t expand_smem_bytes();
+// scan tile size for a stream of c_words: one tile per CTA of the decode grid while that keeps a tile between
+// SCAN_TILE_WORDS (the unit the workspace is sized by) and 8 K words
+uint32_t scan_tile_words(uint64_t c_words);
 cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream);
 cudaError_t launch_expand(const ExpandParams &p, int grid, cudaStream_t stream);
 cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStream_t stream);   // scan + expand, one launch

@@ -1,0 +1,72 @@
+"""Phase timeline of the fused decode kernel (needs a -DWAH_TRACE build: make -C gpu-wah_b200 TRACE=1)."""
+import ctypes, sys, os
+import numpy as np, torch
+sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
+import gpu_wah_b200 as wah
+
+n = 1 << 25
+d = wah.gen_uniform_device(n, float(sys.argv[1]) if len(sys.argv) > 1 else 0.001, 1337)
+cap = wah.max_compressed_words(n)
+out = torch.empty(cap, dtype=torch.int32, device="cuda")
+cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+ws = wah.Workspace.for_compress(n)
+wah.compress_device(d, n, out, cap, cnt, ws, 0)
+c = int(cnt.item())
+dec = torch.empty(n + 32, dtype=torch.int32, device="cuda")
+info = torch.zeros(2, dtype=torch.int64, device="cuda")
+wd = wah.Workspace.for_decompress(c, n + 32)
+NC = 444
+trace = torch.zeros(NC * 64, dtype=torch.int64, device="cuda")
+wah.lib.wah_test_set_trace.argtypes = [ctypes.c_void_p]
+# a second, different stream: decoding it right before the traced launch warms the instruction cache only
+d2 = wah.gen_uniform_device(n, 0.001, 4242)
+out2 = torch.empty(cap, dtype=torch.int32, device="cuda")
+wah.compress_device(d2, n, out2, cap, cnt, ws, 0)
+c2 = int(cnt.item())
+dec2 = torch.empty(n + 32, dtype=torch.int32, device="cuda")
+wd2 = wah.Workspace.for_decompress(c2, n + 32)
+warm = len(sys.argv) > 2 and sys.argv[2] == "warm"
+flush = torch.empty(64 << 20, dtype=torch.int32, device="cuda")
+for it in range(3):
+    flush.zero_()   # 256 MB written: L2 no longer holds the stream
+    if warm:
+        wah.lib.wah_test_set_trace(None)
+        wah.decompress_device(out2, c2, dec2, n + 32, info, wd2)
+    trace.zero_()
+    wah.lib.wah_test_set_trace(trace.data_ptr())
+    wah.decompress_device(out, c, dec, n + 32, info, wd)
+    torch.cuda.synchronize()
+wah.lib.wah_test_set_trace(None)
+t = trace.cpu().numpy().reshape(NC, 64).astype(np.int64)
+us = lambda a: a / 1965.0
+print("c_words", c, "scan tiles", (c + 2047) // 2048, "output tiles", (n * 32 // 31 + 8191) // 8192)
+print("scan phase   us: med %.2f max %.2f" % (np.median(us(t[:, 1] - t[:, 0])), us(t[:, 1] - t[:, 0]).max()))
+act = t[:, 4] > 0
+print("  pass 1 (start -> published)  us: med %.2f max %.2f" % (np.median(us(t[act, 4] - t[act, 0])), us(t[act, 4] - t[act, 0]).max()))
+print("  chained sum                  us: med %.2f max %.2f" % (np.median(us(t[act, 5] - t[act, 4])), us(t[act, 5] - t[act, 4]).max()))
+print("  pass 2 (starts)              us: med %.2f max %.2f" % (np.median(us(t[act, 1] - t[act, 5])), us(t[act, 1] - t[act, 5]).max()))
+print("global wait  us: med %.2f max %.2f" % (np.median(us(t[:, 2] - t[:, 1])), us(t[:, 2] - t[:, 1]).max()))
+print("expand phase us: med %.2f max %.2f" % (np.median(us(t[:, 3] - t[:, 2])), us(t[:, 3] - t[:, 2]).max()))
+print("whole CTA    us: med %.2f max %.2f" % (np.median(us(t[:, 3] - t[:, 0])), us(t[:, 3] - t[:, 0]).max()))
+tt = t[:, 8:48]
+nt = (tt > 0).sum(axis=1)
+print("tiles per CTA: min", nt.min(), "max", nt.max())
+per = []
+for b in range(NC):
+    k = nt[b]
+    if k >= 3:
+        per.append(us(np.diff(tt[b, :k])))
+per = np.concatenate(per)
+print("per-tile time us: med %.2f p10 %.2f p90 %.2f" % (np.median(per), np.percentile(per, 10), np.percentile(per, 90)))
+p1 = us(t[:, 4] - t[:, 0])
+order = np.argsort(-p1)
+print("slowest pass 1:", [(int(b), round(float(p1[b]), 2)) for b in order[:12]])
+print("pass 1 by blockIdx range:", [round(float(np.median(p1[a:a + 37][act[a:a + 37]])), 2) for a in range(0, 407, 37)])
+g = t[:, 6]
+g = g - g.min()
+print("kernel-start globaltimer per CTA (us): p10 %.2f med %.2f p90 %.2f max %.2f" % (np.percentile(g, 10) / 1e3, np.median(g) / 1e3, np.percentile(g, 90) / 1e3, g.max() / 1e3))
+print("start time by blockIdx range (us):", [round(float(np.median(g[a:a + 37])) / 1e3, 2) for a in range(0, 444, 37)])
+sm = t[:, 7]
+print("CTAs per SM: ", np.bincount(np.bincount(sm.astype(int))))
+pub = g / 1e3 + us(t[:, 4] - t[:, 0])
+print("publish time (start + pass 1) us: med %.2f max %.2f" % (np.median(pub[act]), pub[act].max()))

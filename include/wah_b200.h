@@ -99,7 +99,7 @@ int wah_decoded_size_device(const uint32_t *d_in, uint64_t c_words, uint64_t *d_
  * H2D(+allocation) / compute / D2H(+release), like the reference's out-params
  * (compress.cu:205-207, decompress.cu:136-138).  Page-locked inputs are DMAed directly; pageable
  * memory moves through a ring of pinned bounce buffers filled by a few copy threads
- * (WAH_B200_COPY_THREADS, default min(8, cores)).  Calls are serialised by a process-wide lock. */
+ * (WAH_B200_COPY_THREADS, default min(16, cores)).  Calls are serialised by a process-wide lock. */
 int wah_compress_host(const uint32_t *h_in, uint64_t n_words, int mode,
                       uint32_t **h_out, uint64_t *out_words,
                       float *ms_h2d, float *ms_compute, float *ms_d2h);

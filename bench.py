@@ -239,7 +239,6 @@ def run_b200(args):
     assert torch.equal(d_dec[:n_words], inputs[0]), "device round trip failed"
 
     stream = torch.cuda.current_stream()
-    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(args.steps)]
 
     def step(i, events=None):
         b = i % nbuf
@@ -260,19 +259,27 @@ def run_b200(args):
         dist.barrier()
     sampler = ClockSampler(local_rank) if rank == 0 else None
     torch.cuda.synchronize()
+    # ---- the timed region: exactly `steps` steps between two events, nothing else on the stream
     t_start = torch.cuda.Event(enable_timing=True)
     t_end = torch.cuda.Event(enable_timing=True)
     t_start.record(stream)
     for i in range(args.steps):
-        step(i, ev[i])
+        step(i)
     t_end.record(stream)
     torch.cuda.synchronize()
     if world > 1:
         dist.barrier()
-    clocks = sampler.stop() if sampler else None
     total_ms = t_start.elapsed_time(t_end)
-    tc_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / args.steps
-    td_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / args.steps
+    # ---- a second pass with an event between the two halves of every step: per-kernel launch durations for the
+    #      roofline (each includes its own workspace memset and the event records, so it is a little pessimistic)
+    ksteps = min(args.steps, 200)
+    ev = [[torch.cuda.Event(enable_timing=True) for _ in range(3)] for _ in range(ksteps)]
+    for i in range(ksteps):
+        step(i, ev[i])
+    torch.cuda.synchronize()
+    clocks = sampler.stop() if sampler else None
+    tc_ms = sum(e[0].elapsed_time(e[1]) for e in ev) / ksteps
+    td_ms = sum(e[1].elapsed_time(e[2]) for e in ev) / ksteps
     if world > 1:
         t = torch.tensor([total_ms, tc_ms, td_ms], dtype=torch.float64, device=dev)
         dist.all_reduce(t, op=dist.ReduceOp.MAX)
@@ -365,12 +372,19 @@ def run_b200(args):
     peak = float(peaks.get("hbm_gbs", 6650.0))
     peak_src = "measured (MEASURED_PEAKS.json hbm_gbs)" if peaks else "fallback 6650 GB/s (B200_PROFILING.md)"
     alg_bytes = 4.0 * (n_words + c_avg)
+    # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this very
+    # command (profiles/r1_ncu_full_summary.md); known for the default workload only
+    ncu_traffic = {"wah_compress_kernel": 134.27e6 + 4.58e6, "wah_decode_kernel": 11.33e6 + 76.64e6}
+    default_wl = args.workload == "sparse_1gbit" and args.density is None and args.mode == "block1024"
     comp_dom = tc_ms >= td_ms
     dom_ms = tc_ms if comp_dom else td_ms
     roofline = {
-        "bound": "hbm", "kernel": "wah_compress_kernel" if comp_dom else "wah_expand_kernel (+ wah_scan_kernel)",
+        "bound": "hbm", "kernel": "wah_compress_kernel" if comp_dom else "wah_decode_kernel",
         "achieved": alg_bytes / (dom_ms * 1e-3) / 1e9, "peak": peak, "unit": "GB/s",
-        "frac": alg_bytes / (dom_ms * 1e-3) / 1e9 / peak, "traffic": None, "peak_source": peak_src,
+        "frac": alg_bytes / (dom_ms * 1e-3) / 1e9 / peak,
+        "traffic": ncu_traffic["wah_compress_kernel" if comp_dom else "wah_decode_kernel"] if default_wl else None,
+        "traffic_note": "DRAM bytes read + written inside the launch (ncu); output still in the 126 MB L2 at kernel end is not in it",
+        "peak_source": peak_src,
         "algorithmic_bytes_per_launch": alg_bytes, "launch_ms": dom_ms,
         "compress": {"ms": tc_ms, "achieved": alg_bytes / (tc_ms * 1e-3) / 1e9, "frac": alg_bytes / (tc_ms * 1e-3) / 1e9 / peak},
         "decompress": {"ms": td_ms, "achieved": alg_bytes / (td_ms * 1e-3) / 1e9, "frac": alg_bytes / (td_ms * 1e-3) / 1e9 / peak},
@@ -398,8 +412,8 @@ def run_b200(args):
                    "l2": f"{nbuf} distinct input buffers rotated; a step touches {(2 * nbytes + 8 * c_avg) / 2**20:.0f} MiB (> 126 MB L2)",
                    "step": "compress the vector, then decompress it"},
         "compress_gbs": world * nbytes / (tc_ms * 1e-3) / 1e9, "decompress_gbs": world * nbytes / (td_ms * 1e-3) / 1e9,
-        "clocks": clocks, "e2e": e2e, "gpu_launches": 3 * args.steps,
-        "gpu_launches_note": "per step: wah_compress_kernel, wah_scan_kernel, wah_expand_kernel (+2 cudaMemsetAsync)",
+        "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps,
+        "gpu_launches_note": "per step: wah_compress_kernel, wah_decode_kernel (scan + expand fused) (+2 cudaMemsetAsync of the workspaces)",
         "roofline": roofline, "cpu_baseline": cpu_baseline,
     }
     print(json.dumps(line), flush=True)

@@ -223,7 +223,7 @@ static uint64_t max_out_tiles(uint64_t out_capacity_words) { return ceil_div(out
 static size_t ws_desc_off() { return sizeof(DecodeHeader); }
 static size_t ws_starts_off(uint64_t c_words)
 {
-    size_t o = ws_desc_off() + (size_t)scan_tiles(c_words) * sizeof(uint64_t);
+    size_t o = ws_desc_off() + 2 * (size_t)scan_tiles(c_words) * sizeof(uint64_t);   // tile sums + tile offsets
     return (o + 15) & ~(size_t)15;
 }
 
@@ -257,12 +257,13 @@ static int decompress_common(const uint32_t *d_in, uint64_t c_words, uint32_t *d
     sp.n_tiles = (uint32_t)ceil_div(c_words, sp.tile_words);
     sp.hdr = reinterpret_cast<DecodeHeader *>(ws);
     sp.desc = reinterpret_cast<uint64_t *>(ws + ws_desc_off());
+    sp.excl = sp.desc + scan_tiles(c_words);
     sp.starts = expand ? reinterpret_cast<ulonglong2 *>(ws + ws_starts_off(c_words)) : nullptr;
     sp.max_out_tiles = expand ? max_out_tiles(out_cap) : 0;
     sp.out_info = d_out_info;
     sp.trace = g_trace;
     // header, tile descriptors and (their x = 0 means "not recorded yet") the output-tile table
-    CUDA_TRY(cudaMemsetAsync(ws, 0, expand ? need : ws_desc_off() + (size_t)sp.n_tiles * sizeof(uint64_t), stream));
+    CUDA_TRY(cudaMemsetAsync(ws, 0, expand ? need : ws_starts_off(c_words), stream));
     if (!expand) CUDA_TRY(launch_scan(sp, stream));
     if (expand) {
         ExpandParams ep;

@@ -43,6 +43,13 @@ static_assert((1u << TG_SHIFT) == (uint32_t)EXPAND_TILE_GROUPS, "output tile mus
 //   pass 2  row by row, a warp scan gives every word its group offset; record, for every output-tile boundary
 //           k * 8192 that falls into a word, which word that is and where it starts.
 constexpr int SCAN_MAXV = 8;   // 128-bit loads per lane and tile
+
+// An entry of the output-tile table is read by other CTAs while the scan is still running: x (word index + 1,
+// 0 = not recorded) and y (the word's group offset) must appear together -- one 16-byte store, one 16-byte load.
+__device__ __forceinline__ void store_entry(ulonglong2 *e, uint64_t x, uint64_t y)
+{
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(e), "l"(x), "l"(y) : "memory");
+}
 constexpr int SCAN_HEAVY = 64;  // long fills of a tile queued for the CTA-wide boundary writer
 
 // Four consecutive compressed words, the first at group offset `off`: record every output-tile boundary
@@ -68,7 +75,7 @@ __device__ __noinline__ void record_boundaries(ulonglong2 *starts, uint64_t k_li
                     k_end = k_first;   // queued
                 }
             }
-            for (uint64_t k = k_first; k < k_end; k++) starts[k] = make_ulonglong2(wi + j + 1ull, off);
+            for (uint64_t k = k_first; k < k_end; k++) store_entry(starts + k, wi + j + 1ull, off);
         }
         off += c[j];
     }
@@ -82,12 +89,12 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
     __shared__ uint64_t s_lb_sum[NW];
     __shared__ ulonglong4 s_heavy[SCAN_HEAVY];
     __shared__ uint32_t s_nheavy;
+    __shared__ uint32_t s_flag;
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t stride = gridDim.x;
     const uint32_t nv = p.tile_words / (4u * SCAN_THREADS);   // rows of 128 words per warp
     const uint32_t seg_words = nv * 128u;
-    uint64_t own_incl = 0;                                     // groups up to and including my previous tile
     bool first_tile = true;
 
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += stride) {
@@ -144,40 +151,66 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
         if (p.trace && tid == 0 && first_tile) p.trace[(uint64_t)blockIdx.x * 64u + 4u] = (uint64_t)clock64();
 #endif
 
-        // ---- group offset of the tile by a chained sum: the groups before my previous tile, that tile's, and
-        //      the sums of the tiles in between -- published by other CTAs as soon as they have counted them
+        // ---- group offset of the tile.  The tiles of one round (tile / gridDim) are counted at about the same
+        //      time by different CTAs; the LAST CTA to publish its sum scans the round's sums and hands every tile
+        //      its offset.  (Letting every CTA add up the sums below it needs G^2 / 2 descriptor reads per round,
+        //      all polling the same few cache lines: measured 6 us; this is one read per tile.)
         uint64_t excl;
         {
-            const int64_t lo = first_tile ? 0 : (int64_t)tile - (int64_t)stride + 1;
-            uint64_t acc = 0;
-            // (every thread has at most a few descriptors: request them all, then look at them; sleep between
-            //  polls: a spinning CTA must not take issue slots from the CTAs it waits for)
-            for (int64_t lk0 = (int64_t)tile - 1 - (int64_t)tid; lk0 >= lo; lk0 -= 4 * SCAN_THREADS) {
-                uint64_t d[4];
-#pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    const int64_t lk = lk0 - (int64_t)r * SCAN_THREADS;
-                    d[r] = lk >= lo ? ld_relaxed_u64(p.desc + lk) : (ST_AGG << 62);
+            const uint32_t round0 = tile - blockIdx.x;   // first tile of my round
+            const uint32_t m = p.n_tiles - round0 < stride ? p.n_tiles - round0 : stride;   // tiles in it
+            if (tid == 0) {
+                __threadfence();   // my sum is visible before my arrival is
+                s_flag = atomicAdd(&p.hdr->agg_count, 1u) == m - 1u;
+                s_nheavy = 0;
+            }
+            __syncthreads();
+            if (s_flag) {   // (uniform) I am the round's aggregator
+                __threadfence();
+                const uint32_t per = (m + SCAN_THREADS - 1) / SCAN_THREADS;   // consecutive tiles per thread
+                uint64_t mine = 0;
+                for (uint32_t j = 0; j < per; j++) {
+                    const uint32_t k = tid * per + j;
+                    if (k < m) mine += ld_relaxed_u64(p.desc + round0 + k) & VALUE_MASK;
                 }
+                const uint64_t incl = warp_incl_scan_u64(mine);
+                if (lane == 31) s_lb_sum[warp] = incl;
+                const uint64_t base0 = *reinterpret_cast<volatile uint64_t *>(&p.hdr->agg_base);
+                __syncthreads();
+                uint64_t before = base0, total = 0;
 #pragma unroll
-                for (int r = 0; r < 4; r++) {
-                    const int64_t lk = lk0 - (int64_t)r * SCAN_THREADS;
-                    while ((d[r] >> 62) == ST_EMPTY) {
-                        __nanosleep(128);
-                        d[r] = ld_relaxed_u64(p.desc + lk);
+                for (int k = 0; k < NW; k++) {
+                    const uint64_t sv = s_lb_sum[k];
+                    if (k < (int)warp) before += sv;
+                    total += sv;
+                }
+                before += incl - mine;
+                // The counter is reset BEFORE any offset is published: a CTA that has read its offset may arrive
+                // for the next round at once.
+                if (tid == 0) {
+                    p.hdr->agg_count = 0;
+                    *reinterpret_cast<volatile uint64_t *>(&p.hdr->agg_base) = base0 + total;
+                    __threadfence();
+                }
+                __syncthreads();
+                for (uint32_t j = 0; j < per; j++) {
+                    const uint32_t k = tid * per + j;
+                    if (k < m) {
+                        st_relaxed_u64(p.excl + round0 + k, (ST_INCL << 62) | before);
+                        before += ld_relaxed_u64(p.desc + round0 + k) & VALUE_MASK;
                     }
-                    acc += d[r] & VALUE_MASK;
                 }
             }
-            acc = warp_sum_u64(acc);
-            if (lane == 0) s_lb_sum[warp] = acc;
-            if (tid == 0) s_nheavy = 0;
+            if (tid == 0) {
+                uint64_t d = ld_relaxed_u64(p.excl + tile);
+                while ((d >> 62) == ST_EMPTY) {
+                    __nanosleep(64);
+                    d = ld_relaxed_u64(p.excl + tile);
+                }
+                s_lb_sum[0] = d & VALUE_MASK;
+            }
             __syncthreads();
-            uint64_t total = 0;
-#pragma unroll
-            for (int k = 0; k < NW; k++) total += s_lb_sum[k];
-            excl = own_incl + total;
-            own_incl = excl + tile_sum;
+            excl = s_lb_sum[0];
 #ifdef WAH_TRACE
             if (p.trace && tid == 0 && first_tile) p.trace[(uint64_t)blockIdx.x * 64u + 5u] = (uint64_t)clock64();
 #endif
@@ -222,7 +255,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
             const uint32_t nh = s_nheavy < (uint32_t)SCAN_HEAVY ? s_nheavy : (uint32_t)SCAN_HEAVY;
             for (uint32_t e = 0; e < nh; e++) {
                 const ulonglong4 h = s_heavy[e];
-                for (uint64_t k = h.z + tid; k < h.w; k += SCAN_THREADS) p.starts[k] = make_ulonglong2(h.x + 1ull, h.y);
+                for (uint64_t k = h.z + tid; k < h.w; k += SCAN_THREADS) store_entry(p.starts + k, h.x + 1ull, h.y);
             }
         }
         __syncthreads();   // partial sums and the heavy queue are rewritten by the next tile
@@ -257,9 +290,19 @@ __device__ __forceinline__ void bulk_wait_read()
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+#ifdef WAH_TRACE
+#define DCHK(cond, code, val)                                                                     \
+    do {                                                                                          \
+        if (!(cond) && p.trace) atomicMax((unsigned long long *)&p.trace[62], ((unsigned long long)(code) << 48) | ((unsigned long long)(val) & 0xFFFFFFFFFFFFull)); \
+    } while (0)
+#else
+#define DCHK(cond, code, val) \
+    do {                      \
+    } while (0)
+#endif
+
 constexpr int SPARSE_MAX_WORDS = 4096;   // output tiles covered by at most this many compressed words take the bit-scatter path
 constexpr int SP_ROUND = EXPAND_THREADS * 2;   // compressed words per bit-scatter round (two per thread)
-constexpr int SP_LIST = 256;             // long one-fills of a round, finished warp-wide
 
 // OR the stream bits [b0, b1) (tile relative) into the tile image; plain read-modify-write: the caller
 // guarantees that no other thread touches the same words at the same time
@@ -271,7 +314,11 @@ __device__ __forceinline__ void set_bits(uint32_t *img, uint32_t b0, uint32_t b1
         img[w0] |= m0 & m1;
     } else {
         img[w0] |= m0;
-        for (uint32_t w = w0 + 1u; w < w1; w++) img[w] = 0xFFFFFFFFu;
+        // whole words in between: they belong to this run alone (128-bit stores once aligned)
+        uint32_t w = w0 + 1u;
+        for (; w < w1 && (w & 3u); w++) img[w] = 0xFFFFFFFFu;
+        for (; w + 4u <= w1; w += 4u) *reinterpret_cast<uint4 *>(img + w) = make_uint4(~0u, ~0u, ~0u, ~0u);
+        for (; w < w1; w++) img[w] = 0xFFFFFFFFu;
         img[w1] |= m1;
     }
 }
@@ -334,53 +381,79 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         }
     };
 
-    // Software pipeline over this CTA's tiles: a tile's bookkeeping is requested two tiles ahead and its first
-    // compressed words one tile ahead (if known by then), so their load latencies stay off the critical path.
+    // Thread 0 resolves a tile (it may have to wait for the scan) and publishes the result in shared memory, so that
+    // the whole CTA works from the same numbers -- every path below is full of CTA barriers.  The bookkeeping of the
+    // next tiles is requested ahead of time (non-blocking), and so are a tile's first compressed words.
+    struct Resolved {
+        uint64_t ws, we, sy, G, total_words;
+        uint32_t flags, first;   // flags: 1 = stop (no such tile / no room), 2 = the stream's last tile
+    };
+    __shared__ Resolved s_res[2];
     uint32_t w[8];
     Raw cur, nx1, nx2;
     uint2 xpre, xpre_n;
-    bool xpre_ok = false, xpre_n_ok = false;
+    uint64_t xpre_ws = ~0ull, xpre_n_ws = ~0ull;   // which tile start the prefetched words belong to
     uint64_t ot = blockIdx.x;
+    uint32_t it = 0;
     peek(ot, cur);
     peek(ot + gridDim.x, nx1);
-    for (; ot < p.max_out_tiles; ot += gridDim.x, cur = nx1, nx1 = nx2, xpre = xpre_n, xpre_ok = xpre_n_ok) {
+    for (; ot < p.max_out_tiles; ot += gridDim.x, it++, cur = nx1, nx1 = nx2, xpre = xpre_n, xpre_ws = xpre_n_ws) {
         peek(ot + 2ull * gridDim.x, nx2);
-        xpre_n_ok = nx1.sx != 0ull;
-        if (xpre_n_ok) first_words(nx1.sx - 1ull, xpre_n);
+        xpre_n_ws = ~0ull;
+        if (nx1.sx != 0ull) {
+            xpre_n_ws = nx1.sx - 1ull;
+            first_words(xpre_n_ws, xpre_n);
+        }
 
-        // ---- resolve the tile (blocking)
-        bool hdr = false, gone = false, last = false;
-        while (cur.sx == 0ull) {
-            if (!hdr) hdr = header_known();
-            if (hdr && ot >= p.hdr->out_tiles) {
-                gone = true;   // the stream ends before this tile
-                break;
+        // ---- resolve the tile (thread 0, blocking)
+        if (tid == 0) {
+            Resolved r;
+            r.flags = 0;
+            bool hdr = false;
+            while (cur.sx == 0ull) {
+                if (!hdr) hdr = header_known();
+                if (hdr && ot >= p.hdr->out_tiles) {
+                    r.flags = 1;   // the stream ends before this tile
+                    break;
+                }
+                __nanosleep(128);   // polite polling, see scan_body
+                peek(ot, cur);
             }
-            __nanosleep(128);   // polite polling, see scan_body
-            peek(ot, cur);
-        }
-        if (gone) break;
-        while (cur.ex == 0ull) {
-            if (!hdr) hdr = header_known();
-            if (hdr && ot + 1 >= p.hdr->out_tiles) {
-                last = true;   // the stream's last tile: it ends with the last compressed word
-                break;
+            while (r.flags == 0u && cur.ex == 0ull) {
+                if (!hdr) hdr = header_known();
+                if (hdr && ot + 1 >= p.hdr->out_tiles) {
+                    r.flags = 2;   // the stream's last tile: it ends with the last compressed word
+                    break;
+                }
+                __nanosleep(128);
+                peek(ot, cur);
             }
-            __nanosleep(128);
-            peek(ot, cur);
+            if (ot * (uint64_t)EXPAND_TILE_WORDS >= p.out_cap) r.flags = 1;   // no room for this tile (nor any later one)
+            r.ws = cur.sx - 1ull;
+            r.we = (r.flags & 2u) ? p.c_words - 1 : cur.ex - 1ull;
+            r.sy = cur.sy;
+            r.G = ~0ull;                  // only the last tile is cut short by the stream's end
+            r.total_words = p.out_cap;
+            r.first = 0;
+            if (r.flags & 2u) {
+                r.G = p.hdr->groups;
+                if (p.hdr->words < r.total_words) r.total_words = p.hdr->words;
+            }
+            if (!(r.flags & 1u) && r.ws == r.we) r.first = p.in[r.ws];   // a tile inside ONE word is written without decoding
+            s_res[it & 1u] = r;
         }
+        __syncthreads();
+        const Resolved res = s_res[it & 1u];
+        if (res.flags & 1u) break;
+        const bool last = (res.flags & 2u) != 0u;
         const uint64_t w_lo = ot * (uint64_t)EXPAND_TILE_WORDS;
-        if (w_lo >= p.out_cap) break;   // no room for this tile (nor for any later one)
-        const uint64_t ws = cur.sx - 1ull;
-        const uint64_t we = last ? p.c_words - 1 : cur.ex - 1ull;
-        const uint32_t skip = (uint32_t)((ot << TG_SHIFT) - cur.sy);   // groups of word ws that belong to earlier tiles
-        const uint32_t first = (ws == we) ? p.in[ws] : 0u;             // a tile inside ONE word is written without decoding
-        uint64_t G = ~0ull, total_words = p.out_cap;                    // only the last tile is cut short by the stream's end
-        if (last) {
-            G = p.hdr->groups;
-            if (p.hdr->words < total_words) total_words = p.hdr->words;
-        }
-        if (!xpre_ok) first_words(ws, xpre);
+        const uint64_t ws = res.ws, we = res.we;
+        DCHK(ws < p.c_words && we < p.c_words && we >= ws, 4, ((uint64_t)(ws & 0xFFFFFF) << 24) | (we & 0xFFFFFF));
+        DCHK((ot << TG_SHIFT) >= res.sy, 5, ot);
+        const uint32_t skip = (uint32_t)((ot << TG_SHIFT) - res.sy);   // groups of word ws that belong to earlier tiles
+        const uint32_t first = res.first;
+        const uint64_t G = res.G, total_words = res.total_words;
+        if (xpre_ws != ws) first_words(ws, xpre);
 #ifdef WAH_TRACE
         if (p.trace && tid == 0) {
             const uint64_t k = (ot - blockIdx.x) / gridDim.x;
@@ -453,7 +526,6 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 const uint32_t incl = warp_incl_scan(tsum);
                 __syncthreads();   // previous round's s_wsum / list consumed; first round: image cleared
                 if (lane == 31) s_wsum[warp] = incl;
-                if (tid == 0) s_nlist = 0;
                 __syncthreads();
                 int32_t off = running + (int32_t)(incl - tsum);
                 uint32_t round_sum = 0;
@@ -471,39 +543,34 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                         const uint32_t g0 = (uint32_t)off;
                         if (!is_fill(wv)) {   // kernels.cu:351-354, packed at once (kernels.cu:375)
                             const uint32_t bit = 31u * g0, w = bit >> 5, sh = bit & 31u;
+                            DCHK(w < (uint32_t)EXPAND_TILE_WORDS, 1, w);
                             img[w] |= wv << sh;
                             if (sh > 1u) img[w + 1] |= wv >> (32u - sh);
                         } else if (wv & BIT30) {   // one-fill, kernels.cu:337-348
                             uint32_t g1 = g0 + c[i];
                             if (g1 > (uint32_t)EXPAND_TILE_GROUPS) g1 = EXPAND_TILE_GROUPS;
                             const uint32_t b0 = 31u * g0, b1 = 31u * g1;
-                            if (b1 - b0 <= 32u * 48u) {
-                                set_bits(img, b0, b1);
-                            } else {
-                                // long run: its two ragged ends now, the whole words in between warp-wide below
-                                const uint32_t wlo = (b0 + 31u) >> 5, whi = b1 >> 5;
-                                if (b0 & 31u) set_bits(img, b0, wlo << 5);
-                                if (b1 & 31u) set_bits(img, whi << 5, b1);
-                                const uint32_t e = atomicAdd(&s_nlist, 1u);
-                                if (e < (uint32_t)SP_LIST) s_list[e] = make_uint2(wlo, whi);
-                                else for (uint32_t w = wlo; w < whi; w++) img[w] = 0xFFFFFFFFu;
-                            }
+                            DCHK(b1 > b0 && b1 <= 31u * EXPAND_TILE_GROUPS, 2, ((uint64_t)b0 << 24) | b1);
+                            set_bits(img, b0, b1);
                         }
                     }
                     off += (int32_t)c[i];
-                    if (i == 0) __syncthreads();   // even words done before odd words start
-                }
-                __syncthreads();
-                const uint32_t nl = s_nlist < (uint32_t)SP_LIST ? s_nlist : (uint32_t)SP_LIST;
-                for (uint32_t e = warp; e < nl; e += NW) {
-                    const uint2 r = s_list[e];
-                    for (uint32_t w = r.x + lane; w < r.y; w += 32) img[w] = 0xFFFFFFFFu;
+                    __syncthreads();   // even words done before odd words start / before the next round
                 }
                 if (running >= EXPAND_TILE_GROUPS) break;   // uniform: the tile is covered
             }
             fence_async_smem();   // my writes to the image, visible to the bulk copy engine
             __syncthreads();
+            DCHK(w_lo + EXPAND_TILE_WORDS <= p.out_cap, 3, w_lo);
+#ifdef WAH_DBG_NOTMA
+            {
+                const uint4 *src4 = reinterpret_cast<const uint4 *>(img);
+                for (uint32_t i = tid; i < (uint32_t)EXPAND_TILE_WORDS / 4; i += EXPAND_THREADS) st_stream_v4(dst4 + i, src4[i]);
+            }
+            __syncthreads();
+#else
             if (tid == 0) bulk_s2g(dst, (uint32_t)__cvta_generic_to_shared(img), EXPAND_TILE_WORDS * 4u);
+#endif
             continue;
         }
         // the general path below uses both images as scratch: no bulk store may still be reading them

@@ -61,8 +61,9 @@ struct DecodeHeader {
     uint32_t bad_words;     // zero-length fills seen
     uint32_t scan_done;     // scan tiles finished (their `starts` entries are written)
     uint32_t valid;         // groups / words / out_tiles are final
-    uint32_t pad32;
-    uint64_t pad[3];
+    uint32_t agg_count;     // scan tiles of the current round that have published their sum
+    uint64_t agg_base;      // groups before the current round
+    uint64_t pad[2];
 };
 
 struct ScanParams {
@@ -70,7 +71,8 @@ struct ScanParams {
     uint64_t c_words;
     uint32_t n_tiles;        // ceil(c_words / tile_words)
     uint32_t tile_words;     // words per scan tile: a multiple of 4 * SCAN_THREADS (scan_tile_words())
-    uint64_t *desc;          // [n_tiles] zeroed
+    uint64_t *desc;          // [n_tiles] zeroed: tile sums
+    uint64_t *excl;          // [n_tiles] zeroed: tile offsets, written by each round's aggregator
     DecodeHeader *hdr;       // zeroed
     ulonglong2 *starts;      // nullptr (size query) or [max_out_tiles + 1]: {compressed word index, its group offset}
     uint64_t max_out_tiles;

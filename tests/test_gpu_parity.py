@@ -298,3 +298,28 @@ def test_multi_launch_seam(mode):
                 assert np.array_equal(got, want), (name, tiles)
     finally:
         wah.lib.wah_test_set_max_launch_tiles(0)
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("n,density", [(1 << 24, 0.01), (1 << 24, 0.3), ((1 << 23) + 12345, 0.001)])
+def test_large_clustered_round_trip(n, density, mode):
+    """Run-clustered vectors (BASELINE configs[2], scaled down): many output tiles per CTA, long one-runs next to
+    long zero-runs.  Encoder checked against the oracle, decoder by round trip on the device."""
+    x = wah.gen_clustered_device(n, density, 1000.0, 1337)
+    cap = wah.max_compressed_words(n)
+    out = torch.empty(cap, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    ws = wah.Workspace.for_compress(n)
+    wah.compress_device(x, n, out, cap, cnt, ws, mode)
+    c = int(cnt.item())
+    want = orc.compress(to_host(x), mode)
+    assert c == want.size
+    assert np.array_equal(to_host(out[:c]), want)
+    dec = torch.full((n + 32,), -1, dtype=torch.int32, device="cuda")
+    info = torch.zeros(2, dtype=torch.int64, device="cuda")
+    wd = wah.Workspace.for_decompress(c, n + 32)
+    wah.decompress_device(out, c, dec, n + 32, info, wd)
+    words, groups = info.tolist()
+    assert groups == orc.num_groups(n) and words == orc.decoded_words(groups)
+    assert torch.equal(dec[:n], x)
+    assert not bool(dec[n:words].any())

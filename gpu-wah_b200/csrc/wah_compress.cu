@@ -432,6 +432,28 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
         const uint32_t one = p.one;   // 1, opaque to the compiler (see classify_group_rt)
         uint32_t head = 0;   // words this CTA has staged so far (ring position, monotonic, same in every warp)
         uint32_t jd = 0;     // oldest tile of this CTA not yet known to be copied out
+        // An all-literal warp of a dense tile writes its 1024 words straight from the input stage once the tile's
+        // offset is known.  It does not wait for that: the write is deferred until the NEXT tile has been
+        // classified, so the offset's latency is covered (nothing but the stage has to be kept for it).
+        bool pend = false;
+        uint32_t pend_s = 0, pend_q = 0, pend_par = 0;
+        auto flush_pending = [&]() {
+            if (!pend) return;
+            mbar_wait(smem_u32(&sm.pref[pend_q]), pend_par);
+            const uint64_t dstw = sm.meta[pend_q].dst + 1024u * warp;   // every warp of such a tile emits 1024 words... (checked below)
+            const uint32_t room =
+                dstw >= p.out_cap ? 0u : (p.out_cap - dstw >= 1024ull ? 1024u : (uint32_t)(p.out_cap - dstw));
+            uint32_t *dst = p.out + dstw;
+            const uint32_t *wrow = &sm.stage[pend_s][G::PAD_FRONT] + 992u * warp;
+#pragma unroll 8
+            for (uint32_t k = 0; k < 32u; k++) {
+                const uint32_t g = 32u * k + lane;
+                if (g < room) st_stream_u32(dst + g, extract_group(wrow, g));
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sm.empty[pend_s]));
+            pend = false;
+        };
 
         for (uint32_t i = 0; i < n_my; i++) {
             const uint32_t s = i % STAGES, q = i % QDEPTH;
@@ -546,6 +568,7 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
                 }
             }
             if (tid == 0) TRACE(i, 2, clock64());
+            flush_pending();   // the previous tile's deferred words
 
             // compaction of my words into the ring at `origin`: those with warp-relative index in
             // [lo, lo + WARP_RING) when `windowed`, else all of them
@@ -590,6 +613,14 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
                 // ---- too many words for the ring (dense data): wait for the tile's offset and write them here
                 __syncwarp();
                 if (lane == 0) mbar_arrive(smem_u32(&sm.agg[q]));
+                if (all_literal && wprefix == 1024u * warp) {
+                    pend = true;
+                    pend_s = s;
+                    pend_q = q;
+                    pend_par = (i / QDEPTH) & 1u;
+                    if (tid == 0) TRACE(i, 6, clock64());
+                    continue;
+                }
                 while (jd < i) {   // ring drained: my slice of it serves as staging area below
                     mbar_wait(smem_u32(&sm.done[jd % QDEPTH]), (jd / QDEPTH) & 1u);
                     jd++;
@@ -628,6 +659,7 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
             }
             if (tid == 0) TRACE(i, 6, clock64());
         }
+        flush_pending();
     }
 }
 

@@ -481,6 +481,23 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         }
         if (fast) continue;
 
+        if (!last && skip == 0u && we - ws == (uint64_t)EXPAND_TILE_GROUPS && nout == (uint32_t)EXPAND_TILE_WORDS) {
+            // ================= unit path (literal dominated data) =================
+            // 8192 groups from 8192 words: every word is one group (a literal, or a fill of length 1).  A warp
+            // takes 32 rows of 32 words with coalesced loads; output word j of a row needs groups j and j + 1
+            // (kernels.cu:375), i.e. the neighbouring lane's word.  No shared memory, no barrier.
+            const uint32_t *src = p.in + ws + 1024u * warp;
+            uint32_t *o = dst + 992u * warp;
+#pragma unroll 8
+            for (uint32_t k = 0; k < 32u; k++) {
+                const uint32_t x = ld_stream_u32(src + 32u * k + lane);
+                const uint32_t v = is_fill(x) ? ((x & BIT30) ? ONES31 : 0u) : x;
+                const uint32_t nx = __shfl_down_sync(0xffffffffu, v, 1);
+                if (lane < 31u) st_stream_u32(o + 31u * k + lane, (v >> lane) | (nx << (31u - lane)));
+            }
+            continue;
+        }
+
         const uint32_t nw_all = (uint32_t)(we - wa + 1);   // words wa .. we
         if (nw_all <= (uint32_t)SPARSE_MAX_WORDS && nout == (uint32_t)EXPAND_TILE_WORDS) {
             // ================= bit-scatter path (fill dominated data) =================

@@ -195,6 +195,9 @@ def run_b200(args):
     world = int(os.environ.get("WORLD_SIZE", "1"))
     rank = int(os.environ.get("RANK", "0"))
     local_rank = int(os.environ.get("LOCAL_RANK", "0"))
+    # the ranks of one node share its host cores: split them between the ranks' copy threads (host path only)
+    if world > 1 and "WAH_B200_COPY_THREADS" not in os.environ:
+        os.environ["WAH_B200_COPY_THREADS"] = str(max(2, (os.cpu_count() or 16) // world))
     assert torch.cuda.is_available(), "bench.py needs a CUDA device (no CPU fallback)"
     torch.cuda.set_device(local_rank)
     dev = torch.device("cuda", local_rank)

@@ -99,6 +99,42 @@ extern "C" size_t wah_compress_batch_workspace_bytes(uint64_t n_cols, uint64_t w
     return WS_DESC + (size_t)(tiles + 1) * sizeof(uint64_t);
 }
 
+// Tile descriptors carry the number of the launch that wrote them, so the descriptor array is never cleared
+// between calls.  A workspace seen for the first time is cleared once: its content is arbitrary.
+#include <atomic>
+#include <mutex>
+static uint32_t next_epoch()
+{
+    static std::atomic<uint32_t> e{0x5EED0001u};
+    uint32_t v = e.fetch_add(1u);
+    if (v == 0u) v = e.fetch_add(1u);
+    return v;
+}
+// Zero-initialised counters for the decode kernel: a library-owned array of slots per device, one slot per
+// launch in turn.  (The caller's workspace cannot hold them: its content is arbitrary -- allocators recycle
+// memory -- and clearing it would cost a memset node in front of every launch.)
+static int counter_slot(DecodeCounters **slot)
+{
+    constexpr int MAX_DEV = 64, SLOTS = 4096;
+    static std::mutex mu;
+    static DecodeCounters *base[MAX_DEV] = {};
+    static std::atomic<uint32_t> next{0};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= MAX_DEV) return fail(WAH_ERR_INVALID, "device ordinal %d not supported", dev);
+    {
+        std::lock_guard<std::mutex> g(mu);
+        if (!base[dev]) {
+            void *p = nullptr;
+            CUDA_TRY(cudaMalloc(&p, sizeof(DecodeCounters) * SLOTS));
+            CUDA_TRY(cudaMemset(p, 0, sizeof(DecodeCounters) * SLOTS));
+            base[dev] = static_cast<DecodeCounters *>(p);
+        }
+    }
+    *slot = base[dev] + (next.fetch_add(1u) % SLOTS);
+    return WAH_OK;
+}
+
 static int check_mode(int mode)
 {
     if (mode != WAH_BLOCK1024 && mode != WAH_CANONICAL) return fail(WAH_ERR_INVALID, "unknown mode %d", mode);
@@ -152,7 +188,7 @@ extern "C" int wah_compress_batch_device(const uint32_t *d_in, uint64_t n_cols, 
         p.base_in = launch == 0 ? nullptr : slots + (launch & 1);
         p.total_out = slots + ((launch + 1) & 1);
         p.col_offsets = d_col_offsets + c0;
-        CUDA_TRY(cudaMemsetAsync(ws + WS_DESC, 0, (size_t)p.n_tiles * sizeof(uint64_t), stream));
+        p.epoch = next_epoch();
         CUDA_TRY(launch_compress(p, mode, stream));
     }
     return WAH_OK;
@@ -210,7 +246,7 @@ extern "C" int wah_compress_device(const uint32_t *d_in, uint64_t n_words, int m
         p.total_out = last ? d_out_words : slots + ((launch + 1) & 1);
         p.col_offsets = nullptr;
         p.trace = g_trace;
-        CUDA_TRY(cudaMemsetAsync(ws + WS_DESC, 0, (size_t)p.n_tiles * sizeof(uint64_t), stream));
+        p.epoch = next_epoch();
         CUDA_TRY(launch_compress(p, mode, stream));
     }
     return WAH_OK;
@@ -223,7 +259,7 @@ static uint64_t max_out_tiles(uint64_t out_capacity_words) { return ceil_div(out
 static size_t ws_desc_off() { return sizeof(DecodeHeader); }
 static size_t ws_starts_off(uint64_t c_words)
 {
-    size_t o = ws_desc_off() + 2 * (size_t)scan_tiles(c_words) * sizeof(uint64_t);   // tile sums + tile offsets
+    size_t o = ws_desc_off() + 2 * (size_t)scan_tiles(c_words) * sizeof(ulonglong2);   // tile sums + tile offsets
     return (o + 15) & ~(size_t)15;
 }
 
@@ -256,14 +292,14 @@ static int decompress_common(const uint32_t *d_in, uint64_t c_words, uint32_t *d
     sp.tile_words = scan_tile_words(c_words);
     sp.n_tiles = (uint32_t)ceil_div(c_words, sp.tile_words);
     sp.hdr = reinterpret_cast<DecodeHeader *>(ws);
-    sp.desc = reinterpret_cast<uint64_t *>(ws + ws_desc_off());
+    sp.desc = reinterpret_cast<ulonglong2 *>(ws + ws_desc_off());
     sp.excl = sp.desc + scan_tiles(c_words);
+    sp.epoch = next_epoch();
     sp.starts = expand ? reinterpret_cast<ulonglong2 *>(ws + ws_starts_off(c_words)) : nullptr;
     sp.max_out_tiles = expand ? max_out_tiles(out_cap) : 0;
     sp.out_info = d_out_info;
     sp.trace = g_trace;
-    // header, tile descriptors and (their x = 0 means "not recorded yet") the output-tile table
-    CUDA_TRY(cudaMemsetAsync(ws, 0, expand ? need : ws_starts_off(c_words), stream));
+    if (int rc = counter_slot(&sp.ctr)) return rc;
     if (!expand) CUDA_TRY(launch_scan(sp, stream));
     if (expand) {
         ExpandParams ep;
@@ -271,6 +307,7 @@ static int decompress_common(const uint32_t *d_in, uint64_t c_words, uint32_t *d
         ep.in = d_in;
         ep.c_words = c_words;
         ep.hdr = sp.hdr;
+        ep.epoch = sp.epoch;
         ep.starts = sp.starts;
         ep.max_out_tiles = sp.max_out_tiles;
         ep.out = d_out;

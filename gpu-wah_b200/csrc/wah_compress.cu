@@ -36,20 +36,22 @@ namespace wahb200 {
 
 namespace {
 
-// ---- tile descriptor: valid:1 | no_tail:1 | open:30 | count:31 (zero = not published yet) -----
-//   count    words the tile emits
+// ---- tile descriptor: epoch:32 | (unused) | no_tail:1 | open:14 | count:14 ----------------------------
+//   count    words the tile emits (0 .. 8192)
 //   no_tail  the tile holds no run end: its groups all belong to one run that is still open
-//   open     groups after the tile's last run end (the whole tile if no_tail)
+//   open     groups after the tile's last run end (the whole tile, 8192, if no_tail)
+//   epoch    the launch that wrote it.  Every launch gets a fresh number from the host, so whatever an earlier
+//            launch (or nobody) left in the workspace reads as "not published yet": no memset per call.
 // Written once, by the tile's workers, as soon as the tile is classified.
 
-__device__ __forceinline__ uint64_t desc_pack(uint32_t no_tail, uint32_t open, uint32_t count)
+__device__ __forceinline__ uint64_t desc_pack(uint32_t epoch, uint32_t no_tail, uint32_t open, uint32_t count)
 {
-    return (1ull << 63) | ((uint64_t)no_tail << 61) | ((uint64_t)open << 31) | (uint64_t)count;
+    return ((uint64_t)epoch << 32) | (no_tail << 28) | (open << 14) | count;
 }
-__device__ __forceinline__ bool desc_empty(uint64_t d) { return (d >> 63) == 0ull; }
-__device__ __forceinline__ uint32_t desc_no_tail(uint64_t d) { return (uint32_t)(d >> 61) & 1u; }
-__device__ __forceinline__ uint32_t desc_open(uint64_t d) { return (uint32_t)(d >> 31) & MAX_FILL; }
-__device__ __forceinline__ uint32_t desc_count(uint64_t d) { return (uint32_t)d & 0x7FFFFFFFu; }
+__device__ __forceinline__ bool desc_empty(uint64_t d, uint32_t epoch) { return (uint32_t)(d >> 32) != epoch; }
+__device__ __forceinline__ uint32_t desc_no_tail(uint64_t d) { return ((uint32_t)d >> 28) & 1u; }
+__device__ __forceinline__ uint32_t desc_open(uint64_t d) { return ((uint32_t)d >> 14) & 0x3FFFu; }
+__device__ __forceinline__ uint32_t desc_count(uint64_t d) { return (uint32_t)d & 0x3FFFu; }
 
 // ---- mbarrier / bulk-copy primitives (PTX) -----------------------------------------
 
@@ -124,6 +126,7 @@ struct Geom {
     static constexpr int THREADS = (NWORK + 3) * 32;
     static constexpr int RING_WORDS = NWORK * WARP_RING;      // power of two for NWORK = 4, 8
     static_assert((RING_WORDS & (RING_WORDS - 1)) == 0, "ring size must be a power of two");
+    static_assert(TILE_GROUPS <= 8192, "descriptor fields are 14 bits");
     static_assert(TILE_WORDS == COMPRESS_TILE_WORDS, "the C ABI sizes its descriptor array from COMPRESS_TILE_WORDS");
 };
 
@@ -288,7 +291,7 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
 #pragma unroll
             for (int r = 0; r < LBN; r++) {
                 const int64_t lk = hi - (int64_t)lane - 32 * r;
-                d[r] = lk >= lo ? ld_relaxed_u64(p.desc + lk) : 0ull;
+                d[r] = lk >= lo ? ld_relaxed_u64(p.desc + lk) : ~((uint64_t)p.epoch << 32);
             }
         };
         if (n_my > 0) request((int64_t)blockIdx.x - 1, 0);
@@ -323,8 +326,8 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
                     for (int r = 0; r < LBN; r++) {
                         const int64_t lk = hi - (int64_t)lane - 32 * r;
                         const bool in = lk >= lo;
-                        while (__any_sync(0xffffffffu, in && desc_empty(d[r]))) {
-                            if (in && desc_empty(d[r])) d[r] = ld_relaxed_u64(p.desc + lk);
+                        while (__any_sync(0xffffffffu, in && desc_empty(d[r], p.epoch))) {
+                            if (in && desc_empty(d[r], p.epoch)) d[r] = ld_relaxed_u64(p.desc + lk);
 #ifdef WAH_TRACE
                             polls++;
 #endif
@@ -559,7 +562,7 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
                     tile_has = 1;
                 }
                 if (lane == 0) {
-                    st_relaxed_u64(p.desc + sm.info[s].tile, desc_pack(tile_has ^ 1u, tile_open, tile_cnt));
+                    st_relaxed_u64(p.desc + sm.info[s].tile, desc_pack(p.epoch, tile_has ^ 1u, tile_open, tile_cnt));
                     mt.tile_cnt = tile_cnt;
                     mt.tile_open = tile_open;
                     mt.tile_has = tile_has;

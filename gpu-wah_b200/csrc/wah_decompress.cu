@@ -28,8 +28,20 @@ namespace wahb200 {
 
 namespace {
 
-constexpr uint64_t ST_EMPTY = 0, ST_AGG = 1, ST_INCL = 2;
-constexpr uint64_t VALUE_MASK = (1ull << 62) - 1ull;
+// Everything the CTAs exchange through the workspace is tagged with the launch's epoch (a number the host never
+// repeats), so the workspace is not cleared between calls: what an earlier launch left behind reads as "not
+// published yet".  A tile sum / tile offset is a 16-byte cell {value, epoch}, written and read as one access.
+__device__ __forceinline__ void cell_store(ulonglong2 *c, uint64_t v, uint32_t epoch)
+{
+    asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(c), "l"(v), "l"((uint64_t)epoch) : "memory");
+}
+__device__ __forceinline__ bool cell_load(const ulonglong2 *c, uint32_t epoch, uint64_t &v)
+{
+    uint64_t e;
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(v), "=l"(e) : "l"(c) : "memory");
+    return e == (uint64_t)epoch;
+}
+constexpr uint64_t ENTRY_MASK = (1ull << 48) - 1ull;   // output-tile table: low 48 bits value, high 16 bits half of the epoch
 constexpr uint32_t TG_SHIFT = 13;
 static_assert((1u << TG_SHIFT) == (uint32_t)EXPAND_TILE_GROUPS, "output tile must be 8192 groups");
 
@@ -46,9 +58,19 @@ constexpr int SCAN_MAXV = 8;   // 128-bit loads per lane and tile
 
 // An entry of the output-tile table is read by other CTAs while the scan is still running: x (word index + 1,
 // 0 = not recorded) and y (the word's group offset) must appear together -- one 16-byte store, one 16-byte load.
-__device__ __forceinline__ void store_entry(ulonglong2 *e, uint64_t x, uint64_t y)
+__device__ __forceinline__ void store_entry(ulonglong2 *e, uint64_t x, uint64_t y, uint32_t epoch)
 {
+    x |= (uint64_t)(epoch & 0xFFFFu) << 48;
+    y |= (uint64_t)(epoch >> 16) << 48;
     asm volatile("st.volatile.global.v2.u64 [%0], {%1, %2};" ::"l"(e), "l"(x), "l"(y) : "memory");
+}
+// x (word index + 1) and y (group offset) of an entry, or x = 0 if this launch has not written it yet
+__device__ __forceinline__ void load_entry(const ulonglong2 *e, uint32_t epoch, uint64_t &x, uint64_t &y)
+{
+    asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(x), "=l"(y) : "l"(e) : "memory");
+    const bool ok = (uint32_t)(x >> 48) == (epoch & 0xFFFFu) && (uint32_t)(y >> 48) == (epoch >> 16);
+    x = ok ? (x & ENTRY_MASK) : 0ull;
+    y &= ENTRY_MASK;
 }
 constexpr int SCAN_HEAVY = 64;  // long fills of a tile queued for the CTA-wide boundary writer
 
@@ -56,8 +78,8 @@ constexpr int SCAN_HEAVY = 64;  // long fills of a tile queued for the CTA-wide 
 // k * 8192 that falls into one of them (off <= k * 8192 < off + cnt).  A word that covers up to 4 boundaries
 // records them itself; a long fill is queued for the whole CTA.  Out of line: this runs for under 1 % of the
 // words and would otherwise be replicated 8 times in straight-line code that executes once per launch.
-__device__ __noinline__ void record_boundaries(ulonglong2 *starts, uint64_t k_limit, uint64_t wi, uint64_t off, uint4 cnt,
-                                               ulonglong4 *s_heavy, uint32_t *s_nheavy)
+__device__ __noinline__ void record_boundaries(ulonglong2 *starts, uint32_t epoch, uint64_t k_limit, uint64_t wi, uint64_t off,
+                                               uint4 cnt, ulonglong4 *s_heavy, uint32_t *s_nheavy)
 {
     constexpr uint64_t TGM = (uint64_t)EXPAND_TILE_GROUPS - 1ull;
     const uint32_t c[4] = {cnt.x, cnt.y, cnt.z, cnt.w};
@@ -75,7 +97,7 @@ __device__ __noinline__ void record_boundaries(ulonglong2 *starts, uint64_t k_li
                     k_end = k_first;   // queued
                 }
             }
-            for (uint64_t k = k_first; k < k_end; k++) store_entry(starts + k, wi + j + 1ull, off);
+            for (uint64_t k = k_first; k < k_end; k++) store_entry(starts + k, wi + j + 1ull, off, epoch);
         }
         off += c[j];
     }
@@ -133,7 +155,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
         }
         if (__any_sync(0xffffffffu, bad != 0u)) {
             bad = warp_sum(bad);
-            if (lane == 0) atomicAdd(&p.hdr->bad_words, bad);
+            if (lane == 0) atomicAdd(&p.ctr->bad_acc, bad);
         }
         const uint64_t wtotal = warp_sum_u64(lsum);
         __syncthreads();   // the previous tile's partial sums have been consumed
@@ -146,7 +168,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
             if (k < (int)warp) wprefix += sv;
             tile_sum += sv;
         }
-        if (tid == 0) st_relaxed_u64(p.desc + tile, (ST_AGG << 62) | tile_sum);
+        if (tid == 0) cell_store(p.desc + tile, tile_sum, p.epoch);
 #ifdef WAH_TRACE
         if (p.trace && tid == 0 && first_tile) p.trace[(uint64_t)blockIdx.x * 64u + 4u] = (uint64_t)clock64();
 #endif
@@ -161,7 +183,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
             const uint32_t m = p.n_tiles - round0 < stride ? p.n_tiles - round0 : stride;   // tiles in it
             if (tid == 0) {
                 __threadfence();   // my sum is visible before my arrival is
-                s_flag = atomicAdd(&p.hdr->agg_count, 1u) == m - 1u;
+                s_flag = atomicAdd(&p.ctr->agg_count, 1u) == m - 1u;
                 s_nheavy = 0;
             }
             __syncthreads();
@@ -171,11 +193,15 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
                 uint64_t mine = 0;
                 for (uint32_t j = 0; j < per; j++) {
                     const uint32_t k = tid * per + j;
-                    if (k < m) mine += ld_relaxed_u64(p.desc + round0 + k) & VALUE_MASK;
+                    if (k < m) {
+                        uint64_t v;
+                        cell_load(p.desc + round0 + k, p.epoch, v);   // published: its CTA has arrived
+                        mine += v;
+                    }
                 }
                 const uint64_t incl = warp_incl_scan_u64(mine);
                 if (lane == 31) s_lb_sum[warp] = incl;
-                const uint64_t base0 = *reinterpret_cast<volatile uint64_t *>(&p.hdr->agg_base);
+                const uint64_t base0 = *reinterpret_cast<volatile uint64_t *>(&p.ctr->agg_base);
                 __syncthreads();
                 uint64_t before = base0, total = 0;
 #pragma unroll
@@ -188,26 +214,30 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
                 // The counter is reset BEFORE any offset is published: a CTA that has read its offset may arrive
                 // for the next round at once.
                 if (tid == 0) {
-                    p.hdr->agg_count = 0;
-                    *reinterpret_cast<volatile uint64_t *>(&p.hdr->agg_base) = base0 + total;
+                    const bool final_round = round0 + m == p.n_tiles;   // leave the header clean for the next launch
+                    p.ctr->agg_count = 0;
+                    *reinterpret_cast<volatile uint64_t *>(&p.ctr->agg_base) = final_round ? 0ull : base0 + total;
+                    if (final_round) {
+                        // every CTA added its malformed-word count before it arrived for its last tile
+                        p.hdr->bad_words = atomicExch(&p.ctr->bad_acc, 0u);
+                    }
                     __threadfence();
                 }
                 __syncthreads();
                 for (uint32_t j = 0; j < per; j++) {
                     const uint32_t k = tid * per + j;
                     if (k < m) {
-                        st_relaxed_u64(p.excl + round0 + k, (ST_INCL << 62) | before);
-                        before += ld_relaxed_u64(p.desc + round0 + k) & VALUE_MASK;
+                        cell_store(p.excl + round0 + k, before, p.epoch);
+                        uint64_t v;
+                        cell_load(p.desc + round0 + k, p.epoch, v);
+                        before += v;
                     }
                 }
             }
             if (tid == 0) {
-                uint64_t d = ld_relaxed_u64(p.excl + tile);
-                while ((d >> 62) == ST_EMPTY) {
-                    __nanosleep(64);
-                    d = ld_relaxed_u64(p.excl + tile);
-                }
-                s_lb_sum[0] = d & VALUE_MASK;
+                uint64_t v;
+                while (!cell_load(p.excl + tile, p.epoch, v)) __nanosleep(64);
+                s_lb_sum[0] = v;
             }
             __syncthreads();
             excl = s_lb_sum[0];
@@ -228,7 +258,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
                 p.out_info[1] = G;
             }
             __threadfence();
-            *reinterpret_cast<volatile uint32_t *>(&p.hdr->valid) = 1u;   // the expand phase polls this
+            *reinterpret_cast<volatile uint32_t *>(&p.hdr->valid) = p.epoch;   // the expand phase polls this
         }
 
         // ---- pass 2: which compressed word covers each output-tile boundary k * 8192 ?
@@ -247,7 +277,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
                     const uint64_t off = row_base + incl - sl;
                     const uint64_t wi = seg_begin + (uint64_t)(v * 32 + (int)lane) * 4u;
                     if (((off + TGM) >> TG_SHIFT) != ((off + sl + TGM) >> TG_SHIFT))   // rare: a boundary in my 4 words
-                        record_boundaries(p.starts, k_limit, wi, off, make_uint4(c0, c1, c2, c3), s_heavy, &s_nheavy);
+                        record_boundaries(p.starts, p.epoch, k_limit, wi, off, make_uint4(c0, c1, c2, c3), s_heavy, &s_nheavy);
                     row_base += __shfl_sync(0xffffffffu, incl, 31);
                 }
             }
@@ -255,7 +285,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
             const uint32_t nh = s_nheavy < (uint32_t)SCAN_HEAVY ? s_nheavy : (uint32_t)SCAN_HEAVY;
             for (uint32_t e = 0; e < nh; e++) {
                 const ulonglong4 h = s_heavy[e];
-                for (uint64_t k = h.z + tid; k < h.w; k += SCAN_THREADS) store_entry(p.starts + k, h.x + 1ull, h.y);
+                for (uint64_t k = h.z + tid; k < h.w; k += SCAN_THREADS) store_entry(p.starts + k, h.x + 1ull, h.y, p.epoch);
             }
         }
         __syncthreads();   // partial sums and the heavy queue are rewritten by the next tile
@@ -361,12 +391,13 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         r.sx = r.sy = r.ex = 0;
         if (ot_ < p.max_out_tiles) {
             // one 16-byte access: x and y of an entry are written (and read) together
-            asm volatile("ld.volatile.global.v2.u64 {%0, %1}, [%2];" : "=l"(r.sx), "=l"(r.sy) : "l"(p.starts + ot_) : "memory");
-            r.ex = ld_relaxed_u64(reinterpret_cast<const uint64_t *>(p.starts + ot_ + 1));
+            load_entry(p.starts + ot_, p.epoch, r.sx, r.sy);
+            uint64_t ey;
+            load_entry(p.starts + ot_ + 1, p.epoch, r.ex, ey);
         }
     };
     auto header_known = [&]() -> bool {
-        if (*reinterpret_cast<const volatile uint32_t *>(&p.hdr->valid) == 0u) return false;
+        if (*reinterpret_cast<const volatile uint32_t *>(&p.hdr->valid) != p.epoch) return false;
         __threadfence();
         return true;
     };

@@ -27,7 +27,8 @@ struct CompressParams {
     const int32_t *lead_adjust;  // nullptr or device int: added to the launch's first word (launch_seam)
     uint32_t *out;
     uint64_t out_cap;
-    uint64_t *desc;          // [n_tiles] zeroed
+    uint64_t *desc;          // [n_tiles] tile descriptors; need not be cleared (tagged with `epoch`)
+    uint32_t epoch;          // unique per launch (never repeated within 2^32 launches of this process)
     const uint64_t *base_in; // words already in `out` (nullptr = 0)
     uint64_t *total_out;     // receives base + words emitted by this launch
     uint64_t *col_offsets;   // nullptr or [n_cols + 1] for this launch's columns
@@ -58,10 +59,16 @@ struct DecodeHeader {
     uint64_t groups;        // G
     uint64_t words;         // ceil(31 G / 32)
     uint64_t out_tiles;     // ceil(G / EXPAND_TILE_GROUPS)
-    uint32_t bad_words;     // zero-length fills seen
-    uint32_t scan_done;     // scan tiles finished (their `starts` entries are written)
-    uint32_t valid;         // groups / words / out_tiles are final
+    uint32_t bad_words;     // zero-length fills seen (written in the last round)
+    uint32_t valid;         // == the launch's epoch once groups / words / out_tiles are final
+    uint64_t pad[4];
+};
+
+// Counters that must be 0 when a launch starts.  They live in a slot of a small library-owned array (never in the
+// caller's workspace, whose content is arbitrary) and every launch leaves its slot zeroed again.
+struct DecodeCounters {
     uint32_t agg_count;     // scan tiles of the current round that have published their sum
+    uint32_t bad_acc;       // zero-length fills seen so far
     uint64_t agg_base;      // groups before the current round
     uint64_t pad[2];
 };
@@ -71,9 +78,11 @@ struct ScanParams {
     uint64_t c_words;
     uint32_t n_tiles;        // ceil(c_words / tile_words)
     uint32_t tile_words;     // words per scan tile: a multiple of 4 * SCAN_THREADS (scan_tile_words())
-    uint64_t *desc;          // [n_tiles] zeroed: tile sums
-    uint64_t *excl;          // [n_tiles] zeroed: tile offsets, written by each round's aggregator
-    DecodeHeader *hdr;       // zeroed
+    ulonglong2 *desc;        // [n_tiles] tile sums {value, epoch}
+    ulonglong2 *excl;        // [n_tiles] tile offsets {value, epoch}, written by each round's aggregator
+    uint32_t epoch;          // unique per launch: whatever else is in the workspace reads as unpublished
+    DecodeHeader *hdr;       // written by the launch, never read before that
+    DecodeCounters *ctr;     // zero at launch, zero again when the launch is over
     ulonglong2 *starts;      // nullptr (size query) or [max_out_tiles + 1]: {compressed word index, its group offset}
     uint64_t max_out_tiles;
     uint64_t *out_info;      // nullptr or device u64[2] {words, groups}
@@ -84,6 +93,7 @@ struct ExpandParams {
     const uint32_t *in;
     uint64_t c_words;
     const DecodeHeader *hdr;
+    uint32_t epoch;
     const ulonglong2 *starts;
     uint64_t max_out_tiles;
     uint32_t *out;

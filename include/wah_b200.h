@@ -63,7 +63,9 @@ uint64_t wah_decoded_words(uint64_t groups);
  *   d_in            n_words input words, 16-byte aligned
  *   d_out           receives the compressed words; writes past out_capacity_words are dropped
  *   d_out_words     device u64, receives c (the true length even if it exceeds the capacity)
- *   d_workspace     wah_compress_workspace_bytes(n_words) bytes, 16-byte aligned               */
+ *   d_workspace     wah_compress_workspace_bytes(n_words) bytes, 16-byte aligned.  Scratch: its content
+ *                   need not be initialised or preserved (what the kernels exchange through it is tagged
+ *                   with a per-launch number), but it must not be shared by launches that may overlap.  */
 size_t wah_compress_workspace_bytes(uint64_t n_words);
 int wah_compress_device(const uint32_t *d_in, uint64_t n_words, int mode,
                         uint32_t *d_out, uint64_t out_capacity_words, uint64_t *d_out_words,
@@ -83,7 +85,7 @@ int wah_compress_batch_device(const uint32_t *d_in, uint64_t n_cols, uint64_t wo
  *   d_in            c_words compressed words, 16-byte aligned
  *   d_out           receives ceil(31 G / 32) words (16-byte aligned); words past the capacity are dropped
  *   d_out_info      device u64[2]: [0] = decoded words, [1] = decoded groups G
- *   d_workspace     wah_decompress_workspace_bytes(c_words, out_capacity_words) bytes          */
+ *   d_workspace     wah_decompress_workspace_bytes(c_words, out_capacity_words) bytes; scratch as above   */
 size_t wah_decompress_workspace_bytes(uint64_t c_words, uint64_t out_capacity_words);
 int wah_decompress_device(const uint32_t *d_in, uint64_t c_words,
                           uint32_t *d_out, uint64_t out_capacity_words, uint64_t *d_out_info,

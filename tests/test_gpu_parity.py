@@ -323,3 +323,30 @@ def test_large_clustered_round_trip(n, density, mode):
     assert groups == orc.num_groups(n) and words == orc.decoded_words(groups)
     assert torch.equal(dec[:n], x)
     assert not bool(dec[n:words].any())
+
+
+def _random_stream(rng, n_words, p_fill, max_count, p_one):
+    """An arbitrary valid WAH stream (not necessarily one an encoder would produce)."""
+    lit = rng.integers(1, 0x7FFFFFFF, size=n_words, dtype=np.int64).astype(np.uint32)   # never 0 / all ones
+    is_fill = rng.random(n_words) < p_fill
+    cnt = np.minimum(rng.geometric(1.0 / max(max_count / 4.0, 1.0), size=n_words), max_count).astype(np.uint32)
+    one = (rng.random(n_words) < p_one).astype(np.uint32)
+    return np.where(is_fill, np.uint32(0x80000000) | (one << 30) | cnt, lit).astype(np.uint32)
+
+
+@pytest.mark.parametrize("seed,n_words,p_fill,max_count,p_one", [
+    (1, 200_000, 0.0, 1, 0.0),          # literals only: unit path
+    (2, 200_000, 0.02, 1, 0.5),         # literals with length-1 fills: unit path with fills
+    (3, 150_000, 0.5, 40, 0.5),         # short fills of both kinds: bit scatter, many words per tile
+    (4, 60_000, 0.7, 3000, 0.5),        # long fills, long one-runs
+    (5, 5_000, 0.9, 200_000, 0.3),      # fills spanning many output tiles (constant tiles, queued boundaries)
+    (6, 40_000, 0.3, 9000, 0.9),        # one-runs around the tile size
+    (7, 300_000, 0.1, 8, 0.2),          # more than 4096 words per tile but not unit: general path
+])
+def test_decode_random_valid_streams(seed, n_words, p_fill, max_count, p_one):
+    rng = np.random.default_rng(seed)
+    cw = _random_stream(rng, n_words, p_fill, max_count, p_one)
+    want = orc.decompress(cw)
+    got, info = gpu_decompress(cw)
+    assert info == [want.size, orc.decoded_groups(cw)]
+    assert np.array_equal(got, want)

@@ -1,11 +1,11 @@
-"""Executable model of the CUDA kernels' tile algorithms (pure Python, tiny inputs only).
+"""Executable model of the arithmetic inside the CUDA kernels (pure Python, tiny inputs only).
 
-There is no GPU on the development box, so the index arithmetic of
-``gpu-wah_b200/csrc/wah_compress.cu`` and ``wah_decompress.cu`` -- tail masks, the
-open-run carry through thread / warp / tile scans, the look-back monoid over packed
-descriptors, output-tile boundary bookkeeping, the binary search + walk of the expander --
-is restated here step for step and checked against the oracle in ``test_kernel_model.py``.
-This is TEST INFRASTRUCTURE: it is not a fallback and nothing in the product imports it.
+There is no GPU on the development box, so the index arithmetic of ``gpu-wah_b200/csrc/wah_compress.cu`` and
+``wah_decompress.cu`` -- tail masks, the open-run carry through thread / warp / tile aggregates, the aggregate
+monoid over packed tile descriptors (the kernel now sums the descriptors between a CTA's consecutive tiles; the
+monoid and its result are the same as for the look-back walk modelled here), the seam between chained launches,
+output-tile boundary bookkeeping, the word-centric expansion -- is restated here and checked against the oracle in
+``test_kernel_model.py``.  This is TEST INFRASTRUCTURE: it is not a fallback and nothing in the product imports it.
 """
 from __future__ import annotations
 
@@ -97,9 +97,37 @@ def lookback(desc, tile, block_mode, t_in_col, rng, threads=256):
     return excl, carry
 
 
+def seam_model(seg, groups, out):
+    """wah_lead_probe_kernel + wah_seam_kernel (wah_compress.cu): how the leading run of the next launch's
+    segment joins the last word written so far.  May take that word back (out.pop()) or saturate it; returns
+    the amount the next launch adds to its first word."""
+    base, adj = len(out), 0
+    if base > 0 and seg:
+        typ = seg[0] & 1
+        pattern = M32 if typ else 0
+        bits = 32 * len(seg)
+        for i, w in enumerate(seg):
+            x = (w ^ pattern) & M32
+            if x:
+                bits = 32 * i + ffs(x) - 1
+                break
+        lead = groups if (bits == 32 * len(seg) and typ == 0) else bits // 31
+        pw = out[base - 1]
+        if lead > 0 and (pw & BIT31) and ((pw >> 30) & 1) == typ:
+            c1 = pw & MAX_FILL
+            if c1 + lead <= MAX_FILL:
+                out.pop()
+                adj = c1
+            else:
+                out[base - 1] = fill_word(typ, MAX_FILL)
+                adj = c1 - MAX_FILL
+    return adj
+
+
 def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0):
     """cols: list of equally long word lists (one launch).  mode 0 = BLOCK1024, 1 = CANONICAL.
-    merge_prev_words: existing output to append to (CANONICAL append).  Returns (out, col_offsets)."""
+    merge_prev_words: output of the earlier launches of the same stream (chained launches).
+    Returns (out, col_offsets)."""
     rng = random.Random(seed)
     block_mode = mode == 0
     NW = threads // 32
@@ -109,8 +137,8 @@ def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0):
     tiles_per_col = (n_words + TW - 1) // TW
     n_tiles = tiles_per_col * len(cols)
     out = list(merge_prev_words) if merge_prev_words else []
+    lead_adjust = seam_model(cols[0], groups, out) if (merge_prev_words is not None and mode == 1) else 0
     base = len(out)
-    merge_prev = merge_prev_words is not None and mode == 1
     desc = [None] * n_tiles
     col_offsets = [0] * (len(cols) + 1)
 
@@ -187,10 +215,8 @@ def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0):
         if t == tiles_per_col - 1:
             tile_open, tile_has = 0, 1
         excl = carry = 0
-        defer = tile == 0 and merge_prev
         if tile == 0:
-            if not defer:
-                desc[0] = (None, (ST_INCL, 0, tile_open, tile_cnt))
+            desc[0] = (None, (ST_INCL, 0, tile_open, tile_cnt))
         else:
             agg = (ST_AGG, tile_has ^ 1, tile_open, tile_cnt)
             excl, carry = lookback(desc, tile, block_mode, t, rng, threads)
@@ -256,19 +282,6 @@ def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0):
                         off += 1
                         prev, extra = j, 0
         drop = 0
-        if tile == 0 and merge_prev:
-            if base > 0 and tile_cnt > 0:
-                pw, fw = out[base - 1], s_out[0]
-                if (pw & BIT31) and (fw & BIT31) and ((pw ^ fw) & BIT30) == 0:
-                    total = (pw & MAX_FILL) + (fw & MAX_FILL)
-                    ty = (fw >> 30) & 1
-                    if total <= MAX_FILL:
-                        out[base - 1] = fill_word(ty, total)
-                        drop = 1
-                    else:
-                        out[base - 1] = fill_word(ty, MAX_FILL)
-                        s_out[0] = fill_word(ty, total - MAX_FILL)
-            desc[0] = (None, (ST_INCL, 0, tile_open, tile_cnt - drop))
         dst0 = base + s_excl
         if t == 0:
             col_offsets[col] = dst0
@@ -279,7 +292,7 @@ def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0):
             out.extend([None] * (need - len(out)))
         for i in range(drop, tile_cnt):
             assert s_out[i] is not None, (tile, i)
-            out[dst0 + i - drop] = s_out[i]
+            out[dst0 + i - drop] = s_out[i] + (lead_adjust if s_excl + i == 0 else 0)   # the launch's first word
     assert all(w is not None for w in out)
     return out, col_offsets
 

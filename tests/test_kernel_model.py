@@ -48,7 +48,7 @@ def test_compress_model_batch(mode):
 
 
 def test_compress_model_append_merges_seam():
-    # CANONICAL stream compressed as two launches: the second folds its first run into the last word
+    # CANONICAL stream compressed as two launches: the second one's leading run joins the last word (launch_seam)
     a = np.zeros(992 * 3, dtype=np.uint32)
     b = np.zeros(992 * 2, dtype=np.uint32)
     b[-1] = 5
@@ -61,6 +61,17 @@ def test_compress_model_append_merges_seam():
     first, _ = km.compress_model([a2.tolist()], 1)
     both, _ = km.compress_model([b.tolist()], 1, merge_prev_words=first)
     assert np.array_equal(np.array(both, dtype=np.uint32), orc.compress(np.concatenate([a2, b]), 1))
+    # a leading run that spans the whole second segment, then a third launch continues it
+    z = np.zeros(992 * 2, dtype=np.uint32)
+    first, _ = km.compress_model([a.tolist()], 1)
+    second, _ = km.compress_model([z.tolist()], 1, merge_prev_words=first)
+    third, _ = km.compress_model([b.tolist()], 1, merge_prev_words=second)
+    assert np.array_equal(np.array(third, dtype=np.uint32), orc.compress(np.concatenate([a, z, b]), 1))
+    # the merged run would overflow the 30-bit counter: the previous word is saturated instead
+    prev = [km.fill_word(0, km.MAX_FILL - 100)]
+    both, _ = km.compress_model([b.tolist()], 1, merge_prev_words=prev)
+    lead = (32 * (992 * 2 - 1)) // 31
+    assert both[:2] == [km.fill_word(0, km.MAX_FILL), km.fill_word(0, lead - 100)]
 
 
 def _streams():

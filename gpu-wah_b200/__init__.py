@@ -17,6 +17,7 @@ from .wah import (  # noqa: F401
     compress_device,
     decoded_words,
     decompress,
+    decompress_batch_device,
     decompress_device,
     decoded_size_device,
     gen_clustered_device,
@@ -32,7 +33,7 @@ from . import mgpu  # noqa: F401
 
 __all__ = [
     "WAH_BLOCK1024", "WAH_CANONICAL", "WahError", "Workspace", "compress", "decompress",
-    "compress_device", "compress_batch_device", "decompress_device", "decoded_size_device",
+    "compress_device", "compress_batch_device", "decompress_device", "decompress_batch_device", "decoded_size_device",
     "num_groups", "max_compressed_words", "decoded_words", "gen_uniform_device",
     "gen_clustered_device", "shard_record_device", "stitch_plan", "lib", "lib_path", "mgpu",
 ]

@@ -270,7 +270,7 @@ extern "C" size_t wah_decompress_workspace_bytes(uint64_t c_words, uint64_t out_
 
 static int decompress_common(const uint32_t *d_in, uint64_t c_words, uint32_t *d_out, uint64_t out_cap,
                              uint64_t *d_out_info, void *d_workspace, size_t workspace_bytes, bool expand,
-                             cudaStream_t stream)
+                             cudaStream_t stream, uint32_t skip_words = 0)
 {
     if (!d_out_info) return fail(WAH_ERR_INVALID, "d_out_info is null");
     if (c_words == 0) {
@@ -289,6 +289,7 @@ static int decompress_common(const uint32_t *d_in, uint64_t c_words, uint32_t *d
     memset(&sp, 0, sizeof(sp));
     sp.in = d_in;
     sp.c_words = c_words;
+    sp.skip_words = skip_words;
     sp.tile_words = scan_tile_words(c_words);
     sp.n_tiles = (uint32_t)ceil_div(c_words, sp.tile_words);
     sp.hdr = reinterpret_cast<DecodeHeader *>(ws);
@@ -331,6 +332,37 @@ extern "C" int wah_decoded_size_device(const uint32_t *d_in, uint64_t c_words, u
 {
     return decompress_common(d_in, c_words, nullptr, 0, d_out_info, d_workspace, workspace_bytes, false,
                              (cudaStream_t)stream);
+}
+
+// bitmap-index batch: column j's stream is d_in[h_col_offsets[j] .. h_col_offsets[j+1]) (the layout
+// wah_compress_batch_device writes), decoded to d_out + j * out_col_stride_words.  One launch per column on
+// `stream`; the workspace is reused from column to column.
+extern "C" size_t wah_decompress_batch_workspace_bytes(uint64_t max_col_c_words, uint64_t out_col_capacity_words)
+{
+    return wah_decompress_workspace_bytes(max_col_c_words + 3, out_col_capacity_words);
+}
+
+extern "C" int wah_decompress_batch_device(const uint32_t *d_in, const uint64_t *h_col_offsets, uint64_t n_cols,
+                                           uint32_t *d_out, uint64_t out_col_stride_words,
+                                           uint64_t out_col_capacity_words, uint64_t *d_out_info, void *d_workspace,
+                                           size_t workspace_bytes, void *stream)
+{
+    if (n_cols == 0) return WAH_OK;
+    if (!h_col_offsets || !d_out_info) return fail(WAH_ERR_INVALID, "null argument");
+    if (!aligned16(d_in)) return fail(WAH_ERR_INVALID, "device buffers must be 16-byte aligned");
+    if (out_col_stride_words % 4 != 0) return fail(WAH_ERR_INVALID, "out_col_stride_words must be a multiple of 4");
+    if (out_col_capacity_words > out_col_stride_words && n_cols > 1)
+        return fail(WAH_ERR_INVALID, "out_col_capacity_words > out_col_stride_words");
+    for (uint64_t j = 0; j < n_cols; j++) {
+        const uint64_t a = h_col_offsets[j], b = h_col_offsets[j + 1];
+        if (b < a) return fail(WAH_ERR_INVALID, "column offsets must not decrease");
+        const uint32_t skip = (uint32_t)(a & 3ull);
+        const int rc = decompress_common(d_in + (a - skip), b - a ? (b - a) + skip : 0, d_out + j * out_col_stride_words,
+                                         out_col_capacity_words, d_out_info + 2 * j, d_workspace, workspace_bytes, true,
+                                         (cudaStream_t)stream, skip);
+        if (rc) return rc;
+    }
+    return WAH_OK;
 }
 
 // ----------------------------------------------------------------- range sharding

@@ -138,6 +138,12 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
                     if (i0 + 1 < p.c_words) x[v].y = p.in[i0 + 1];
                     if (i0 + 2 < p.c_words) x[v].z = p.in[i0 + 2];
                 }
+                if (i0 < (uint64_t)p.skip_words) {
+                    // the stream starts up to 3 words into its first 16-byte unit: what lies before is not part of it
+                    if (i0 + 0 < p.skip_words) x[v].x = BIT31;
+                    if (i0 + 1 < p.skip_words) x[v].y = BIT31;
+                    if (i0 + 2 < p.skip_words) x[v].z = BIT31;
+                }
             }
         }
         uint64_t lsum = 0;
@@ -150,8 +156,8 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
             lsum += (uint64_t)c0 + c1 + c2 + c3;
             // zero-length fills inside the stream are malformed (padding words behind its end are not)
             if ((uint32_t)v < nv)
-                bad += (c0 == 0u && i0 < p.c_words) + (c1 == 0u && i0 + 1 < p.c_words) + (c2 == 0u && i0 + 2 < p.c_words) +
-                       (c3 == 0u && i0 + 3 < p.c_words);
+                bad += (c0 == 0u && i0 < p.c_words && i0 >= p.skip_words) + (c1 == 0u && i0 + 1 < p.c_words && i0 + 1 >= p.skip_words) +
+                       (c2 == 0u && i0 + 2 < p.c_words && i0 + 2 >= p.skip_words) + (c3 == 0u && i0 + 3 < p.c_words);
         }
         if (__any_sync(0xffffffffu, bad != 0u)) {
             bad = warp_sum(bad);

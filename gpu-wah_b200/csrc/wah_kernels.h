@@ -75,7 +75,8 @@ struct DecodeCounters {
 
 struct ScanParams {
     const uint32_t *in;
-    uint64_t c_words;
+    uint64_t c_words;        // words from `in` to the end of the stream
+    uint32_t skip_words;     // 0..3: words at `in` that precede the stream (in is 16-byte aligned, the stream need not be)
     uint32_t n_tiles;        // ceil(c_words / tile_words)
     uint32_t tile_words;     // words per scan tile: a multiple of 4 * SCAN_THREADS (scan_tile_words())
     ulonglong2 *desc;        // [n_tiles] tile sums {value, epoch}

@@ -155,3 +155,18 @@ def compress_columns_sharded(local_cols: torch.Tensor, mode: int = wah.WAH_BLOCK
         dist.all_gather(allv, padded, group=group)
         lengths = [allv[r][: int(sizes[r].item())] for r in range(world)]
     return out, offs, lengths
+
+
+def decompress_columns(out: torch.Tensor, offs: torch.Tensor, words_per_col: int) -> torch.Tensor:
+    """Decode this rank's columns again (the result of ``compress_columns_sharded``): [cols, words_per_col].
+    Local work only, no collective."""
+    n_cols = offs.numel() - 1
+    dev = out.device
+    offs_h = [int(v) for v in offs.cpu().tolist()]
+    stride = (words_per_col + 1 + 3) // 4 * 4
+    back = torch.empty(max(n_cols, 1) * stride, dtype=torch.int32, device=dev)
+    info = torch.zeros(2 * max(n_cols, 1), dtype=torch.int64, device=dev)
+    longest = max([offs_h[j + 1] - offs_h[j] for j in range(n_cols)] + [1])
+    ws = wah.Workspace.for_decompress_batch(longest, words_per_col + 1, dev)
+    wah.decompress_batch_device(out, offs_h, back, stride, words_per_col + 1, info, ws)
+    return back.view(max(n_cols, 1), stride)[:n_cols, :words_per_col]

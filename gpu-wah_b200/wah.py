@@ -85,6 +85,8 @@ _sig("wah_compress_batch_workspace_bytes", _sz, _u64, _u64)
 _sig("wah_compress_batch_device", ctypes.c_int, _vp, _u64, _u64, _u64, ctypes.c_int, _vp, _u64, _vp, _vp, _sz, _vp)
 _sig("wah_decompress_workspace_bytes", _sz, _u64, _u64)
 _sig("wah_decompress_device", ctypes.c_int, _vp, _u64, _vp, _u64, _vp, _vp, _sz, _vp)
+_sig("wah_decompress_batch_workspace_bytes", _sz, _u64, _u64)
+_sig("wah_decompress_batch_device", ctypes.c_int, _vp, ctypes.POINTER(_u64), _u64, _vp, _u64, _u64, _vp, _vp, _sz, _vp)
 _sig("wah_decoded_size_device", ctypes.c_int, _vp, _u64, _vp, _vp, _sz, _vp)
 _sig("wah_compress_host", ctypes.c_int, _vp, _u64, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_u64), _pf, _pf, _pf)
 _sig("wah_decompress_host", ctypes.c_int, _vp, _u64, ctypes.POINTER(_vp), ctypes.POINTER(_u64), _pf, _pf, _pf)
@@ -218,6 +220,10 @@ class Workspace:
     def for_decompress(cls, c_words: int, out_capacity_words: int, device="cuda"):
         return cls(lib.wah_decompress_workspace_bytes(c_words, out_capacity_words), device)
 
+    @classmethod
+    def for_decompress_batch(cls, max_col_c_words: int, out_col_capacity_words: int, device="cuda"):
+        return cls(lib.wah_decompress_batch_workspace_bytes(max_col_c_words, out_col_capacity_words), device)
+
 
 def compress_device(d_in, n_words: int, d_out, out_capacity_words: int, d_out_words, workspace,
                     mode: int = WAH_BLOCK1024, stream=None) -> None:
@@ -241,6 +247,17 @@ def decompress_device(d_in, c_words: int, d_out, out_capacity_words: int, d_out_
     """Asynchronous decode; ``d_out_info``: device int64[2] receiving (decoded words, decoded groups)."""
     _check(lib.wah_decompress_device(_ptr(d_in), c_words, _ptr(d_out), out_capacity_words,
                                      _ptr(d_out_info), _ptr(workspace), workspace.nbytes, _stream(stream)))
+
+
+def decompress_batch_device(d_in, col_offsets, d_out, out_col_stride_words: int, out_col_capacity_words: int,
+                            d_out_info, workspace, stream=None) -> None:
+    """Decode ``len(col_offsets) - 1`` bitmap-index columns laid out as ``compress_batch_device`` writes them.
+    ``col_offsets``: HOST sequence of word offsets; ``d_out_info``: device int64[2 * n_cols]."""
+    n_cols = len(col_offsets) - 1
+    offs = (_u64 * (n_cols + 1))(*[int(v) for v in col_offsets])
+    _check(lib.wah_decompress_batch_device(_ptr(d_in), offs, n_cols, _ptr(d_out), out_col_stride_words,
+                                           out_col_capacity_words, _ptr(d_out_info), _ptr(workspace),
+                                           workspace.nbytes, _stream(stream)))
 
 
 def decoded_size_device(d_in, c_words: int, d_out_info, workspace, stream=None) -> None:

@@ -90,6 +90,14 @@ size_t wah_decompress_workspace_bytes(uint64_t c_words, uint64_t out_capacity_wo
 int wah_decompress_device(const uint32_t *d_in, uint64_t c_words,
                           uint32_t *d_out, uint64_t out_capacity_words, uint64_t *d_out_info,
                           void *d_workspace, size_t workspace_bytes, void *stream);
+/* bitmap-index batch: column j's stream is d_in[h_col_offsets[j] .. h_col_offsets[j+1]) (the layout
+ * wah_compress_batch_device writes; the offsets are a HOST array here), decoded to
+ * d_out + j * out_col_stride_words (a multiple of 4).  d_out_info: device u64[2 * n_cols].  One launch per
+ * column on `stream`; d_workspace holds wah_decompress_batch_workspace_bytes(longest stream, capacity) bytes. */
+size_t wah_decompress_batch_workspace_bytes(uint64_t max_col_c_words, uint64_t out_col_capacity_words);
+int wah_decompress_batch_device(const uint32_t *d_in, const uint64_t *h_col_offsets, uint64_t n_cols,
+                                uint32_t *d_out, uint64_t out_col_stride_words, uint64_t out_col_capacity_words,
+                                uint64_t *d_out_info, void *d_workspace, size_t workspace_bytes, void *stream);
 /* size query only (the scan half of the above); d_out_info as above */
 int wah_decoded_size_device(const uint32_t *d_in, uint64_t c_words, uint64_t *d_out_info,
                             void *d_workspace, size_t workspace_bytes, void *stream);

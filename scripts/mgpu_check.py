@@ -51,6 +51,7 @@ def main():
         out_h = out.cpu().numpy().view(np.uint32)
         good = all(np.array_equal(out_h[offs_h[j]: offs_h[j + 1]], orc.compress(cols[c0 + j], mode)) for j in range(c1 - c0))
         good = good and torch.cat(lengths).cpu().tolist() == [orc.compress(c, mode).size for c in cols]
+        good = good and torch.equal(mgpu.decompress_columns(out, offs, cols.shape[1]), mine)
         ok = ok and good
         if rank == 0:
             print(f"column-sharded mode {mode}: {'ok' if good else 'MISMATCH'}", flush=True)

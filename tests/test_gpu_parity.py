@@ -168,6 +168,19 @@ def test_batch_columns(mode):
     assert np.array_equal(got_offs, offs)
     assert np.array_equal(to_host(d_out[: int(offs[-1])]), want)
 
+    # and back: every column decoded to its own slot (the streams start at arbitrary word offsets)
+    stride = (wpc + 1 + 3) // 4 * 4
+    d_back = torch.full((n_cols * stride,), -1, dtype=torch.int32, device="cuda")
+    d_info = torch.full((2 * n_cols,), -1, dtype=torch.int64, device="cuda")
+    lens = np.diff(offs.astype(np.int64))
+    wsd = wah.Workspace.for_decompress_batch(int(lens.max()), wpc + 1)
+    wah.decompress_batch_device(d_out, [int(v) for v in offs], d_back, stride, wpc + 1, d_info, wsd)
+    back = to_host(d_back).reshape(n_cols, stride)
+    info = d_info.cpu().numpy().reshape(n_cols, 2)
+    for j in range(n_cols):
+        assert info[j, 1] == orc.num_groups(wpc) and info[j, 0] == orc.decoded_words(orc.num_groups(wpc))
+        assert np.array_equal(back[j, :wpc], cols[j]), j
+
 
 def test_host_entry_points_mirror_the_reference():
     # compress()/decompress() semantics: host in, host out, optional ms timers (compress.h:12-18)

@@ -553,20 +553,20 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 for (uint32_t i = tid; i < (uint32_t)EXPAND_TILE_WORDS / 4; i += EXPAND_THREADS) z[i] = make_uint4(0, 0, 0, 0);
             }
             int32_t running = 0;   // group offset (tile relative) of the round's first word
+            auto words_at = [&](uint64_t i0, uint2 &x2) {
+                if (i0 + 2 <= p.c_words) {
+                    x2 = *reinterpret_cast<const uint2 *>(p.in + i0);
+                } else {
+                    x2.x = i0 < p.c_words ? p.in[i0] : BIT31;
+                    x2.y = BIT31;
+                }
+            };
+            uint2 xc = xpre, xn = xpre;
             for (uint32_t c0 = 0; c0 < nw_all; c0 += SP_ROUND) {
                 const uint64_t i0 = wa + c0 + 2ull * tid;   // my two consecutive words
-                uint32_t x[2];
-                if (c0 == 0) {
-                    x[0] = xpre.x;
-                    x[1] = xpre.y;
-                } else if (i0 + 2 <= p.c_words) {
-                    const uint2 v = *reinterpret_cast<const uint2 *>(p.in + i0);
-                    x[0] = v.x;
-                    x[1] = v.y;
-                } else {
-                    x[0] = i0 < p.c_words ? p.in[i0] : BIT31;
-                    x[1] = BIT31;
-                }
+                if (c0 + SP_ROUND < nw_all) words_at(i0 + SP_ROUND, xn);   // the next round's words, a round ahead
+                const uint32_t x[2] = {xc.x, xc.y};
+                xc = xn;
                 uint32_t c[2];
 #pragma unroll
                 for (int i = 0; i < 2; i++) {

@@ -5,7 +5,7 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gpu_wah_b200 as wah
 
 n = 1 << 25
-d = wah.gen_uniform_device(n, 0.001, 1337)
+d = wah.gen_uniform_device(n, float(sys.argv[1]) if len(sys.argv) > 1 else 0.001, 1337)
 cap = wah.max_compressed_words(n)
 out = torch.empty(cap, dtype=torch.int32, device="cuda")
 cnt = torch.zeros(1, dtype=torch.int64, device="cuda")

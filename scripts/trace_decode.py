@@ -5,7 +5,9 @@ sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gpu_wah_b200 as wah
 
 n = 1 << 25
-d = wah.gen_uniform_device(n, float(sys.argv[1]) if len(sys.argv) > 1 else 0.001, 1337)
+dens = float(sys.argv[1]) if len(sys.argv) > 1 else 0.001
+clustered = len(sys.argv) > 3 and sys.argv[3] == "clustered"
+d = wah.gen_clustered_device(n, dens, 1000.0, 1337) if clustered else wah.gen_uniform_device(n, dens, 1337)
 cap = wah.max_compressed_words(n)
 out = torch.empty(cap, dtype=torch.int32, device="cuda")
 cnt = torch.zeros(1, dtype=torch.int64, device="cuda")

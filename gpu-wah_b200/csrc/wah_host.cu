@@ -13,6 +13,7 @@
 #include "../../include/wah_b200.h"
 #include "wah_kernels.h"
 
+#include <emmintrin.h>
 #include <sys/mman.h>
 
 #include <algorithm>
@@ -44,6 +45,32 @@ constexpr size_t CHUNK = 16u << 20;  // bytes per pinned bounce buffer
 constexpr int NSLOT = 4;             // bounce buffers in the ring
 
 // ------------------------------------------------------------------ copy threads
+
+// Copy with non-temporal stores: the destination (a result buffer the caller reads later, or a bounce buffer
+// the DMA engine reads) is not wanted in this core's cache, and streaming stores spare the read-for-ownership
+// of every destination line.
+inline void stream_copy(void *dst, const void *src, size_t bytes)
+{
+    char *d = static_cast<char *>(dst);
+    const char *s = static_cast<const char *>(src);
+    const size_t head = std::min(bytes, (size_t)((16 - ((uintptr_t)d & 15)) & 15));
+    memcpy(d, s, head);
+    d += head;
+    s += head;
+    bytes -= head;
+    size_t n16 = bytes / 16;
+    for (; n16 >= 4; n16 -= 4, d += 64, s += 64) {
+        const __m128i a = _mm_loadu_si128((const __m128i *)(s)), b = _mm_loadu_si128((const __m128i *)(s + 16));
+        const __m128i c = _mm_loadu_si128((const __m128i *)(s + 32)), e = _mm_loadu_si128((const __m128i *)(s + 48));
+        _mm_stream_si128((__m128i *)(d), a);
+        _mm_stream_si128((__m128i *)(d + 16), b);
+        _mm_stream_si128((__m128i *)(d + 32), c);
+        _mm_stream_si128((__m128i *)(d + 48), e);
+    }
+    for (; n16; n16--, d += 16, s += 16) _mm_stream_si128((__m128i *)d, _mm_loadu_si128((const __m128i *)s));
+    _mm_sfence();
+    memcpy(d, s, bytes & 15);
+}
 
 class CopyPool {
    public:
@@ -97,7 +124,7 @@ class CopyPool {
         parallel([&](int i) {
             for (uintptr_t r = first + (uintptr_t)i * piece; r < d1; r += (uintptr_t)n_ * piece) {
                 const uintptr_t a = std::max(r, d0), b = std::min(r + piece, d1);
-                memcpy((void *)a, (const char *)src + (a - d0), b - a);
+                stream_copy((void *)a, (const char *)src + (a - d0), b - a);
             }
         });
     }

@@ -189,7 +189,10 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
             const uint32_t m = p.n_tiles - round0 < stride ? p.n_tiles - round0 : stride;   // tiles in it
             if (tid == 0) {
                 __threadfence();   // my sum is visible before my arrival is
-                s_flag = atomicAdd(&p.ctr->agg_count, 1u) == m - 1u;
+                // Arrivals are counted over the whole launch: a CTA arrives for round r + 1 only after it has read its
+                // round-r offset, which exists only after ALL round-r arrivals -- so the count at the end of round r
+                // is exactly round0 + m, and nothing has to be reset (or fenced) between rounds.
+                s_flag = atomicAdd(&p.ctr->agg_count, 1u) == round0 + m - 1u;
                 s_nheavy = 0;
             }
             __syncthreads();
@@ -205,31 +208,23 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
                         mine += v;
                     }
                 }
+                // groups before this round = offset + sum of the previous round's last tile (both published)
+                uint64_t base0 = 0;
+                if (round0 != 0u) {
+                    uint64_t pe, ps;
+                    while (!cell_load(p.excl + round0 - 1, p.epoch, pe)) {
+                    }
+                    cell_load(p.desc + round0 - 1, p.epoch, ps);
+                    base0 = pe + ps;
+                }
                 const uint64_t incl = warp_incl_scan_u64(mine);
                 if (lane == 31) s_lb_sum[warp] = incl;
-                const uint64_t base0 = *reinterpret_cast<volatile uint64_t *>(&p.ctr->agg_base);
                 __syncthreads();
-                uint64_t before = base0, total = 0;
+                uint64_t before = base0;
 #pragma unroll
-                for (int k = 0; k < NW; k++) {
-                    const uint64_t sv = s_lb_sum[k];
-                    if (k < (int)warp) before += sv;
-                    total += sv;
-                }
+                for (int k = 0; k < NW; k++)
+                    if (k < (int)warp) before += s_lb_sum[k];
                 before += incl - mine;
-                // The counter is reset BEFORE any offset is published: a CTA that has read its offset may arrive
-                // for the next round at once.
-                if (tid == 0) {
-                    const bool final_round = round0 + m == p.n_tiles;   // leave the header clean for the next launch
-                    p.ctr->agg_count = 0;
-                    *reinterpret_cast<volatile uint64_t *>(&p.ctr->agg_base) = final_round ? 0ull : base0 + total;
-                    if (final_round) {
-                        // every CTA added its malformed-word count before it arrived for its last tile
-                        p.hdr->bad_words = atomicExch(&p.ctr->bad_acc, 0u);
-                    }
-                    __threadfence();
-                }
-                __syncthreads();
                 for (uint32_t j = 0; j < per; j++) {
                     const uint32_t k = tid * per + j;
                     if (k < m) {
@@ -239,6 +234,13 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
                         before += v;
                     }
                 }
+                if (tid == 0 && round0 + m == p.n_tiles) {
+                    // the last round: nobody arrives any more; leave the counters zeroed for the next launch
+                    // (every CTA added its malformed-word count before it arrived for its last tile)
+                    p.ctr->agg_count = 0;
+                    p.hdr->bad_words = atomicExch(&p.ctr->bad_acc, 0u);
+                }
+                __syncthreads();   // s_lb_sum is reused below
             }
             if (tid == 0) {
                 uint64_t v;

@@ -67,10 +67,9 @@ struct DecodeHeader {
 // Counters that must be 0 when a launch starts.  They live in a slot of a small library-owned array (never in the
 // caller's workspace, whose content is arbitrary) and every launch leaves its slot zeroed again.
 struct DecodeCounters {
-    uint32_t agg_count;     // scan tiles of the current round that have published their sum
+    uint32_t agg_count;     // scan tiles that have published their sum so far
     uint32_t bad_acc;       // zero-length fills seen so far
-    uint64_t agg_base;      // groups before the current round
-    uint64_t pad[2];
+    uint64_t pad[3];
 };
 
 struct ScanParams {

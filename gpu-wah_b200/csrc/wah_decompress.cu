@@ -115,49 +115,62 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t stride = gridDim.x;
-    const uint32_t nv = p.tile_words / (4u * SCAN_THREADS);   // rows of 128 words per warp
-    const uint32_t seg_words = nv * 128u;
+    // A tile is walked in sub-tiles of up to 8192 words (SCAN_MAXV rows of 128 words per warp).  A tile of ONE
+    // sub-tile -- every stream up to gridDim * 8192 words -- keeps its words in registers between the passes; a longer
+    // tile is read a second time in pass 2 rather than split into several tiles, because every extra tile per CTA is an
+    // extra round of the offset exchange below (measured: 10 us per round).
+    const uint32_t rows = p.tile_words / (4u * SCAN_THREADS);   // rows of 128 words per warp and tile
+    const uint32_t nsub = (rows + SCAN_MAXV - 1) / SCAN_MAXV;
     bool first_tile = true;
 
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += stride) {
-        const uint64_t seg_begin = (uint64_t)tile * p.tile_words + (uint64_t)warp * seg_words;
-
-        // ---- pass 1
+        const uint64_t tile_begin = (uint64_t)tile * p.tile_words;
+        uint32_t nv = 0;          // rows of the sub-tile at hand
+        uint64_t seg_begin = 0;   // first word of my warp's part of it
+        uint4 x[SCAN_MAXV];
         // (all loads are issued before the first use: a warp executes in order, a use right behind its load
         //  would put one HBM round trip on every one of them)
-        uint4 x[SCAN_MAXV];
+        auto load_sub = [&](uint32_t sub) {
+            nv = rows - sub * SCAN_MAXV < (uint32_t)SCAN_MAXV ? rows - sub * SCAN_MAXV : (uint32_t)SCAN_MAXV;
+            seg_begin = tile_begin + (uint64_t)sub * (SCAN_MAXV * 4u * SCAN_THREADS) + (uint64_t)warp * (nv * 128u);
 #pragma unroll
-        for (int v = 0; v < SCAN_MAXV; v++) {
-            const uint64_t i0 = seg_begin + (uint64_t)(v * 32 + (int)lane) * 4u;
-            x[v] = make_uint4(BIT31, BIT31, BIT31, BIT31);   // fills of 0 groups: neutral, see `valid` below
-            if ((uint32_t)v < nv) {
-                if (i0 + 4 <= p.c_words) {
-                    x[v] = ld_stream_v4(reinterpret_cast<const uint4 *>(p.in + i0));
-                } else if (i0 < p.c_words) {
-                    x[v].x = p.in[i0];
-                    if (i0 + 1 < p.c_words) x[v].y = p.in[i0 + 1];
-                    if (i0 + 2 < p.c_words) x[v].z = p.in[i0 + 2];
-                }
-                if (i0 < (uint64_t)p.skip_words) {
-                    // the stream starts up to 3 words into its first 16-byte unit: what lies before is not part of it
-                    if (i0 + 0 < p.skip_words) x[v].x = BIT31;
-                    if (i0 + 1 < p.skip_words) x[v].y = BIT31;
-                    if (i0 + 2 < p.skip_words) x[v].z = BIT31;
+            for (int v = 0; v < SCAN_MAXV; v++) {
+                const uint64_t i0 = seg_begin + (uint64_t)(v * 32 + (int)lane) * 4u;
+                x[v] = make_uint4(BIT31, BIT31, BIT31, BIT31);   // fills of 0 groups: neutral
+                if ((uint32_t)v < nv) {
+                    if (i0 + 4 <= p.c_words) {
+                        x[v] = ld_stream_v4(reinterpret_cast<const uint4 *>(p.in + i0));
+                    } else if (i0 < p.c_words) {
+                        x[v].x = p.in[i0];
+                        if (i0 + 1 < p.c_words) x[v].y = p.in[i0 + 1];
+                        if (i0 + 2 < p.c_words) x[v].z = p.in[i0 + 2];
+                    }
+                    if (i0 < (uint64_t)p.skip_words) {
+                        // the stream starts up to 3 words into its first 16-byte unit: what lies before is not part of it
+                        if (i0 + 0 < p.skip_words) x[v].x = BIT31;
+                        if (i0 + 1 < p.skip_words) x[v].y = BIT31;
+                        if (i0 + 2 < p.skip_words) x[v].z = BIT31;
+                    }
                 }
             }
-        }
+        };
+
+        // ---- pass 1
         uint64_t lsum = 0;
         uint32_t bad = 0;
+        for (uint32_t sub = 0; sub < nsub; sub++) {
+            load_sub(sub);
 #pragma unroll
-        for (int v = 0; v < SCAN_MAXV; v++) {
-            const uint64_t i0 = seg_begin + (uint64_t)(v * 32 + (int)lane) * 4u;
-            const uint32_t c0 = word_groups(x[v].x), c1 = word_groups(x[v].y), c2 = word_groups(x[v].z),
-                           c3 = word_groups(x[v].w);
-            lsum += (uint64_t)c0 + c1 + c2 + c3;
-            // zero-length fills inside the stream are malformed (padding words behind its end are not)
-            if ((uint32_t)v < nv)
-                bad += (c0 == 0u && i0 < p.c_words && i0 >= p.skip_words) + (c1 == 0u && i0 + 1 < p.c_words && i0 + 1 >= p.skip_words) +
-                       (c2 == 0u && i0 + 2 < p.c_words && i0 + 2 >= p.skip_words) + (c3 == 0u && i0 + 3 < p.c_words);
+            for (int v = 0; v < SCAN_MAXV; v++) {
+                const uint64_t i0 = seg_begin + (uint64_t)(v * 32 + (int)lane) * 4u;
+                const uint32_t c0 = word_groups(x[v].x), c1 = word_groups(x[v].y), c2 = word_groups(x[v].z),
+                               c3 = word_groups(x[v].w);
+                lsum += (uint64_t)c0 + c1 + c2 + c3;
+                // zero-length fills inside the stream are malformed (padding words behind its end are not)
+                if ((uint32_t)v < nv)
+                    bad += (c0 == 0u && i0 < p.c_words && i0 >= p.skip_words) + (c1 == 0u && i0 + 1 < p.c_words && i0 + 1 >= p.skip_words) +
+                           (c2 == 0u && i0 + 2 < p.c_words && i0 + 2 >= p.skip_words) + (c3 == 0u && i0 + 3 < p.c_words);
+            }
         }
         if (__any_sync(0xffffffffu, bad != 0u)) {
             bad = warp_sum(bad);
@@ -167,11 +180,11 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
         __syncthreads();   // the previous tile's partial sums have been consumed
         if (lane == 0) s_wsum[warp] = wtotal;
         __syncthreads();
-        uint64_t tile_sum = 0, wprefix = 0;
+        uint64_t tile_sum = 0, wprefix1 = 0;   // wprefix1: groups in the lower warps' parts (meaningful if nsub == 1)
 #pragma unroll
         for (int k = 0; k < NW; k++) {
             const uint64_t sv = s_wsum[k];
-            if (k < (int)warp) wprefix += sv;
+            if (k < (int)warp) wprefix1 += sv;
             tile_sum += sv;
         }
         if (tid == 0) cell_store(p.desc + tile, tile_sum, p.epoch);
@@ -274,19 +287,41 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
         //      thousand output tiles) is queued and written by the whole CTA afterwards.
         if (p.starts != nullptr) {
             const uint64_t k_limit = p.max_out_tiles + 1ull;
-            uint64_t row_base = excl + wprefix;   // group offset of the row's first word
+            uint64_t sub_base = excl;   // group offset of the sub-tile's first word
+            for (uint32_t sub = 0; sub < nsub; sub++) {
+                uint64_t row_base = sub_base;   // group offset of the row's first word
+                if (nsub > 1u) {
+                    load_sub(sub);
+                    uint64_t lsub = 0;
 #pragma unroll
-            for (int v = 0; v < SCAN_MAXV; v++) {
-                if ((uint32_t)v < nv) {   // uniform
-                    const uint32_t c0 = word_groups(x[v].x), c1 = word_groups(x[v].y), c2 = word_groups(x[v].z),
-                                   c3 = word_groups(x[v].w);
-                    const uint64_t sl = (uint64_t)c0 + c1 + c2 + c3;
-                    const uint64_t incl = warp_incl_scan_u64(sl);
-                    const uint64_t off = row_base + incl - sl;
-                    const uint64_t wi = seg_begin + (uint64_t)(v * 32 + (int)lane) * 4u;
-                    if (((off + TGM) >> TG_SHIFT) != ((off + sl + TGM) >> TG_SHIFT))   // rare: a boundary in my 4 words
-                        record_boundaries(p.starts, p.epoch, k_limit, wi, off, make_uint4(c0, c1, c2, c3), s_heavy, &s_nheavy);
-                    row_base += __shfl_sync(0xffffffffu, incl, 31);
+                    for (int v = 0; v < SCAN_MAXV; v++)
+                        lsub += (uint64_t)word_groups(x[v].x) + word_groups(x[v].y) + word_groups(x[v].z) + word_groups(x[v].w);
+                    const uint64_t wsub = warp_sum_u64(lsub);
+                    __syncthreads();   // s_wsum: the previous sub-tile's (or pass 1's) sums have been consumed
+                    if (lane == 0) s_wsum[warp] = wsub;
+                    __syncthreads();
+#pragma unroll
+                    for (int k = 0; k < NW; k++) {
+                        const uint64_t sv = s_wsum[k];
+                        if (k < (int)warp) row_base += sv;
+                        sub_base += sv;
+                    }
+                } else {
+                    row_base += wprefix1;   // one sub-tile: its words are still in registers, its warp sums known
+                }
+#pragma unroll
+                for (int v = 0; v < SCAN_MAXV; v++) {
+                    if ((uint32_t)v < nv) {   // uniform
+                        const uint32_t c0 = word_groups(x[v].x), c1 = word_groups(x[v].y), c2 = word_groups(x[v].z),
+                                       c3 = word_groups(x[v].w);
+                        const uint64_t sl = (uint64_t)c0 + c1 + c2 + c3;
+                        const uint64_t incl = warp_incl_scan_u64(sl);
+                        const uint64_t off = row_base + incl - sl;
+                        const uint64_t wi = seg_begin + (uint64_t)(v * 32 + (int)lane) * 4u;
+                        if (((off + TGM) >> TG_SHIFT) != ((off + sl + TGM) >> TG_SHIFT))   // rare: a boundary in my 4 words
+                            record_boundaries(p.starts, p.epoch, k_limit, wi, off, make_uint4(c0, c1, c2, c3), s_heavy, &s_nheavy);
+                        row_base += __shfl_sync(0xffffffffu, incl, 31);
+                    }
                 }
             }
             __syncthreads();
@@ -795,7 +830,7 @@ uint32_t scan_tile_words(uint64_t c_words)
     const uint64_t unit = 4ull * SCAN_THREADS;
     uint64_t tw = ((c_words + grid - 1) / grid + unit - 1) / unit * unit;
     if (tw < (uint64_t)SCAN_TILE_WORDS) tw = SCAN_TILE_WORDS;
-    if (tw > 8192ull) tw = 8192ull;   // SCAN_MAXV 128-bit loads per lane
+    if (tw > 0xFFFFF000ull) tw = 0xFFFFF000ull;   // (a tile is walked in sub-tiles of 8192 words; one tile per CTA)
     return (uint32_t)tw;
 }
 

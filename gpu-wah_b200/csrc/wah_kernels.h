@@ -103,7 +103,7 @@ struct ExpandParams {
 
 size_t expand_smem_bytes();
 // scan tile size for a stream of c_words: one tile per CTA of the decode grid while that keeps a tile between
-// SCAN_TILE_WORDS (the unit the workspace is sized by) and 8 K words
+// at least SCAN_TILE_WORDS (the unit the workspace is sized by)
 uint32_t scan_tile_words(uint64_t c_words);
 cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream);
 cudaError_t launch_expand(const ExpandParams &p, int grid, cudaStream_t stream);

@@ -285,7 +285,17 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
         // ---- pass 2: which compressed word covers each output-tile boundary k * 8192 ?
         //      A word that covers up to 4 boundaries records them itself; a long fill (it may span a hundred
         //      thousand output tiles) is queued and written by the whole CTA afterwards.
-        if (p.starts != nullptr) {
+        // A tile whose every word is one group (literal-dense data: sum == number of words) needs no second look at
+        // its words: boundary k * 8192 falls on word (k * 8192 - excl) of the tile.
+        const uint64_t w_first = tile_begin > (uint64_t)p.skip_words ? tile_begin : (uint64_t)p.skip_words;
+        const uint64_t w_last = tile_begin + p.tile_words < p.c_words ? tile_begin + p.tile_words : p.c_words;
+        const bool unit_tile = w_last > w_first && tile_sum == w_last - w_first;
+        if (p.starts != nullptr && unit_tile) {
+            uint64_t k_end = (excl + tile_sum + TGM) >> TG_SHIFT;
+            if (k_end > p.max_out_tiles + 1ull) k_end = p.max_out_tiles + 1ull;
+            for (uint64_t k = ((excl + TGM) >> TG_SHIFT) + tid; k < k_end; k += SCAN_THREADS)
+                store_entry(p.starts + k, w_first + ((k << TG_SHIFT) - excl) + 1ull, k << TG_SHIFT, p.epoch);
+        } else if (p.starts != nullptr) {
             const uint64_t k_limit = p.max_out_tiles + 1ull;
             uint64_t sub_base = excl;   // group offset of the sub-tile's first word
             for (uint32_t sub = 0; sub < nsub; sub++) {

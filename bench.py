@@ -109,7 +109,8 @@ def run_reference(args):
     if args.density is not None:
         density = args.density
     mode = 0 if args.mode == "block1024" else 1
-    threads = orc.max_threads()
+    # all host cores, whatever OMP_NUM_THREADS says (torchrun sets it to 1 for every rank)
+    threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
     # bounded sample: the first 2^23 words (256 Mbit) of the workload's vector per step
     sample_words = min(n_words, 1 << 23)
     data = host_input(sample_words, gen, density, 1337)
@@ -400,7 +401,7 @@ def run_b200(args):
 
         sample_words = min(n_words, 1 << 23)
         data = inputs[0][:sample_words].cpu().numpy().view(np.uint32)
-        threads = orc.max_threads()
+        threads = len(os.sched_getaffinity(0)) if hasattr(os, "sched_getaffinity") else (os.cpu_count() or 1)
         r = cpu_arm(data, 0 if mode == wah.WAH_BLOCK1024 else 1, 10.0, threads)
         cpu_baseline = {"value": r["value"], "unit": UNIT, "cores": threads, "kind": "port",
                         "sample": f"first {sample_words} words of rank 0's vector, {r['reps']} round trips",

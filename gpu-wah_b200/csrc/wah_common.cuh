@@ -62,6 +62,14 @@ __device__ __forceinline__ void st_stream_u32(uint32_t *p, uint32_t v)
     asm volatile("st.global.L1::no_allocate.u32 [%0], %1;" ::"l"(p), "r"(v) : "memory");
 }
 
+// ---------------------------------------------------------------- programmatic dependent launch
+// The two big kernels of a compress / decompress pipeline follow each other on one stream.  Launched with
+// programmatic stream serialisation, the next kernel's CTAs are scheduled as soon as the previous kernel's CTAs
+// leave their SMs and wait here until that kernel has completed and flushed its memory: its launch latency and the
+// previous kernel's drain overlap.  Nothing that another kernel may have written is touched before pdl_wait().
+__device__ __forceinline__ void pdl_wait() { asm volatile("griddepcontrol.wait;" ::: "memory"); }
+__device__ __forceinline__ void pdl_launch_dependents() { asm volatile("griddepcontrol.launch_dependents;" ::: "memory"); }
+
 // ---------------------------------------------------------------- warp helpers
 
 __device__ __forceinline__ uint32_t lane_id()

@@ -213,6 +213,7 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
     const uint32_t stride = gridDim.x;
     const uint32_t n_my = blockIdx.x < p.n_tiles ? (p.n_tiles - blockIdx.x + stride - 1u) / stride : 0u;
 
+    pdl_launch_dependents();   // the next kernel on the stream may take the SMs as this one leaves them
     if (tid == 0) {
         for (int s = 0; s < STAGES; s++) {
             mbar_init(smem_u32(&sm.full[s]), 1);
@@ -225,6 +226,7 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
+    pdl_wait();   // the previous kernel on the stream is complete: its output (our input, the workspace) is visible
     __syncthreads();
 
     if (warp == NWORK + 1) {
@@ -790,7 +792,7 @@ cudaError_t launch_compress(const CompressParams &p, int mode, cudaStream_t stre
         return e && e[0] == '1';
     }();
     if (cooperative) return cudaLaunchCooperativeKernel(kernel, dim3(grid), dim3(THREADS), args, smem, stream);
-    return cudaLaunchKernel(kernel, dim3(grid), dim3(THREADS), args, smem, stream);
+    return launch_pdl(kernel, grid, THREADS, args, smem, stream);
 }
 
 }  // namespace wahb200

@@ -121,7 +121,9 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
     // extra round of the offset exchange below (measured: 10 us per round).
     const uint32_t rows = p.tile_words / (4u * SCAN_THREADS);   // rows of 128 words per warp and tile
     const uint32_t nsub = (rows + SCAN_MAXV - 1) / SCAN_MAXV;
+#ifdef WAH_TRACE
     bool first_tile = true;
+#endif
 
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += stride) {
         const uint64_t tile_begin = (uint64_t)tile * p.tile_words;
@@ -265,7 +267,9 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
 #ifdef WAH_TRACE
             if (p.trace && tid == 0 && first_tile) p.trace[(uint64_t)blockIdx.x * 64u + 5u] = (uint64_t)clock64();
 #endif
+#ifdef WAH_TRACE
             first_tile = false;
+#endif
         }
         if (tid == 0 && tile == p.n_tiles - 1u) {
             // decompress.cu:82-93: G = last offset + last count, realSize = ceil(31 G / 32)
@@ -801,6 +805,8 @@ static_assert(SCAN_THREADS == EXPAND_THREADS, "the fused kernel runs both phases
 #endif
 __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_decode_kernel(const ScanParams sp, const ExpandParams ep)
 {
+    pdl_launch_dependents();
+    pdl_wait();   // the previous kernel on the stream (typically the compressor) is complete
     DTRACE(0, clock64());
 #ifdef WAH_TRACE
     {
@@ -889,7 +895,7 @@ cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStre
     ScanParams a = sp;
     ExpandParams b = ep;
     void *args[] = {&a, &b};
-    return cudaLaunchKernel((const void *)wah_decode_kernel, dim3(grid), dim3(EXPAND_THREADS), args, smem, stream);
+    return launch_pdl((const void *)wah_decode_kernel, grid, EXPAND_THREADS, args, smem, stream);
 }
 
 cudaError_t launch_expand(const ExpandParams &p, int grid, cudaStream_t stream)

@@ -88,7 +88,6 @@ class CopyPool {
         cv_.notify_all();
         for (auto &t : threads_) t.join();
     }
-    int size() const { return n_; }
     // run job(i) for i in [0, size()) on the pool; the calling thread takes i = 0
     void parallel(const std::function<void(int)> &job)
     {

@@ -52,7 +52,6 @@ constexpr int SCAN_TILE_WORDS = SCAN_THREADS * SCAN_ITEMS;     // 2048
 constexpr int EXPAND_THREADS = 256;
 constexpr int EXPAND_TILE_GROUPS = EXPAND_THREADS * 32;        // 8192 groups per output tile
 constexpr int EXPAND_TILE_WORDS = EXPAND_THREADS * 31;         // 7936 output words
-constexpr int EXPAND_MAX_CWORDS = EXPAND_TILE_GROUPS + 8;      // compressed words one output tile can need
 
 // header written by the scan kernel, read by the expand kernel and the host
 struct DecodeHeader {
@@ -108,6 +107,22 @@ uint32_t scan_tile_words(uint64_t c_words);
 cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream);
 cudaError_t launch_expand(const ExpandParams &p, int grid, cudaStream_t stream);
 cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStream_t stream);   // scan + expand, one launch
+
+// launch with programmatic stream serialisation (see pdl_wait in wah_common.cuh)
+inline cudaError_t launch_pdl(const void *kernel, int grid, int threads, void **args, size_t smem, cudaStream_t stream)
+{
+    cudaLaunchConfig_t cfg = {};
+    cfg.gridDim = dim3(grid);
+    cfg.blockDim = dim3(threads);
+    cfg.dynamicSmemBytes = smem;
+    cfg.stream = stream;
+    cudaLaunchAttribute attr[1];
+    attr[0].id = cudaLaunchAttributeProgrammaticStreamSerialization;
+    attr[0].val.programmaticStreamSerializationAllowed = 1;
+    cfg.attrs = attr;
+    cfg.numAttrs = 1;
+    return cudaLaunchKernelExC(&cfg, kernel, args);
+}
 
 // --------------------------------------------------------------------- misc
 

@@ -313,6 +313,7 @@ static int decompress_common(const uint32_t *d_in, uint64_t c_words, uint32_t *d
         ep.max_out_tiles = sp.max_out_tiles;
         ep.out = d_out;
         ep.out_cap = out_cap;
+        ep.ctr = sp.ctr;
         ep.trace = g_trace;
         CUDA_TRY(launch_decode(sp, ep, stream));
     }

@@ -72,6 +72,7 @@ __device__ __forceinline__ void load_entry(const ulonglong2 *e, uint32_t epoch, 
     x = ok ? (x & ENTRY_MASK) : 0ull;
     y &= ENTRY_MASK;
 }
+constexpr int EXPAND_STATIC_ROUNDS = 4;   // output tiles of the first rounds are dealt round robin, later ones by ticket
 constexpr int SCAN_HEAVY = 64;  // long fills of a tile queued for the CTA-wide boundary writer
 
 // Four consecutive compressed words, the first at group offset `off`: record every output-tile boundary
@@ -97,17 +98,43 @@ __device__ __noinline__ void record_boundaries(ulonglong2 *starts, uint32_t epoc
                     k_end = k_first;   // queued
                 }
             }
+#pragma unroll 1
             for (uint64_t k = k_first; k < k_end; k++) store_entry(starts + k, wi + j + 1ull, off, epoch);
         }
         off += c[j];
     }
 }
 
-__device__ __forceinline__ void scan_body(const ScanParams &p)
+// 16 bytes global -> shared without passing through registers (LDGSTS): `bytes` (0..16) are read, the rest of the
+// 16 is zero filled.  The scan issues a whole sub-tile of these from a rolled loop -- every load is in flight before
+// the first is used, and the code stays a few hundred bytes.  (It used to keep the words in registers, which needs
+// every loop over them unrolled: 40 KB of straight-line code that runs once per launch, i.e. straight from DRAM --
+// the instruction fetch, not the data, was what the scan phase waited for.)
+__device__ __forceinline__ void cp_async16(uint32_t dst_smem, const void *src, uint32_t bytes)
+{
+    asm volatile("cp.async.cg.shared.global [%0], [%1], 16, %2;" ::"r"(dst_smem), "l"(src), "r"(bytes) : "memory");
+}
+__device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
+template <int N>
+__device__ __forceinline__ void cp_async_wait()
+{
+    asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
+}
+constexpr int SCAN_SUB_WORDS = SCAN_MAXV * 4 * SCAN_THREADS;   // 8192 words = 32 KB: one sub-tile
+
+__device__ __forceinline__ uint64_t pack_groups(const uint4 x)
+{
+    return (uint64_t)word_groups(x.x) + word_groups(x.y) + word_groups(x.z) + word_groups(x.w);
+}
+__device__ __forceinline__ uint32_t zero_fill(uint32_t x) { return (x & ~BIT30) == BIT31; }   // a fill of 0 groups
+
+// `smem`: 2 * SCAN_SUB_WORDS words (the expand phase's shared memory, not in use yet).
+__device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
 {
     constexpr int NW = SCAN_THREADS / 32;
     constexpr uint64_t TGM = (uint64_t)EXPAND_TILE_GROUPS - 1ull;
     __shared__ uint64_t s_wsum[NW];
+    __shared__ uint32_t s_wbad[NW];
     __shared__ uint64_t s_lb_sum[NW];
     __shared__ ulonglong4 s_heavy[SCAN_HEAVY];
     __shared__ uint32_t s_nheavy;
@@ -115,72 +142,85 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t stride = gridDim.x;
-    // A tile is walked in sub-tiles of up to 8192 words (SCAN_MAXV rows of 128 words per warp).  A tile of ONE
-    // sub-tile -- every stream up to gridDim * 8192 words -- keeps its words in registers between the passes; a longer
-    // tile is read a second time in pass 2 rather than split into several tiles, because every extra tile per CTA is an
-    // extra round of the offset exchange below (measured: 10 us per round).
+    // A tile is walked in sub-tiles of up to 8192 words (SCAN_MAXV rows of 128 words per warp), staged in shared
+    // memory, two buffers.  A tile of ONE sub-tile -- every stream up to gridDim * 8192 words -- is still there in
+    // pass 2; a longer tile is read a second time rather than split into several tiles, because every extra tile per
+    // CTA is an extra round of the offset exchange below (measured: 10 us per round).
     const uint32_t rows = p.tile_words / (4u * SCAN_THREADS);   // rows of 128 words per warp and tile
     const uint32_t nsub = (rows + SCAN_MAXV - 1) / SCAN_MAXV;
+    uint64_t *s_loc = reinterpret_cast<uint64_t *>(smem + SCAN_SUB_WORDS);   // one sub-tile: the second buffer is free
 #ifdef WAH_TRACE
     bool first_tile = true;
 #endif
 
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += stride) {
         const uint64_t tile_begin = (uint64_t)tile * p.tile_words;
+        const uint64_t w_first = tile_begin > (uint64_t)p.skip_words ? tile_begin : (uint64_t)p.skip_words;
+        const uint64_t w_last = tile_begin + p.tile_words < p.c_words ? tile_begin + p.tile_words : p.c_words;
+        const bool ragged = w_last - w_first != (uint64_t)p.tile_words;   // words of my packs lie outside the stream
         uint32_t nv = 0;          // rows of the sub-tile at hand
         uint64_t seg_begin = 0;   // first word of my warp's part of it
-        uint4 x[SCAN_MAXV];
-        // (all loads are issued before the first use: a warp executes in order, a use right behind its load
-        //  would put one HBM round trip on every one of them)
-        auto load_sub = [&](uint32_t sub) {
+        // A thread only ever reads back the 16-byte packs it fetched itself: no barrier between fetch and use.
+        auto my_pack = [&](uint32_t buf, uint32_t v) -> uint4 * {
+            return reinterpret_cast<uint4 *>(smem + buf * SCAN_SUB_WORDS) + (warp * SCAN_MAXV + v) * 32u + lane;
+        };
+        auto geometry = [&](uint32_t sub) {
             nv = rows - sub * SCAN_MAXV < (uint32_t)SCAN_MAXV ? rows - sub * SCAN_MAXV : (uint32_t)SCAN_MAXV;
-            seg_begin = tile_begin + (uint64_t)sub * (SCAN_MAXV * 4u * SCAN_THREADS) + (uint64_t)warp * (nv * 128u);
-#pragma unroll
-            for (int v = 0; v < SCAN_MAXV; v++) {
-                const uint64_t i0 = seg_begin + (uint64_t)(v * 32 + (int)lane) * 4u;
-                x[v] = make_uint4(BIT31, BIT31, BIT31, BIT31);   // fills of 0 groups: neutral
-                if ((uint32_t)v < nv) {
-                    if (i0 + 4 <= p.c_words) {
-                        x[v] = ld_stream_v4(reinterpret_cast<const uint4 *>(p.in + i0));
-                    } else if (i0 < p.c_words) {
-                        x[v].x = p.in[i0];
-                        if (i0 + 1 < p.c_words) x[v].y = p.in[i0 + 1];
-                        if (i0 + 2 < p.c_words) x[v].z = p.in[i0 + 2];
-                    }
-                    if (i0 < (uint64_t)p.skip_words) {
-                        // the stream starts up to 3 words into its first 16-byte unit: what lies before is not part of it
-                        if (i0 + 0 < p.skip_words) x[v].x = BIT31;
-                        if (i0 + 1 < p.skip_words) x[v].y = BIT31;
-                        if (i0 + 2 < p.skip_words) x[v].z = BIT31;
-                    }
+            seg_begin = tile_begin + (uint64_t)sub * SCAN_SUB_WORDS + (uint64_t)warp * (nv * 128u);
+        };
+        auto fetch_sub = [&](uint32_t sub) {   // (leaves nv / seg_begin set for `sub`)
+            geometry(sub);
+#pragma unroll 1
+            for (uint32_t v = 0; v < nv; v++) {
+                const uint64_t i0 = seg_begin + (uint64_t)(v * 32u + lane) * 4u;
+                const uint32_t bytes = i0 + 4 <= p.c_words ? 16u : (i0 < p.c_words ? (uint32_t)(p.c_words - i0) * 4u : 0u);
+                cp_async16((uint32_t)__cvta_generic_to_shared(my_pack(sub & 1u, v)), p.in + (i0 < p.c_words ? i0 : 0), bytes);
+            }
+            cp_async_commit();
+        };
+        // Words of my packs that are not part of the stream (behind its end; up to 3 before its start when it does
+        // not begin on a 16-byte boundary) become fills of 0 groups.  First and last tile only.
+        auto patch_sub = [&](uint32_t sub) {
+#pragma unroll 1
+            for (uint32_t v = 0; v < nv; v++) {
+                const uint64_t i0 = seg_begin + (uint64_t)(v * 32u + lane) * 4u;
+                if (i0 + 4 > p.c_words || i0 < (uint64_t)p.skip_words) {
+                    uint32_t *w = reinterpret_cast<uint32_t *>(my_pack(sub & 1u, v));
+#pragma unroll 1
+                    for (uint32_t j = 0; j < 4u; j++)
+                        if (i0 + j >= p.c_words || i0 + j < (uint64_t)p.skip_words) w[j] = BIT31;
                 }
             }
         };
 
-        // ---- pass 1
+        // ---- pass 1: groups in the tile (getCounts, kernels.cu:298-304)
         uint64_t lsum = 0;
-        uint32_t bad = 0;
+        uint32_t zc = 0;   // fills of 0 groups among my words: malformed -- unless they are my own padding
+        fetch_sub(0);
+#pragma unroll 1
         for (uint32_t sub = 0; sub < nsub; sub++) {
-            load_sub(sub);
-#pragma unroll
-            for (int v = 0; v < SCAN_MAXV; v++) {
-                const uint64_t i0 = seg_begin + (uint64_t)(v * 32 + (int)lane) * 4u;
-                const uint32_t c0 = word_groups(x[v].x), c1 = word_groups(x[v].y), c2 = word_groups(x[v].z),
-                               c3 = word_groups(x[v].w);
-                lsum += (uint64_t)c0 + c1 + c2 + c3;
-                // zero-length fills inside the stream are malformed (padding words behind its end are not)
-                if ((uint32_t)v < nv)
-                    bad += (c0 == 0u && i0 < p.c_words && i0 >= p.skip_words) + (c1 == 0u && i0 + 1 < p.c_words && i0 + 1 >= p.skip_words) +
-                           (c2 == 0u && i0 + 2 < p.c_words && i0 + 2 >= p.skip_words) + (c3 == 0u && i0 + 3 < p.c_words);
+            if (sub + 1u < nsub) {
+                fetch_sub(sub + 1u);   // into the other buffer (which this thread has finished reading)
+                cp_async_wait<1>();
+            } else {
+                cp_async_wait<0>();
+            }
+            geometry(sub);
+            if (ragged) patch_sub(sub);
+#pragma unroll 2
+            for (uint32_t v = 0; v < nv; v++) {
+                const uint4 x = *my_pack(sub & 1u, v);
+                lsum += pack_groups(x);
+                zc += zero_fill(x.x) + zero_fill(x.y) + zero_fill(x.z) + zero_fill(x.w);
             }
         }
-        if (__any_sync(0xffffffffu, bad != 0u)) {
-            bad = warp_sum(bad);
-            if (lane == 0) atomicAdd(&p.ctr->bad_acc, bad);
-        }
         const uint64_t wtotal = warp_sum_u64(lsum);
+        const uint32_t wbad = warp_sum(zc);
         __syncthreads();   // the previous tile's partial sums have been consumed
-        if (lane == 0) s_wsum[warp] = wtotal;
+        if (lane == 0) {
+            s_wsum[warp] = wtotal;
+            s_wbad[warp] = wbad;
+        }
         __syncthreads();
         uint64_t tile_sum = 0, wprefix1 = 0;   // wprefix1: groups in the lower warps' parts (meaningful if nsub == 1)
 #pragma unroll
@@ -189,8 +229,23 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
             if (k < (int)warp) wprefix1 += sv;
             tile_sum += sv;
         }
-        if (tid == 0) cell_store(p.desc + tile, tile_sum, p.epoch);
+        if (tid == 0) {
+            uint32_t bad = 0;
+#pragma unroll
+            for (int k = 0; k < NW; k++) bad += s_wbad[k];
+            bad -= p.tile_words - (uint32_t)(w_last - w_first);   // my padding
+            if (bad) atomicAdd(&p.ctr->bad_acc, bad);
+            cell_store(p.desc + tile, tile_sum, p.epoch);
+        }
+        // A tile whose every word is one group (literal-dense data: sum == number of words) needs no second look at
+        // its words: boundary k * 8192 falls on word (k * 8192 - excl) of the tile.
+        const bool unit_tile = w_last > w_first && tile_sum == w_last - w_first;
+        const bool pre_scan = p.starts != nullptr && !unit_tile && nsub == 1u;
 #ifdef WAH_TRACE
+        if (p.trace && tid == 0 && first_tile) {
+            p.trace[(uint64_t)blockIdx.x * 64u + 62u] = ((uint64_t)unit_tile << 63) | ((uint64_t)nsub << 48) | tile_sum;
+            p.trace[(uint64_t)blockIdx.x * 64u + 63u] = w_last - w_first;
+        }
         if (p.trace && tid == 0 && first_tile) p.trace[(uint64_t)blockIdx.x * 64u + 4u] = (uint64_t)clock64();
 #endif
 
@@ -203,7 +258,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
             const uint32_t round0 = tile - blockIdx.x;   // first tile of my round
             const uint32_t m = p.n_tiles - round0 < stride ? p.n_tiles - round0 : stride;   // tiles in it
             if (tid == 0) {
-                __threadfence();   // my sum is visible before my arrival is
+                __threadfence();   // my sum (and my malformed-word count) is visible before my arrival is
                 // Arrivals are counted over the whole launch: a CTA arrives for round r + 1 only after it has read its
                 // round-r offset, which exists only after ALL round-r arrivals -- so the count at the end of round r
                 // is exactly round0 + m, and nothing has to be reset (or fenced) between rounds.
@@ -215,6 +270,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
                 __threadfence();
                 const uint32_t per = (m + SCAN_THREADS - 1) / SCAN_THREADS;   // consecutive tiles per thread
                 uint64_t mine = 0;
+#pragma unroll 1
                 for (uint32_t j = 0; j < per; j++) {
                     const uint32_t k = tid * per + j;
                     if (k < m) {
@@ -240,6 +296,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
                 for (int k = 0; k < NW; k++)
                     if (k < (int)warp) before += s_lb_sum[k];
                 before += incl - mine;
+#pragma unroll 1
                 for (uint32_t j = 0; j < per; j++) {
                     const uint32_t k = tid * per + j;
                     if (k < m) {
@@ -257,6 +314,18 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
                 }
                 __syncthreads();   // s_lb_sum is reused below
             }
+            // While the offset is on its way: everything pass 2 needs that does not depend on it -- the group offset
+            // of each of my 4-word packs relative to the tile (one 64-bit warp scan per row).
+            if (pre_scan) {
+                uint64_t row_base = wprefix1;
+#pragma unroll 1
+                for (uint32_t v = 0; v < nv; v++) {
+                    const uint64_t sl = pack_groups(*my_pack(0, v));
+                    const uint64_t incl = warp_incl_scan_u64(sl);
+                    s_loc[v * SCAN_THREADS + tid] = row_base + incl - sl;
+                    row_base += __shfl_sync(0xffffffffu, incl, 31);
+                }
+            }
             if (tid == 0) {
                 uint64_t v;
                 while (!cell_load(p.excl + tile, p.epoch, v)) __nanosleep(64);
@@ -266,8 +335,6 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
             excl = s_lb_sum[0];
 #ifdef WAH_TRACE
             if (p.trace && tid == 0 && first_tile) p.trace[(uint64_t)blockIdx.x * 64u + 5u] = (uint64_t)clock64();
-#endif
-#ifdef WAH_TRACE
             first_tile = false;
 #endif
         }
@@ -289,59 +356,76 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
         // ---- pass 2: which compressed word covers each output-tile boundary k * 8192 ?
         //      A word that covers up to 4 boundaries records them itself; a long fill (it may span a hundred
         //      thousand output tiles) is queued and written by the whole CTA afterwards.
-        // A tile whose every word is one group (literal-dense data: sum == number of words) needs no second look at
-        // its words: boundary k * 8192 falls on word (k * 8192 - excl) of the tile.
-        const uint64_t w_first = tile_begin > (uint64_t)p.skip_words ? tile_begin : (uint64_t)p.skip_words;
-        const uint64_t w_last = tile_begin + p.tile_words < p.c_words ? tile_begin + p.tile_words : p.c_words;
-        const bool unit_tile = w_last > w_first && tile_sum == w_last - w_first;
+        const uint64_t k_limit = p.max_out_tiles + 1ull;
         if (p.starts != nullptr && unit_tile) {
             uint64_t k_end = (excl + tile_sum + TGM) >> TG_SHIFT;
-            if (k_end > p.max_out_tiles + 1ull) k_end = p.max_out_tiles + 1ull;
+            if (k_end > k_limit) k_end = k_limit;
+#pragma unroll 1
             for (uint64_t k = ((excl + TGM) >> TG_SHIFT) + tid; k < k_end; k += SCAN_THREADS)
                 store_entry(p.starts + k, w_first + ((k << TG_SHIFT) - excl) + 1ull, k << TG_SHIFT, p.epoch);
+        } else if (pre_scan) {
+            // one sub-tile: the words are still in shared memory and their tile-relative offsets are known
+#pragma unroll 1
+            for (uint32_t v = 0; v < nv; v++) {
+                const uint4 x = *my_pack(0, v);
+                const uint64_t sl = pack_groups(x);
+                const uint64_t off = excl + s_loc[v * SCAN_THREADS + tid];
+                if (((off + TGM) >> TG_SHIFT) != ((off + sl + TGM) >> TG_SHIFT))   // rare: a boundary in my 4 words
+                    record_boundaries(p.starts, p.epoch, k_limit, seg_begin + (uint64_t)(v * 32u + lane) * 4u, off,
+                                      make_uint4(word_groups(x.x), word_groups(x.y), word_groups(x.z), word_groups(x.w)),
+                                      s_heavy, &s_nheavy);
+            }
+#ifdef WAH_TRACE
+            if (p.trace && lane == 0) p.trace[(uint64_t)blockIdx.x * 64u + 50u + warp] = (uint64_t)clock64();
+#endif
         } else if (p.starts != nullptr) {
-            const uint64_t k_limit = p.max_out_tiles + 1ull;
             uint64_t sub_base = excl;   // group offset of the sub-tile's first word
+            fetch_sub(0);
+#pragma unroll 1
             for (uint32_t sub = 0; sub < nsub; sub++) {
-                uint64_t row_base = sub_base;   // group offset of the row's first word
-                if (nsub > 1u) {
-                    load_sub(sub);
-                    uint64_t lsub = 0;
-#pragma unroll
-                    for (int v = 0; v < SCAN_MAXV; v++)
-                        lsub += (uint64_t)word_groups(x[v].x) + word_groups(x[v].y) + word_groups(x[v].z) + word_groups(x[v].w);
-                    const uint64_t wsub = warp_sum_u64(lsub);
-                    __syncthreads();   // s_wsum: the previous sub-tile's (or pass 1's) sums have been consumed
-                    if (lane == 0) s_wsum[warp] = wsub;
-                    __syncthreads();
-#pragma unroll
-                    for (int k = 0; k < NW; k++) {
-                        const uint64_t sv = s_wsum[k];
-                        if (k < (int)warp) row_base += sv;
-                        sub_base += sv;
-                    }
+                if (sub + 1u < nsub) {
+                    fetch_sub(sub + 1u);
+                    cp_async_wait<1>();
                 } else {
-                    row_base += wprefix1;   // one sub-tile: its words are still in registers, its warp sums known
+                    cp_async_wait<0>();
                 }
+                geometry(sub);
+                if (ragged) patch_sub(sub);
+                uint64_t lsub = 0;
+#pragma unroll 2
+                for (uint32_t v = 0; v < nv; v++) lsub += pack_groups(*my_pack(sub & 1u, v));
+                const uint64_t wsub = warp_sum_u64(lsub);
+                __syncthreads();   // s_wsum: the previous sub-tile's (or pass 1's) sums have been consumed
+                if (lane == 0) s_wsum[warp] = wsub;
+                __syncthreads();
+                uint64_t row_base = sub_base;   // group offset of the row's first word
 #pragma unroll
-                for (int v = 0; v < SCAN_MAXV; v++) {
-                    if ((uint32_t)v < nv) {   // uniform
-                        const uint32_t c0 = word_groups(x[v].x), c1 = word_groups(x[v].y), c2 = word_groups(x[v].z),
-                                       c3 = word_groups(x[v].w);
-                        const uint64_t sl = (uint64_t)c0 + c1 + c2 + c3;
-                        const uint64_t incl = warp_incl_scan_u64(sl);
-                        const uint64_t off = row_base + incl - sl;
-                        const uint64_t wi = seg_begin + (uint64_t)(v * 32 + (int)lane) * 4u;
-                        if (((off + TGM) >> TG_SHIFT) != ((off + sl + TGM) >> TG_SHIFT))   // rare: a boundary in my 4 words
-                            record_boundaries(p.starts, p.epoch, k_limit, wi, off, make_uint4(c0, c1, c2, c3), s_heavy, &s_nheavy);
-                        row_base += __shfl_sync(0xffffffffu, incl, 31);
-                    }
+                for (int k = 0; k < NW; k++) {
+                    const uint64_t sv = s_wsum[k];
+                    if (k < (int)warp) row_base += sv;
+                    sub_base += sv;
+                }
+#pragma unroll 1
+                for (uint32_t v = 0; v < nv; v++) {
+                    const uint4 x = *my_pack(sub & 1u, v);
+                    const uint64_t sl = pack_groups(x);
+                    const uint64_t incl = warp_incl_scan_u64(sl);
+                    const uint64_t off = row_base + incl - sl;
+                    if (((off + TGM) >> TG_SHIFT) != ((off + sl + TGM) >> TG_SHIFT))   // rare: a boundary in my 4 words
+                        record_boundaries(p.starts, p.epoch, k_limit, seg_begin + (uint64_t)(v * 32u + lane) * 4u, off,
+                                          make_uint4(word_groups(x.x), word_groups(x.y), word_groups(x.z), word_groups(x.w)),
+                                          s_heavy, &s_nheavy);
+                    row_base += __shfl_sync(0xffffffffu, incl, 31);
                 }
             }
+        }
+        if (p.starts != nullptr && !unit_tile) {
             __syncthreads();
             const uint32_t nh = s_nheavy < (uint32_t)SCAN_HEAVY ? s_nheavy : (uint32_t)SCAN_HEAVY;
+#pragma unroll 1
             for (uint32_t e = 0; e < nh; e++) {
                 const ulonglong4 h = s_heavy[e];
+#pragma unroll 1
                 for (uint64_t k = h.z + tid; k < h.w; k += SCAN_THREADS) store_entry(p.starts + k, h.x + 1ull, h.y, p.epoch);
             }
         }
@@ -351,7 +435,8 @@ __device__ __forceinline__ void scan_body(const ScanParams &p)
 
 __global__ void __launch_bounds__(SCAN_THREADS) wah_scan_kernel(const ScanParams p)
 {
-    scan_body(p);
+    extern __shared__ __align__(16) uint32_t scan_smem[];
+    scan_body(p, scan_smem);
 }
 
 // ---------------------------------------------------------------- expand kernel
@@ -473,7 +558,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     // the whole CTA works from the same numbers -- every path below is full of CTA barriers.  The bookkeeping of the
     // next tiles is requested ahead of time (non-blocking), and so are a tile's first compressed words.
     struct Resolved {
-        uint64_t ws, we, sy, G, total_words;
+        uint64_t ws, we, sy, G, total_words, next;   // next: the tile this CTA expands three iterations from now
         uint32_t flags, first;   // flags: 1 = stop (no such tile / no room), 2 = the stream's last tile
     };
     __shared__ Resolved s_res[2];
@@ -481,12 +566,36 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     Raw cur, nx1, nx2;
     uint2 xpre, xpre_n;
     uint64_t xpre_ws = ~0ull, xpre_n_ws = ~0ull;   // which tile start the prefetched words belong to
-    uint64_t ot = blockIdx.x;
+    // Which tiles a CTA expands: the first EXPAND_STATIC_ROUNDS rounds are dealt round robin (no communication, and
+    // known before the scan phase is over); after that a CTA draws a ticket whenever it starts a tile -- the tile it
+    // will expand four iterations later, so that the ticket, the tile's bookkeeping and its first words are all on
+    // their way long before they are needed.  Tiles differ in cost and SMs in speed: with a fixed deal the slowest CTA
+    // finished 5 us (of 36) after the median one.
+    const uint64_t GD = gridDim.x;
+    const bool dyn = p.ctr != nullptr;
+    uint64_t ot = blockIdx.x, ot1 = ot + GD, ot2 = ot + 2ull * GD, ot3 = 0;
+    uint32_t tk_prev = 0, tk_new = 0;   // thread 0: tickets drawn one / zero iterations ago
     uint32_t it = 0;
     peek(ot, cur);
-    peek(ot + gridDim.x, nx1);
-    for (; ot < p.max_out_tiles; ot += gridDim.x, it++, cur = nx1, nx1 = nx2, xpre = xpre_n, xpre_ws = xpre_n_ws) {
-        peek(ot + 2ull * gridDim.x, nx2);
+    peek(ot1, nx1);
+    for (; ot < p.max_out_tiles; ot = ot1, ot1 = ot2, ot2 = ot3, it++, cur = nx1, nx1 = nx2, xpre = xpre_n, xpre_ws = xpre_n_ws) {
+        peek(ot2, nx2);
+        {
+            // Thread 0 draws a ticket.  (ptxas wraps an atom.add on a provably uniform address in its warp-aggregation
+            // idiom, whose shuffle waits for the result on the spot, and a draw inside a branch is copied -- i.e.
+            // waited for -- at the branch's end: hence an address the compiler cannot prove uniform (p.zero is 0) and a
+            // predicated instruction.  The result is first used an iteration later.)
+            tk_prev = tk_new;
+            asm volatile(
+                "{\n\t"
+                ".reg .pred q;\n\t"
+                "setp.ne.u32 q, %2, 0;\n\t"
+                "@q atom.relaxed.gpu.global.add.u32 %0, [%1], 1;\n\t"
+                "}"
+                : "+r"(tk_new)
+                : "l"(&p.ctr->ticket + (size_t)lane * p.zero), "r"((uint32_t)(dyn && tid == 0))
+                : "memory");
+        }
         xpre_n_ws = ~0ull;
         if (nx1.sx != 0ull) {
             xpre_n_ws = nx1.sx - 1ull;
@@ -528,12 +637,14 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 if (p.hdr->words < r.total_words) r.total_words = p.hdr->words;
             }
             if (!(r.flags & 1u) && r.ws == r.we) r.first = p.in[r.ws];   // a tile inside ONE word is written without decoding
+            r.next = (!dyn || it == 0u) ? ot2 + GD : (uint64_t)EXPAND_STATIC_ROUNDS * GD + tk_prev;
             s_res[it & 1u] = r;
         }
         __syncthreads();
         const Resolved res = s_res[it & 1u];
         if (res.flags & 1u) break;
         const bool last = (res.flags & 2u) != 0u;
+        ot3 = res.next;
         const uint64_t w_lo = ot * (uint64_t)EXPAND_TILE_WORDS;
         const uint64_t ws = res.ws, we = res.we;
         DCHK(ws < p.c_words && we < p.c_words && we >= ws, 4, ((uint64_t)(ws & 0xFFFFFF) << 24) | (we & 0xFFFFFF));
@@ -544,8 +655,10 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         if (xpre_ws != ws) first_words(ws, xpre);
 #ifdef WAH_TRACE
         if (p.trace && tid == 0) {
-            const uint64_t k = (ot - blockIdx.x) / gridDim.x;
+            const uint64_t k = it;
             if (k < 40) p.trace[(uint64_t)blockIdx.x * 64u + 8u + k] = (uint64_t)clock64();
+            p.trace[(uint64_t)blockIdx.x * 64u + 58u] = ot;
+            p.trace[(uint64_t)blockIdx.x * 64u + 59u] = ((uint64_t)res.flags << 32) | (uint64_t)(we - ws);
         }
 #endif
 
@@ -587,7 +700,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         }
 
         const uint32_t nw_all = (uint32_t)(we - wa + 1);   // words wa .. we
-        if (nw_all <= (uint32_t)SPARSE_MAX_WORDS && nout == (uint32_t)EXPAND_TILE_WORDS) {
+        if (nw_all <= (uint32_t)SPARSE_MAX_WORDS) {
             // ================= bit-scatter path (fill dominated data) =================
             // The tile image (7936 words) is cleared in shared memory, every literal ORs its 31 bits into
             // the one or two words it touches, every one-fill sets its bit range, zero fills cost nothing;
@@ -666,16 +779,16 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             }
             fence_async_smem();   // my writes to the image, visible to the bulk copy engine
             __syncthreads();
-            DCHK(w_lo + EXPAND_TILE_WORDS <= p.out_cap, 3, w_lo);
-#ifdef WAH_DBG_NOTMA
-            {
+            if (nout == (uint32_t)EXPAND_TILE_WORDS) {
+                if (tid == 0) bulk_s2g(dst, (uint32_t)__cvta_generic_to_shared(img), EXPAND_TILE_WORDS * 4u);
+            } else {
+                // the stream's last tile, or one cut short by the output capacity: the part that exists, by hand
+                // (this used to take the general path -- code no other tile of a sparse stream runs, fetched from
+                //  DRAM instruction by instruction by the one CTA everybody else is waiting for: 8 us)
                 const uint4 *src4 = reinterpret_cast<const uint4 *>(img);
-                for (uint32_t i = tid; i < (uint32_t)EXPAND_TILE_WORDS / 4; i += EXPAND_THREADS) st_stream_v4(dst4 + i, src4[i]);
+                for (uint32_t i = tid; i < nvec; i += EXPAND_THREADS) st_stream_v4(dst4 + i, src4[i]);
+                for (uint32_t i = (nvec << 2) + tid; i < nout; i += EXPAND_THREADS) dst[i] = img[i];
             }
-            __syncthreads();
-#else
-            if (tid == 0) bulk_s2g(dst, (uint32_t)__cvta_generic_to_shared(img), EXPAND_TILE_WORDS * 4u);
-#endif
             continue;
         }
         // the general path below uses both images as scratch: no bulk store may still be reading them
@@ -781,7 +894,23 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         // no barrier here: the next tile's clear touches s_grp only, and its first barrier orders this
         // tile's staging reads before the next repack writes
     }
+#ifdef WAH_TRACE
+    if (p.trace && tid == 0) p.trace[(uint64_t)blockIdx.x * 64u + 60u] = (uint64_t)clock64();
+#endif
     if (tid == 0) bulk_wait_read<0>();   // shared memory must outlive the bulk stores that read it
+#ifdef WAH_TRACE
+    if (p.trace && tid == 0) p.trace[(uint64_t)blockIdx.x * 64u + 61u] = (uint64_t)clock64();
+#endif
+    if (dyn && tid == 0) {
+        // the last CTA to leave zeroes the counters for the next launch (my own draws are performed before that:
+        // the fence orders them before my `done`)
+        __threadfence();
+        if (atomicAdd(&p.ctr->done, 1u) == gridDim.x - 1u) {
+            __threadfence();
+            p.ctr->ticket = 0;
+            p.ctr->done = 0;
+        }
+    }
 }
 
 __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const ExpandParams p)
@@ -792,6 +921,7 @@ __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const Exp
 // Both phases in one persistent launch: every CTA first takes its share of the scan tiles, then its share of the
 // output tiles, each of which waits only for its own two `starts` entries.  Saves a launch, the idle tail / ramp
 // between two kernels, and the wait for the slowest scan tile.
+static_assert(2 * SCAN_SUB_WORDS <= GRP_WORDS + EXPAND_TILE_WORDS, "the scan phase's two sub-tile buffers live in the expand phase's shared memory");
 static_assert(SCAN_THREADS == EXPAND_THREADS, "the fused kernel runs both phases with one CTA shape");
 #ifdef WAH_TRACE
 #define DTRACE(slot, val)                                                                      \
@@ -818,7 +948,8 @@ __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_decode_kernel(const Sca
         DTRACE(7, smid);
     }
 #endif
-    scan_body(sp);
+    extern __shared__ __align__(16) uint32_t decode_smem[];   // the scan phase borrows the expand phase's tile images
+    scan_body(sp, decode_smem);
     DTRACE(1, clock64());
     __syncthreads();
     DTRACE(2, clock64());
@@ -852,15 +983,18 @@ uint32_t scan_tile_words(uint64_t c_words)
 
 cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream)
 {
-    // persistent + cooperative: the look-back spins on tiles owned by other CTAs, all must be resident
+    // persistent + cooperative: the offset exchange spins on tiles owned by other CTAs, all must be resident
+    constexpr size_t smem = 2 * SCAN_SUB_WORDS * sizeof(uint32_t);
     static int max_grid = 0;
     if (max_grid == 0) {
+        cudaError_t e = cudaFuncSetAttribute(wah_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
         int dev = 0, sms = 0, per_sm = 0;
-        cudaError_t e = cudaGetDevice(&dev);
+        e = cudaGetDevice(&dev);
         if (e != cudaSuccess) return e;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wah_scan_kernel, SCAN_THREADS, 0);
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wah_scan_kernel, SCAN_THREADS, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         if (per_sm > 4) per_sm = 4;
@@ -870,7 +1004,7 @@ cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream)
     if ((uint32_t)grid > p.n_tiles) grid = (int)p.n_tiles;
     ScanParams params = p;
     void *args[] = {&params};
-    return cudaLaunchCooperativeKernel((const void *)wah_scan_kernel, dim3(grid), dim3(SCAN_THREADS), args, 0, stream);
+    return cudaLaunchCooperativeKernel((const void *)wah_scan_kernel, dim3(grid), dim3(SCAN_THREADS), args, smem, stream);
 }
 
 cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStream_t stream)

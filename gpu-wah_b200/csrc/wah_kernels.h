@@ -68,7 +68,9 @@ struct DecodeHeader {
 struct DecodeCounters {
     uint32_t agg_count;     // scan tiles that have published their sum so far
     uint32_t bad_acc;       // zero-length fills seen so far
-    uint64_t pad[3];
+    uint32_t ticket;        // expand phase: output tiles handed out beyond the static rounds
+    uint32_t done;          // expand phase: CTAs that have left it (the last one zeroes ticket and done)
+    uint64_t pad[2];
 };
 
 struct ScanParams {
@@ -97,6 +99,8 @@ struct ExpandParams {
     uint64_t max_out_tiles;
     uint32_t *out;
     uint64_t out_cap;
+    uint32_t zero;           // 0 (opaque to the compiler, see the ticket draw in expand_body)
+    DecodeCounters *ctr;     // nullptr: tiles are dealt round robin; else: dynamically after EXPAND_STATIC_ROUNDS rounds
     uint64_t *trace;         // nullptr; phase timestamps in -DWAH_TRACE builds (scripts/trace_decode.py)
 };
 

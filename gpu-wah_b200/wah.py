@@ -23,7 +23,8 @@ WAH_CANONICAL = 1  # maximal runs
 WAH_MAX_SEAM_WORDS = 8
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
-lib_path = os.path.join(_HERE, "lib", "libwah_b200.so")
+# WAH_B200_LIB: developer override (scripts/ load a -DWAH_TRACE or experimental build of the same library)
+lib_path = os.environ.get("WAH_B200_LIB") or os.path.join(_HERE, "lib", "libwah_b200.so")
 
 
 class WahError(RuntimeError):

@@ -72,3 +72,21 @@ sm = t[:, 7]
 print("CTAs per SM: ", np.bincount(np.bincount(sm.astype(int))))
 pub = g / 1e3 + us(t[:, 4] - t[:, 0])
 print("publish time (start + pass 1) us: med %.2f max %.2f" % (np.median(pub[act]), pub[act].max()))
+end = g / 1e3 + us(t[:, 3] - t[:, 0])
+sc_end = g / 1e3 + us(t[:, 1] - t[:, 0])
+ex_start = g / 1e3 + us(t[:, 2] - t[:, 0])
+print("global timeline (us from first CTA start): scan end med %.2f max %.2f | expand start med %.2f max %.2f | CTA end p10 %.2f med %.2f p90 %.2f max %.2f"
+      % (np.median(sc_end), sc_end.max(), np.median(ex_start), ex_start.max(), np.percentile(end, 10), np.median(end), np.percentile(end, 90), end.max()))
+first_tile = g / 1e3 + us(tt[:, 0] - t[:, 0])
+print("first expand tile resolved at (us): med %.2f max %.2f" % (np.median(first_tile), first_tile.max()))
+print("end by blockIdx range (us):", [round(float(np.median(end[a:a + 37])), 2) for a in range(0, 444, 37)])
+p2w = us(t[:, 50:58] - t[:, 5:6])
+if (t[:, 50] > 0).any():
+    print("pass 2, offset known -> warp done (us): fastest warp med %.2f, slowest warp med %.2f max %.2f" % (np.median(p2w.min(axis=1)), np.median(p2w.max(axis=1)), p2w.max()))
+    print("pass 2, slowest warp done -> scan_body left (us): med %.2f" % np.median(us(t[:, 1:2] - t[:, 50:58]).min(axis=1)))
+late = np.argsort(-end)[:6]
+for b in late:
+    k = nt[b]
+    print("late CTA %d: end %.2f tiles %d tile starts (us, global):" % (b, end[b], k), np.round(g[b] / 1e3 + us(tt[b, :k] - t[b, 0]), 1))
+    print("     last tile id %d flags %d words %d | loop left at %.2f, bulk stores drained at %.2f" % (t[b, 58], t[b, 59] >> 32, t[b, 59] & 0xFFFFFFFF, g[b] / 1e3 + us(t[b, 60] - t[b, 0]), g[b] / 1e3 + us(t[b, 61] - t[b, 0])))
+print("scan tiles: unit", int((t[:, 62] >> 63).sum()), "of", int((t[:, 63] > 0).sum()), "| nsub", int((t[0, 62] >> 48) & 0x7FFF), "| tile 0: groups", int(t[0, 62] & ((1 << 48) - 1)), "words", int(t[0, 63]))

@@ -135,6 +135,16 @@ static int counter_slot(DecodeCounters **slot)
     return WAH_OK;
 }
 
+// WAH_B200_STATIC_TILES=1: deal the decoder's output tiles round robin (the scheme before tickets; for A/B timing)
+static bool static_tiles()
+{
+    static const bool v = [] {
+        const char *e = getenv("WAH_B200_STATIC_TILES");
+        return e && e[0] == '1';
+    }();
+    return v;
+}
+
 static int check_mode(int mode)
 {
     if (mode != WAH_BLOCK1024 && mode != WAH_CANONICAL) return fail(WAH_ERR_INVALID, "unknown mode %d", mode);
@@ -313,7 +323,7 @@ static int decompress_common(const uint32_t *d_in, uint64_t c_words, uint32_t *d
         ep.max_out_tiles = sp.max_out_tiles;
         ep.out = d_out;
         ep.out_cap = out_cap;
-        ep.ctr = sp.ctr;
+        ep.ctr = static_tiles() ? nullptr : sp.ctr;
         ep.trace = g_trace;
         CUDA_TRY(launch_decode(sp, ep, stream));
     }

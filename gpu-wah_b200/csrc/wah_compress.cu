@@ -83,6 +83,24 @@ __device__ __forceinline__ void mbar_wait(uint32_t bar, uint32_t parity)
         "r"(parity)
         : "memory");
 }
+// The same for a warp that is in no hurry (producer: three stages ahead; writer: behind by design): it sleeps between
+// tries instead of re-issuing try_wait back to back on a scheduler the worker warps need every issue slot of.
+__device__ __forceinline__ void mbar_wait_relaxed(uint32_t bar, uint32_t parity)
+{
+    uint32_t ok;
+    do {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred p;\n\t"
+            "mbarrier.try_wait.parity.shared::cta.b64 p, [%1], %2;\n\t"
+            "selp.u32 %0, 1, 0, p;\n\t"
+            "}"
+            : "=r"(ok)
+            : "r"(bar), "r"(parity)
+            : "memory");
+        if (!ok) __nanosleep(128);
+    } while (!ok);
+}
 // global -> shared bulk copy (TMA engine), completion counted in bytes on an mbarrier
 __device__ __forceinline__ void bulk_g2s(uint32_t dst, const void *src, uint32_t bytes, uint32_t bar)
 {
@@ -233,7 +251,7 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
         // =========================================================== producer warp
         for (uint32_t i = 0; i < n_my; i++) {
             const uint32_t s = i % STAGES, use = i / STAGES;
-            if (use > 0) mbar_wait(smem_u32(&sm.empty[s]), (use - 1u) & 1u);
+            if (use > 0) mbar_wait_relaxed(smem_u32(&sm.empty[s]), (use - 1u) & 1u);
             const uint32_t tile = blockIdx.x + i * stride;
             const uint32_t col = tile / p.tiles_per_col;
             const uint32_t t = tile - col * p.tiles_per_col;
@@ -396,7 +414,7 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
         for (uint32_t i = 0; i < n_my; i++) {
             const uint32_t q = i % QDEPTH;
             TileMeta<NWORK> &mt = sm.meta[q];
-            mbar_wait(smem_u32(&sm.pref[q]), (i / QDEPTH) & 1u);
+            mbar_wait_relaxed(smem_u32(&sm.pref[q]), (i / QDEPTH) & 1u);
             if (mt.mode == MODE_RING) {
                 const uint32_t tile_cnt = mt.tile_cnt;
                 const uint64_t dst0 = mt.dst;

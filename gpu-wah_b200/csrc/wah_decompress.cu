@@ -146,8 +146,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
     // memory, two buffers.  A tile of ONE sub-tile -- every stream up to gridDim * 8192 words -- is still there in
     // pass 2; a longer tile is read a second time rather than split into several tiles, because every extra tile per
     // CTA is an extra round of the offset exchange below (measured: 10 us per round).
-    const uint32_t rows = p.tile_words / (4u * SCAN_THREADS);   // rows of 128 words per warp and tile
-    const uint32_t nsub = (rows + SCAN_MAXV - 1) / SCAN_MAXV;
+    const uint32_t rows_full = p.tile_words / (4u * SCAN_THREADS);   // rows of 128 words per warp and tile
     uint64_t *s_loc = reinterpret_cast<uint64_t *>(smem + SCAN_SUB_WORDS);   // one sub-tile: the second buffer is free
 #ifdef WAH_TRACE
     bool first_tile = true;
@@ -157,7 +156,13 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
         const uint64_t tile_begin = (uint64_t)tile * p.tile_words;
         const uint64_t w_first = tile_begin > (uint64_t)p.skip_words ? tile_begin : (uint64_t)p.skip_words;
         const uint64_t w_last = tile_begin + p.tile_words < p.c_words ? tile_begin + p.tile_words : p.c_words;
-        const bool ragged = w_last - w_first != (uint64_t)p.tile_words;   // words of my packs lie outside the stream
+        // (the stream's last tile stops at the row that holds the last word: it is the tile everybody's offset waits for)
+        const uint32_t rows = w_last - tile_begin < (uint64_t)p.tile_words
+                                  ? (uint32_t)((w_last - tile_begin + 4u * SCAN_THREADS - 1u) / (4u * SCAN_THREADS))
+                                  : rows_full;
+        const uint32_t nsub = (rows + SCAN_MAXV - 1) / SCAN_MAXV;
+        const uint32_t padding = rows * (4u * SCAN_THREADS) - (uint32_t)(w_last - w_first);
+        const bool ragged = padding != 0u;   // words of my packs lie outside the stream
         uint32_t nv = 0;          // rows of the sub-tile at hand
         uint64_t seg_begin = 0;   // first word of my warp's part of it
         // A thread only ever reads back the 16-byte packs it fetched itself: no barrier between fetch and use.
@@ -185,10 +190,14 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
             for (uint32_t v = 0; v < nv; v++) {
                 const uint64_t i0 = seg_begin + (uint64_t)(v * 32u + lane) * 4u;
                 if (i0 + 4 > p.c_words || i0 < (uint64_t)p.skip_words) {
-                    uint32_t *w = reinterpret_cast<uint32_t *>(my_pack(sub & 1u, v));
-#pragma unroll 1
-                    for (uint32_t j = 0; j < 4u; j++)
-                        if (i0 + j >= p.c_words || i0 + j < (uint64_t)p.skip_words) w[j] = BIT31;
+                    uint4 *pk = my_pack(sub & 1u, v);
+                    uint4 x = *pk;
+                    const uint64_t lo = p.skip_words, hi = p.c_words;
+                    x.x = (i0 >= lo && i0 < hi) ? x.x : BIT31;
+                    x.y = (i0 + 1 >= lo && i0 + 1 < hi) ? x.y : BIT31;
+                    x.z = (i0 + 2 >= lo && i0 + 2 < hi) ? x.z : BIT31;
+                    x.w = (i0 + 3 >= lo && i0 + 3 < hi) ? x.w : BIT31;
+                    *pk = x;
                 }
             }
         };
@@ -233,7 +242,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
             uint32_t bad = 0;
 #pragma unroll
             for (int k = 0; k < NW; k++) bad += s_wbad[k];
-            bad -= p.tile_words - (uint32_t)(w_last - w_first);   // my padding
+            bad -= padding;
             if (bad) atomicAdd(&p.ctr->bad_acc, bad);
             cell_store(p.desc + tile, tile_sum, p.epoch);
         }

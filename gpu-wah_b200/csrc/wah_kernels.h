@@ -68,8 +68,8 @@ struct DecodeHeader {
 struct DecodeCounters {
     uint32_t agg_count;     // scan tiles that have published their sum so far
     uint32_t bad_acc;       // zero-length fills seen so far
-    uint32_t ticket;        // expand phase: output tiles handed out beyond the static rounds
-    uint32_t done;          // expand phase: CTAs that have left it (the last one zeroes ticket and done)
+    uint32_t ticket;        // tiles handed out beyond the static rounds (decode: output tiles of the expand phase)
+    uint32_t done;          // CTAs that draw no more tickets (the last one zeroes ticket and done)
     uint64_t pad[2];
 };
 

@@ -363,3 +363,35 @@ def test_decode_random_valid_streams(seed, n_words, p_fill, max_count, p_one):
     got, info = gpu_decompress(cw)
     assert info == [want.size, orc.decoded_groups(cw)]
     assert np.array_equal(got, want)
+
+
+@pytest.mark.parametrize("n_words,n_bad", [
+    (1000, 0),            # one scan tile, its packs reach far behind the stream's end (padding is not malformed)
+    (1000, 3),
+    (700_001, 5),         # one tile per CTA, one sub-tile each, ragged last tile
+    (4_500_003, 1),       # tiles of several sub-tiles (double buffered), ragged last sub-tile
+    (4_500_003, 257),
+])
+def test_zero_length_fills_are_counted_and_rejected(n_words, n_bad):
+    """A fill of 0 groups is malformed (the reference's decoder would loop 0 times and desynchronise its scan,
+    kernels.cu:298-304): the scan counts them -- the words of its own padding excluded -- and the host entry point
+    refuses the stream."""
+    rng = np.random.default_rng(n_words + n_bad)
+    cw = _random_stream(rng, n_words, 0.3, 50, 0.5)
+    pos = rng.choice(n_words, size=n_bad, replace=False)
+    cw[pos] = np.where(rng.random(n_bad) < 0.5, np.uint32(0x80000000), np.uint32(0xC0000000))
+    d_in = to_dev(cw)
+    d_info = torch.zeros(2, dtype=torch.int64, device="cuda")
+    ws = wah.Workspace.for_decompress(n_words, 0)
+    wah.decoded_size_device(d_in, n_words, d_info, ws)
+    torch.cuda.synchronize()
+    hdr = ws.buf[:32].cpu().numpy()
+    assert int(hdr[24:28].view(np.uint32)[0]) == n_bad          # DecodeHeader.bad_words
+    good = np.delete(cw, pos)
+    assert d_info.tolist()[1] == orc.decoded_groups(good)        # zero-length fills add no groups
+    if n_bad:
+        with pytest.raises(wah.WahError) as e:
+            wah.decompress(cw)
+        assert e.value.code == 5                                 # WAH_ERR_FORMAT
+    else:
+        assert np.array_equal(wah.decompress(cw), orc.decompress(cw))

@@ -395,3 +395,103 @@ def test_zero_length_fills_are_counted_and_rejected(n_words, n_bad):
         assert e.value.code == 5                                 # WAH_ERR_FORMAT
     else:
         assert np.array_equal(wah.decompress(cw), orc.decompress(cw))
+
+
+# --------------------------------------------------------------------------- BASELINE.json configs at full size
+#
+# The oracle cannot be run over 16 GiB in a test, so the full-size cases are checked through properties that do
+# not depend on the size: (1) decompress(compress(x)) == x, compared on the device; (2) a checksum of checksums:
+# the set bits of x, counted from x, equal the set bits counted from the compressed stream alone (literals by
+# popcount, one-fills as 31 * length); (3) in BLOCK1024 mode 1024-group blocks are independent, so the oracle's
+# output for the first blocks is a prefix of the stream; (4) the sizes the reference reports
+# (decompress.cu:82-93).
+
+_POPC8 = None
+
+
+def _popcount_words(t):
+    """set bits of an int32 device tensor (chunked byte-table lookup)"""
+    global _POPC8
+    if _POPC8 is None:
+        _POPC8 = torch.tensor([bin(i).count("1") for i in range(256)], dtype=torch.int64, device="cuda")
+    total = 0
+    step = 1 << 26
+    for i in range(0, t.numel(), step):
+        total += int(_POPC8[t[i:i + step].view(torch.uint8).long()].sum().item())
+    return total
+
+
+def _popcount_stream(cw):
+    """set bits of the vector a WAH stream stands for, from the stream alone"""
+    total = 0
+    step = 1 << 26
+    for i in range(0, cw.numel(), step):
+        w = cw[i:i + step]
+        fill = w < 0                                     # bit 31
+        lit = torch.where(fill, torch.zeros_like(w), w)
+        total += _popcount_words(lit)
+        ones = fill & ((w & 0x40000000) != 0)
+        total += 31 * int((w & 0x3FFFFFFF).long()[ones].sum().item())
+    return total
+
+
+@pytest.mark.parametrize("name,n,gen,density,mode", [
+    ("C2_sparse_1gbit", 1 << 25, "uniform", 0.001, 0),
+    ("C2_sparse_1gbit_canonical", 1 << 25, "uniform", 0.001, 1),
+    ("C3_clustered_16gbit", 1 << 29, "clustered", 0.01, 0),
+    ("C3_clustered_16gbit_d05_canonical", 1 << 29, "clustered", 0.5, 1),
+    ("C5_128gbit_single_vector", 1 << 32, "clustered", 0.001, 0),
+    ("C5_128gbit_single_vector_canonical", 1 << 32, "clustered", 0.1, 1),
+])
+def test_full_size_configs(name, n, gen, density, mode):
+    x = (wah.gen_uniform_device(n, density, 4711) if gen == "uniform"
+         else wah.gen_clustered_device(n, density, 1000.0, 4711))
+    # room for the stream: these vectors compress at least 4 : 1 (the capacity is enforced by the kernel anyway)
+    cap = n // 4 + 1024
+    out = torch.empty(cap, dtype=torch.int32, device="cuda")
+    cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    wah.compress_device(x, n, out, cap, cnt, wah.Workspace.for_compress(n), mode)
+    c = int(cnt.item())
+    assert 0 < c <= cap, (c, cap)
+    # (3) the oracle on the first 2^21 words (a multiple of 992 words = whole blocks: 2114 * 992)
+    k = 2114 * 992
+    want = orc.compress(to_host(x[:k]), 0)
+    if mode == 0:
+        assert np.array_equal(to_host(out[:want.size]), want)
+    # (2) checksum of checksums
+    bits = _popcount_words(x)
+    assert _popcount_stream(out[:c]) == bits
+    # (1) + (4) round trip
+    dec = torch.empty(n + 4, dtype=torch.int32, device="cuda")
+    info = torch.zeros(2, dtype=torch.int64, device="cuda")
+    wah.decompress_device(out, c, dec, n + 4, info, wah.Workspace.for_decompress(c, n + 4))
+    words, groups = info.tolist()
+    assert groups == orc.num_groups(n) and words == orc.decoded_words(groups)
+    assert torch.equal(dec[:n], x)
+    assert not bool(dec[n:words].any())
+
+
+def test_full_size_bitmap_index_columns():
+    """BASELINE configs[3]: 1024 columns x 64 Mbit, one batched launch; every column a stream of its own."""
+    n_cols, wpc = 1024, 1 << 21
+    x = wah.gen_clustered_device(n_cols * wpc, 0.02, 1000.0, 99)
+    cap = n_cols * wpc // 4 + 4096
+    out = torch.empty(cap, dtype=torch.int32, device="cuda")
+    offs = torch.zeros(n_cols + 1, dtype=torch.int64, device="cuda")
+    wah.compress_batch_device(x, n_cols, wpc, wpc, out, cap, offs, wah.Workspace.for_compress_batch(n_cols, wpc), 0)
+    h_offs = offs.cpu().numpy()
+    assert (np.diff(h_offs) > 0).all() and h_offs[-1] <= cap
+    # a few columns against the oracle, the checksum over all of them
+    for j in (0, 511, 1023):
+        want = orc.compress(to_host(x[j * wpc:(j + 1) * wpc]), 0)
+        assert np.array_equal(to_host(out[h_offs[j]:h_offs[j + 1]]), want), j
+    assert _popcount_stream(out[: int(h_offs[-1])]) == _popcount_words(x)
+    # and back
+    stride = wpc + 4
+    back = torch.empty(n_cols * stride, dtype=torch.int32, device="cuda")
+    info = torch.zeros(2 * n_cols, dtype=torch.int64, device="cuda")
+    lens = np.diff(h_offs)
+    wsd = wah.Workspace.for_decompress_batch(int(lens.max()), wpc + 1)
+    wah.decompress_batch_device(out, [int(v) for v in h_offs], back, stride, wpc + 1, info, wsd)
+    assert torch.equal(back.view(n_cols, stride)[:, :wpc], x.view(n_cols, wpc))
+    assert (info.view(n_cols, 2)[:, 1] == orc.num_groups(wpc)).all()

@@ -5,22 +5,19 @@
 // 8-byte count per compressed word and a one-group-per-int intermediate array in
 // HBM and expand every fill with a serial per-thread loop (kernels.cu:346-348).
 //
-// Here:
-//   scan kernel   : one pass over the compressed words; per-tile group sums with a
-//                   decoupled look-back (CTA-wide window) give every tile its group
-//                   offset, and each tile records, for every OUTPUT tile boundary
-//                   (multiples of 8192 groups) that falls into it, which compressed
-//                   word covers it.
-//   expand kernel : output-centric, hence load balanced whatever the fill lengths
-//                   are.  A persistent grid walks output tiles of 8192 groups = 7936
-//                   words.  Per tile the one-group-per-int array of the reference
-//                   lives in SHARED memory: compressed words are read coalesced,
-//                   scanned in registers and scattered (literal = one store, zero
-//                   fill = nothing, one fill = a run of stores); then one thread
-//                   repacks 32 groups into 31 words with compile-time funnel shifts
-//                   (mergeWords, kernels.cu:375) and the tile leaves as 128-bit lines.
-// Output tiles are aligned in group space to multiples of 32 groups = 31 words, so no
-// output word is shared between threads or tiles and nothing needs atomics.
+// Here: ONE persistent launch (wah_decode_kernel, 3 CTAs per SM), two phases per CTA:
+//   scan phase    one pass over the compressed words, one tile per CTA: per-tile group sums, exchanged through a
+//                 round aggregator, give every tile its group offset; each tile then records, for every OUTPUT
+//                 tile boundary (multiples of 8192 groups) that falls into it, which compressed word covers it.
+//   expand phase  output-centric, hence load balanced whatever the fill lengths are.  The grid walks output tiles
+//                 of 8192 groups = 7936 words; a tile waits only for its own two boundary entries.  Fill
+//                 dominated tiles are assembled as a bit image in SHARED memory (a literal ORs its 31 bits in,
+//                 a one-fill sets a bit range, zero fills cost nothing) and leave through a TMA bulk store;
+//                 literal dominated tiles are repacked in registers with one shuffle per word; anything else
+//                 goes through the reference's one-group-per-int array (kernels.cu:321-359), kept in shared
+//                 memory, and the 32 -> 31 repack of mergeWords (kernels.cu:375).
+// Output tiles are aligned in group space to multiples of 32 groups = 31 words, so no output word is shared
+// between threads or tiles and nothing needs atomics.  wah_scan_kernel is the scan phase alone (size query).
 #include "wah_common.cuh"
 #include "wah_kernels.h"
 
@@ -45,16 +42,17 @@ constexpr uint64_t ENTRY_MASK = (1ull << 48) - 1ull;   // output-tile table: low
 constexpr uint32_t TG_SHIFT = 13;
 static_assert((1u << TG_SHIFT) == (uint32_t)EXPAND_TILE_GROUPS, "output tile must be 8192 groups");
 
-// ------------------------------------------------------------------ scan kernel
+// ------------------------------------------------------------------ scan phase
 
-// One scan tile = p.tile_words compressed words (a multiple of 1024, at most 8192, chosen by the host so that a
-// short stream is one tile per CTA).  A warp owns a contiguous eighth of the tile and reads it with coalesced
-// 128-bit loads, lane l taking words 4l .. 4l+3 of every 128-word row; the words stay in registers:
+// One scan tile = p.tile_words compressed words (a multiple of 1024, chosen by the host so that every stream is one
+// tile per CTA; a tile longer than 8192 words is walked in sub-tiles).  A warp owns a contiguous eighth of a
+// sub-tile, lane l fetching words 4l .. 4l+3 of every 128-word row into shared memory (cp.async):
 //   pass 1  count the groups of my words (getCounts, kernels.cu:298-304), publish the tile sum;
-//   offset  chained sum over the other CTAs' tile sums (see wah_compress.cu);
-//   pass 2  row by row, a warp scan gives every word its group offset; record, for every output-tile boundary
-//           k * 8192 that falls into a word, which word that is and where it starts.
-constexpr int SCAN_MAXV = 8;   // 128-bit loads per lane and tile
+//   offset  the last CTA of a round to publish scans the round's sums and hands every tile its offset;
+//   pass 2  row by row, a warp scan gives every 4-word pack its group offset (done while the offset is in flight
+//           when the tile is one sub-tile); record, for every output-tile boundary k * 8192 that falls into a
+//           word, which word that is and where it starts.
+constexpr int SCAN_MAXV = 8;   // 128-bit packs per lane and sub-tile
 
 // An entry of the output-tile table is read by other CTAs while the scan is still running: x (word index + 1,
 // 0 = not recorded) and y (the word's group offset) must appear together -- one 16-byte store, one 16-byte load.
@@ -448,7 +446,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) wah_scan_kernel(const ScanParams
     scan_body(p, scan_smem);
 }
 
-// ---------------------------------------------------------------- expand kernel
+// ---------------------------------------------------------------- expand phase
 
 constexpr int EXP_CHUNK = EXPAND_THREADS * 8;          // compressed words scanned per round
 constexpr int GRP_WORDS = EXPAND_TILE_GROUPS + EXPAND_TILE_GROUPS / 32;   // rows of 32 groups padded to 33
@@ -922,11 +920,6 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     }
 }
 
-__global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_expand_kernel(const ExpandParams p)
-{
-    expand_body(p);
-}
-
 // Both phases in one persistent launch: every CTA first takes its share of the scan tiles, then its share of the
 // output tiles, each of which waits only for its own two `starts` entries.  Saves a launch, the idle tail / ramp
 // between two kernels, and the wait for the slowest scan tile.
@@ -1039,19 +1032,6 @@ cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStre
     ExpandParams b = ep;
     void *args[] = {&a, &b};
     return launch_pdl((const void *)wah_decode_kernel, grid, EXPAND_THREADS, args, smem, stream);
-}
-
-cudaError_t launch_expand(const ExpandParams &p, int grid, cudaStream_t stream)
-{
-    const size_t smem = expand_smem_bytes();
-    static bool configured = false;
-    if (!configured) {
-        cudaError_t e = cudaFuncSetAttribute(wah_expand_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        configured = true;
-    }
-    wah_expand_kernel<<<grid, EXPAND_THREADS, smem, stream>>>(p);
-    return cudaGetLastError();
 }
 
 }  // namespace wahb200

@@ -109,7 +109,6 @@ size_t expand_smem_bytes();
 // at least SCAN_TILE_WORDS (the unit the workspace is sized by)
 uint32_t scan_tile_words(uint64_t c_words);
 cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream);
-cudaError_t launch_expand(const ExpandParams &p, int grid, cudaStream_t stream);
 cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStream_t stream);   // scan + expand, one launch
 
 // launch with programmatic stream serialisation (see pdl_wait in wah_common.cuh)

@@ -337,7 +337,7 @@ def grp_pos(g):
 
 
 def expand_model(cw, out_cap=None):
-    """Mirror of wah_expand_kernel: per output tile, scatter the compressed words into a padded
+    """Mirror of the general path of wah_decode_kernel's expand phase: per output tile, scatter the compressed words into a padded
     one-group-per-int array, then repack rows of 32 groups into 31 words."""
     c = len(cw)
     CLAMP = 2 * TG

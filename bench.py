@@ -409,7 +409,7 @@ def run_b200(args):
     alg_bytes = 4.0 * (n_words + c_avg)
     # dram__bytes_read.sum + dram__bytes_write.sum per launch from the committed ncu --set full capture of this very
     # command (profiles/r1_ncu_full_summary.md); known for the default workload only
-    ncu_traffic = {"wah_compress_kernel": 134.29e6 + 5.03e6, "wah_decode_kernel": 10.97e6 + 76.79e6}
+    ncu_traffic = {"wah_compress_kernel": 134.29e6 + 6.62e6, "wah_decode_kernel": 10.84e6 + 75.51e6}
     default_wl = args.workload == "sparse_1gbit" and args.density is None and args.mode == "block1024"
     comp_dom = tc_ms >= td_ms
     dom_ms = tc_ms if comp_dom else td_ms

@@ -531,8 +531,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     // An output tile can be expanded as soon as the scan has recorded where it starts and where the next one
     // starts (starts[k].x = word index + 1, 0 = not recorded yet) -- the offsets of the low tiles are known long
     // before a straggling scan tile at the far end of the stream is done.  The decoded size (the header) is only
-    // needed to recognise the stream's last tile.  Every thread resolves this for itself: the data only ever
-    // goes from "unknown" to its final value, so all threads arrive at the same answer.
+    // needed to recognise the stream's last tile.
     struct Raw {
         uint64_t sx, sy, ex;
     };
@@ -544,6 +543,42 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             uint64_t ey;
             load_entry(p.starts + ot_ + 1, p.epoch, r.ex, ey);
         }
+    };
+    // The same two entries, requested but not looked at (thread 0 only).  The epoch check of load_entry() consumes
+    // the loaded words on the spot, i.e. waits out the L2 round trip: with every thread peeking ahead that way at the
+    // top of every tile, 12 % of the kernel's warp time went into waiting for look-AHEAD data.  Here the registers
+    // are only written (a predicated load with read-write operands, so that no copy -- no wait -- follows it); they
+    // are decoded when the tile comes up, a tile or two later.
+    struct RawPeek {
+        uint64_t ax, ay, bx;   // entry ot: x, y; entry ot + 1: x
+        uint32_t by_hi;        // ... and the upper half of its y (its epoch tag; the offset below it is not needed)
+    };
+    // (x and y each carry half of the epoch, so an entry read in pieces is either complete or reads as unpublished;
+    //  every register is loaded exactly as wide as it is used -- the compiler copies the live part of a partly dead
+    //  register right behind the load, which is a wait)
+    auto request = [&](uint64_t ot_, RawPeek &r) {
+        r.ax = r.ay = r.bx = 0;
+        r.by_hi = 0;
+        const uint32_t go = tid == 0 && ot_ < p.max_out_tiles;
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q;\n\t"
+            "setp.ne.u32 q, %5, 0;\n\t"
+            "@q ld.volatile.global.v2.u64 {%0, %1}, [%4];\n\t"
+            "@q ld.volatile.global.u64 %2, [%4+16];\n\t"
+            "@q ld.volatile.global.u32 %3, [%4+28];\n\t"
+            "}"
+            : "+l"(r.ax), "+l"(r.ay), "+l"(r.bx), "+r"(r.by_hi)
+            : "l"(p.starts + (go ? ot_ : 0)), "r"(go)
+            : "memory");
+    };
+    auto decode_peek = [&](const RawPeek &r, Raw &o) {
+        const uint32_t e_lo = p.epoch & 0xFFFFu, e_hi = p.epoch >> 16;
+        const bool oka = (uint32_t)(r.ax >> 48) == e_lo && (uint32_t)(r.ay >> 48) == e_hi;
+        const bool okb = (uint32_t)(r.bx >> 48) == e_lo && (r.by_hi >> 16) == e_hi;
+        o.sx = oka ? (r.ax & ENTRY_MASK) : 0ull;
+        o.sy = r.ay & ENTRY_MASK;
+        o.ex = okb ? (r.bx & ENTRY_MASK) : 0ull;
     };
     auto header_known = [&]() -> bool {
         if (*reinterpret_cast<const volatile uint32_t *>(&p.hdr->valid) != p.epoch) return false;
@@ -566,11 +601,12 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     // next tiles is requested ahead of time (non-blocking), and so are a tile's first compressed words.
     struct Resolved {
         uint64_t ws, we, sy, G, total_words, next;   // next: the tile this CTA expands three iterations from now
+        uint64_t next_ws;                            // first compressed word of the CTA's next tile, ~0 = not known yet
         uint32_t flags, first;   // flags: 1 = stop (no such tile / no room), 2 = the stream's last tile
     };
     __shared__ Resolved s_res[2];
     uint32_t w[8];
-    Raw cur, nx1, nx2;
+    RawPeek rq0, rq1, rq2;   // thread 0: the entries of this tile and the next two, as requested
     uint2 xpre, xpre_n;
     uint64_t xpre_ws = ~0ull, xpre_n_ws = ~0ull;   // which tile start the prefetched words belong to
     // Which tiles a CTA expands: the first EXPAND_STATIC_ROUNDS rounds are dealt round robin (no communication, and
@@ -583,10 +619,10 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     uint64_t ot = blockIdx.x, ot1 = ot + GD, ot2 = ot + 2ull * GD, ot3 = 0;
     uint32_t tk_prev = 0, tk_new = 0;   // thread 0: tickets drawn one / zero iterations ago
     uint32_t it = 0;
-    peek(ot, cur);
-    peek(ot1, nx1);
-    for (; ot < p.max_out_tiles; ot = ot1, ot1 = ot2, ot2 = ot3, it++, cur = nx1, nx1 = nx2, xpre = xpre_n, xpre_ws = xpre_n_ws) {
-        peek(ot2, nx2);
+    request(ot, rq0);
+    request(ot1, rq1);
+    for (; ot < p.max_out_tiles; ot = ot1, ot1 = ot2, ot2 = ot3, it++, rq0 = rq1, rq1 = rq2, xpre = xpre_n, xpre_ws = xpre_n_ws) {
+        request(ot2, rq2);
         {
             // Thread 0 draws a ticket.  (ptxas wraps an atom.add on a provably uniform address in its warp-aggregation
             // idiom, whose shuffle waits for the result on the spot, and a draw inside a branch is copied -- i.e.
@@ -603,17 +639,16 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 : "l"(&p.ctr->ticket + (size_t)lane * p.zero), "r"((uint32_t)(dyn && tid == 0))
                 : "memory");
         }
-        xpre_n_ws = ~0ull;
-        if (nx1.sx != 0ull) {
-            xpre_n_ws = nx1.sx - 1ull;
-            first_words(xpre_n_ws, xpre_n);
-        }
 
         // ---- resolve the tile (thread 0, blocking)
         if (tid == 0) {
             Resolved r;
             r.flags = 0;
             bool hdr = false;
+            Raw cur, nx1;
+            decode_peek(rq0, cur);   // requested two tiles ago
+            decode_peek(rq1, nx1);   // requested one tile ago
+            r.next_ws = nx1.sx != 0ull ? nx1.sx - 1ull : ~0ull;
             while (cur.sx == 0ull) {
                 if (!hdr) hdr = header_known();
                 if (hdr && ot >= p.hdr->out_tiles) {
@@ -652,6 +687,8 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         if (res.flags & 1u) break;
         const bool last = (res.flags & 2u) != 0u;
         ot3 = res.next;
+        xpre_n_ws = res.next_ws;
+        if (xpre_n_ws != ~0ull) first_words(xpre_n_ws, xpre_n);   // the next tile's first words, a tile ahead
         const uint64_t w_lo = ot * (uint64_t)EXPAND_TILE_WORDS;
         const uint64_t ws = res.ws, we = res.we;
         DCHK(ws < p.c_words && we < p.c_words && we >= ws, 4, ((uint64_t)(ws & 0xFFFFFF) << 24) | (we & 0xFFFFFF));

@@ -15,6 +15,8 @@ from .wah import (  # noqa: F401
     compress,
     compress_batch_device,
     compress_device,
+    container_pack,
+    container_unpack,
     decoded_words,
     decompress,
     decompress_batch_device,
@@ -35,5 +37,6 @@ __all__ = [
     "WAH_BLOCK1024", "WAH_CANONICAL", "WahError", "Workspace", "compress", "decompress",
     "compress_device", "compress_batch_device", "decompress_device", "decompress_batch_device", "decoded_size_device",
     "num_groups", "max_compressed_words", "decoded_words", "gen_uniform_device",
-    "gen_clustered_device", "shard_record_device", "stitch_plan", "lib", "lib_path", "mgpu",
+    "gen_clustered_device", "shard_record_device", "stitch_plan", "container_pack", "container_unpack", "lib", "lib_path",
+    "mgpu",
 ]

@@ -100,6 +100,10 @@ _sig("wah_stitch_plan", ctypes.c_int, ctypes.POINTER(ShardRecord), ctypes.c_int,
      ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_uint32),
      ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(_u64))
 _sig("wah_test_set_max_launch_tiles", None, _u64)
+_sig("wah_container_bytes", _u64, _u64, _u64)
+_sig("wah_container_pack", ctypes.c_int, _vp, _u64, ctypes.c_int, _u64, _u64, _vp, _vp)
+_sig("wah_container_unpack", ctypes.c_int, _vp, _u64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_u64),
+     ctypes.POINTER(_u64), ctypes.POINTER(_vp), ctypes.POINTER(_vp), ctypes.POINTER(_u64))
 _sig("wah_gen_uniform_device", ctypes.c_int, _vp, _u64, ctypes.c_double, _u64, _vp)
 _sig("wah_gen_paint_runs_device", ctypes.c_int, _vp, _u64, _vp, _vp, _u64, _vp)
 
@@ -171,6 +175,43 @@ def decompress(data, timings: dict | None = None) -> np.ndarray:
     if timings is not None:
         timings.update(h2d_ms=t[0].value, compute_ms=t[1].value, d2h_ms=t[2].value)
     return _wrap_malloced(out.value, n.value)
+
+
+# --------------------------------------------------------------------------- container (host only)
+
+
+def container_pack(words, mode: int = WAH_BLOCK1024, words_per_stream: int = 0, stream_offsets=None) -> np.ndarray:
+    """Wrap compressed words (one stream, or several back to back with their ``stream_offsets``: columns of a bitmap
+    index as ``compress_batch_device`` lays them out, shards of one vector) into a self-describing byte buffer:
+    header, offset table, words (``wah_container_pack``)."""
+    w = _host_u32(words)
+    offs = np.ascontiguousarray([0, w.size] if stream_offsets is None else stream_offsets, dtype=np.uint64)
+    n_streams = offs.size - 1
+    if n_streams < 1:
+        raise WahError(1, "a container holds at least one stream")
+    total = int(offs[-1])
+    if total != w.size:
+        raise WahError(1, "the last stream offset must be the number of words")
+    out = np.empty(lib.wah_container_bytes(n_streams, total) // 8 + 1, dtype=np.uint64)   # 8-byte aligned storage
+    nbytes = lib.wah_container_bytes(n_streams, total)
+    _check(lib.wah_container_pack(out.ctypes.data, nbytes, mode, n_streams, words_per_stream, offs.ctypes.data,
+                                  w.ctypes.data))
+    return out.view(np.uint8)[:nbytes]
+
+
+def container_unpack(buf):
+    """-> (mode, words_per_stream, stream_offsets, words); validates magic, version, sizes, offsets, checksum."""
+    raw = np.frombuffer(buf, dtype=np.uint8) if not isinstance(buf, np.ndarray) else buf.view(np.uint8).reshape(-1)
+    store = np.empty(raw.size // 8 + 1, dtype=np.uint64)   # an 8-byte aligned copy the returned views refer to
+    store.view(np.uint8)[: raw.size] = raw
+    mode, ns, wps, tw = ctypes.c_int(), _u64(), _u64(), _u64()
+    p_offs, p_words = _vp(), _vp()
+    _check(lib.wah_container_unpack(store.ctypes.data, raw.size, ctypes.byref(mode), ctypes.byref(ns), ctypes.byref(wps),
+                                    ctypes.byref(p_offs), ctypes.byref(p_words), ctypes.byref(tw)))
+    base = store.ctypes.data
+    offs = store.view(np.uint8)[p_offs.value - base: p_offs.value - base + 8 * (ns.value + 1)].view(np.uint64)
+    words = store.view(np.uint8)[p_words.value - base: p_words.value - base + 4 * tw.value].view(np.uint32)
+    return mode.value, wps.value, offs, words
 
 
 # --------------------------------------------------------------------------- device API

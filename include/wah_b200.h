@@ -160,6 +160,23 @@ int wah_stitch_plan(const wah_shard_record *records, int n_shards, int mode,
                     uint64_t *seam_offset, uint32_t *seam_count, uint32_t *seam_words,
                     uint64_t *total_words);
 
+/* ---- container: compressed streams that leave the process (host only) ---------------- */
+
+/* The reference keeps a compressed vector as a bare word array plus a length in a local variable (its only trace of
+ * a file format is a commented-out dump, tests.cpp:278-281).  The container adds what those locals held: a 64-byte
+ * header (magic "WAHB200", version, mode, n_streams, words_per_stream, total_words, checksum, header_bytes), the
+ * word offset of every stream (columns of a bitmap index as wah_compress_batch_device lays them out, shards of one
+ * vector, or a single stream), then the words.  Little endian; layout in gpu-wah_b200/csrc/wah_container.cpp.   */
+uint64_t wah_container_bytes(uint64_t n_streams, uint64_t total_words);
+/* stream_offsets: n_streams + 1 word offsets, first 0, last = total words */
+int wah_container_pack(void *dst, uint64_t dst_bytes, int mode, uint64_t n_streams, uint64_t words_per_stream,
+                       const uint64_t *stream_offsets, const uint32_t *words);
+/* Validates magic, version, sizes against src_bytes, the offset table and the checksum (WAH_ERR_FORMAT otherwise);
+ * the out-pointers (each may be NULL) receive views INTO src, which must be 8-byte aligned.                      */
+int wah_container_unpack(const void *src, uint64_t src_bytes, int *mode, uint64_t *n_streams,
+                         uint64_t *words_per_stream, const uint64_t **stream_offsets, const uint32_t **words,
+                         uint64_t *total_words);
+
 /* ---- synthetic bitvector generators used by bench.py / the tests (device) ---------- */
 
 /* i.i.d. Bernoulli(density) bits, counter-based (splitmix64), reproducible for (seed, word index) */

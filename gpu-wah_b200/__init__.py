@@ -26,6 +26,12 @@ from .wah import (  # noqa: F401
     gen_uniform_device,
     lib,
     lib_path,
+    logical_device,
+    popcount_device,
+    WAH_OP_AND,
+    WAH_OP_OR,
+    WAH_OP_XOR,
+    WAH_OP_ANDNOT,
     max_compressed_words,
     num_groups,
     shard_record_device,
@@ -37,6 +43,7 @@ __all__ = [
     "WAH_BLOCK1024", "WAH_CANONICAL", "WahError", "Workspace", "compress", "decompress",
     "compress_device", "compress_batch_device", "decompress_device", "decompress_batch_device", "decoded_size_device",
     "num_groups", "max_compressed_words", "decoded_words", "gen_uniform_device",
-    "gen_clustered_device", "shard_record_device", "stitch_plan", "container_pack", "container_unpack", "lib", "lib_path",
+    "gen_clustered_device", "shard_record_device", "stitch_plan", "container_pack", "container_unpack", "logical_device", "popcount_device",
+    "WAH_OP_AND", "WAH_OP_OR", "WAH_OP_XOR", "WAH_OP_ANDNOT", "lib", "lib_path",
     "mgpu",
 ]

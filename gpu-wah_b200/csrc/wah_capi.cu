@@ -467,6 +467,57 @@ extern "C" int wah_stitch_plan(const wah_shard_record *rec, int n_shards, int mo
     return WAH_OK;
 }
 
+// --------------------------------------------------------------------- query operators
+
+extern "C" int wah_popcount_device(const uint32_t *d_in, uint64_t c_words, uint64_t *d_bits, void *stream)
+{
+    if (!d_bits || (c_words && !d_in)) return fail(WAH_ERR_INVALID, "null device pointer");
+    CUDA_TRY(launch_popcount(d_in, c_words, d_bits, (cudaStream_t)stream));
+    return WAH_OK;
+}
+
+// workspace of wah_logical_device: two decoded operands, the decoder's and the encoder's scratch, 64 B of scalars
+static size_t logical_operand_bytes(uint64_t n_words) { return (size_t)((n_words + 8 + 3) / 4 * 4) * 4; }
+static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
+
+extern "C" size_t wah_logical_workspace_bytes(uint64_t n_words, uint64_t ca_words, uint64_t cb_words)
+{
+    const uint64_t cmax = ca_words > cb_words ? ca_words : cb_words;
+    return 2 * align256(logical_operand_bytes(n_words)) + 256 + align256(wah_decompress_workspace_bytes(cmax, n_words + 8)) +
+           align256(wah_compress_workspace_bytes(n_words));
+}
+
+extern "C" int wah_logical_device(int op, const uint32_t *d_a, uint64_t ca_words, const uint32_t *d_b, uint64_t cb_words,
+                                  uint64_t n_words, int mode, uint32_t *d_out, uint64_t out_capacity_words,
+                                  uint64_t *d_out_words, void *d_workspace, size_t workspace_bytes, void *stream_)
+{
+    cudaStream_t stream = (cudaStream_t)stream_;
+    if (op < WAH_OP_AND || op > WAH_OP_ANDNOT) return fail(WAH_ERR_INVALID, "unknown operator %d", op);
+    if (check_mode(mode)) return WAH_ERR_INVALID;
+    if (!d_workspace || !aligned16(d_workspace)) return fail(WAH_ERR_INVALID, "workspace must be a 16-byte aligned device buffer");
+    const size_t need = wah_logical_workspace_bytes(n_words, ca_words, cb_words);
+    if (workspace_bytes < need) return fail(WAH_ERR_CAPACITY, "workspace too small: %zu < %zu", workspace_bytes, need);
+    // First version: both operands are expanded into scratch, combined word by word, and the result is compressed
+    // again -- three validated kernels and one trivial one, about 5 x 4n bytes of traffic.  Operating on the runs
+    // themselves (a merge of the two streams' group offsets; cost proportional to the compressed sizes) is the next
+    // step; this call's contract will not change with it.
+    char *ws = static_cast<char *>(d_workspace);
+    const size_t ob = align256(logical_operand_bytes(n_words));
+    uint32_t *buf_a = reinterpret_cast<uint32_t *>(ws), *buf_b = reinterpret_cast<uint32_t *>(ws + ob);
+    uint64_t *info = reinterpret_cast<uint64_t *>(ws + 2 * ob);
+    const uint64_t cmax = ca_words > cb_words ? ca_words : cb_words;
+    const size_t dws_bytes = align256(wah_decompress_workspace_bytes(cmax, n_words + 8));
+    void *dws = ws + 2 * ob + 256;
+    void *cws = ws + 2 * ob + 256 + dws_bytes;
+    // a stream that decodes to fewer than n_words words counts as zero-extended
+    CUDA_TRY(cudaMemsetAsync(buf_a, 0, 2 * ob, stream));
+    if (int rc = wah_decompress_device(d_a, ca_words, buf_a, n_words + 8, info, dws, dws_bytes, stream)) return rc;
+    if (int rc = wah_decompress_device(d_b, cb_words, buf_b, n_words + 8, info + 2, dws, dws_bytes, stream)) return rc;
+    CUDA_TRY(launch_logical(op, buf_a, buf_b, n_words, stream));
+    return wah_compress_device(buf_a, n_words, mode, d_out, out_capacity_words, d_out_words, cws,
+                               wah_compress_workspace_bytes(n_words), stream);
+}
+
 // --------------------------------------------------------------------- generators
 
 extern "C" int wah_gen_uniform_device(uint32_t *d_out, uint64_t n_words, double density, uint64_t seed,

@@ -131,6 +131,8 @@ inline cudaError_t launch_pdl(const void *kernel, int grid, int threads, void **
 
 cudaError_t launch_shard_probe(const uint32_t *d_shard, uint64_t words, uint64_t *d_result /*[6]*/,
                                cudaStream_t stream);
+cudaError_t launch_popcount(const uint32_t *d_in, uint64_t c_words, uint64_t *d_bits, cudaStream_t stream);
+cudaError_t launch_logical(int op, uint32_t *d_a, const uint32_t *d_b, uint64_t n_words, cudaStream_t stream);
 cudaError_t launch_gen_uniform(uint32_t *d_out, uint64_t n_words, double density, uint64_t seed,
                                cudaStream_t stream);
 cudaError_t launch_gen_paint_runs(uint32_t *d_out, uint64_t n_words, const int64_t *d_start,

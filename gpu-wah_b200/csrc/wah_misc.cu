@@ -87,6 +87,37 @@ __global__ void wah_gen_paint_runs_kernel(uint32_t *out, uint64_t n_words, const
 
 }  // namespace
 
+// ---- query operators -------------------------------------------------------------------------
+
+// set bits of the vector a stream stands for, straight from the stream: a literal contributes its popcount, a
+// one-fill 31 bits per group (kernels.cu:337-348 is what a decoder would expand it to), a zero-fill nothing
+__global__ void wah_popcount_kernel(const uint32_t *in, uint64_t c_words, unsigned long long *bits)
+{
+    unsigned long long mine = 0;
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < c_words; i += (uint64_t)gridDim.x * blockDim.x) {
+        const uint32_t w = in[i];
+        mine += is_fill(w) ? ((w & BIT30) ? 31ull * fill_count(w) : 0ull) : (unsigned long long)__popc(w);
+    }
+    mine = warp_sum_u64(mine);
+    if ((threadIdx.x & 31u) == 0 && mine) atomicAdd(bits, mine);
+}
+
+// a[i] = a[i] op b[i] on decoded vectors, 128 bits per thread and step (n4 = number of uint4)
+__global__ void wah_logical_kernel(int op, uint4 *a, const uint4 *b, uint64_t n4)
+{
+    for (uint64_t i = (uint64_t)blockIdx.x * blockDim.x + threadIdx.x; i < n4; i += (uint64_t)gridDim.x * blockDim.x) {
+        uint4 x = a[i];
+        const uint4 y = b[i];
+        switch (op) {
+        case 0: x.x &= y.x; x.y &= y.y; x.z &= y.z; x.w &= y.w; break;
+        case 1: x.x |= y.x; x.y |= y.y; x.z |= y.z; x.w |= y.w; break;
+        case 2: x.x ^= y.x; x.y ^= y.y; x.z ^= y.z; x.w ^= y.w; break;
+        default: x.x &= ~y.x; x.y &= ~y.y; x.z &= ~y.z; x.w &= ~y.w; break;
+        }
+        a[i] = x;
+    }
+}
+
 cudaError_t launch_shard_probe(const uint32_t *d_shard, uint64_t words, uint64_t *d_result, cudaStream_t stream)
 {
     wah_shard_probe_kernel<<<1, 32, 0, stream>>>(d_shard, words, d_result);
@@ -114,6 +145,24 @@ cudaError_t launch_gen_paint_runs(uint32_t *d_out, uint64_t n_words, const int64
     const uint64_t blocks = (n_runs + 255) / 256;
     const int grid = (int)(blocks < 148ull * 16 ? blocks : 148ull * 16);
     wah_gen_paint_runs_kernel<<<grid, 256, 0, stream>>>(d_out, n_words, d_start, d_len, n_runs);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_popcount(const uint32_t *d_in, uint64_t c_words, uint64_t *d_bits, cudaStream_t stream)
+{
+    cudaError_t e = cudaMemsetAsync(d_bits, 0, sizeof(uint64_t), stream);
+    if (e != cudaSuccess || c_words == 0) return e;
+    const uint64_t want = (c_words + 1023) / 1024;
+    wah_popcount_kernel<<<(unsigned)(want < 1184 ? want : 1184), 256, 0, stream>>>(d_in, c_words, (unsigned long long *)d_bits);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_logical(int op, uint32_t *d_a, const uint32_t *d_b, uint64_t n_words, cudaStream_t stream)
+{
+    const uint64_t n4 = (n_words + 3) / 4;   // the buffers are padded to whole 16-byte units
+    if (n4 == 0) return cudaSuccess;
+    const uint64_t want = (n4 + 1023) / 1024;
+    wah_logical_kernel<<<(unsigned)(want < 1184 ? want : 1184), 256, 0, stream>>>(op, (uint4 *)d_a, (const uint4 *)d_b, n4);
     return cudaGetLastError();
 }
 

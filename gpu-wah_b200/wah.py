@@ -21,6 +21,7 @@ WAH_BLOCK1024 = 0  # bit-exact to the reference encoder (runs never cross 1024 g
 WAH_CANONICAL = 1  # maximal runs
 
 WAH_MAX_SEAM_WORDS = 8
+WAH_OP_AND, WAH_OP_OR, WAH_OP_XOR, WAH_OP_ANDNOT = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
 # WAH_B200_LIB: developer override (scripts/ load a -DWAH_TRACE or experimental build of the same library)
@@ -100,6 +101,9 @@ _sig("wah_stitch_plan", ctypes.c_int, ctypes.POINTER(ShardRecord), ctypes.c_int,
      ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_uint32),
      ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(_u64))
 _sig("wah_test_set_max_launch_tiles", None, _u64)
+_sig("wah_popcount_device", ctypes.c_int, _vp, _u64, _vp, _vp)
+_sig("wah_logical_workspace_bytes", _sz, _u64, _u64, _u64)
+_sig("wah_logical_device", ctypes.c_int, ctypes.c_int, _vp, _u64, _vp, _u64, _u64, ctypes.c_int, _vp, _u64, _vp, _vp, _sz, _vp)
 _sig("wah_container_bytes", _u64, _u64, _u64)
 _sig("wah_container_pack", ctypes.c_int, _vp, _u64, ctypes.c_int, _u64, _u64, _vp, _vp)
 _sig("wah_container_unpack", ctypes.c_int, _vp, _u64, ctypes.POINTER(ctypes.c_int), ctypes.POINTER(_u64),
@@ -263,6 +267,10 @@ class Workspace:
         return cls(lib.wah_decompress_workspace_bytes(c_words, out_capacity_words), device)
 
     @classmethod
+    def for_logical(cls, n_words: int, ca_words: int, cb_words: int, device="cuda"):
+        return cls(lib.wah_logical_workspace_bytes(n_words, ca_words, cb_words), device)
+
+    @classmethod
     def for_decompress_batch(cls, max_col_c_words: int, out_col_capacity_words: int, device="cuda"):
         return cls(lib.wah_decompress_batch_workspace_bytes(max_col_c_words, out_col_capacity_words), device)
 
@@ -308,6 +316,20 @@ def decoded_size_device(d_in, c_words: int, d_out_info, workspace, stream=None) 
 
 
 # -------------------------------------------------------------------- range sharding
+
+
+def popcount_device(d_in, c_words: int, d_bits, stream=None) -> None:
+    """``d_bits`` (device int64 scalar) = set bits of the vector the stream stands for, from the stream alone."""
+    _check(lib.wah_popcount_device(_ptr(d_in), c_words, _ptr(d_bits), _stream(stream)))
+
+
+def logical_device(op: int, d_a, ca_words: int, d_b, cb_words: int, n_words: int, d_out, out_capacity_words: int,
+                   d_out_words, workspace, mode: int = WAH_BLOCK1024, stream=None) -> None:
+    """``out = compress(decompress(a) op decompress(b))`` for two compressed vectors of ``n_words`` words each
+    (``WAH_OP_AND`` / ``OR`` / ``XOR`` / ``ANDNOT``); workspace: ``Workspace.for_logical``."""
+    _check(lib.wah_logical_device(op, _ptr(d_a), ca_words, _ptr(d_b), cb_words, n_words, mode, _ptr(d_out),
+                                  out_capacity_words, _ptr(d_out_words), _ptr(workspace), workspace.nbytes,
+                                  _stream(stream)))
 
 
 def shard_record_device(d_shard, words: int, groups: int, stream=None) -> ShardRecord:

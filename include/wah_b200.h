@@ -160,6 +160,24 @@ int wah_stitch_plan(const wah_shard_record *records, int n_shards, int mode,
                     uint64_t *seam_offset, uint32_t *seam_count, uint32_t *seam_words,
                     uint64_t *total_words);
 
+/* ---- query operators on compressed vectors (not in the reference) --------- */
+
+/* *d_bits = number of set bits of the vector the stream stands for, computed from the stream alone */
+int wah_popcount_device(const uint32_t *d_in, uint64_t c_words, uint64_t *d_bits, void *stream);
+
+#define WAH_OP_AND    0
+#define WAH_OP_OR     1
+#define WAH_OP_XOR    2
+#define WAH_OP_ANDNOT 3 /* a & ~b */
+/* out = compress(decompress(a) op decompress(b)) for two streams that stand for vectors of n_words words each (a
+ * stream that decodes to fewer words counts as zero-extended), in either encoder mode; bit-identical to what
+ * wah_compress_device produces for the combined vector.  This version expands both operands into the workspace;
+ * d_out / d_out_words / capacity as for wah_compress_device.  Asynchronous on `stream`.                       */
+size_t wah_logical_workspace_bytes(uint64_t n_words, uint64_t ca_words, uint64_t cb_words);
+int wah_logical_device(int op, const uint32_t *d_a, uint64_t ca_words, const uint32_t *d_b, uint64_t cb_words,
+                       uint64_t n_words, int mode, uint32_t *d_out, uint64_t out_capacity_words,
+                       uint64_t *d_out_words, void *d_workspace, size_t workspace_bytes, void *stream);
+
 /* ---- container: compressed streams that leave the process (host only) ---------------- */
 
 /* The reference keeps a compressed vector as a bare word array plus a length in a local variable (its only trace of

@@ -495,3 +495,36 @@ def test_full_size_bitmap_index_columns():
     wah.decompress_batch_device(out, [int(v) for v in h_offs], back, stride, wpc + 1, info, wsd)
     assert torch.equal(back.view(n_cols, stride)[:, :wpc], x.view(n_cols, wpc))
     assert (info.view(n_cols, 2)[:, 1] == orc.num_groups(wpc)).all()
+
+
+# --------------------------------------------------------------------------- query operators
+
+_NP_OPS = {0: lambda a, b: a & b, 1: lambda a, b: a | b, 2: lambda a, b: a ^ b, 3: lambda a, b: a & ~b}
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("name,n,gen_a,gen_b", [
+    ("sparse_x_sparse", 992 * 40 + 5, lambda n: datagen.uniform(n, 0.001, 1), lambda n: datagen.uniform(n, 0.002, 2)),
+    ("clustered_x_dense", 3 * TW + 100, lambda n: datagen.clustered(n, 0.3, 1000, 3), lambda n: datagen.uniform(n, 0.5, 4)),
+    ("ones_x_zeros", 2 * TW, lambda n: np.full(n, 0xFFFFFFFF, dtype=np.uint32), lambda n: np.zeros(n, dtype=np.uint32)),
+    ("clustered_x_clustered_1M", 1 << 20, lambda n: datagen.clustered(n, 0.05, 1000, 5), lambda n: datagen.clustered(n, 0.2, 300, 6)),
+    ("tiny", 7, lambda n: datagen.uniform(n, 0.5, 7), lambda n: datagen.uniform(n, 0.5, 8)),
+])
+def test_logical_operators_and_popcount(name, n, gen_a, gen_b, mode):
+    a, b = gen_a(n), gen_b(n)
+    ca, cb = orc.compress(a, mode), orc.compress(b, 1 - mode)      # the operands need not share a mode
+    d_a, d_b = to_dev(ca), to_dev(cb)
+    cap = wah.max_compressed_words(n)
+    d_out = torch.full((cap,), -1, dtype=torch.int32, device="cuda")
+    d_cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    d_bits = torch.full((1,), -1, dtype=torch.int64, device="cuda")
+    ws = wah.Workspace.for_logical(n, ca.size, cb.size)
+    for op, f in _NP_OPS.items():
+        wah.logical_device(op, d_a, ca.size, d_b, cb.size, n, d_out, cap, d_cnt, ws, mode)
+        c = int(d_cnt.item())
+        want_vec = f(a, b)
+        want = orc.compress(want_vec, mode)
+        assert c == want.size, (name, op)
+        assert np.array_equal(to_host(d_out[:c]), want), (name, op)
+        wah.popcount_device(d_out, c, d_bits)
+        assert int(d_bits.item()) == int(np.unpackbits(want_vec.view(np.uint8)).sum()), (name, op)

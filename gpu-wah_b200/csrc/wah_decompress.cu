@@ -250,8 +250,8 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
         const bool pre_scan = p.starts != nullptr && !unit_tile && nsub == 1u;
 #ifdef WAH_TRACE
         if (p.trace && tid == 0 && first_tile) {
-            p.trace[(uint64_t)blockIdx.x * 64u + 62u] = ((uint64_t)unit_tile << 63) | ((uint64_t)nsub << 48) | tile_sum;
-            p.trace[(uint64_t)blockIdx.x * 64u + 63u] = w_last - w_first;
+            p.trace[(uint64_t)blockIdx.x * 64u + 48u] = ((uint64_t)unit_tile << 63) | ((uint64_t)nsub << 48) | tile_sum;
+            p.trace[(uint64_t)blockIdx.x * 64u + 49u] = w_last - w_first;
         }
         if (p.trace && tid == 0 && first_tile) p.trace[(uint64_t)blockIdx.x * 64u + 4u] = (uint64_t)clock64();
 #endif
@@ -469,6 +469,8 @@ __device__ __forceinline__ void bulk_wait_read()
 }
 __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.async.shared::cta;" ::: "memory"); }
 
+// invariants of the expand phase, checked in -DWAH_TRACE builds only: the first violation's code and value end up in
+// trace[62] (compute-sanitizer is not available on the GPU pool; this found what it would have)
 #ifdef WAH_TRACE
 #define DCHK(cond, code, val)                                                                     \
     do {                                                                                          \

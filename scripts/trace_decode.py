@@ -89,4 +89,6 @@ for b in late:
     k = nt[b]
     print("late CTA %d: end %.2f tiles %d tile starts (us, global):" % (b, end[b], k), np.round(g[b] / 1e3 + us(tt[b, :k] - t[b, 0]), 1))
     print("     last tile id %d flags %d words %d | loop left at %.2f, bulk stores drained at %.2f" % (t[b, 58], t[b, 59] >> 32, t[b, 59] & 0xFFFFFFFF, g[b] / 1e3 + us(t[b, 60] - t[b, 0]), g[b] / 1e3 + us(t[b, 61] - t[b, 0])))
-print("scan tiles: unit", int((t[:, 62] >> 63).sum()), "of", int((t[:, 63] > 0).sum()), "| nsub", int((t[0, 62] >> 48) & 0x7FFF), "| tile 0: groups", int(t[0, 62] & ((1 << 48) - 1)), "words", int(t[0, 63]))
+print("scan tiles: unit", int((t[:, 48] >> 63).sum()), "of", int((t[:, 49] > 0).sum()), "| nsub", int((t[0, 48] >> 48) & 0x7FFF), "| tile 0: groups", int(t[0, 48] & ((1 << 48) - 1)), "words", int(t[0, 49]))
+if t[0, 62]:
+    print("INVARIANT VIOLATED (DCHK): code", int(t[0, 62]) >> 48, "value", int(t[0, 62]) & ((1 << 48) - 1))

@@ -125,3 +125,17 @@ def test_stitch_plan_on_real_shards():
             shards = [orc.compress(p, mode) for p in parts]
             plan = wah.stitch_plan([_record(s) for s in shards], mode)
             assert np.array_equal(_apply_plan(shards, plan), orc.compress(data, mode))
+
+
+def test_query_operator_argument_validation():
+    # rejected before any CUDA call: works without a device
+    assert wah.lib.wah_logical_device(9, None, 0, None, 0, 10, 0, None, 0, None, None, 0, None) == 1
+    assert b"operator" in wah.lib.wah_last_error_string()
+    assert wah.lib.wah_logical_device(0, None, 0, None, 0, 10, 7, None, 0, None, None, 0, None) == 1     # mode
+    assert wah.lib.wah_logical_device(0, None, 0, None, 0, 10, 0, None, 0, None, None, 0, None) == 1     # workspace
+    assert wah.lib.wah_popcount_device(None, 5, None, None) == 1
+    # the workspace holds both decoded operands plus the scratch of one decode and one compress
+    n = 1 << 20
+    need = wah.lib.wah_logical_workspace_bytes(n, 1000, 70000)
+    assert need >= 2 * 4 * n + wah.lib.wah_decompress_workspace_bytes(70000, n + 8) + wah.lib.wah_compress_workspace_bytes(n)
+    assert need < 2 * 4 * n + (4 << 20)

@@ -412,3 +412,56 @@ def expand_model(cw, out_cap=None):
             out[w_lo + i] = stage[i]
     assert all(w is not None for w in out)
     return out, words, G
+
+
+# ---------------------------------------------------------------- scan phase geometry (wah_decompress.cu scan_body)
+import numpy as np  # noqa: E402
+
+SCAN_MAXV = 8                      # 16-byte packs per lane and sub-tile
+SCAN_SUB_WORDS = SCAN_MAXV * 4 * SCAN_THREADS
+
+
+def scan_tile_words_model(c_words, grid=444):
+    """scan_tile_words(): one tile per CTA of the decode grid, a multiple of 1024 words, at least 2048"""
+    unit = 4 * SCAN_THREADS
+    tw = ((c_words + grid - 1) // grid + unit - 1) // unit * unit
+    return max(tw, SCAN_TILE)
+
+
+def scan_geometry_model(cw, skip_words=0, grid=444):
+    """Walks the stream the way scan_body does -- tiles, sub-tiles of up to 8 rows per warp, 16-byte packs fetched
+    with a byte count (cp.async zero-fills the rest), padding patched to fills of 0 groups -- and returns what pass 1
+    publishes per tile: (groups, malformed words, is unit tile).  Asserts that every word of the stream is fetched
+    exactly once and nothing behind it is read."""
+    c = len(cw)
+    tw = scan_tile_words_model(c, grid)
+    n_tiles = (c + tw - 1) // tw
+    assert n_tiles <= grid
+    seen = np.zeros(c, dtype=np.int32)
+    out = []
+    for tile in range(n_tiles):
+        tile_begin = tile * tw
+        w_first, w_last = max(tile_begin, skip_words), min(tile_begin + tw, c)
+        rows = (w_last - tile_begin + 4 * SCAN_THREADS - 1) // (4 * SCAN_THREADS) if w_last - tile_begin < tw else tw // (4 * SCAN_THREADS)
+        nsub = (rows + SCAN_MAXV - 1) // SCAN_MAXV
+        padding = rows * 4 * SCAN_THREADS - (w_last - w_first)
+        groups = zero_fills = 0
+        for sub in range(nsub):
+            nv = min(SCAN_MAXV, rows - sub * SCAN_MAXV)
+            for warp in range(SCAN_THREADS // 32):
+                seg_begin = tile_begin + sub * SCAN_SUB_WORDS + warp * nv * 128
+                for v in range(nv):
+                    for lane in range(32):
+                        i0 = seg_begin + (v * 32 + lane) * 4
+                        nbytes = 16 if i0 + 4 <= c else (max(c - i0, 0) * 4)
+                        pack = [int(cw[i0 + j]) if j * 4 < nbytes else 0 for j in range(4)]     # zero filled
+                        seen[i0:i0 + nbytes // 4] += 1
+                        for j in range(4):                                                        # patch_sub
+                            if i0 + j >= c or i0 + j < skip_words:
+                                pack[j] = BIT31
+                        for w in pack:
+                            groups += word_groups(w)
+                            zero_fills += (w & ~BIT30 & 0xFFFFFFFF) == BIT31
+        out.append((groups, zero_fills - padding, w_last > w_first and groups == w_last - w_first))
+    assert (seen == 1).all()
+    return out

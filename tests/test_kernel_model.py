@@ -97,3 +97,31 @@ def test_expand_model_matches_oracle(name, cw, data):
     if data is not None:
         assert np.array_equal(want[: data.size], data)
         assert not want[data.size:].any()
+
+
+@pytest.mark.parametrize("c_words,skip,n_bad,grid", [
+    (1, 0, 0, 444), (1000, 0, 2, 444), (2048, 3, 0, 444), (2049, 0, 1, 444), (200_001, 2, 5, 444),
+    (6 * 8192 + 17, 0, 3, 6),        # (a grid of 6 CTAs:) tiles of two sub-tiles, the second one row long
+    (6 * 8192 * 3 - 5000, 1, 0, 6),  # three sub-tiles, a ragged last tile several rows shorter than the others
+    (6 * 8192 * 2, 0, 1, 6),         # exact fit: no padding anywhere
+])
+def test_scan_geometry_covers_the_stream_once_and_counts_padding_out(c_words, skip, n_bad, grid):
+    """The decoder's scan phase: every word fetched exactly once, tile sums add up to the stream's groups, fills of
+    0 groups are counted as malformed but the scan's own padding is not (wah_decompress.cu scan_body)."""
+    rng = np.random.default_rng(c_words)
+    cw = np.where(rng.random(c_words) < 0.3, np.uint32(0x80000000) | rng.integers(1, 50, c_words).astype(np.uint32),
+                  rng.integers(1, 0x7FFFFFFF, c_words).astype(np.uint32)).astype(np.uint32)
+    bad_pos = skip + rng.choice(c_words - skip, size=min(n_bad, c_words - skip), replace=False) if n_bad else []
+    cw[bad_pos] = 0xC0000000
+    tiles = km.scan_geometry_model(cw, skip, grid)
+    counts = np.where(cw >> 31, cw & 0x3FFFFFFF, 1).astype(np.int64)
+    assert sum(t[0] for t in tiles) == int(counts[skip:].sum())
+    assert sum(t[1] for t in tiles) == len(bad_pos)
+    assert all(t[1] >= 0 for t in tiles)
+
+
+def test_scan_geometry_recognises_unit_tiles():
+    cw = np.arange(1, 5000, dtype=np.uint32)          # literals only
+    assert all(t[2] for t in km.scan_geometry_model(cw))
+    cw[100] = 0x80000002
+    assert not km.scan_geometry_model(cw)[0][2]

@@ -362,3 +362,70 @@ uint64_t wah_oracle_compress_batch(const uint32_t *in, uint64_t n_cols, uint64_t
     offsets[n_cols] = c;
     return c;
 }
+
+/* ------------------------------------------------------------------ query operators on the runs themselves
+ *
+ * Not in the reference.  Two streams that stand for vectors of the same length have the same 31-bit groups, so
+ * a logical operator can walk both run sequences side by side: where both operands are inside fills the result
+ * is a fill of min(remaining) groups (no group is looked at), where one is a literal the result is one group.
+ * The result goes through the same encoder state as wah_oracle_compress, so it equals
+ * compress(decompress(a) op decompress(b)) word for word, in either mode.  This is the specification (and the
+ * checker) of a compressed-domain kernel; cost O(ca + cb), independent of the uncompressed length. */
+
+typedef struct { const uint32_t *w; uint64_t c, i; uint64_t rem; uint32_t val; int fill; } cursor_t;
+
+static inline void cur_next(cursor_t *q)
+{
+    while (q->rem == 0) {
+        if (q->i >= q->c) { q->fill = 1; q->val = 0u; q->rem = ~0ull; return; }   /* zero-extended */
+        uint32_t x = q->w[q->i++];
+        if (x & BIT31) { q->fill = 1; q->val = (x & BIT30) ? ONES31 : 0u; q->rem = x & (BIT30 - 1u); }
+        else { q->fill = 0; q->val = x; q->rem = 1; }
+    }
+}
+
+static inline uint32_t apply_op(int op, uint32_t a, uint32_t b)
+{
+    switch (op) {
+    case 0: return a & b;
+    case 1: return a | b;
+    case 2: return a ^ b;
+    default: return a & ~b & ONES31;
+    }
+}
+
+uint64_t wah_oracle_logical(int op, const uint32_t *a, uint64_t ca, const uint32_t *b, uint64_t cb,
+                            uint64_t groups, int mode, uint32_t *out)
+{
+    const int block = mode == WAH_ORACLE_BLOCK1024;
+    enc_t e = { out, 0, -1, 0 };
+    cursor_t x = { a, ca, 0, 0, 0u, 1 }, y = { b, cb, 0, 0, 0u, 1 };
+    uint64_t k = 0;
+    while (k < groups) {
+        if (block && (k & 1023u) == 0) enc_flush(&e);
+        cur_next(&x);
+        cur_next(&y);
+        uint64_t take = 1;
+        if (x.fill && y.fill) {
+            take = x.rem < y.rem ? x.rem : y.rem;
+            if (take > groups - k) take = groups - k;
+            if (block && take > 1024u - (k & 1023u)) take = 1024u - (k & 1023u);
+        }
+        const uint32_t r = apply_op(op, x.val, y.val) & ONES31;
+        if (take == 1) {
+            enc_group(&e, r);
+        } else {
+            uint64_t left = take;                       /* r is 0 or ONES31: both operands are constant here */
+            while (left) {
+                uint32_t part = left > MAXFILL ? MAXFILL : (uint32_t)left;
+                enc_fill(&e, r == ONES31, part);
+                left -= part;
+            }
+        }
+        x.rem -= take;
+        y.rem -= take;
+        k += take;
+    }
+    enc_flush(&e);
+    return e.c;
+}

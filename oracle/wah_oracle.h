@@ -69,6 +69,12 @@ int wah_oracle_max_threads(void);
 uint64_t wah_oracle_compress_batch(const uint32_t *in, uint64_t n_cols, uint64_t words_per_col,
                                    int mode, uint32_t *out, uint64_t *offsets);
 
+/* out = a op b (0 AND, 1 OR, 2 XOR, 3 ANDNOT) computed on the runs of two streams that stand for vectors of
+ * `groups` groups each (a shorter stream counts as zero-extended); equals
+ * compress(decompress(a) op decompress(b)) word for word.  out must hold `groups` words.  Returns the length. */
+uint64_t wah_oracle_logical(int op, const uint32_t *a, uint64_t ca_words, const uint32_t *b, uint64_t cb_words,
+                            uint64_t groups, int mode, uint32_t *out);
+
 #ifdef __cplusplus
 }
 #endif

@@ -86,3 +86,14 @@ def compress_batch(cols, mode=BLOCK1024):
     offs = np.zeros(n_cols + 1, dtype=np.uint64)
     c = _lib.wah_oracle_compress_batch(a.ctypes.data, n_cols, wpc, mode, out.ctypes.data, offs.ctypes.data)
     return out[:c].copy(), offs
+
+
+def logical(op, a, b, groups, mode=BLOCK1024):
+    """a op b on the runs of two compressed streams (0 AND, 1 OR, 2 XOR, 3 ANDNOT)"""
+    x, y = _u32(a), _u32(b)
+    out = np.empty(max(groups, 1), dtype=np.uint32)
+    _lib.wah_oracle_logical.restype = ctypes.c_uint64
+    _lib.wah_oracle_logical.argtypes = [ctypes.c_int, ctypes.c_void_p, ctypes.c_uint64, ctypes.c_void_p, ctypes.c_uint64,
+                                        ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p]
+    c = _lib.wah_oracle_logical(op, x.ctypes.data, x.size, y.ctypes.data, y.size, groups, mode, out.ctypes.data)
+    return out[:c].copy()

@@ -133,3 +133,39 @@ def test_oracle_canonical_splits_runs_at_the_counter_limit():
     got = orc.canonicalize(cw)
     assert got.tolist() == [BIT31 | M, BIT31 | M, BIT31 | 5, BIT31 | BIT30 | M, BIT31 | BIT30 | 7, 9]
     assert orc.decoded_groups(got) == orc.decoded_groups(cw)
+
+
+# --------------------------------------------------------------------------- query operators on the runs themselves
+
+_NP_OPS = {0: lambda a, b: a & b, 1: lambda a, b: a | b, 2: lambda a, b: a ^ b, 3: lambda a, b: a & ~b}
+
+
+@pytest.mark.parametrize("mode", [orc.BLOCK1024, orc.CANONICAL])
+@pytest.mark.parametrize("name,n,gen_a,gen_b", [
+    ("sparse_x_sparse", 992 * 40 + 5, lambda n: datagen.uniform(n, 0.001, 1), lambda n: datagen.uniform(n, 0.002, 2)),
+    ("clustered_x_dense", 3 * 7936 + 100, lambda n: datagen.clustered(n, 0.3, 1000, 3), lambda n: datagen.uniform(n, 0.5, 4)),
+    ("ones_x_zeros", 2 * 7936, lambda n: np.full(n, 0xFFFFFFFF, dtype=np.uint32), lambda n: np.zeros(n, dtype=np.uint32)),
+    ("ones_x_clustered", 5000, lambda n: np.full(n, 0xFFFFFFFF, dtype=np.uint32), lambda n: datagen.clustered(n, 0.5, 300, 9)),
+    ("clustered_x_clustered", 1 << 18, lambda n: datagen.clustered(n, 0.05, 1000, 5), lambda n: datagen.clustered(n, 0.2, 300, 6)),
+    ("tiny", 7, lambda n: datagen.uniform(n, 0.5, 7), lambda n: datagen.uniform(n, 0.5, 8)),
+    ("one_word", 1, lambda n: np.array([0x80000001], dtype=np.uint32), lambda n: np.array([0xFFFFFFFF], dtype=np.uint32)),
+])
+def test_logical_on_runs_equals_compress_of_the_combined_vector(name, n, gen_a, gen_b, mode):
+    """The compressed-domain operator (specification of the next kernel) against the plain route: decode both,
+    combine word by word, encode.  The operands may come from either encoder mode."""
+    a, b = gen_a(n), gen_b(n)
+    ca, cb = orc.compress(a, mode), orc.compress(b, 1 - mode)
+    for op, f in _NP_OPS.items():
+        want = orc.compress(f(a, b), mode)
+        got = orc.logical(op, ca, cb, orc.num_groups(n), mode)
+        assert np.array_equal(got, want), (name, op)
+
+
+def test_logical_on_runs_zero_extends_a_short_operand():
+    a = datagen.clustered(4000, 0.4, 200, 11)
+    b = datagen.uniform(1000, 0.3, 12)
+    b_ext = np.concatenate([b, np.zeros(3000, dtype=np.uint32)])
+    ca, cb = orc.compress(a, 1), orc.compress(b, 1)
+    # (b's own last group is zero padded, exactly as the zero extension continues it)
+    for op, f in _NP_OPS.items():
+        assert np.array_equal(orc.logical(op, ca, cb, orc.num_groups(4000), 1), orc.compress(f(a, b_ext), 1)), op

@@ -9,6 +9,9 @@ CUDA).  There is no CPU fallback: if the library is missing, import raises.
 from .wah import (  # noqa: F401
     WAH_BLOCK1024,
     WAH_CANONICAL,
+    WAH_STATUS_BAD_WORDS_MASK,
+    WAH_STATUS_BATCH_LENGTH,
+    WAH_STATUS_TIMEOUT,
     ShardRecord,
     WahError,
     Workspace,
@@ -40,7 +43,7 @@ from .wah import (  # noqa: F401
 from . import mgpu  # noqa: F401
 
 __all__ = [
-    "WAH_BLOCK1024", "WAH_CANONICAL", "WahError", "Workspace", "compress", "decompress",
+    "WAH_BLOCK1024", "WAH_CANONICAL", "WAH_STATUS_BAD_WORDS_MASK", "WAH_STATUS_TIMEOUT", "WAH_STATUS_BATCH_LENGTH", "WahError", "Workspace", "compress", "decompress",
     "compress_device", "compress_batch_device", "decompress_device", "decompress_batch_device", "decoded_size_device",
     "num_groups", "max_compressed_words", "decoded_words", "gen_uniform_device",
     "gen_clustered_device", "shard_record_device", "stitch_plan", "container_pack", "container_unpack", "logical_device", "popcount_device",

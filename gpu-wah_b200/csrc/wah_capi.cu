@@ -110,31 +110,6 @@ static uint32_t next_epoch()
     if (v == 0u) v = e.fetch_add(1u);
     return v;
 }
-// Zero-initialised counters for the decode kernel: a library-owned array of slots per device, one slot per
-// launch in turn.  (The caller's workspace cannot hold them: its content is arbitrary -- allocators recycle
-// memory -- and clearing it would cost a memset node in front of every launch.)
-static int counter_slot(DecodeCounters **slot)
-{
-    constexpr int MAX_DEV = 64, SLOTS = 4096;
-    static std::mutex mu;
-    static DecodeCounters *base[MAX_DEV] = {};
-    static std::atomic<uint32_t> next{0};
-    int dev = 0;
-    CUDA_TRY(cudaGetDevice(&dev));
-    if (dev < 0 || dev >= MAX_DEV) return fail(WAH_ERR_INVALID, "device ordinal %d not supported", dev);
-    {
-        std::lock_guard<std::mutex> g(mu);
-        if (!base[dev]) {
-            void *p = nullptr;
-            CUDA_TRY(cudaMalloc(&p, sizeof(DecodeCounters) * SLOTS));
-            CUDA_TRY(cudaMemset(p, 0, sizeof(DecodeCounters) * SLOTS));
-            base[dev] = static_cast<DecodeCounters *>(p);
-        }
-    }
-    *slot = base[dev] + (next.fetch_add(1u) % SLOTS);
-    return WAH_OK;
-}
-
 // WAH_B200_STATIC_TILES=1: deal the decoder's output tiles round robin (the scheme before tickets; for A/B timing)
 static bool static_tiles()
 {
@@ -199,6 +174,8 @@ extern "C" int wah_compress_batch_device(const uint32_t *d_in, uint64_t n_cols, 
         p.total_out = slots + ((launch + 1) & 1);
         p.col_offsets = d_col_offsets + c0;
         p.epoch = next_epoch();
+        LaunchOrder order(stream);
+        CUDA_TRY(order.status());
         CUDA_TRY(launch_compress(p, mode, stream));
     }
     return WAH_OK;
@@ -257,6 +234,8 @@ extern "C" int wah_compress_device(const uint32_t *d_in, uint64_t n_words, int m
         p.col_offsets = nullptr;
         p.trace = g_trace;
         p.epoch = next_epoch();
+        LaunchOrder order(stream);
+        CUDA_TRY(order.status());
         CUDA_TRY(launch_compress(p, mode, stream));
     }
     return WAH_OK;
@@ -272,62 +251,111 @@ static size_t ws_starts_off(uint64_t c_words)
     size_t o = ws_desc_off() + 2 * (size_t)scan_tiles(c_words) * sizeof(ulonglong2);   // tile sums + tile offsets
     return (o + 15) & ~(size_t)15;
 }
+// workspace: header | one tile sum and one tile offset per 2048-word scan tile | one table entry per output tile
+static size_t decode_ws_bytes(uint64_t c_words, uint64_t table_entries)
+{
+    return ws_starts_off(c_words) + (size_t)(table_entries + 2) * sizeof(ulonglong2);
+}
 
 extern "C" size_t wah_decompress_workspace_bytes(uint64_t c_words, uint64_t out_capacity_words)
 {
-    return ws_starts_off(c_words) + (size_t)(max_out_tiles(out_capacity_words) + 2) * sizeof(ulonglong2);
+    return decode_ws_bytes(c_words, max_out_tiles(out_capacity_words));
+}
+
+// One decode launch.  Single stream: n_cols = 1, col_groups = ~0, out_cap = capacity of d_out.  Batch: n_cols columns
+// of col_groups groups each, out_cap = words written per column, column j at d_out + j * col_stride.
+struct DecodeJob {
+    const uint32_t *d_in;
+    uint64_t c_words;
+    uint32_t skip_words;
+    uint32_t *d_out;
+    uint64_t out_cap;
+    uint64_t n_cols, col_groups, col_stride;
+    bool expand;
+};
+
+static int decode_launch(const DecodeJob &job, uint64_t *d_out_info, void *d_workspace, size_t workspace_bytes,
+                         cudaStream_t stream)
+{
+    const bool batch = job.col_groups != ~0ull;
+    const uint64_t tpc = batch ? ceil_div(job.col_groups, EXPAND_TILE_GROUPS) : (job.expand ? max_out_tiles(job.out_cap) : 0);
+    if (tpc > 0xFFFFFFF0ull || job.n_cols > 0xFFFFFFF0ull || job.n_cols * tpc > 0xFFFFFFF0ull)
+        return fail(WAH_ERR_INVALID, "too many output tiles for one launch");
+    const uint64_t entries = job.expand ? job.n_cols * tpc : 0;
+    const size_t need = decode_ws_bytes(job.c_words, entries);
+    if (workspace_bytes < need) return fail(WAH_ERR_CAPACITY, "workspace too small: %zu < %zu", workspace_bytes, need);
+    if (scan_tiles(job.c_words) > 0x7FFFFFFFull) return fail(WAH_ERR_INVALID, "compressed stream too long");
+
+    char *ws = static_cast<char *>(d_workspace);
+    ScanParams sp;
+    memset(&sp, 0, sizeof(sp));
+    sp.in = job.d_in;
+    sp.c_words = job.c_words;
+    sp.skip_words = job.skip_words;
+    CUDA_TRY(scan_tile_words(job.c_words, &sp.tile_words));
+    sp.n_tiles = (uint32_t)ceil_div(job.c_words, sp.tile_words);
+    sp.hdr = reinterpret_cast<DecodeHeader *>(ws);
+    sp.desc = reinterpret_cast<ulonglong2 *>(ws + ws_desc_off());
+    sp.excl = sp.desc + scan_tiles(job.c_words);
+    sp.epoch = next_epoch();
+    sp.starts = job.expand ? reinterpret_cast<ulonglong2 *>(ws + ws_starts_off(job.c_words)) : nullptr;
+    sp.max_out_tiles = tpc;
+    sp.out_info = d_out_info;
+    sp.col_groups = job.col_groups;
+    sp.n_cols = (uint32_t)job.n_cols;
+    sp.trace = g_trace;
+    LaunchOrder order(stream);
+    CUDA_TRY(order.status());
+    CUDA_TRY(order.counter_slots(&sp.ctr, &sp.next_ctr));
+    if (!job.expand) {
+        CUDA_TRY(launch_scan(sp, stream));
+        return WAH_OK;
+    }
+    ExpandParams ep;
+    memset(&ep, 0, sizeof(ep));
+    ep.in = job.d_in;
+    ep.c_words = job.c_words;
+    ep.hdr = sp.hdr;
+    ep.hdr_rw = sp.hdr;
+    ep.epoch = sp.epoch;
+    ep.starts = sp.starts;
+    ep.max_out_tiles = tpc;
+    ep.out = job.d_out;
+    ep.out_cap = job.out_cap;
+    ep.col_groups = job.col_groups;
+    ep.col_stride = job.col_stride;
+    ep.n_cols = (uint32_t)job.n_cols;
+    ep.out_info = d_out_info;
+    ep.dynamic_tiles = static_tiles() ? 0u : 1u;
+    ep.ctr = sp.ctr;
+    ep.trace = g_trace;
+    CUDA_TRY(launch_decode(sp, ep, stream));
+    return WAH_OK;
 }
 
 static int decompress_common(const uint32_t *d_in, uint64_t c_words, uint32_t *d_out, uint64_t out_cap,
                              uint64_t *d_out_info, void *d_workspace, size_t workspace_bytes, bool expand,
-                             cudaStream_t stream, uint32_t skip_words = 0)
+                             cudaStream_t stream)
 {
     if (!d_out_info) return fail(WAH_ERR_INVALID, "d_out_info is null");
     if (c_words == 0) {
-        CUDA_TRY(cudaMemsetAsync(d_out_info, 0, 2 * sizeof(uint64_t), stream));
+        CUDA_TRY(cudaMemsetAsync(d_out_info, 0, 3 * sizeof(uint64_t), stream));
         return WAH_OK;
     }
     if (!d_in || !d_workspace || (expand && !d_out)) return fail(WAH_ERR_INVALID, "null device pointer");
     if (!aligned16(d_in) || !aligned16(d_workspace) || (expand && !aligned16(d_out)))
         return fail(WAH_ERR_INVALID, "device buffers must be 16-byte aligned");
-    if (scan_tiles(c_words) > 0x7FFFFFFFull) return fail(WAH_ERR_INVALID, "compressed stream too long");
-    const size_t need = wah_decompress_workspace_bytes(c_words, expand ? out_cap : 0);
-    if (workspace_bytes < need) return fail(WAH_ERR_CAPACITY, "workspace too small: %zu < %zu", workspace_bytes, need);
-
-    char *ws = static_cast<char *>(d_workspace);
-    ScanParams sp;
-    memset(&sp, 0, sizeof(sp));
-    sp.in = d_in;
-    sp.c_words = c_words;
-    sp.skip_words = skip_words;
-    sp.tile_words = scan_tile_words(c_words);
-    sp.n_tiles = (uint32_t)ceil_div(c_words, sp.tile_words);
-    sp.hdr = reinterpret_cast<DecodeHeader *>(ws);
-    sp.desc = reinterpret_cast<ulonglong2 *>(ws + ws_desc_off());
-    sp.excl = sp.desc + scan_tiles(c_words);
-    sp.epoch = next_epoch();
-    sp.starts = expand ? reinterpret_cast<ulonglong2 *>(ws + ws_starts_off(c_words)) : nullptr;
-    sp.max_out_tiles = expand ? max_out_tiles(out_cap) : 0;
-    sp.out_info = d_out_info;
-    sp.trace = g_trace;
-    if (int rc = counter_slot(&sp.ctr)) return rc;
-    if (!expand) CUDA_TRY(launch_scan(sp, stream));
-    if (expand) {
-        ExpandParams ep;
-        memset(&ep, 0, sizeof(ep));
-        ep.in = d_in;
-        ep.c_words = c_words;
-        ep.hdr = sp.hdr;
-        ep.epoch = sp.epoch;
-        ep.starts = sp.starts;
-        ep.max_out_tiles = sp.max_out_tiles;
-        ep.out = d_out;
-        ep.out_cap = out_cap;
-        ep.ctr = static_tiles() ? nullptr : sp.ctr;
-        ep.trace = g_trace;
-        CUDA_TRY(launch_decode(sp, ep, stream));
-    }
-    return WAH_OK;
+    DecodeJob job;
+    job.d_in = d_in;
+    job.c_words = c_words;
+    job.skip_words = 0;
+    job.d_out = d_out;
+    job.out_cap = expand ? out_cap : 0;
+    job.n_cols = 1;
+    job.col_groups = ~0ull;
+    job.col_stride = 0;
+    job.expand = expand;
+    return decode_launch(job, d_out_info, d_workspace, workspace_bytes, stream);
 }
 
 extern "C" int wah_decompress_device(const uint32_t *d_in, uint64_t c_words, uint32_t *d_out,
@@ -345,34 +373,49 @@ extern "C" int wah_decoded_size_device(const uint32_t *d_in, uint64_t c_words, u
                              (cudaStream_t)stream);
 }
 
-// bitmap-index batch: column j's stream is d_in[h_col_offsets[j] .. h_col_offsets[j+1]) (the layout
-// wah_compress_batch_device writes), decoded to d_out + j * out_col_stride_words.  One launch per column on
-// `stream`; the workspace is reused from column to column.
-extern "C" size_t wah_decompress_batch_workspace_bytes(uint64_t max_col_c_words, uint64_t out_col_capacity_words)
+// bitmap-index batch: n_cols compressed columns back to back (the layout wah_compress_batch_device writes), ONE launch.
+// The reference decodes one vector per call (decompress.cu:61-115: three kernels, a Thrust scan and four
+// cudaMalloc / cudaFree pairs each); its callers would loop over the columns.
+extern "C" size_t wah_decompress_batch_workspace_bytes(uint64_t n_cols, uint64_t c_total_words, uint64_t words_per_col)
 {
-    return wah_decompress_workspace_bytes(max_col_c_words + 3, out_col_capacity_words);
+    return decode_ws_bytes(c_total_words, n_cols * ceil_div(wah_num_groups(words_per_col), EXPAND_TILE_GROUPS));
 }
 
-extern "C" int wah_decompress_batch_device(const uint32_t *d_in, const uint64_t *h_col_offsets, uint64_t n_cols,
-                                           uint32_t *d_out, uint64_t out_col_stride_words,
-                                           uint64_t out_col_capacity_words, uint64_t *d_out_info, void *d_workspace,
+extern "C" int wah_decompress_batch_device(const uint32_t *d_in, uint64_t c_total_words, uint64_t n_cols,
+                                           uint64_t words_per_col, uint32_t *d_out, uint64_t out_col_stride_words,
+                                           uint64_t out_col_words, uint64_t *d_out_info, void *d_workspace,
                                            size_t workspace_bytes, void *stream)
 {
-    if (n_cols == 0) return WAH_OK;
-    if (!h_col_offsets || !d_out_info) return fail(WAH_ERR_INVALID, "null argument");
-    if (!aligned16(d_in)) return fail(WAH_ERR_INVALID, "device buffers must be 16-byte aligned");
-    if (out_col_stride_words % 4 != 0) return fail(WAH_ERR_INVALID, "out_col_stride_words must be a multiple of 4");
-    if (out_col_capacity_words > out_col_stride_words && n_cols > 1)
-        return fail(WAH_ERR_INVALID, "out_col_capacity_words > out_col_stride_words");
-    for (uint64_t j = 0; j < n_cols; j++) {
-        const uint64_t a = h_col_offsets[j], b = h_col_offsets[j + 1];
-        if (b < a) return fail(WAH_ERR_INVALID, "column offsets must not decrease");
-        const uint32_t skip = (uint32_t)(a & 3ull);
-        const int rc = decompress_common(d_in + (a - skip), b - a ? (b - a) + skip : 0, d_out + j * out_col_stride_words,
-                                         out_col_capacity_words, d_out_info + 2 * j, d_workspace, workspace_bytes, true,
-                                         (cudaStream_t)stream, skip);
-        if (rc) return rc;
+    if (!d_out_info) return fail(WAH_ERR_INVALID, "d_out_info is null");
+    if (n_cols == 0 || words_per_col == 0 || c_total_words == 0) {
+        CUDA_TRY(cudaMemsetAsync(d_out_info, 0, 3 * sizeof(uint64_t), (cudaStream_t)stream));
+        if (n_cols != 0 && words_per_col != 0) return fail(WAH_ERR_FORMAT, "an empty stream cannot hold %llu columns", (unsigned long long)n_cols);
+        return WAH_OK;
     }
+    if (!d_in || !d_out || !d_workspace) return fail(WAH_ERR_INVALID, "null device pointer");
+    if (!aligned16(d_in) || !aligned16(d_out) || !aligned16(d_workspace))
+        return fail(WAH_ERR_INVALID, "device buffers must be 16-byte aligned");
+    if (out_col_stride_words % 4 != 0) return fail(WAH_ERR_INVALID, "out_col_stride_words must be a multiple of 4");
+    if (out_col_words > out_col_stride_words && n_cols > 1)
+        return fail(WAH_ERR_INVALID, "out_col_words > out_col_stride_words");
+    const uint64_t groups = wah_num_groups(words_per_col);
+    if (out_col_words > wah_decoded_words(groups)) out_col_words = wah_decoded_words(groups);
+    DecodeJob job;
+    job.d_in = d_in;
+    job.c_words = c_total_words;
+    job.skip_words = 0;
+    job.d_out = d_out;
+    job.out_cap = out_col_words;
+    job.n_cols = n_cols;
+    job.col_groups = groups;
+    job.col_stride = out_col_stride_words;
+    job.expand = true;
+    return decode_launch(job, d_out_info, d_workspace, workspace_bytes, (cudaStream_t)stream);
+}
+
+extern "C" int wah_test_poison_counter_slots(void)
+{
+    CUDA_TRY(poison_counter_slots());
     return WAH_OK;
 }
 
@@ -512,7 +555,7 @@ extern "C" int wah_logical_device(int op, const uint32_t *d_a, uint64_t ca_words
     // a stream that decodes to fewer than n_words words counts as zero-extended
     CUDA_TRY(cudaMemsetAsync(buf_a, 0, 2 * ob, stream));
     if (int rc = wah_decompress_device(d_a, ca_words, buf_a, n_words + 8, info, dws, dws_bytes, stream)) return rc;
-    if (int rc = wah_decompress_device(d_b, cb_words, buf_b, n_words + 8, info + 2, dws, dws_bytes, stream)) return rc;
+    if (int rc = wah_decompress_device(d_b, cb_words, buf_b, n_words + 8, info + 4, dws, dws_bytes, stream)) return rc;
     CUDA_TRY(launch_logical(op, buf_a, buf_b, n_words, stream));
     return wah_compress_device(buf_a, n_words, mode, d_out, out_capacity_words, d_out_words, cws,
                                wah_compress_workspace_bytes(n_words), stream);

@@ -305,6 +305,11 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
         constexpr int LBN = 10;   // descriptors per lane and round (32 * LBN = 320 >= 2 CTAs x 148 SMs)
         const uint64_t base = p.base_in ? *p.base_in : 0ull;
         const int32_t lead_adjust = p.lead_adjust ? *p.lead_adjust : 0;
+        // Descriptor fetches this warp may still spend waiting for other CTAs (about 2 s).  Every CTA of the grid has
+        // to be resident for the aggregates to appear; if that ever fails the launch ends with *total_out = ~0
+        // (WAH_ERR_CUDA at the host entry points) instead of hanging the GPU.
+        uint32_t budget = COMPRESS_SPIN_LIMIT;
+        bool failed = base == ~0ull;   // an earlier launch of a chained stream failed
         uint32_t own_cnt = 0, own_open = 0;   // words of this launch up to / run open at the end of my previous tile
         uint64_t d[LBN];                      // first window of the next tile, requested one tile ahead
         auto request = [&](int64_t hi, int64_t lo) {
@@ -347,6 +352,12 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
                         const int64_t lk = hi - (int64_t)lane - 32 * r;
                         const bool in = lk >= lo;
                         while (__any_sync(0xffffffffu, in && desc_empty(d[r], p.epoch))) {
+                            if (budget == 0u) {   // (uniform) give up: the tile counts as empty, the launch as failed
+                                if (in && desc_empty(d[r], p.epoch)) d[r] = (uint64_t)p.epoch << 32;
+                                failed = true;
+                                break;
+                            }
+                            budget--;
                             if (in && desc_empty(d[r], p.epoch)) d[r] = ld_relaxed_u64(p.desc + lk);
 #ifdef WAH_TRACE
                             polls++;
@@ -402,7 +413,8 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
             if (lane == 0) {
                 if (p.col_offsets && t == 0u) p.col_offsets[col] = dst0;
                 if (tile == p.n_tiles - 1u) {
-                    const uint64_t total = dst0 + tile_cnt;
+                    // (the last tile's offset depends on every other CTA's aggregates: it is the one that notices)
+                    const uint64_t total = failed ? ~0ull : dst0 + tile_cnt;
                     *p.total_out = total;
                     if (p.col_offsets) p.col_offsets[p.n_cols] = total;
                 }
@@ -783,25 +795,29 @@ cudaError_t launch_compress(const CompressParams &p, int mode, cudaStream_t stre
     // foreign work on the GPU merely delay the others.)  WAH_B200_COOPERATIVE=1 makes the launch
     // cooperative, which has the driver verify co-residency at the price of a slower launch.
     constexpr int THREADS = Geom<CFG_NWORK, CFG_STAGES>::THREADS;
+    constexpr int MAX_DEV = 64;
     const size_t smem = compress_smem_bytes();
-    static int grids[2] = {0, 0};
+    // per device: the dynamic shared memory attribute and SMs x occupancy belong to the device current at launch time
+    static int grids[MAX_DEV][2] = {};
     const int m = mode == 0 ? 0 : 1;
     const void *kernel = m == 0 ? (const void *)wah_compress_kernel<CFG_NWORK, CFG_STAGES, true>
                                 : (const void *)wah_compress_kernel<CFG_NWORK, CFG_STAGES, false>;
-    if (grids[m] == 0) {
-        cudaError_t e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0;
+    cudaError_t e = cudaGetDevice(&dev);
+    if (e != cudaSuccess) return e;
+    if (dev < 0 || dev >= MAX_DEV) return cudaErrorInvalidDevice;
+    if (grids[dev][m] == 0) {
+        e = cudaFuncSetAttribute(kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        int dev = 0, sms = 0, per_sm = 0;
-        e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
+        int sms = 0, per_sm = 0;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, kernel, THREADS, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-        grids[m] = sms * per_sm;
+        grids[dev][m] = sms * per_sm;
     }
-    int grid = grids[m];
+    int grid = grids[dev][m];
     if ((uint32_t)grid > p.n_tiles) grid = (int)p.n_tiles;
     CompressParams params = p;
     void *args[] = {&params};

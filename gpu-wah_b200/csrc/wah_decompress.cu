@@ -8,16 +8,21 @@
 // Here: ONE persistent launch (wah_decode_kernel, 3 CTAs per SM), two phases per CTA:
 //   scan phase    one pass over the compressed words, one tile per CTA: per-tile group sums, exchanged through a
 //                 round aggregator, give every tile its group offset; each tile then records, for every OUTPUT
-//                 tile boundary (multiples of 8192 groups) that falls into it, which compressed word covers it.
+//                 tile boundary that falls into it, which compressed word covers it.
 //   expand phase  output-centric, hence load balanced whatever the fill lengths are.  The grid walks output tiles
-//                 of 8192 groups = 7936 words; a tile waits only for its own two boundary entries.  Fill
-//                 dominated tiles are assembled as a bit image in SHARED memory (a literal ORs its 31 bits in,
-//                 a one-fill sets a bit range, zero fills cost nothing) and leave through a TMA bulk store;
-//                 literal dominated tiles are repacked in registers with one shuffle per word; anything else
-//                 goes through the reference's one-group-per-int array (kernels.cu:321-359), kept in shared
-//                 memory, and the 32 -> 31 repack of mergeWords (kernels.cu:375).
+//                 of 8192 groups = 7936 words; a tile waits only for its own two boundary entries.  A tile is
+//                 assembled as a bit image in SHARED memory -- a literal ORs its 31 bits in, a one-fill ORs its two
+//                 partial words in and marks its whole words in a 248-bit-per-warp coverage map, which one
+//                 prefix-XOR per warp turns into 128-bit stores of ones; zero fills cost nothing -- and leaves
+//                 through a TMA bulk store.  All-literal tiles are repacked in registers with one shuffle per word;
+//                 tiles with more than 4096 words go through the reference's one-group-per-int array
+//                 (kernels.cu:321-359), kept in shared memory, and the 32 -> 31 repack of mergeWords (kernels.cu:375).
 // Output tiles are aligned in group space to multiples of 32 groups = 31 words, so no output word is shared
-// between threads or tiles and nothing needs atomics.  wah_scan_kernel is the scan phase alone (size query).
+// between threads or tiles and nothing in HBM needs atomics.  wah_scan_kernel is the scan phase alone (size query).
+//
+// A bitmap-index batch (n_cols streams back to back, each decoding to the same number of groups) is ONE launch as
+// well: group offsets run over the concatenation, output tile k of column j starts at group j * col_groups + k * 8192
+// and lands at out + j * col_stride + k * 7936.
 #include "wah_common.cuh"
 #include "wah_kernels.h"
 
@@ -42,6 +47,20 @@ constexpr uint64_t ENTRY_MASK = (1ull << 48) - 1ull;   // output-tile table: low
 constexpr uint32_t TG_SHIFT = 13;
 static_assert((1u << TG_SHIFT) == (uint32_t)EXPAND_TILE_GROUPS, "output tile must be 8192 groups");
 
+// A CTA that waits for another CTA of the grid polls politely and not for ever: after SPIN_LIMIT polls (about 2 s) it
+// flags the launch as failed and carries on with whatever it has; the launch then ends with STATUS_TIMEOUT in
+// d_out_info[2] instead of hanging the GPU.  Once one CTA has given up, the others notice within 1024 polls.
+__device__ __forceinline__ bool spin_ok(uint32_t &left, DecodeHeader *hdr, uint32_t epoch)
+{
+    if (left != 0u) {
+        left--;
+        if ((left & 1023u) != 0u || *reinterpret_cast<volatile uint32_t *>(&hdr->error) != epoch) return true;
+    }
+    left = 0;
+    *reinterpret_cast<volatile uint32_t *>(&hdr->error) = epoch;
+    return false;
+}
+
 // ------------------------------------------------------------------ scan phase
 
 // One scan tile = p.tile_words compressed words (a multiple of 1024, chosen by the host so that every stream is one
@@ -50,8 +69,8 @@ static_assert((1u << TG_SHIFT) == (uint32_t)EXPAND_TILE_GROUPS, "output tile mus
 //   pass 1  count the groups of my words (getCounts, kernels.cu:298-304), publish the tile sum;
 //   offset  the last CTA of a round to publish scans the round's sums and hands every tile its offset;
 //   pass 2  row by row, a warp scan gives every 4-word pack its group offset (done while the offset is in flight
-//           when the tile is one sub-tile); record, for every output-tile boundary k * 8192 that falls into a
-//           word, which word that is and where it starts.
+//           when the tile is one sub-tile); record, for every output-tile boundary that falls into a word, which
+//           word that is and where it starts.
 constexpr int SCAN_MAXV = 8;   // 128-bit packs per lane and sub-tile
 
 // An entry of the output-tile table is read by other CTAs while the scan is still running: x (word index + 1,
@@ -73,31 +92,67 @@ __device__ __forceinline__ void load_entry(const ulonglong2 *e, uint32_t epoch, 
 constexpr int EXPAND_STATIC_ROUNDS = 4;   // output tiles of the first rounds are dealt round robin, later ones by ticket
 constexpr int SCAN_HEAVY = 64;  // long fills of a tile queued for the CTA-wide boundary writer
 
-// Four consecutive compressed words, the first at group offset `off`: record every output-tile boundary
-// k * 8192 that falls into one of them (off <= k * 8192 < off + cnt).  A word that covers up to 4 boundaries
-// records them itself; a long fill is queued for the whole CTA.  Out of line: this runs for under 1 % of the
-// words and would otherwise be replicated 8 times in straight-line code that executes once per launch.
-__device__ __noinline__ void record_boundaries(ulonglong2 *starts, uint32_t epoch, uint64_t k_limit, uint64_t wi, uint64_t off,
-                                               uint4 cnt, ulonglong4 *s_heavy, uint32_t *s_nheavy)
+// Where the output tiles start, in the group numbering of the whole stream.  A single stream: tile k at group
+// k * 8192, table index k (cg = ~0, j stays 0).  A batch of columns of cg groups each: tile k of column j at group
+// j * cg + k * 8192, table index j * tpc + k.  `base` / `j` are the column that holds the group offset last asked for.
+struct ColumnCursor {
+    uint64_t base;
+    uint32_t j;
+};
+__device__ __forceinline__ void col_seek(ColumnCursor &c, uint64_t off, uint64_t cg)
+{
+    if (off - c.base >= cg) {   // (never for a single stream)
+        if (off - c.base >= (cg << 2)) {
+            c.j = (uint32_t)(off / cg);
+            c.base = (uint64_t)c.j * cg;
+        } else {
+            do {
+                c.base += cg;
+                c.j++;
+            } while (off - c.base >= cg);
+        }
+    }
+}
+
+struct BoundaryGeom {
+    uint64_t cg;      // groups per column, ~0 for a single stream
+    uint64_t k_lim;   // table entries per column that may be written (single stream: one more, the end of the last tile)
+    uint32_t tpc;     // table indices per column
+    uint32_t n_cols;
+};
+
+// Four consecutive compressed words, the first at group offset `off`: record every output-tile boundary that falls
+// into one of them (off <= boundary < off + cnt).  A word that covers up to 4 boundaries records them itself; a long
+// fill is queued for the whole CTA.  Out of line: this runs for under 1 % of the words and would otherwise be
+// replicated 8 times in straight-line code that executes once per launch.
+__device__ __noinline__ void record_boundaries(ulonglong2 *starts, uint32_t epoch, const BoundaryGeom g, ColumnCursor cur,
+                                               uint64_t wi, uint64_t off, uint4 cnt, ulonglong4 *s_heavy, uint32_t *s_nheavy)
 {
     constexpr uint64_t TGM = (uint64_t)EXPAND_TILE_GROUPS - 1ull;
     const uint32_t c[4] = {cnt.x, cnt.y, cnt.z, cnt.w};
 #pragma unroll 1
     for (int j = 0; j < 4; j++) {
-        uint64_t k_first = (off + TGM) >> TG_SHIFT;
-        uint64_t k_end = (off + c[j] + TGM) >> TG_SHIFT;
-        if (k_end != k_first) {
-            if (k_end > k_limit) k_end = k_limit;
-            if (k_first > k_end) k_first = k_end;
-            if (k_end - k_first > 4ull) {
-                const uint32_t e = atomicAdd(s_nheavy, 1u);
-                if (e < (uint32_t)SCAN_HEAVY) {
-                    s_heavy[e] = make_ulonglong4(wi + j, off, k_first, k_end);
-                    k_end = k_first;   // queued
+        if (c[j] != 0u) {
+            col_seek(cur, off, g.cg);
+            const uint64_t rel = off - cur.base;
+            uint64_t k_first = (rel + TGM) >> TG_SHIFT;
+            uint64_t k_end = (rel + c[j] + TGM) >> TG_SHIFT;
+            // (a batch whose stream holds more columns than declared: the first boundary behind the last declared
+            //  column is still recorded -- it is where that column's last tile ends)
+            const uint64_t lim = cur.j < g.n_cols ? g.k_lim : ((cur.j == g.n_cols && g.tpc != 0u) ? 1ull : 0ull);
+            if (k_end > lim) k_end = lim;
+            if (k_first < k_end) {
+                const uint64_t i0 = (uint64_t)cur.j * g.tpc;
+                if (k_end - k_first > 4ull) {
+                    const uint32_t e = atomicAdd(s_nheavy, 1u);
+                    if (e < (uint32_t)SCAN_HEAVY) {
+                        s_heavy[e] = make_ulonglong4(wi + j, off, i0 + k_first, i0 + k_end);
+                        k_end = k_first;   // queued
+                    }
                 }
-            }
 #pragma unroll 1
-            for (uint64_t k = k_first; k < k_end; k++) store_entry(starts + k, wi + j + 1ull, off, epoch);
+                for (uint64_t k = k_first; k < k_end; k++) store_entry(starts + i0 + k, wi + j + 1ull, off, epoch);
+            }
         }
         off += c[j];
     }
@@ -140,15 +195,30 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
     const uint32_t stride = gridDim.x;
+    const bool batch = p.col_groups != ~0ull;
+    BoundaryGeom geo;
+    geo.cg = p.col_groups;
+    geo.tpc = batch ? (uint32_t)p.max_out_tiles : 0u;
+    geo.k_lim = batch ? p.max_out_tiles : p.max_out_tiles + 1ull;
+    geo.n_cols = p.n_cols;
     // A tile is walked in sub-tiles of up to 8192 words (SCAN_MAXV rows of 128 words per warp), staged in shared
     // memory, two buffers.  A tile of ONE sub-tile -- every stream up to gridDim * 8192 words -- is still there in
     // pass 2; a longer tile is read a second time rather than split into several tiles, because every extra tile per
     // CTA is an extra round of the offset exchange below (measured: 10 us per round).
     const uint32_t rows_full = p.tile_words / (4u * SCAN_THREADS);   // rows of 128 words per warp and tile
     uint64_t *s_loc = reinterpret_cast<uint64_t *>(smem + SCAN_SUB_WORDS);   // one sub-tile: the second buffer is free
+    uint32_t budget = SPIN_LIMIT;   // polls this thread may still spend waiting for other CTAs
 #ifdef WAH_TRACE
     bool first_tile = true;
 #endif
+    // the counters of the NEXT launch on this device start from zero whatever an aborted launch left in them
+    // (launches of one device are ordered by the library, so nobody is using that slot now)
+    if (blockIdx.x == 0 && tid == 0 && p.next_ctr != nullptr && p.next_ctr != p.ctr) {
+        p.next_ctr->agg_count = 0;
+        p.next_ctr->bad_acc = 0;
+        p.next_ctr->ticket = 0;
+        p.next_ctr->done = 0;
+    }
 
     for (uint32_t tile = blockIdx.x; tile < p.n_tiles; tile += stride) {
         const uint64_t tile_begin = (uint64_t)tile * p.tile_words;
@@ -245,8 +315,8 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
             cell_store(p.desc + tile, tile_sum, p.epoch);
         }
         // A tile whose every word is one group (literal-dense data: sum == number of words) needs no second look at
-        // its words: boundary k * 8192 falls on word (k * 8192 - excl) of the tile.
-        const bool unit_tile = w_last > w_first && tile_sum == w_last - w_first;
+        // its words: boundary k * 8192 falls on word (k * 8192 - excl) of the tile.  (Single stream only.)
+        const bool unit_tile = !batch && w_last > w_first && tile_sum == w_last - w_first;
         const bool pre_scan = p.starts != nullptr && !unit_tile && nsub == 1u;
 #ifdef WAH_TRACE
         if (p.trace && tid == 0 && first_tile) {
@@ -289,8 +359,10 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
                 // groups before this round = offset + sum of the previous round's last tile (both published)
                 uint64_t base0 = 0;
                 if (round0 != 0u) {
-                    uint64_t pe, ps;
+                    uint64_t pe = 0, ps = 0;
                     while (!cell_load(p.excl + round0 - 1, p.epoch, pe)) {
+                        if (!spin_ok(budget, p.hdr, p.epoch)) break;
+                        __nanosleep(64);
                     }
                     cell_load(p.desc + round0 - 1, p.epoch, ps);
                     base0 = pe + ps;
@@ -314,10 +386,18 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
                     }
                 }
                 if (tid == 0 && round0 + m == p.n_tiles) {
-                    // the last round: nobody arrives any more; leave the counters zeroed for the next launch
-                    // (every CTA added its malformed-word count before it arrived for its last tile)
-                    p.ctr->agg_count = 0;
-                    p.hdr->bad_words = atomicExch(&p.ctr->bad_acc, 0u);
+                    // the last round: every CTA added its malformed-word count before it arrived for its last tile
+                    const uint32_t bad = atomicAdd(&p.ctr->bad_acc, 0u);
+                    p.hdr->bad_words = bad;
+                    if (p.starts == nullptr) {
+                        // size query: nobody arrives any more; leave the counters zeroed for the next launch and
+                        // report the status (a full decode does both when its last CTA leaves the expand phase)
+                        p.ctr->agg_count = 0;
+                        p.ctr->bad_acc = 0;
+                        if (p.out_info)
+                            p.out_info[2] = (uint64_t)bad |
+                                            (*reinterpret_cast<volatile uint32_t *>(&p.hdr->error) == p.epoch ? STATUS_TIMEOUT : 0ull);
+                    }
                 }
                 __syncthreads();   // s_lb_sum is reused below
             }
@@ -334,8 +414,11 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
                 }
             }
             if (tid == 0) {
-                uint64_t v;
-                while (!cell_load(p.excl + tile, p.epoch, v)) __nanosleep(64);
+                uint64_t v = 0;
+                while (!cell_load(p.excl + tile, p.epoch, v)) {
+                    if (!spin_ok(budget, p.hdr, p.epoch)) break;
+                    __nanosleep(64);
+                }
                 s_lb_sum[0] = v;
             }
             __syncthreads();
@@ -353,20 +436,23 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
             p.hdr->words = words;
             p.hdr->out_tiles = (G + TGM) >> TG_SHIFT;
             if (p.out_info) {
-                p.out_info[0] = words;
+                // (a batch reports the words one column decodes to)
+                p.out_info[0] = batch ? (p.col_groups >> 5) * 31ull + (((p.col_groups & 31ull) * 31ull + 31ull) >> 5) : words;
                 p.out_info[1] = G;
             }
             __threadfence();
             *reinterpret_cast<volatile uint32_t *>(&p.hdr->valid) = p.epoch;   // the expand phase polls this
         }
 
-        // ---- pass 2: which compressed word covers each output-tile boundary k * 8192 ?
+        // ---- pass 2: which compressed word covers each output-tile boundary ?
         //      A word that covers up to 4 boundaries records them itself; a long fill (it may span a hundred
         //      thousand output tiles) is queued and written by the whole CTA afterwards.
-        const uint64_t k_limit = p.max_out_tiles + 1ull;
+        ColumnCursor cur;
+        cur.base = 0;
+        cur.j = 0;
         if (p.starts != nullptr && unit_tile) {
             uint64_t k_end = (excl + tile_sum + TGM) >> TG_SHIFT;
-            if (k_end > k_limit) k_end = k_limit;
+            if (k_end > geo.k_lim) k_end = geo.k_lim;
 #pragma unroll 1
             for (uint64_t k = ((excl + TGM) >> TG_SHIFT) + tid; k < k_end; k += SCAN_THREADS)
                 store_entry(p.starts + k, w_first + ((k << TG_SHIFT) - excl) + 1ull, k << TG_SHIFT, p.epoch);
@@ -377,8 +463,10 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
                 const uint4 x = *my_pack(0, v);
                 const uint64_t sl = pack_groups(x);
                 const uint64_t off = excl + s_loc[v * SCAN_THREADS + tid];
-                if (((off + TGM) >> TG_SHIFT) != ((off + sl + TGM) >> TG_SHIFT))   // rare: a boundary in my 4 words
-                    record_boundaries(p.starts, p.epoch, k_limit, seg_begin + (uint64_t)(v * 32u + lane) * 4u, off,
+                col_seek(cur, off, geo.cg);
+                const uint64_t rel = off - cur.base;
+                if (((rel + TGM) >> TG_SHIFT) != ((rel + sl + TGM) >> TG_SHIFT) || rel + sl > geo.cg)   // rare: a boundary in my 4 words
+                    record_boundaries(p.starts, p.epoch, geo, cur, seg_begin + (uint64_t)(v * 32u + lane) * 4u, off,
                                       make_uint4(word_groups(x.x), word_groups(x.y), word_groups(x.z), word_groups(x.w)),
                                       s_heavy, &s_nheavy);
             }
@@ -418,8 +506,10 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
                     const uint64_t sl = pack_groups(x);
                     const uint64_t incl = warp_incl_scan_u64(sl);
                     const uint64_t off = row_base + incl - sl;
-                    if (((off + TGM) >> TG_SHIFT) != ((off + sl + TGM) >> TG_SHIFT))   // rare: a boundary in my 4 words
-                        record_boundaries(p.starts, p.epoch, k_limit, seg_begin + (uint64_t)(v * 32u + lane) * 4u, off,
+                    col_seek(cur, off, geo.cg);
+                    const uint64_t rel = off - cur.base;
+                    if (((rel + TGM) >> TG_SHIFT) != ((rel + sl + TGM) >> TG_SHIFT) || rel + sl > geo.cg)   // rare: a boundary in my 4 words
+                        record_boundaries(p.starts, p.epoch, geo, cur, seg_begin + (uint64_t)(v * 32u + lane) * 4u, off,
                                           make_uint4(word_groups(x.x), word_groups(x.y), word_groups(x.z), word_groups(x.w)),
                                           s_heavy, &s_nheavy);
                     row_base += __shfl_sync(0xffffffffu, incl, 31);
@@ -438,6 +528,8 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
         }
         __syncthreads();   // partial sums and the heavy queue are rewritten by the next tile
     }
+    // a size query that went wrong says so even if no aggregator of a last round ever gets to report
+    if (tid == 0 && p.starts == nullptr && p.out_info != nullptr && budget == 0u) p.out_info[2] = STATUS_TIMEOUT;
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) wah_scan_kernel(const ScanParams p)
@@ -448,7 +540,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) wah_scan_kernel(const ScanParams
 
 // ---------------------------------------------------------------- expand phase
 
-constexpr int EXP_CHUNK = EXPAND_THREADS * 8;          // compressed words scanned per round
+constexpr int EXP_CHUNK = EXPAND_THREADS * 8;          // compressed words scanned per round of the general path
 constexpr int GRP_WORDS = EXPAND_TILE_GROUPS + EXPAND_TILE_GROUPS / 32;   // rows of 32 groups padded to 33
 constexpr int EXP_LIST = 512;                          // long one-fills deferred to a warp-wide store loop
 constexpr uint32_t EXP_CLAMP = 2u * EXPAND_TILE_GROUPS;   // any count >= the tile span behaves the same
@@ -482,27 +574,30 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
     } while (0)
 #endif
 
-constexpr int SPARSE_MAX_WORDS = 4096;   // output tiles covered by at most this many compressed words take the bit-scatter path
-constexpr int SP_ROUND = EXPAND_THREADS * 2;   // compressed words per bit-scatter round (two per thread)
+constexpr int SPARSE_MAX_WORDS = 4096;          // output tiles covered by at most this many compressed words take the scatter path
+constexpr int SC_ROUND = EXPAND_THREADS * 4;    // compressed words per scatter round (one 16-byte pack per thread)
+constexpr int COV_WORDS = EXPAND_TILE_WORDS / 32;   // 248: one coverage bit per word of the tile image
+constexpr int COV_PER_WARP = COV_WORDS / (EXPAND_THREADS / 32);   // 31 coverage words = 992 image words per warp
+static_assert(COV_PER_WARP * (EXPAND_THREADS / 32) == COV_WORDS && COV_PER_WARP <= 31, "coverage map: one word per lane");
+constexpr uint32_t FILL_DIRECT_WORDS = 2;       // whole words of a one-fill its owner writes itself
 
-// OR the stream bits [b0, b1) (tile relative) into the tile image; plain read-modify-write: the caller
-// guarantees that no other thread touches the same words at the same time
-__device__ __forceinline__ void set_bits(uint32_t *img, uint32_t b0, uint32_t b1)
-{
-    const uint32_t w0 = b0 >> 5, w1 = (b1 - 1u) >> 5;
-    const uint32_t m0 = 0xFFFFFFFFu << (b0 & 31u), m1 = 0xFFFFFFFFu >> (31u - ((b1 - 1u) & 31u));
-    if (w0 == w1) {
-        img[w0] |= m0 & m1;
-    } else {
-        img[w0] |= m0;
-        // whole words in between: they belong to this run alone (128-bit stores once aligned)
-        uint32_t w = w0 + 1u;
-        for (; w < w1 && (w & 3u); w++) img[w] = 0xFFFFFFFFu;
-        for (; w + 4u <= w1; w += 4u) *reinterpret_cast<uint4 *>(img + w) = make_uint4(~0u, ~0u, ~0u, ~0u);
-        for (; w < w1; w++) img[w] = 0xFFFFFFFFu;
-        img[w1] |= m1;
-    }
-}
+// how a tile is expanded (decided by thread 0, which has the numbers in registers)
+enum : uint32_t { PATH_STOP = 0, PATH_SKIP, PATH_CONST, PATH_UNIT, PATH_SCATTER, PATH_GENERAL };
+
+// Thread 0 resolves a tile (it may have to wait for the scan) and publishes the result in shared memory, so that
+// the whole CTA works from the same numbers -- every path below has CTA barriers.
+struct TileRes {
+    uint64_t ws;        // first compressed word of the tile
+    uint64_t dst;       // word offset of the tile's first output word in p.out
+    uint64_t next;      // the tile this CTA expands three iterations from now
+    uint64_t next_ws;   // first compressed word of the CTA's next tile, ~0 = not known yet
+    uint32_t nw;        // words (ws & ~3) .. we, the tile's last word
+    uint32_t skip;      // groups of word ws that belong to earlier tiles
+    uint32_t tg;        // groups in the tile: 8192, fewer at the end of a column / of the stream
+    uint32_t nout;      // output words to write
+    uint32_t path;
+    uint32_t first;     // PATH_CONST: the fill word the tile lies in
+};
 
 __device__ __forceinline__ void load8(const ExpandParams &p, uint64_t i0, uint32_t (&w)[8])
 {
@@ -521,14 +616,21 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
 {
     constexpr int NW = EXPAND_THREADS / 32;
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *s_grp = smem;                  // GRP_WORDS: one group per int, rows of 32 padded to 33
-    uint32_t *s_stage = smem + GRP_WORDS;    // EXPAND_TILE_WORDS output words
-    __shared__ uint32_t s_wsum[NW];
+    uint32_t *s_grp = smem;                  // GRP_WORDS: one group per int, rows of 32 padded to 33 / tile image 1
+    uint32_t *s_stage = smem + GRP_WORDS;    // EXPAND_TILE_WORDS output words / tile image 0
+    uint32_t *s_cov = smem + EXPAND_TILE_WORDS;   // 256 words behind image 1 (inside s_grp's padding): the coverage map
+    static_assert(GRP_WORDS - EXPAND_TILE_WORDS >= 256, "coverage map lives behind tile image 1");
+    __shared__ uint32_t s_wsum[2][NW];
     __shared__ uint2 s_list[EXP_LIST];
     __shared__ uint32_t s_nlist;
-    uint32_t n_sparse = 0;   // bit-scatter tiles so far: they alternate between the two tile images
+    __shared__ uint32_t s_marks;
+    __shared__ TileRes s_res[2];
+    uint32_t n_img = 0;   // scatter tiles so far: they alternate between the two tile images
 
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const bool batch = p.col_groups != ~0ull;
+    const uint32_t tpc = (uint32_t)p.max_out_tiles;
+    const uint64_t n_total = batch ? (uint64_t)p.n_cols * tpc : p.max_out_tiles;
 
     // An output tile can be expanded as soon as the scan has recorded where it starts and where the next one
     // starts (starts[k].x = word index + 1, 0 = not recorded yet) -- the offsets of the low tiles are known long
@@ -538,19 +640,14 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         uint64_t sx, sy, ex;
     };
     auto peek = [&](uint64_t ot_, Raw &r) {   // non-blocking
-        r.sx = r.sy = r.ex = 0;
-        if (ot_ < p.max_out_tiles) {
-            // one 16-byte access: x and y of an entry are written (and read) together
-            load_entry(p.starts + ot_, p.epoch, r.sx, r.sy);
-            uint64_t ey;
-            load_entry(p.starts + ot_ + 1, p.epoch, r.ex, ey);
-        }
+        uint64_t ey;
+        load_entry(p.starts + ot_, p.epoch, r.sx, r.sy);
+        load_entry(p.starts + ot_ + 1, p.epoch, r.ex, ey);
     };
     // The same two entries, requested but not looked at (thread 0 only).  The epoch check of load_entry() consumes
-    // the loaded words on the spot, i.e. waits out the L2 round trip: with every thread peeking ahead that way at the
-    // top of every tile, 12 % of the kernel's warp time went into waiting for look-AHEAD data.  Here the registers
-    // are only written (a predicated load with read-write operands, so that no copy -- no wait -- follows it); they
-    // are decoded when the tile comes up, a tile or two later.
+    // the loaded words on the spot, i.e. waits out the L2 round trip.  Here the registers are only written (a
+    // predicated load with read-write operands, so that no copy -- no wait -- follows it); they are decoded when the
+    // tile comes up, a tile or two later.
     struct RawPeek {
         uint64_t ax, ay, bx;   // entry ot: x, y; entry ot + 1: x
         uint32_t by_hi;        // ... and the upper half of its y (its epoch tag; the offset below it is not needed)
@@ -561,7 +658,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     auto request = [&](uint64_t ot_, RawPeek &r) {
         r.ax = r.ay = r.bx = 0;
         r.by_hi = 0;
-        const uint32_t go = tid == 0 && ot_ < p.max_out_tiles;
+        const uint32_t go = tid == 0 && ot_ < n_total;
         asm volatile(
             "{\n\t"
             ".reg .pred q;\n\t"
@@ -587,43 +684,40 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         __threadfence();
         return true;
     };
-    // the first two words a thread handles in the bit-scatter path
-    auto first_words = [&](uint64_t ws_, uint2 &x) {
-        const uint64_t i0 = (ws_ & ~3ull) + 2ull * tid;
-        if (i0 + 2 <= p.c_words) {
-            x = *reinterpret_cast<const uint2 *>(p.in + i0);
+    // the 16-byte pack a thread handles in the first round of the scatter path
+    auto pack_at = [&](uint64_t i0, uint4 &x) {
+        if (i0 + 4 <= p.c_words) {
+            x = *reinterpret_cast<const uint4 *>(p.in + i0);
         } else {
             x.x = i0 < p.c_words ? p.in[i0] : BIT31;
-            x.y = BIT31;
+            x.y = i0 + 1 < p.c_words ? p.in[i0 + 1] : BIT31;
+            x.z = i0 + 2 < p.c_words ? p.in[i0 + 2] : BIT31;
+            x.w = BIT31;
         }
     };
 
-    // Thread 0 resolves a tile (it may have to wait for the scan) and publishes the result in shared memory, so that
-    // the whole CTA works from the same numbers -- every path below is full of CTA barriers.  The bookkeeping of the
-    // next tiles is requested ahead of time (non-blocking), and so are a tile's first compressed words.
-    struct Resolved {
-        uint64_t ws, we, sy, G, total_words, next;   // next: the tile this CTA expands three iterations from now
-        uint64_t next_ws;                            // first compressed word of the CTA's next tile, ~0 = not known yet
-        uint32_t flags, first;   // flags: 1 = stop (no such tile / no room), 2 = the stream's last tile
-    };
-    __shared__ Resolved s_res[2];
     uint32_t w[8];
     RawPeek rq0, rq1, rq2;   // thread 0: the entries of this tile and the next two, as requested
-    uint2 xpre, xpre_n;
+    uint4 xpre = make_uint4(0, 0, 0, 0), xpre_n = make_uint4(0, 0, 0, 0);
     uint64_t xpre_ws = ~0ull, xpre_n_ws = ~0ull;   // which tile start the prefetched words belong to
+    // a finished tile image whose bulk store has not been issued yet: thread 0 issues it behind the NEXT tile's first
+    // barrier, which is the one that orders every thread's writes to the image before it
+    uint32_t pend_bytes = 0, pend_src = 0;
+    uint32_t *pend_dst = nullptr;
+    uint32_t budget = SPIN_LIMIT;
     // Which tiles a CTA expands: the first EXPAND_STATIC_ROUNDS rounds are dealt round robin (no communication, and
     // known before the scan phase is over); after that a CTA draws a ticket whenever it starts a tile -- the tile it
     // will expand four iterations later, so that the ticket, the tile's bookkeeping and its first words are all on
     // their way long before they are needed.  Tiles differ in cost and SMs in speed: with a fixed deal the slowest CTA
     // finished 5 us (of 36) after the median one.
     const uint64_t GD = gridDim.x;
-    const bool dyn = p.ctr != nullptr;
+    const bool tickets = p.dynamic_tiles != 0u;
     uint64_t ot = blockIdx.x, ot1 = ot + GD, ot2 = ot + 2ull * GD, ot3 = 0;
     uint32_t tk_prev = 0, tk_new = 0;   // thread 0: tickets drawn one / zero iterations ago
     uint32_t it = 0;
     request(ot, rq0);
     request(ot1, rq1);
-    for (; ot < p.max_out_tiles; ot = ot1, ot1 = ot2, ot2 = ot3, it++, rq0 = rq1, rq1 = rq2, xpre = xpre_n, xpre_ws = xpre_n_ws) {
+    for (;; ot = ot1, ot1 = ot2, ot2 = ot3, it++, rq0 = rq1, rq1 = rq2, xpre = xpre_n, xpre_ws = xpre_n_ws) {
         request(ot2, rq2);
         {
             // Thread 0 draws a ticket.  (ptxas wraps an atom.add on a provably uniform address in its warp-aggregation
@@ -638,97 +732,144 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 "@q atom.relaxed.gpu.global.add.u32 %0, [%1], 1;\n\t"
                 "}"
                 : "+r"(tk_new)
-                : "l"(&p.ctr->ticket + (size_t)lane * p.zero), "r"((uint32_t)(dyn && tid == 0))
+                : "l"(&p.ctr->ticket + (size_t)lane * p.zero), "r"((uint32_t)(tickets && tid == 0 && ot < n_total))
                 : "memory");
         }
 
         // ---- resolve the tile (thread 0, blocking)
         if (tid == 0) {
-            Resolved r;
-            r.flags = 0;
-            bool hdr = false;
-            Raw cur, nx1;
-            decode_peek(rq0, cur);   // requested two tiles ago
-            decode_peek(rq1, nx1);   // requested one tile ago
-            r.next_ws = nx1.sx != 0ull ? nx1.sx - 1ull : ~0ull;
-            while (cur.sx == 0ull) {
-                if (!hdr) hdr = header_known();
-                if (hdr && ot >= p.hdr->out_tiles) {
-                    r.flags = 1;   // the stream ends before this tile
-                    break;
+            TileRes r;
+            r.path = PATH_STOP;
+            r.ws = 0;
+            r.dst = 0;
+            r.nw = r.skip = r.nout = r.first = 0;
+            r.tg = EXPAND_TILE_GROUPS;
+            r.next_ws = ~0ull;
+            r.next = (!tickets || it == 0u) ? ot2 + GD : (uint64_t)EXPAND_STATIC_ROUNDS * GD + tk_prev;
+            if (ot < n_total) {
+                // where the tile starts in the stream's group numbering, and how many groups it holds
+                uint32_t j = 0, k = (uint32_t)ot;
+                uint64_t g_start = ot << TG_SHIFT;
+                uint32_t tg = EXPAND_TILE_GROUPS;
+                if (batch) {
+                    j = (uint32_t)ot / tpc;
+                    k = (uint32_t)ot - j * tpc;
+                    const uint64_t in_col = (uint64_t)k << TG_SHIFT;
+                    g_start = (uint64_t)j * p.col_groups + in_col;
+                    if (p.col_groups - in_col < (uint64_t)EXPAND_TILE_GROUPS) tg = (uint32_t)(p.col_groups - in_col);
                 }
-                __nanosleep(128);   // polite polling, see scan_body
-                peek(ot, cur);
-            }
-            while (r.flags == 0u && cur.ex == 0ull) {
-                if (!hdr) hdr = header_known();
-                if (hdr && ot + 1 >= p.hdr->out_tiles) {
-                    r.flags = 2;   // the stream's last tile: it ends with the last compressed word
-                    break;
+                const uint64_t g_end = g_start + tg;   // where the next tile starts
+                bool stop = false, last = false, hdr = false;
+                Raw cur, nx1;
+                decode_peek(rq0, cur);   // requested two tiles ago
+                decode_peek(rq1, nx1);   // requested one tile ago
+                r.next_ws = nx1.sx != 0ull ? nx1.sx - 1ull : ~0ull;
+                while (cur.sx == 0ull) {
+                    if (!hdr) hdr = header_known();
+                    if (hdr && g_start >= p.hdr->groups) {
+                        stop = true;   // the stream ends before this tile
+                        break;
+                    }
+                    if (!spin_ok(budget, p.hdr_rw, p.epoch)) {
+                        stop = true;
+                        break;
+                    }
+                    __nanosleep(128);   // polite polling, see scan_body
+                    peek(ot, cur);
                 }
-                __nanosleep(128);
-                peek(ot, cur);
+                while (!stop && cur.ex == 0ull) {
+                    if (!hdr) hdr = header_known();
+                    if (hdr && g_end >= p.hdr->groups) {
+                        last = true;   // the stream's last tile: it ends with the last compressed word
+                        break;
+                    }
+                    if (!spin_ok(budget, p.hdr_rw, p.epoch)) {
+                        stop = true;
+                        break;
+                    }
+                    __nanosleep(128);
+                    peek(ot, cur);
+                }
+                // room for the tile's words
+                uint64_t w_lo = (uint64_t)k * EXPAND_TILE_WORDS;   // word offset in the column / the stream
+                uint64_t total_words = p.out_cap;                  // single stream: capacity; batch: words per column
+                if (last) {
+                    const uint64_t G = p.hdr->groups;
+                    if (G - g_start < (uint64_t)tg) tg = (uint32_t)(G - g_start);
+                    if (!batch && p.hdr->words < total_words) total_words = p.hdr->words;
+                }
+                if (!stop) {
+                    const uint64_t avail = w_lo < total_words ? total_words - w_lo : 0ull;
+                    const uint32_t nout = avail < (uint64_t)EXPAND_TILE_WORDS ? (uint32_t)avail : (uint32_t)EXPAND_TILE_WORDS;
+                    const uint64_t ws = cur.sx - 1ull;
+                    const uint64_t we = last ? p.c_words - 1ull : cur.ex - 1ull;
+                    const uint64_t span = we - (ws & ~3ull) + 1ull;
+                    r.ws = ws;
+                    r.dst = (uint64_t)j * p.col_stride + w_lo;
+                    r.nw = span > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)span;
+                    r.skip = (uint32_t)(g_start - cur.sy);   // groups of word ws that belong to earlier tiles
+                    r.tg = tg;
+                    r.nout = nout;
+                    DCHK(ws < p.c_words && we < p.c_words && we >= ws, 4, ((uint64_t)(ws & 0xFFFFFF) << 24) | (we & 0xFFFFFF));
+                    DCHK(g_start >= cur.sy, 5, ot);
+                    if (nout == 0u) {
+                        // no room: a single stream is cut short by the capacity here and for good, a column only here
+                        r.path = batch ? PATH_SKIP : PATH_STOP;
+                    } else if (ws == we) {
+                        // the tile lies inside ONE word: written without decoding if that is a fill (the stream's
+                        // last tile may end in a partly padded group: a one-fill there is expanded like any other tile)
+                        r.first = p.in[ws];
+                        r.path = (is_fill(r.first) && (!last || !(r.first & BIT30))) ? PATH_CONST : PATH_SCATTER;
+                    } else if (!last && r.skip == 0u && we - ws == (uint64_t)EXPAND_TILE_GROUPS && tg == (uint32_t)EXPAND_TILE_GROUPS &&
+                               nout == (uint32_t)EXPAND_TILE_WORDS) {
+                        r.path = PATH_UNIT;   // 8192 groups from 8192 words: every word is one group
+                    } else {
+                        r.path = r.nw <= (uint32_t)SPARSE_MAX_WORDS ? PATH_SCATTER : PATH_GENERAL;
+                    }
+                }
             }
-            if (ot * (uint64_t)EXPAND_TILE_WORDS >= p.out_cap) r.flags = 1;   // no room for this tile (nor any later one)
-            r.ws = cur.sx - 1ull;
-            r.we = (r.flags & 2u) ? p.c_words - 1 : cur.ex - 1ull;
-            r.sy = cur.sy;
-            r.G = ~0ull;                  // only the last tile is cut short by the stream's end
-            r.total_words = p.out_cap;
-            r.first = 0;
-            if (r.flags & 2u) {
-                r.G = p.hdr->groups;
-                if (p.hdr->words < r.total_words) r.total_words = p.hdr->words;
-            }
-            if (!(r.flags & 1u) && r.ws == r.we) r.first = p.in[r.ws];   // a tile inside ONE word is written without decoding
-            r.next = (!dyn || it == 0u) ? ot2 + GD : (uint64_t)EXPAND_STATIC_ROUNDS * GD + tk_prev;
+            if (r.path == PATH_SCATTER || r.path == PATH_GENERAL || r.path == PATH_STOP) bulk_wait_read<0>();   // the image this tile is built in is no longer being read
             s_res[it & 1u] = r;
         }
         __syncthreads();
-        const Resolved res = s_res[it & 1u];
-        if (res.flags & 1u) break;
-        const bool last = (res.flags & 2u) != 0u;
+        if (tid == 0 && pend_bytes != 0u) {
+            bulk_s2g(pend_dst, pend_src, pend_bytes);   // (every thread fenced its writes to the image before the barrier)
+            pend_bytes = 0;
+        }
+        const TileRes &res = s_res[it & 1u];
+        const uint32_t path = res.path;
+        if (path == PATH_STOP) break;
         ot3 = res.next;
         xpre_n_ws = res.next_ws;
-        if (xpre_n_ws != ~0ull) first_words(xpre_n_ws, xpre_n);   // the next tile's first words, a tile ahead
-        const uint64_t w_lo = ot * (uint64_t)EXPAND_TILE_WORDS;
-        const uint64_t ws = res.ws, we = res.we;
-        DCHK(ws < p.c_words && we < p.c_words && we >= ws, 4, ((uint64_t)(ws & 0xFFFFFF) << 24) | (we & 0xFFFFFF));
-        DCHK((ot << TG_SHIFT) >= res.sy, 5, ot);
-        const uint32_t skip = (uint32_t)((ot << TG_SHIFT) - res.sy);   // groups of word ws that belong to earlier tiles
-        const uint32_t first = res.first;
-        const uint64_t G = res.G, total_words = res.total_words;
-        if (xpre_ws != ws) first_words(ws, xpre);
+        if (xpre_n_ws != ~0ull) pack_at((xpre_n_ws & ~3ull) + 4ull * tid, xpre_n);   // the next tile's first words, a tile ahead
+        if (path == PATH_SKIP) continue;
+        const uint64_t ws = res.ws;
+        const uint32_t skip = res.skip, tg = res.tg, nout = res.nout;
+        uint32_t *dst = p.out + res.dst;
+        uint4 *dst4 = reinterpret_cast<uint4 *>(dst);
+        const uint32_t nvec = nout >> 2;
+        const uint64_t wa = ws & ~3ull;   // 16-byte aligned start; words before ws are ignored
+        const uint32_t nw = res.nw;       // words wa .. we
+        const uint32_t w_end = nw - 1u;   // index of we relative to wa
+        const uint32_t w_beg = (uint32_t)(ws - wa);
 #ifdef WAH_TRACE
         if (p.trace && tid == 0) {
             const uint64_t k = it;
             if (k < 40) p.trace[(uint64_t)blockIdx.x * 64u + 8u + k] = (uint64_t)clock64();
             p.trace[(uint64_t)blockIdx.x * 64u + 58u] = ot;
-            p.trace[(uint64_t)blockIdx.x * 64u + 59u] = ((uint64_t)res.flags << 32) | (uint64_t)(we - ws);
+            p.trace[(uint64_t)blockIdx.x * 64u + 59u] = ((uint64_t)path << 32) | (uint64_t)nw;
         }
 #endif
 
-        const uint64_t g_lo = ot << TG_SHIFT;
-        const uint64_t avail = total_words - w_lo;
-        const uint32_t nout = avail < (uint64_t)EXPAND_TILE_WORDS ? (uint32_t)avail : (uint32_t)EXPAND_TILE_WORDS;
-        uint32_t *dst = p.out + w_lo;
-        uint4 *dst4 = reinterpret_cast<uint4 *>(dst);
-        const uint32_t nvec = nout >> 2;
-        const uint64_t wa = ws & ~3ull;   // 16-byte aligned start; words before ws are ignored
-
-        bool fast = false;
-        if (ws == we && is_fill(first) && (!last || !(first & BIT30))) {
-            // the whole tile lies inside one fill word (the stream's last tile may end in a partly
-            // padded word: a one-fill there takes the general path)
-            fast = true;
-            const uint32_t f = (first & BIT30) ? 0xFFFFFFFFu : 0u;
+        if (path == PATH_CONST) {
+            const uint32_t f = (res.first & BIT30) ? 0xFFFFFFFFu : 0u;
             const uint4 v = make_uint4(f, f, f, f);
             for (uint32_t i = tid; i < nvec; i += EXPAND_THREADS) st_stream_v4(dst4 + i, v);
             for (uint32_t i = (nvec << 2) + tid; i < nout; i += EXPAND_THREADS) dst[i] = f;
+            continue;
         }
-        if (fast) continue;
 
-        if (!last && skip == 0u && we - ws == (uint64_t)EXPAND_TILE_GROUPS && nout == (uint32_t)EXPAND_TILE_WORDS) {
+        if (path == PATH_UNIT) {
             // ================= unit path (literal dominated data) =================
             // 8192 groups from 8192 words: every word is one group (a literal, or a fill of length 1).  A warp
             // takes 32 rows of 32 words with coalesced loads; output word j of a row needs groups j and j + 1
@@ -745,100 +886,155 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             continue;
         }
 
-        const uint32_t nw_all = (uint32_t)(we - wa + 1);   // words wa .. we
-        if (nw_all <= (uint32_t)SPARSE_MAX_WORDS) {
-            // ================= bit-scatter path (fill dominated data) =================
-            // The tile image (7936 words) is cleared in shared memory, every literal ORs its 31 bits into
-            // the one or two words it touches, every one-fill sets its bit range, zero fills cost nothing;
-            // the finished image leaves through one bulk (TMA) store while the next tile is assembled in
-            // the other image.  Words 2k and 2k+1 of the compressed stream are handled in separate phases:
-            // two words handled at the same time are then at least two groups (62 bits) apart and never
-            // touch the same 32-bit word, so plain read-modify-writes suffice.
-            uint32_t *img = (n_sparse & 1u) ? s_grp : s_stage;
-            n_sparse++;
-            if (tid == 0) bulk_wait_read<1>();   // the store that last read this image is done
-            __syncthreads();
+        if (path == PATH_SCATTER) {
+            // ================= scatter path =================
+            // The tile image (7936 words) is cleared in shared memory; every literal ORs its 31 bits into the one or
+            // two words it touches; a one-fill ORs the partial words at its two ends in and marks the whole words in
+            // between in the coverage map (bit i = image word i): a toggle where they begin, a toggle where they
+            // end.  A prefix XOR over the map -- 31 words per warp, one per lane -- then tells every word of the
+            // image whether it lies inside a one-fill, and the warp writes those words 128 bits at a time.  Zero
+            // fills cost nothing.  Whatever the mix of runs, the work is spread evenly over the threads (the owner of
+            // a long one-fill used to write all of it himself while 255 threads waited at the next barrier).
+            // Shared-memory atomics (two per literal) keep this free of ordering constraints between threads.
+            uint32_t *img = (n_img & 1u) ? s_grp : s_stage;
+            n_img++;
             {
                 uint4 *z = reinterpret_cast<uint4 *>(img);
                 for (uint32_t i = tid; i < (uint32_t)EXPAND_TILE_WORDS / 4; i += EXPAND_THREADS) z[i] = make_uint4(0, 0, 0, 0);
+                if (tid < 64u) reinterpret_cast<uint4 *>(s_cov)[tid] = make_uint4(0, 0, 0, 0);
+                if (tid == 0) s_marks = 0;
             }
-            int32_t running = 0;   // group offset (tile relative) of the round's first word
-            auto words_at = [&](uint64_t i0, uint2 &x2) {
-                if (i0 + 2 <= p.c_words) {
-                    x2 = *reinterpret_cast<const uint2 *>(p.in + i0);
-                } else {
-                    x2.x = i0 < p.c_words ? p.in[i0] : BIT31;
-                    x2.y = BIT31;
-                }
-            };
-            uint2 xc = xpre, xn = xpre;
-            for (uint32_t c0 = 0; c0 < nw_all; c0 += SP_ROUND) {
-                const uint64_t i0 = wa + c0 + 2ull * tid;   // my two consecutive words
-                if (c0 + SP_ROUND < nw_all) words_at(i0 + SP_ROUND, xn);   // the next round's words, a round ahead
-                const uint32_t x[2] = {xc.x, xc.y};
+            uint32_t running = 0;   // group offset (tile relative) of the round's first word
+            uint4 xc = xpre;
+            if (xpre_ws != ws) pack_at(wa + 4ull * tid, xc);
+            uint4 xn = xc;
+            uint32_t rnd = 0;
+            for (uint32_t c0 = 0; c0 < nw; c0 += SC_ROUND, rnd++) {
+                const uint32_t r0 = c0 + 4u * tid;   // my four consecutive words, relative to wa
+                if (c0 + SC_ROUND < nw) pack_at(wa + r0 + SC_ROUND, xn);   // the next round's words, a round ahead
+                const uint32_t x[4] = {xc.x, xc.y, xc.z, xc.w};
                 xc = xn;
-                uint32_t c[2];
+                uint32_t c[4];
+                uint32_t tsum = 0;
 #pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    const uint64_t gi = i0 + i;
+                for (int i = 0; i < 4; i++) {
+                    const uint32_t ri = r0 + i;
                     uint32_t v = word_groups(x[i]);
-                    if (gi < ws || gi > we) v = 0;   // outside this tile's word range
-                    else if (gi == ws) v -= skip;    // part of the first word belongs to earlier tiles
+                    if (ri < w_beg || ri > w_end) v = 0;   // outside this tile's word range
+                    else if (ri == w_beg) v -= skip;       // part of the first word belongs to earlier tiles
                     c[i] = v > EXP_CLAMP ? EXP_CLAMP : v;
+                    tsum += c[i];
                 }
-                const uint32_t tsum = c[0] + c[1];
                 const uint32_t incl = warp_incl_scan(tsum);
-                __syncthreads();   // previous round's s_wsum / list consumed; first round: image cleared
-                if (lane == 31) s_wsum[warp] = incl;
-                __syncthreads();
-                int32_t off = running + (int32_t)(incl - tsum);
+                if (lane == 31) s_wsum[rnd & 1u][warp] = incl;
+                __syncthreads();   // the warp sums are there (first round: and the image is cleared)
+                uint32_t off = running + (incl - tsum);
                 uint32_t round_sum = 0;
 #pragma unroll
                 for (int k = 0; k < NW; k++) {
-                    const uint32_t sv = s_wsum[k];
-                    if (k < (int)warp) off += (int32_t)sv;
+                    const uint32_t sv = s_wsum[rnd & 1u][k];
+                    if (k < (int)warp) off += sv;
                     round_sum += sv;
                 }
-                running += (int32_t)round_sum;
+                running += round_sum;
 #pragma unroll
-                for (int i = 0; i < 2; i++) {
-                    if (c[i] != 0u && off < EXPAND_TILE_GROUPS) {
+                for (int i = 0; i < 4; i++) {
+                    if (c[i] != 0u && off < tg) {
                         const uint32_t wv = x[i];
-                        const uint32_t g0 = (uint32_t)off;
                         if (!is_fill(wv)) {   // kernels.cu:351-354, packed at once (kernels.cu:375)
-                            const uint32_t bit = 31u * g0, w = bit >> 5, sh = bit & 31u;
-                            DCHK(w < (uint32_t)EXPAND_TILE_WORDS, 1, w);
-                            img[w] |= wv << sh;
-                            if (sh > 1u) img[w + 1] |= wv >> (32u - sh);
+                            const uint32_t bit = 31u * off, wi = bit >> 5, sh = bit & 31u;
+                            DCHK(wi < (uint32_t)EXPAND_TILE_WORDS, 1, wi);
+                            atomicOr(img + wi, wv << sh);
+                            if (sh > 1u) atomicOr(img + wi + 1, wv >> (32u - sh));
                         } else if (wv & BIT30) {   // one-fill, kernels.cu:337-348
-                            uint32_t g1 = g0 + c[i];
-                            if (g1 > (uint32_t)EXPAND_TILE_GROUPS) g1 = EXPAND_TILE_GROUPS;
-                            const uint32_t b0 = 31u * g0, b1 = 31u * g1;
+                            uint32_t g1 = off + c[i];
+                            if (g1 > tg) g1 = tg;
+                            const uint32_t b0 = 31u * off, b1 = 31u * g1;
                             DCHK(b1 > b0 && b1 <= 31u * EXPAND_TILE_GROUPS, 2, ((uint64_t)b0 << 24) | b1);
-                            set_bits(img, b0, b1);
+                            const uint32_t w0 = b0 >> 5, w1 = (b1 - 1u) >> 5;
+                            const uint32_t m0 = 0xFFFFFFFFu << (b0 & 31u), m1 = 0xFFFFFFFFu >> (31u - ((b1 - 1u) & 31u));
+                            if (w0 == w1) {
+                                atomicOr(img + w0, m0 & m1);
+                            } else {
+                                atomicOr(img + w0, m0);
+                                atomicOr(img + w1, m1);
+                                const uint32_t inner = w1 - w0 - 1u;   // whole words w0 + 1 .. w1 - 1: this run's alone
+                                if (inner > FILL_DIRECT_WORDS) {
+                                    atomicXor(s_cov + ((w0 + 1u) >> 5), 1u << ((w0 + 1u) & 31u));
+                                    atomicXor(s_cov + (w1 >> 5), 1u << (w1 & 31u));
+                                    s_marks = 1;
+                                } else if (inner != 0u) {
+                                    img[w0 + 1u] = 0xFFFFFFFFu;
+                                    if (inner == 2u) img[w0 + 2u] = 0xFFFFFFFFu;
+                                }
+                            }
                         }
                     }
-                    off += (int32_t)c[i];
-                    __syncthreads();   // even words done before odd words start / before the next round
+                    off += c[i];
                 }
-                if (running >= EXPAND_TILE_GROUPS) break;   // uniform: the tile is covered
+                if (running >= tg) break;   // uniform: the tile is covered
             }
-            fence_async_smem();   // my writes to the image, visible to the bulk copy engine
-            __syncthreads();
+            __syncthreads();   // every mark is in the coverage map
+            if (s_marks != 0u) {
+                // prefix XOR over the map: my warp's 31 words (lane 31 idles), then the parity of everything below
+                // them, which every warp works out for itself (8 loads per lane) rather than wait for the others
+                const uint32_t cbase = (uint32_t)COV_PER_WARP * warp;
+                uint32_t below = 0;
+#pragma unroll
+                for (int k = 0; k < COV_WORDS / 32 + 1; k++) {
+                    const uint32_t idx = lane + 32u * k;
+                    if (idx < cbase) below ^= s_cov[idx];
+                }
+                below = __reduce_xor_sync(0xffffffffu, below);
+                uint32_t cv = lane < (uint32_t)COV_PER_WARP ? s_cov[cbase + lane] : 0u;
+                cv ^= cv << 1;
+                cv ^= cv << 2;
+                cv ^= cv << 4;
+                cv ^= cv << 8;
+                cv ^= cv << 16;
+                const uint32_t tops = __ballot_sync(0xffffffffu, (cv >> 31) != 0u);
+                if ((__popc(below) + __popc(tops & lanemask_lt())) & 1u) cv = ~cv;
+                if (lane >= (uint32_t)COV_PER_WARP) cv = 0;
+                if (__any_sync(0xffffffffu, cv != 0u)) {
+                    // bit i of lane l's word: image word 992 warp + 32 l + i lies inside a one-fill.  128-bit stores,
+                    // lane after lane: 16-byte unit u of the warp's part takes its 4 bits from lane u / 8.
+                    uint32_t *part = img + 992u * warp;
+#pragma unroll
+                    for (uint32_t r8 = 0; r8 < 8u; r8++) {
+                        const uint32_t u = r8 * 32u + lane;
+                        const uint32_t nib = (__shfl_sync(0xffffffffu, cv, u >> 3) >> ((u & 7u) * 4u)) & 0xFu;
+                        if (nib == 0xFu) {
+                            reinterpret_cast<uint4 *>(part)[u] = make_uint4(~0u, ~0u, ~0u, ~0u);
+                        } else if (nib != 0u) {
+                            if (nib & 1u) part[4u * u] = 0xFFFFFFFFu;
+                            if (nib & 2u) part[4u * u + 1u] = 0xFFFFFFFFu;
+                            if (nib & 4u) part[4u * u + 2u] = 0xFFFFFFFFu;
+                            if (nib & 8u) part[4u * u + 3u] = 0xFFFFFFFFu;
+                        }
+                    }
+                }
+            }
             if (nout == (uint32_t)EXPAND_TILE_WORDS) {
-                if (tid == 0) bulk_s2g(dst, (uint32_t)__cvta_generic_to_shared(img), EXPAND_TILE_WORDS * 4u);
+                fence_async_smem();   // my writes to the image, visible to the bulk copy engine
+                if (tid == 0) {       // issued behind the next tile's first barrier
+                    pend_bytes = EXPAND_TILE_WORDS * 4u;
+                    pend_src = (uint32_t)__cvta_generic_to_shared(img);
+                    pend_dst = dst;
+                }
             } else {
-                // the stream's last tile, or one cut short by the output capacity: the part that exists, by hand
-                // (this used to take the general path -- code no other tile of a sparse stream runs, fetched from
-                //  DRAM instruction by instruction by the one CTA everybody else is waiting for: 8 us)
+                // the last tile of a column or of the stream, or one cut short by the output capacity: the part that
+                // exists, by hand
+                __syncthreads();
                 const uint4 *src4 = reinterpret_cast<const uint4 *>(img);
                 for (uint32_t i = tid; i < nvec; i += EXPAND_THREADS) st_stream_v4(dst4 + i, src4[i]);
                 for (uint32_t i = (nvec << 2) + tid; i < nout; i += EXPAND_THREADS) dst[i] = img[i];
             }
             continue;
         }
-        // the general path below uses both images as scratch: no bulk store may still be reading them
-        if (n_sparse) {
+
+        // ================= general path (more than 4096 words in the tile) =================
+        // uses both images as scratch: the bulk store issued above may still be reading one of them
+        if (n_img != 0u) {
             if (tid == 0) bulk_wait_read<0>();
             __syncthreads();
         }
@@ -849,48 +1045,47 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             for (uint32_t i = tid; i < GRP_WORDS / 4; i += EXPAND_THREADS) z[i] = make_uint4(0, 0, 0, 0);
             if (tid == 0) s_nlist = 0;
         }
-        __syncthreads();   // also: the previous tile's staging area has been written out
+        __syncthreads();
 
         // ---- 2. scan the compressed words of the tile in rounds of EXP_CHUNK and scatter them
-        const uint32_t nw = (uint32_t)(we - wa + 1);    // words wa .. we
-        int32_t running = 0;                            // group offset (tile relative) of the round's first word
+        uint32_t running = 0;                           // group offset (tile relative) of the round's first word
         for (uint32_t c0 = 0; c0 < nw; c0 += EXP_CHUNK) {
-            const uint64_t i0 = wa + c0 + 8ull * tid;   // my 8 consecutive words
-            load8(p, i0, w);
+            const uint32_t r0 = c0 + 8u * tid;          // my 8 consecutive words, relative to wa
+            load8(p, wa + r0, w);
             uint32_t c[8];
             uint32_t tsum = 0;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                const uint64_t gi = i0 + i;
+                const uint32_t ri = r0 + i;
                 uint32_t x = word_groups(w[i]);
-                if (gi < ws || gi > we) x = 0;           // outside this tile's word range
-                else if (gi == ws) x -= skip;            // part of the first word belongs to earlier tiles
+                if (ri < w_beg || ri > w_end) x = 0;     // outside this tile's word range
+                else if (ri == w_beg) x -= skip;         // part of the first word belongs to earlier tiles
                 c[i] = x > EXP_CLAMP ? EXP_CLAMP : x;
                 tsum += c[i];
             }
             const uint32_t incl = warp_incl_scan(tsum);
             if (c0 != 0) __syncthreads();   // previous round's s_wsum consumed
-            if (lane == 31) s_wsum[warp] = incl;
+            if (lane == 31) s_wsum[0][warp] = incl;
             __syncthreads();
-            int32_t off = running + (int32_t)(incl - tsum);
+            uint32_t off = running + (incl - tsum);
             uint32_t round_sum = 0;
 #pragma unroll
             for (int k = 0; k < NW; k++) {
-                const uint32_t sv = s_wsum[k];
-                if (k < (int)warp) off += (int32_t)sv;
+                const uint32_t sv = s_wsum[0][k];
+                if (k < (int)warp) off += sv;
                 round_sum += sv;
             }
-            running += (int32_t)round_sum;
+            running += round_sum;
 #pragma unroll
             for (int i = 0; i < 8; i++) {
-                if (c[i] != 0u && off < EXPAND_TILE_GROUPS) {
+                if (c[i] != 0u && off < tg) {
                     const uint32_t wv = w[i];
                     if (!is_fill(wv)) {
-                        s_grp[grp_pos((uint32_t)off)] = wv;                      // kernels.cu:351-354
+                        s_grp[grp_pos(off)] = wv;                                 // kernels.cu:351-354
                     } else if (wv & BIT30) {                                      // one-fill, kernels.cu:337-348
-                        const uint32_t lo = (uint32_t)off;
+                        const uint32_t lo = off;
                         uint32_t hi = lo + c[i];
-                        if (hi > (uint32_t)EXPAND_TILE_GROUPS) hi = EXPAND_TILE_GROUPS;
+                        if (hi > tg) hi = tg;
                         if (hi - lo <= 8u) {
                             for (uint32_t g = lo; g < hi; g++) s_grp[grp_pos(g)] = ONES31;
                         } else {
@@ -900,9 +1095,9 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                         }
                     }
                 }
-                off += (int32_t)c[i];
+                off += c[i];
             }
-            if (running >= EXPAND_TILE_GROUPS) break;   // uniform: the tile is covered
+            if (running >= tg) break;   // uniform: the tile is covered
         }
         __syncthreads();
 
@@ -918,7 +1113,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
 
         // ---- 4. my 32 groups -> 31 output words (mergeWords, kernels.cu:375:
         //         word j = group[j] >> j | group[j+1] << (31-j)); rows padded to 33 = conflict free
-        if (g_lo + 32ull * tid < G) {
+        if (32u * tid < tg) {
             const uint32_t *r = s_grp + 33u * tid;
             uint32_t *o = s_stage + 31u * tid;
             uint32_t a = r[0];
@@ -937,8 +1132,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             for (uint32_t i = tid; i < nvec; i += EXPAND_THREADS) st_stream_v4(dst4 + i, src4[i]);
             for (uint32_t i = (nvec << 2) + tid; i < nout; i += EXPAND_THREADS) dst[i] = s_stage[i];
         }
-        // no barrier here: the next tile's clear touches s_grp only, and its first barrier orders this
-        // tile's staging reads before the next repack writes
+        // no barrier here: whatever the next tile does to shared memory happens behind its first barrier
     }
 #ifdef WAH_TRACE
     if (p.trace && tid == 0) p.trace[(uint64_t)blockIdx.x * 64u + 60u] = (uint64_t)clock64();
@@ -947,12 +1141,23 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
 #ifdef WAH_TRACE
     if (p.trace && tid == 0) p.trace[(uint64_t)blockIdx.x * 64u + 61u] = (uint64_t)clock64();
 #endif
-    if (dyn && tid == 0) {
-        // the last CTA to leave zeroes the counters for the next launch (my own draws are performed before that:
-        // the fence orders them before my `done`)
+    if (p.ctr != nullptr && tid == 0) {
+        // The last CTA to leave reports the launch's status and zeroes the counters for the next launch -- all of them,
+        // so that a launch that went wrong (a CTA gave up waiting) still leaves its slot clean.  (My own draws are
+        // performed before that: the fence orders them before my `done`.)
+        // (a CTA that saw the launch fail says so itself: with poisoned counters there may be no "last CTA")
+        if (p.out_info && *reinterpret_cast<volatile uint32_t *>(&p.hdr_rw->error) == p.epoch) p.out_info[2] = STATUS_TIMEOUT;
         __threadfence();
         if (atomicAdd(&p.ctr->done, 1u) == gridDim.x - 1u) {
             __threadfence();
+            if (p.out_info) {
+                uint64_t st = (uint64_t)p.hdr->bad_words;
+                if (*reinterpret_cast<volatile uint32_t *>(&p.hdr_rw->error) == p.epoch) st |= STATUS_TIMEOUT;
+                if (batch && p.hdr->groups != (uint64_t)p.n_cols * p.col_groups) st |= STATUS_BATCH_LENGTH;
+                p.out_info[2] = st;
+            }
+            p.ctr->agg_count = 0;
+            p.ctr->bad_acc = 0;
             p.ctr->ticket = 0;
             p.ctr->done = 0;
         }
@@ -1005,43 +1210,81 @@ size_t expand_smem_bytes()
     return (size_t)(GRP_WORDS + EXPAND_TILE_WORDS) * sizeof(uint32_t);
 }
 
-static int decode_grid_cached = 0;
+// ---- launch geometry, per device (a process may drive several devices: SM count, occupancy and the >48 KB dynamic
+//      shared memory attribute belong to the device that is current at launch time)
 
-uint32_t scan_tile_words(uint64_t c_words)
+namespace {
+constexpr int MAX_DEVICES = 64;
+struct DecodeLaunchState {
+    int decode_grid = 0;   // SMs x occupancy of wah_decode_kernel
+    int scan_grid = 0;     // ... of wah_scan_kernel
+};
+DecodeLaunchState g_dls[MAX_DEVICES];
+
+cudaError_t current_device(int *dev)
 {
-    int sms = 148;
-    if (decode_grid_cached == 0) {
-        int dev = 0;
-        if (cudaGetDevice(&dev) == cudaSuccess) cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+    cudaError_t e = cudaGetDevice(dev);
+    if (e != cudaSuccess) return e;
+    if (*dev < 0 || *dev >= MAX_DEVICES) return cudaErrorInvalidDevice;
+    return cudaSuccess;
+}
+
+cudaError_t decode_grid_for_device(int dev, int *grid)
+{
+    DecodeLaunchState &s = g_dls[dev];
+    if (s.decode_grid == 0) {
+        const size_t smem = expand_smem_bytes();
+        cudaError_t e = cudaFuncSetAttribute(wah_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int sms = 0, per_sm = 0;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wah_decode_kernel, EXPAND_THREADS, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        s.decode_grid = sms * per_sm;
     }
-    const uint64_t grid = decode_grid_cached ? (uint64_t)decode_grid_cached : (uint64_t)sms * 3;
+    *grid = s.decode_grid;
+    return cudaSuccess;
+}
+}  // namespace
+
+cudaError_t scan_tile_words(uint64_t c_words, uint32_t *tile_words)
+{
+    int dev = 0, grid = 0;
+    cudaError_t e = current_device(&dev);
+    if (e != cudaSuccess) return e;
+    e = decode_grid_for_device(dev, &grid);
+    if (e != cudaSuccess) return e;
     const uint64_t unit = 4ull * SCAN_THREADS;
-    uint64_t tw = ((c_words + grid - 1) / grid + unit - 1) / unit * unit;
+    uint64_t tw = ((c_words + (uint64_t)grid - 1) / (uint64_t)grid + unit - 1) / unit * unit;
     if (tw < (uint64_t)SCAN_TILE_WORDS) tw = SCAN_TILE_WORDS;
     if (tw > 0xFFFFF000ull) tw = 0xFFFFF000ull;   // (a tile is walked in sub-tiles of 8192 words; one tile per CTA)
-    return (uint32_t)tw;
+    *tile_words = (uint32_t)tw;
+    return cudaSuccess;
 }
 
 cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream)
 {
     // persistent + cooperative: the offset exchange spins on tiles owned by other CTAs, all must be resident
     constexpr size_t smem = 2 * SCAN_SUB_WORDS * sizeof(uint32_t);
-    static int max_grid = 0;
-    if (max_grid == 0) {
-        cudaError_t e = cudaFuncSetAttribute(wah_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+    int dev = 0;
+    cudaError_t e = current_device(&dev);
+    if (e != cudaSuccess) return e;
+    DecodeLaunchState &s = g_dls[dev];
+    if (s.scan_grid == 0) {
+        e = cudaFuncSetAttribute(wah_scan_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
         if (e != cudaSuccess) return e;
-        int dev = 0, sms = 0, per_sm = 0;
-        e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
+        int sms = 0, per_sm = 0;
         e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
         if (e != cudaSuccess) return e;
         e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wah_scan_kernel, SCAN_THREADS, smem);
         if (e != cudaSuccess) return e;
         if (per_sm < 1) return cudaErrorLaunchOutOfResources;
         if (per_sm > 4) per_sm = 4;
-        max_grid = sms * per_sm;
+        s.scan_grid = sms * per_sm;
     }
-    int grid = max_grid;
+    int grid = s.scan_grid;
     if ((uint32_t)grid > p.n_tiles) grid = (int)p.n_tiles;
     ScanParams params = p;
     void *args[] = {&params};
@@ -1051,26 +1294,15 @@ cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream)
 cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStream_t stream)
 {
     // persistent, every CTA resident (both phases spin on results of other CTAs): SMs x occupancy CTAs
-    const size_t smem = expand_smem_bytes();
-    static int grid = 0;
-    if (grid == 0) {
-        cudaError_t e = cudaFuncSetAttribute(wah_decode_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
-        if (e != cudaSuccess) return e;
-        int dev = 0, sms = 0, per_sm = 0;
-        e = cudaGetDevice(&dev);
-        if (e != cudaSuccess) return e;
-        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
-        if (e != cudaSuccess) return e;
-        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wah_decode_kernel, EXPAND_THREADS, smem);
-        if (e != cudaSuccess) return e;
-        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
-        grid = sms * per_sm;
-        decode_grid_cached = grid;
-    }
+    int dev = 0, grid = 0;
+    cudaError_t e = current_device(&dev);
+    if (e != cudaSuccess) return e;
+    e = decode_grid_for_device(dev, &grid);
+    if (e != cudaSuccess) return e;
     ScanParams a = sp;
     ExpandParams b = ep;
     void *args[] = {&a, &b};
-    return launch_pdl((const void *)wah_decode_kernel, grid, EXPAND_THREADS, args, smem, stream);
+    return launch_pdl((const void *)wah_decode_kernel, grid, EXPAND_THREADS, args, expand_smem_bytes(), stream);
 }
 
 }  // namespace wahb200

@@ -117,7 +117,9 @@ class CopyPool {
         static const uintptr_t piece = [] {
             const char *e = getenv("WAH_B200_PIECE_KB");
             const long kb = e ? atol(e) : 1024;
-            return (uintptr_t)(kb < 64 ? 64 : kb) << 10;
+            uintptr_t v = 64u << 10;   // a power of two (the pieces are aligned by masking), at least 64 KiB
+            while ((long)(v >> 10) * 2 <= kb && v < ((uintptr_t)1 << 30)) v <<= 1;
+            return v;
         }();
         const uintptr_t d0 = (uintptr_t)dst, d1 = d0 + bytes, first = d0 & ~(piece - 1);
         parallel([&](int i) {
@@ -246,7 +248,11 @@ struct HostCtx {
         if (t0) cudaEventDestroy(t0);
         if (t1) cudaEventDestroy(t1);
         t0 = t1 = nullptr;
-        if (stream) cudaStreamDestroy(stream);
+        if (stream) {
+            cudaStreamSynchronize(stream);
+            forget_stream(stream);   // the per-device launch order must not record events on it any more
+            cudaStreamDestroy(stream);
+        }
         stream = nullptr;
         device = -1;
     }
@@ -377,6 +383,8 @@ extern "C" int wah_compress_host(const uint32_t *h_in, uint64_t n_words, int mod
     uint64_t cw = 0;
     CUDA_TRY(cudaMemcpyAsync(&cw, d_cnt, sizeof(cw), cudaMemcpyDeviceToHost, c.stream));
     const float t_compute = c.lap();   // drains the stream: cw is valid
+    if (cw == ~0ull)
+        return wah_set_error(WAH_ERR_CUDA, "the compress kernel gave up waiting for part of its grid (is another context holding the GPU?)");
     // -- segment 3: D2H into a malloc()ed buffer (compress.cu:177-202)
     uint32_t *host = alloc_result(cw);
     if (!host) return wah_set_error(WAH_ERR_NOMEM, "malloc of %llu words failed", (unsigned long long)cw);
@@ -393,6 +401,52 @@ extern "C" int wah_compress_host(const uint32_t *h_in, uint64_t n_words, int mod
     return WAH_OK;
 }
 
+namespace {
+
+// Decodes the stream in c.a into c.b and returns its size.  The reference sizes its output between two of its kernels
+// (decompress.cu:72-97: two 8-byte copies and a scan, then cudaMalloc); here the output buffer of the previous call is
+// still there, so one launch does both whenever that buffer is large enough -- the decoder reports the true size
+// whatever the capacity -- and only a stream that needs more is decoded a second time into a larger buffer.
+int decode_resident(HostCtx &c, uint64_t c_words, uint64_t want_cap, uint64_t *words_out)
+{
+    uint64_t *d_info = (uint64_t *)c.small.p;
+    uint64_t info[3] = {0, 0, 0};
+    uint64_t cap = c.b.cap / 4;
+    if (want_cap != 0) {
+        CUDA_TRY(c.b.reserve(want_cap * 4 + 16));
+        cap = want_cap;
+    }
+    for (int attempt = 0; attempt < 2; attempt++) {
+        if (cap == 0) {
+            // nothing to decode into yet: size query (the scan phase alone)
+            const size_t ws0 = wah_decompress_workspace_bytes(c_words, 0);
+            CUDA_TRY(c.ws.reserve(ws0));
+            if (int rc = wah_decoded_size_device((const uint32_t *)c.a.p, c_words, d_info, c.ws.p, ws0, c.stream)) return rc;
+        } else {
+            const size_t ws_bytes = wah_decompress_workspace_bytes(c_words, cap);
+            CUDA_TRY(c.ws.reserve(ws_bytes));
+            if (int rc = wah_decompress_device((const uint32_t *)c.a.p, c_words, (uint32_t *)c.b.p, cap, d_info, c.ws.p,
+                                               ws_bytes, c.stream))
+                return rc;
+        }
+        CUDA_TRY(cudaMemcpyAsync(info, d_info, sizeof(info), cudaMemcpyDeviceToHost, c.stream));
+        CUDA_TRY(cudaStreamSynchronize(c.stream));
+        if (info[2] & WAH_STATUS_TIMEOUT)
+            return wah_set_error(WAH_ERR_CUDA, "the decode kernel gave up waiting for part of its grid (is another context holding the GPU?)");
+        if (info[2] & WAH_STATUS_BAD_WORDS_MASK)
+            return wah_set_error(WAH_ERR_FORMAT, "%llu zero-length fill words in the stream",
+                                 (unsigned long long)(info[2] & WAH_STATUS_BAD_WORDS_MASK));
+        if (cap != 0 && info[0] <= cap) break;
+        if (want_cap != 0) break;   // the caller's capacity is what it is
+        CUDA_TRY(c.b.reserve(info[0] * 4 + 16));
+        cap = c.b.cap / 4;
+    }
+    *words_out = info[0];
+    return WAH_OK;
+}
+
+}  // namespace
+
 extern "C" int wah_decompress_host(const uint32_t *h_in, uint64_t c_words, uint32_t **h_out,
                                    uint64_t *out_words, float *ms_h2d, float *ms_compute, float *ms_d2h)
 {
@@ -407,28 +461,12 @@ extern "C" int wah_decompress_host(const uint32_t *h_in, uint64_t c_words, uint3
     CUDA_TRY(c.a.reserve(c_words * 4 + 16));
     if (int rc = upload(c, c.a.p, h_in, c_words * 4)) return rc;
     const float t_h2d = c.lap();
-    // -- segment 2: size query, output buffer, expansion (decompress.cu:66-124)
-    uint64_t *d_info = (uint64_t *)c.small.p;
-    uint64_t info[2] = {0, 0};
-    {
-        const size_t ws0 = wah_decompress_workspace_bytes(c_words, 0);
-        CUDA_TRY(c.ws.reserve(ws0));
-        if (int rc = wah_decoded_size_device((const uint32_t *)c.a.p, c_words, d_info, c.ws.p, ws0, c.stream)) return rc;
-        CUDA_TRY(cudaMemcpyAsync(info, d_info, sizeof(info), cudaMemcpyDeviceToHost, c.stream));
-        CUDA_TRY(cudaStreamSynchronize(c.stream));
+    // -- segment 2: output size, output buffer, expansion (decompress.cu:66-124)
+    uint64_t words = 0;
+    if (c_words != 0) {
+        if (int rc = decode_resident(c, c_words, 0, &words)) return rc;
     }
-    const uint64_t words = info[0];
-    const size_t ws_bytes = wah_decompress_workspace_bytes(c_words, words);
-    CUDA_TRY(c.ws.reserve(ws_bytes));
-    CUDA_TRY(c.b.reserve(words * 4 + 16));
-    if (int rc = wah_decompress_device((const uint32_t *)c.a.p, c_words, (uint32_t *)c.b.p, words, d_info, c.ws.p,
-                                       ws_bytes, c.stream))
-        return rc;
-    uint32_t bad = 0;
-    CUDA_TRY(cudaMemcpyAsync(&bad, (char *)c.ws.p + offsetof(DecodeHeader, bad_words), sizeof(bad),
-                             cudaMemcpyDeviceToHost, c.stream));
     const float t_compute = c.lap();
-    if (bad) return wah_set_error(WAH_ERR_FORMAT, "%u zero-length fill words in the stream", bad);
     // -- segment 3: D2H into a malloc()ed buffer (decompress.cu:127-133)
     uint32_t *host = alloc_result(words);
     if (!host) return wah_set_error(WAH_ERR_NOMEM, "malloc of %llu words failed", (unsigned long long)words);
@@ -468,6 +506,8 @@ extern "C" int wah_compress_host_into(const uint32_t *h_in, uint64_t n_words, in
     uint64_t cw = 0;
     CUDA_TRY(cudaMemcpyAsync(&cw, d_cnt, sizeof(cw), cudaMemcpyDeviceToHost, c.stream));
     CUDA_TRY(cudaStreamSynchronize(c.stream));
+    if (cw == ~0ull)
+        return wah_set_error(WAH_ERR_CUDA, "the compress kernel gave up waiting for part of its grid (is another context holding the GPU?)");
     *out_words = cw;
     if (cw > out_capacity_words)
         return wah_set_error(WAH_ERR_CAPACITY, "result needs %llu words, buffer holds %llu", (unsigned long long)cw,
@@ -486,23 +526,22 @@ extern "C" int wah_decompress_host_into(const uint32_t *h_in, uint64_t c_words, 
     CUDA_TRY(c.a.reserve(c_words * 4 + 16));
     if (int rc = upload(c, c.a.p, h_in, c_words * 4)) return rc;
     // the caller's capacity bounds the output, so one pass does both the size and the expansion
-    uint64_t *d_info = (uint64_t *)c.small.p;
-    const size_t ws_bytes = wah_decompress_workspace_bytes(c_words, out_capacity_words);
-    CUDA_TRY(c.ws.reserve(ws_bytes));
-    CUDA_TRY(c.b.reserve(out_capacity_words * 4 + 16));
-    if (int rc = wah_decompress_device((const uint32_t *)c.a.p, c_words, (uint32_t *)c.b.p, out_capacity_words, d_info,
-                                       c.ws.p, ws_bytes, c.stream))
-        return rc;
-    uint64_t info[2] = {0, 0};
-    uint32_t bad = 0;
-    CUDA_TRY(cudaMemcpyAsync(info, d_info, sizeof(info), cudaMemcpyDeviceToHost, c.stream));
-    CUDA_TRY(cudaMemcpyAsync(&bad, (char *)c.ws.p + offsetof(DecodeHeader, bad_words), sizeof(bad),
-                             cudaMemcpyDeviceToHost, c.stream));
-    CUDA_TRY(cudaStreamSynchronize(c.stream));
-    if (bad) return wah_set_error(WAH_ERR_FORMAT, "%u zero-length fill words in the stream", bad);
-    *out_words = info[0];
-    if (info[0] > out_capacity_words)
+    uint64_t words = 0;
+    if (c_words != 0 && out_capacity_words != 0) {
+        if (int rc = decode_resident(c, c_words, out_capacity_words, &words)) return rc;
+    } else if (c_words != 0) {
+        uint64_t *d_info = (uint64_t *)c.small.p;
+        uint64_t info[3] = {0, 0, 0};
+        const size_t ws0 = wah_decompress_workspace_bytes(c_words, 0);
+        CUDA_TRY(c.ws.reserve(ws0));
+        if (int rc = wah_decoded_size_device((const uint32_t *)c.a.p, c_words, d_info, c.ws.p, ws0, c.stream)) return rc;
+        CUDA_TRY(cudaMemcpyAsync(info, d_info, sizeof(info), cudaMemcpyDeviceToHost, c.stream));
+        CUDA_TRY(cudaStreamSynchronize(c.stream));
+        words = info[0];
+    }
+    *out_words = words;
+    if (words > out_capacity_words)
         return wah_set_error(WAH_ERR_CAPACITY, "result needs %llu words, buffer holds %llu",
-                             (unsigned long long)info[0], (unsigned long long)out_capacity_words);
-    return download(c, h_out, c.b.p, info[0] * 4, false);
+                             (unsigned long long)words, (unsigned long long)out_capacity_words);
+    return download(c, h_out, c.b.p, words * 4, false);
 }

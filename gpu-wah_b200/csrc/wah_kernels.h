@@ -8,10 +8,12 @@ namespace wahb200 {
 
 // ------------------------------------------------------------------ compress
 
-// One launch covers at most MAX_LAUNCH_GROUPS groups so that a tile descriptor
-// (status:2 | no_tail:1 | open:30 | count:31) fits one 64-bit word.
+// One launch covers at most MAX_LAUNCH_GROUPS groups: the length of a run that is still open is carried from tile to
+// tile in 32-bit arithmetic and ends up in a 30-bit fill counter.  (A tile descriptor itself is
+// epoch:32 | no_tail:1 | open:14 | count:14, see wah_compress.cu.)
 constexpr uint64_t MAX_LAUNCH_GROUPS = 0x3FFFFFFFull;
 
+constexpr uint32_t COMPRESS_SPIN_LIMIT = 1u << 21;            // descriptor polls (an L2 round trip each) before a control warp gives up
 constexpr int COMPRESS_THREADS = 256;                         // 8 warps = 8 reference blocks per tile
 constexpr int COMPRESS_TILE_WORDS = COMPRESS_THREADS * 31;    // 7936 words  (31 744 B)
 constexpr int COMPRESS_TILE_GROUPS = COMPRESS_THREADS * 32;   // 8192 groups
@@ -46,8 +48,7 @@ cudaError_t launch_seam(const uint32_t *d_in, uint64_t n_words, uint64_t groups,
 // ---------------------------------------------------------------- decompress
 
 constexpr int SCAN_THREADS = 256;
-constexpr int SCAN_ITEMS = 8;                                  // compressed words per thread
-constexpr int SCAN_TILE_WORDS = SCAN_THREADS * SCAN_ITEMS;     // 2048
+constexpr int SCAN_TILE_WORDS = SCAN_THREADS * 8;              // 2048: smallest scan tile, the unit the workspace is sized by
 
 constexpr int EXPAND_THREADS = 256;
 constexpr int EXPAND_TILE_GROUPS = EXPAND_THREADS * 32;        // 8192 groups per output tile
@@ -60,8 +61,19 @@ struct DecodeHeader {
     uint64_t out_tiles;     // ceil(G / EXPAND_TILE_GROUPS)
     uint32_t bad_words;     // zero-length fills seen (written in the last round)
     uint32_t valid;         // == the launch's epoch once groups / words / out_tiles are final
-    uint64_t pad[4];
+    uint32_t error;         // == the launch's epoch if a CTA gave up waiting for another CTA (WAH_STATUS_TIMEOUT)
+    uint32_t pad0;
+    uint64_t pad[3];
 };
+
+// status word of a decode launch: d_out_info[2] (include/wah_b200.h)
+constexpr uint64_t STATUS_BAD_MASK = 0xFFFFFFFFull;      // number of zero-length fill words in the stream
+constexpr uint64_t STATUS_TIMEOUT = 1ull << 32;          // a CTA gave up waiting for another CTA of the grid
+constexpr uint64_t STATUS_BATCH_LENGTH = 1ull << 33;     // batch: the stream does not decode to n_cols * groups_per_col groups
+// polls (an L2 round trip and a __nanosleep of >= 64 ns each) after which a CTA that waits for another CTA gives up: about 2 s.
+// The kernels need every CTA of the grid resident at the same time; if that ever fails (a foreign context holding SMs,
+// a poisoned counter slot) they end with an error instead of hanging the GPU.
+constexpr uint32_t SPIN_LIMIT = 1u << 21;
 
 // Counters that must be 0 when a launch starts.  They live in a slot of a small library-owned array (never in the
 // caller's workspace, whose content is arbitrary) and every launch leaves its slot zeroed again.
@@ -84,9 +96,15 @@ struct ScanParams {
     uint32_t epoch;          // unique per launch: whatever else is in the workspace reads as unpublished
     DecodeHeader *hdr;       // written by the launch, never read before that
     DecodeCounters *ctr;     // zero at launch, zero again when the launch is over
-    ulonglong2 *starts;      // nullptr (size query) or [max_out_tiles + 1]: {compressed word index, its group offset}
-    uint64_t max_out_tiles;
-    uint64_t *out_info;      // nullptr or device u64[2] {words, groups}
+    ulonglong2 *starts;      // nullptr (size query) or [n_cols * tiles_per_col + 2]: {compressed word index + 1, its group offset}
+    uint64_t max_out_tiles;  // output tiles per column the table has room for (single stream: from the capacity)
+    uint64_t *out_info;      // nullptr or device u64[3] {words, groups, status}
+    // bitmap-index batch: the stream is n_cols columns back to back, each decoding to col_groups groups; output tile
+    // (j, k) = tile k of column j has table index j * max_out_tiles + k and starts at group j * col_groups + k * 8192.
+    // Single stream: n_cols = 1, col_groups = ~0.
+    uint64_t col_groups;
+    uint32_t n_cols;
+    DecodeCounters *next_ctr;   // the slot the NEXT launch will use: zeroed by this launch's first CTA
     uint64_t *trace;         // nullptr; -DWAH_TRACE builds only
 };
 
@@ -96,18 +114,24 @@ struct ExpandParams {
     const DecodeHeader *hdr;
     uint32_t epoch;
     const ulonglong2 *starts;
-    uint64_t max_out_tiles;
+    uint64_t max_out_tiles;  // output tiles per column (single stream: tiles the capacity has room for)
     uint32_t *out;
-    uint64_t out_cap;
+    uint64_t out_cap;        // single stream: capacity of out; batch: words to write per column (<= decoded words of a column)
+    uint64_t col_groups;     // batch: groups per column; single stream: ~0
+    uint64_t col_stride;     // batch: words between the columns' first output words
+    uint32_t n_cols;         // 1 = single stream
+    DecodeHeader *hdr_rw;    // == hdr (the expand phase reports a timeout through it)
+    uint64_t *out_info;      // nullptr or device u64[3]: the last CTA to leave writes the status into [2]
     uint32_t zero;           // 0 (opaque to the compiler, see the ticket draw in expand_body)
-    DecodeCounters *ctr;     // nullptr: tiles are dealt round robin; else: dynamically after EXPAND_STATIC_ROUNDS rounds
+    uint32_t dynamic_tiles;  // 0: tiles are dealt round robin; else: by ticket after EXPAND_STATIC_ROUNDS rounds
+    DecodeCounters *ctr;     // zero at launch; the last CTA to leave zeroes it again
     uint64_t *trace;         // nullptr; phase timestamps in -DWAH_TRACE builds (scripts/trace_decode.py)
 };
 
 size_t expand_smem_bytes();
 // scan tile size for a stream of c_words: one tile per CTA of the decode grid while that keeps a tile between
 // at least SCAN_TILE_WORDS (the unit the workspace is sized by)
-uint32_t scan_tile_words(uint64_t c_words);
+cudaError_t scan_tile_words(uint64_t c_words, uint32_t *tile_words);
 cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream);
 cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStream_t stream);   // scan + expand, one launch
 
@@ -127,9 +151,31 @@ inline cudaError_t launch_pdl(const void *kernel, int grid, int threads, void **
     return cudaLaunchKernelExC(&cfg, kernel, args);
 }
 
+// ----------------------------------------------------------- per-device launch state (wah_device.cu)
+
+// Held around every launch of a persistent kernel: launches of one device are ordered (see wah_device.cu).
+class LaunchOrder {
+   public:
+    explicit LaunchOrder(cudaStream_t stream);
+    ~LaunchOrder();
+    LaunchOrder(const LaunchOrder &) = delete;
+    LaunchOrder &operator=(const LaunchOrder &) = delete;
+    cudaError_t status() const { return err_; }
+    int device() const { return dev_; }
+    // the decode kernel's counter slot for this launch, and the slot the next launch will get
+    cudaError_t counter_slots(DecodeCounters **mine, DecodeCounters **next);
+
+   private:
+    cudaStream_t stream_;
+    int dev_ = -1;
+    cudaError_t err_ = cudaSuccess;
+};
+void forget_stream(cudaStream_t stream);
+cudaError_t poison_counter_slots();
+
 // --------------------------------------------------------------------- misc
 
-cudaError_t launch_shard_probe(const uint32_t *d_shard, uint64_t words, uint64_t *d_result /*[6]*/,
+cudaError_t launch_shard_probe(const uint32_t *d_shard, uint64_t words, uint64_t *d_result /*[5]*/,
                                cudaStream_t stream);
 cudaError_t launch_popcount(const uint32_t *d_in, uint64_t c_words, uint64_t *d_bits, cudaStream_t stream);
 cudaError_t launch_logical(int op, uint32_t *d_a, const uint32_t *d_b, uint64_t n_words, cudaStream_t stream);

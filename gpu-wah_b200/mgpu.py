@@ -157,16 +157,22 @@ def compress_columns_sharded(local_cols: torch.Tensor, mode: int = wah.WAH_BLOCK
     return out, offs, lengths
 
 
-def decompress_columns(out: torch.Tensor, offs: torch.Tensor, words_per_col: int) -> torch.Tensor:
+def decompress_columns(out: torch.Tensor, offs: torch.Tensor, words_per_col: int, c_total: int | None = None) -> torch.Tensor:
     """Decode this rank's columns again (the result of ``compress_columns_sharded``): [cols, words_per_col].
-    Local work only, no collective."""
+    Local work only, no collective: ONE launch for all columns.  ``c_total`` = ``offs[-1]`` if the caller knows it
+    (saves the device -> host read of that one number)."""
     n_cols = offs.numel() - 1
     dev = out.device
-    offs_h = [int(v) for v in offs.cpu().tolist()]
+    if n_cols == 0:
+        return torch.empty(0, words_per_col, dtype=torch.int32, device=dev)
+    if c_total is None:
+        c_total = int(offs[-1].item())
     stride = (words_per_col + 1 + 3) // 4 * 4
-    back = torch.empty(max(n_cols, 1) * stride, dtype=torch.int32, device=dev)
-    info = torch.zeros(2 * max(n_cols, 1), dtype=torch.int64, device=dev)
-    longest = max([offs_h[j + 1] - offs_h[j] for j in range(n_cols)] + [1])
-    ws = wah.Workspace.for_decompress_batch(longest, words_per_col + 1, dev)
-    wah.decompress_batch_device(out, offs_h, back, stride, words_per_col + 1, info, ws)
-    return back.view(max(n_cols, 1), stride)[:n_cols, :words_per_col]
+    back = torch.empty(n_cols * stride, dtype=torch.int32, device=dev)
+    info = torch.zeros(3, dtype=torch.int64, device=dev)
+    ws = wah.Workspace.for_decompress_batch(n_cols, c_total, words_per_col, dev)
+    wah.decompress_batch_device(out, c_total, n_cols, words_per_col, back, stride, words_per_col + 1, info, ws)
+    status = int(info[2].item())
+    if status:
+        raise wah.WahError(5, f"batch decode status {status:#x}")
+    return back.view(n_cols, stride)[:, :words_per_col]

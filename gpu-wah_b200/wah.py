@@ -21,6 +21,10 @@ WAH_BLOCK1024 = 0  # bit-exact to the reference encoder (runs never cross 1024 g
 WAH_CANONICAL = 1  # maximal runs
 
 WAH_MAX_SEAM_WORDS = 8
+# d_out_info[2] of the decoders (include/wah_b200.h)
+WAH_STATUS_BAD_WORDS_MASK = 0xFFFFFFFF
+WAH_STATUS_TIMEOUT = 1 << 32
+WAH_STATUS_BATCH_LENGTH = 1 << 33
 WAH_OP_AND, WAH_OP_OR, WAH_OP_XOR, WAH_OP_ANDNOT = 0, 1, 2, 3
 
 _HERE = os.path.dirname(os.path.abspath(__file__))
@@ -87,8 +91,8 @@ _sig("wah_compress_batch_workspace_bytes", _sz, _u64, _u64)
 _sig("wah_compress_batch_device", ctypes.c_int, _vp, _u64, _u64, _u64, ctypes.c_int, _vp, _u64, _vp, _vp, _sz, _vp)
 _sig("wah_decompress_workspace_bytes", _sz, _u64, _u64)
 _sig("wah_decompress_device", ctypes.c_int, _vp, _u64, _vp, _u64, _vp, _vp, _sz, _vp)
-_sig("wah_decompress_batch_workspace_bytes", _sz, _u64, _u64)
-_sig("wah_decompress_batch_device", ctypes.c_int, _vp, ctypes.POINTER(_u64), _u64, _vp, _u64, _u64, _vp, _vp, _sz, _vp)
+_sig("wah_decompress_batch_workspace_bytes", _sz, _u64, _u64, _u64)
+_sig("wah_decompress_batch_device", ctypes.c_int, _vp, _u64, _u64, _u64, _vp, _u64, _u64, _vp, _vp, _sz, _vp)
 _sig("wah_decoded_size_device", ctypes.c_int, _vp, _u64, _vp, _vp, _sz, _vp)
 _sig("wah_compress_host", ctypes.c_int, _vp, _u64, ctypes.c_int, ctypes.POINTER(_vp), ctypes.POINTER(_u64), _pf, _pf, _pf)
 _sig("wah_decompress_host", ctypes.c_int, _vp, _u64, ctypes.POINTER(_vp), ctypes.POINTER(_u64), _pf, _pf, _pf)
@@ -101,6 +105,7 @@ _sig("wah_stitch_plan", ctypes.c_int, ctypes.POINTER(ShardRecord), ctypes.c_int,
      ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_uint32),
      ctypes.POINTER(ctypes.c_uint32), ctypes.POINTER(_u64))
 _sig("wah_test_set_max_launch_tiles", None, _u64)
+_sig("wah_test_poison_counter_slots", ctypes.c_int)
 _sig("wah_popcount_device", ctypes.c_int, _vp, _u64, _vp, _vp)
 _sig("wah_logical_workspace_bytes", _sz, _u64, _u64, _u64)
 _sig("wah_logical_device", ctypes.c_int, ctypes.c_int, _vp, _u64, _vp, _u64, _u64, ctypes.c_int, _vp, _u64, _vp, _vp, _sz, _vp)
@@ -271,8 +276,8 @@ class Workspace:
         return cls(lib.wah_logical_workspace_bytes(n_words, ca_words, cb_words), device)
 
     @classmethod
-    def for_decompress_batch(cls, max_col_c_words: int, out_col_capacity_words: int, device="cuda"):
-        return cls(lib.wah_decompress_batch_workspace_bytes(max_col_c_words, out_col_capacity_words), device)
+    def for_decompress_batch(cls, n_cols: int, c_total_words: int, words_per_col: int, device="cuda"):
+        return cls(lib.wah_decompress_batch_workspace_bytes(n_cols, c_total_words, words_per_col), device)
 
 
 def compress_device(d_in, n_words: int, d_out, out_capacity_words: int, d_out_words, workspace,
@@ -294,19 +299,19 @@ def compress_batch_device(d_in, n_cols: int, words_per_col: int, col_stride_word
 
 def decompress_device(d_in, c_words: int, d_out, out_capacity_words: int, d_out_info, workspace,
                       stream=None) -> None:
-    """Asynchronous decode; ``d_out_info``: device int64[2] receiving (decoded words, decoded groups)."""
+    """Asynchronous decode; ``d_out_info``: device int64[3] receiving (decoded words, decoded groups, status:
+    0 or ``WAH_STATUS_*`` bits)."""
     _check(lib.wah_decompress_device(_ptr(d_in), c_words, _ptr(d_out), out_capacity_words,
                                      _ptr(d_out_info), _ptr(workspace), workspace.nbytes, _stream(stream)))
 
 
-def decompress_batch_device(d_in, col_offsets, d_out, out_col_stride_words: int, out_col_capacity_words: int,
-                            d_out_info, workspace, stream=None) -> None:
-    """Decode ``len(col_offsets) - 1`` bitmap-index columns laid out as ``compress_batch_device`` writes them.
-    ``col_offsets``: HOST sequence of word offsets; ``d_out_info``: device int64[2 * n_cols]."""
-    n_cols = len(col_offsets) - 1
-    offs = (_u64 * (n_cols + 1))(*[int(v) for v in col_offsets])
-    _check(lib.wah_decompress_batch_device(_ptr(d_in), offs, n_cols, _ptr(d_out), out_col_stride_words,
-                                           out_col_capacity_words, _ptr(d_out_info), _ptr(workspace),
+def decompress_batch_device(d_in, c_total_words: int, n_cols: int, words_per_col: int, d_out,
+                            out_col_stride_words: int, out_col_words: int, d_out_info, workspace, stream=None) -> None:
+    """Decode ``n_cols`` bitmap-index columns laid out back to back as ``compress_batch_device`` writes them, in ONE
+    launch; column j goes to ``d_out + j * out_col_stride_words``.  ``d_out_info``: device int64[3] receiving
+    (words one column decodes to, groups in the whole stream, status)."""
+    _check(lib.wah_decompress_batch_device(_ptr(d_in), c_total_words, n_cols, words_per_col, _ptr(d_out),
+                                           out_col_stride_words, out_col_words, _ptr(d_out_info), _ptr(workspace),
                                            workspace.nbytes, _stream(stream)))
 
 

@@ -31,7 +31,7 @@
 extern "C" {
 #endif
 
-#define WAH_B200_VERSION 100
+#define WAH_B200_VERSION 200
 
 /* encoder modes */
 #define WAH_BLOCK1024 0 /* bit-exact to the reference encoder: runs never cross a block of
@@ -57,12 +57,19 @@ uint64_t wah_max_compressed_words(uint64_t n_words);
 /* ceil(31 G / 32): words a stream of G groups decodes to (decompress.cu:82-93) */
 uint64_t wah_decoded_words(uint64_t groups);
 
-/* ---- device-resident API (buffers in HBM, asynchronous on `stream`) ---------------- */
+/* ---- device-resident API (buffers in HBM, asynchronous on `stream`) ----------------
+ *
+ * Both big kernels are persistent grids whose CTAs exchange results with each other, so two of them must not run on
+ * one device at the same time: the library orders its own launches per device (a launch on another stream than the
+ * previous one waits for an event behind it; launches on one stream pay nothing).  A CTA that waits for another CTA
+ * gives up after about two seconds: compress then reports *d_out_words = UINT64_MAX, decompress
+ * WAH_STATUS_TIMEOUT in d_out_info[2] -- an error instead of a hung GPU (e.g. when a foreign context holds SMs).   */
 
 /* replaces compressData + thrust::exclusive_scan + moveData (kernels.cu:51-280, compress.cu:129-166).
  *   d_in            n_words input words, 16-byte aligned
  *   d_out           receives the compressed words; writes past out_capacity_words are dropped
- *   d_out_words     device u64, receives c (the true length even if it exceeds the capacity)
+ *   d_out_words     device u64, receives c (the true length even if it exceeds the capacity); UINT64_MAX if the
+ *                   launch failed (see above)
  *   d_workspace     wah_compress_workspace_bytes(n_words) bytes, 16-byte aligned.  Scratch: its content
  *                   need not be initialised or preserved (what the kernels exchange through it is tagged
  *                   with a per-launch number), but it must not be shared by launches that may overlap.  */
@@ -84,19 +91,24 @@ int wah_compress_batch_device(const uint32_t *d_in, uint64_t n_cols, uint64_t wo
  * (kernels.cu:291-385, decompress.cu:66-115).
  *   d_in            c_words compressed words, 16-byte aligned
  *   d_out           receives ceil(31 G / 32) words (16-byte aligned); words past the capacity are dropped
- *   d_out_info      device u64[2]: [0] = decoded words, [1] = decoded groups G
+ *   d_out_info      device u64[3]: [0] = decoded words, [1] = decoded groups G, [2] = status of the launch:
+ *                   0 = fine, else WAH_STATUS_* bits (the reference checks nothing in decompress(): decompress.cu:48-52)
  *   d_workspace     wah_decompress_workspace_bytes(c_words, out_capacity_words) bytes; scratch as above   */
+#define WAH_STATUS_BAD_WORDS_MASK 0xFFFFFFFFull  /* number of malformed words (fills of 0 groups) in the stream        */
+#define WAH_STATUS_TIMEOUT        (1ull << 32)   /* the kernel gave up waiting for part of its own grid (see below)     */
+#define WAH_STATUS_BATCH_LENGTH   (1ull << 33)   /* batch: the stream does not decode to n_cols equal columns           */
 size_t wah_decompress_workspace_bytes(uint64_t c_words, uint64_t out_capacity_words);
 int wah_decompress_device(const uint32_t *d_in, uint64_t c_words,
                           uint32_t *d_out, uint64_t out_capacity_words, uint64_t *d_out_info,
                           void *d_workspace, size_t workspace_bytes, void *stream);
-/* bitmap-index batch: column j's stream is d_in[h_col_offsets[j] .. h_col_offsets[j+1]) (the layout
- * wah_compress_batch_device writes; the offsets are a HOST array here), decoded to
- * d_out + j * out_col_stride_words (a multiple of 4).  d_out_info: device u64[2 * n_cols].  One launch per
- * column on `stream`; d_workspace holds wah_decompress_batch_workspace_bytes(longest stream, capacity) bytes. */
-size_t wah_decompress_batch_workspace_bytes(uint64_t max_col_c_words, uint64_t out_col_capacity_words);
-int wah_decompress_batch_device(const uint32_t *d_in, const uint64_t *h_col_offsets, uint64_t n_cols,
-                                uint32_t *d_out, uint64_t out_col_stride_words, uint64_t out_col_capacity_words,
+/* bitmap-index batch, ONE launch: d_in holds n_cols compressed columns back to back (the layout
+ * wah_compress_batch_device writes; c_total_words = its d_col_offsets[n_cols]), every column the compressed form
+ * of words_per_col input words, i.e. of wah_num_groups(words_per_col) groups.  Column j is decoded to
+ * d_out + j * out_col_stride_words (a multiple of 4); out_col_words (<= the stride) words are written per column.
+ * d_out_info: device u64[3]: [0] = words one column decodes to, [1] = groups in the whole stream, [2] = status.   */
+size_t wah_decompress_batch_workspace_bytes(uint64_t n_cols, uint64_t c_total_words, uint64_t words_per_col);
+int wah_decompress_batch_device(const uint32_t *d_in, uint64_t c_total_words, uint64_t n_cols, uint64_t words_per_col,
+                                uint32_t *d_out, uint64_t out_col_stride_words, uint64_t out_col_words,
                                 uint64_t *d_out_info, void *d_workspace, size_t workspace_bytes, void *stream);
 /* size query only (the scan half of the above); d_out_info as above */
 int wah_decoded_size_device(const uint32_t *d_in, uint64_t c_words, uint64_t *d_out_info,
@@ -209,6 +221,10 @@ int wah_gen_paint_runs_device(uint32_t *d_out, uint64_t n_words, const int64_t *
  * chained launches.  This shrinks the per-launch segment to `tiles` tiles of 7936 words so that
  * the tests can drive that path with small inputs; 0 restores the default.  Not thread safe.   */
 void wah_test_set_max_launch_tiles(uint64_t tiles);
+/* Overwrites the decode kernel's library-owned counter slots of the current device with garbage -- what a launch that
+ * was killed half way would leave behind.  The next decode launch then times out (WAH_STATUS_TIMEOUT), the one after
+ * it works again: every launch zeroes its successor's slot.  Synchronises the device.                             */
+int wah_test_poison_counter_slots(void);
 
 #ifdef __cplusplus
 }

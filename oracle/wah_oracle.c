@@ -363,6 +363,36 @@ uint64_t wah_oracle_compress_batch(const uint32_t *in, uint64_t n_cols, uint64_t
     return c;
 }
 
+/* Bench helper (bitmap index, BASELINE.json configs[3]): every column compressed and decoded again, the columns dealt
+ * to the threads, each with its own scratch.  Returns the total number of compressed words; *mismatches = columns that
+ * did not round trip (only looked at when verify != 0, so that the comparison stays out of the timed loop). */
+uint64_t wah_oracle_roundtrip_columns_mt(const uint32_t *in, uint64_t n_cols, uint64_t words_per_col, int mode,
+                                         int nthreads, int verify, uint64_t *mismatches)
+{
+    int T = nthreads > 0 ? nthreads : wah_oracle_max_threads();
+    if ((uint64_t)T > n_cols) T = (int)(n_cols ? n_cols : 1);
+    const uint64_t G = wah_oracle_num_groups(words_per_col);
+    const uint64_t W = wah_oracle_decoded_words(G);
+    uint64_t total = 0, bad = 0;
+#pragma omp parallel num_threads(T) reduction(+ : total, bad)
+    {
+        uint32_t *comp = (uint32_t *)malloc((size_t)(G ? G : 1) * 4);
+        uint32_t *dec = (uint32_t *)malloc((size_t)(W ? W : 1) * 4);
+#pragma omp for schedule(dynamic, 1)
+        for (int64_t j = 0; j < (int64_t)n_cols; j++) {
+            const uint32_t *col = in + (uint64_t)j * words_per_col;
+            const uint64_t c = wah_oracle_compress(col, words_per_col, mode, comp);
+            wah_oracle_decompress(comp, c, dec);
+            total += c;
+            if (verify && memcmp(dec, col, (size_t)words_per_col * 4) != 0) bad++;
+        }
+        free(comp);
+        free(dec);
+    }
+    if (mismatches) *mismatches = bad;
+    return total;
+}
+
 /* ------------------------------------------------------------------ query operators on the runs themselves
  *
  * Not in the reference.  Two streams that stand for vectors of the same length have the same 31-bit groups, so

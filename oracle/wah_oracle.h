@@ -69,11 +69,20 @@ int wah_oracle_max_threads(void);
 uint64_t wah_oracle_compress_batch(const uint32_t *in, uint64_t n_cols, uint64_t words_per_col,
                                    int mode, uint32_t *out, uint64_t *offsets);
 
+/* bench helper: compress + decompress of every column, columns dealt to the threads (see wah_oracle.c) */
+uint64_t wah_oracle_roundtrip_columns_mt(const uint32_t *in, uint64_t n_cols, uint64_t words_per_col, int mode,
+                                         int nthreads, int verify, uint64_t *mismatches);
+
 /* out = a op b (0 AND, 1 OR, 2 XOR, 3 ANDNOT) computed on the runs of two streams that stand for vectors of
  * `groups` groups each (a shorter stream counts as zero-extended); equals
  * compress(decompress(a) op decompress(b)) word for word.  out must hold `groups` words.  Returns the length. */
 uint64_t wah_oracle_logical(int op, const uint32_t *a, uint64_t ca_words, const uint32_t *b, uint64_t cb_words,
                             uint64_t groups, int mode, uint32_t *out);
+
+/* Host-side synthetic inputs for the CPU arms of bench.py (wah_datagen.c): run clustered (two-state Markov chain,
+ * 1-runs of mean mean_run_bits) and i.i.d. Bernoulli(density) bits, LSB first, written as packed words. */
+void wah_oracle_gen_clustered(uint32_t *out, uint64_t n_words, double density, double mean_run_bits, uint64_t seed);
+void wah_oracle_gen_uniform(uint32_t *out, uint64_t n_words, double density, uint64_t seed);
 
 #ifdef __cplusplus
 }

@@ -12,7 +12,7 @@ cs = []
 for b in range(nbuf):
     wah.compress_device(ins[b], n, out, cap, cnt, ws, 0)
     cs.append(int(cnt.item()))
-info = torch.zeros(2, dtype=torch.int64, device="cuda")
+info = torch.zeros(3, dtype=torch.int64, device="cuda")
 wd = wah.Workspace.for_decompress(max(cs), n + 32)
 dec = torch.empty(n + 32, dtype=torch.int32, device="cuda")
 def step(b):

@@ -25,7 +25,7 @@ for name, pat in pats.items():
     c = cw.size
     n = (G * 31 + 31) // 32 + 64
     dec = torch.empty(n, dtype=torch.int32, device="cuda")
-    info = torch.zeros(2, dtype=torch.int64, device="cuda")
+    info = torch.zeros(3, dtype=torch.int64, device="cuda")
     wd = wah.Workspace.for_decompress(c, n)
     ts = []
     for _ in range(12):

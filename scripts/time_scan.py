@@ -9,7 +9,7 @@ cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
 ws = wah.Workspace.for_compress(n)
 wah.compress_device(d, n, out, cap, cnt, ws, 0)
 c = int(cnt.item())
-info = torch.zeros(2, dtype=torch.int64, device="cuda")
+info = torch.zeros(3, dtype=torch.int64, device="cuda")
 wd = wah.Workspace.for_decompress(c, n + 32)
 dec = torch.empty(n + 32, dtype=torch.int32, device="cuda")
 flush = torch.empty(64 << 20, dtype=torch.int32, device="cuda")

@@ -15,7 +15,7 @@ ws = wah.Workspace.for_compress(n)
 wah.compress_device(d, n, out, cap, cnt, ws, 0)
 c = int(cnt.item())
 dec = torch.empty(n + 32, dtype=torch.int32, device="cuda")
-info = torch.zeros(2, dtype=torch.int64, device="cuda")
+info = torch.zeros(3, dtype=torch.int64, device="cuda")
 wd = wah.Workspace.for_decompress(c, n + 32)
 NC = 444
 trace = torch.zeros(NC * 64, dtype=torch.int64, device="cuda")

@@ -22,6 +22,9 @@ for name, res, args in [
     ("wah_oracle_decompress_mt", _u64, [_vp, _u64, _vp, ctypes.c_int]),
     ("wah_oracle_max_threads", ctypes.c_int, []),
     ("wah_oracle_compress_batch", _u64, [_vp, _u64, _u64, ctypes.c_int, _vp, _vp]),
+    ("wah_oracle_roundtrip_columns_mt", _u64, [_vp, _u64, _u64, ctypes.c_int, ctypes.c_int, ctypes.c_int, _vp]),
+    ("wah_oracle_gen_clustered", None, [_vp, _u64, ctypes.c_double, ctypes.c_double, _u64]),
+    ("wah_oracle_gen_uniform", None, [_vp, _u64, ctypes.c_double, _u64]),
 ]:
     f = getattr(_lib, name)
     f.restype, f.argtypes = res, args
@@ -97,3 +100,27 @@ def logical(op, a, b, groups, mode=BLOCK1024):
                                         ctypes.c_uint64, ctypes.c_int, ctypes.c_void_p]
     c = _lib.wah_oracle_logical(op, x.ctypes.data, x.size, y.ctypes.data, y.size, groups, mode, out.ctypes.data)
     return out[:c].copy()
+
+
+def gen_clustered(n_words, density, mean_run_bits=1000.0, seed=1337, out=None):
+    """run-clustered bitvector (two-state Markov chain), packed words written directly (no byte-per-bit array)"""
+    out = np.empty(n_words, dtype=np.uint32) if out is None else out
+    _lib.wah_oracle_gen_clustered(out.ctypes.data, n_words, density, mean_run_bits, seed)
+    return out
+
+
+def gen_uniform(n_words, density, seed=1337, out=None):
+    """i.i.d. Bernoulli(density) bits, packed words written directly"""
+    out = np.empty(n_words, dtype=np.uint32) if out is None else out
+    _lib.wah_oracle_gen_uniform(out.ctypes.data, n_words, density, seed)
+    return out
+
+
+def roundtrip_columns(cols, mode=BLOCK1024, threads=0, verify=False):
+    """compress + decompress of every column of a [n_cols, words_per_col] array, the columns dealt to the threads;
+    returns (total compressed words, columns that did not round trip -- 0 unless ``verify``)"""
+    a = _u32(cols)
+    n_cols, wpc = a.shape
+    bad = ctypes.c_uint64(0)
+    c = _lib.wah_oracle_roundtrip_columns_mt(a.ctypes.data, n_cols, wpc, mode, threads, 1 if verify else 0, ctypes.byref(bad))
+    return int(c), int(bad.value)

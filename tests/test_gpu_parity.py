@@ -45,11 +45,12 @@ def gpu_decompress(cw, cap=None):
     words = orc.decoded_words(orc.decoded_groups(cw))
     cap = words if cap is None else cap
     d_out = torch.full((max(cap, 1),), -1, dtype=torch.int32, device="cuda")
-    d_info = torch.full((2,), -1, dtype=torch.int64, device="cuda")
+    d_info = torch.full((3,), -1, dtype=torch.int64, device="cuda")
     ws = wah.Workspace.for_decompress(c, cap)
     wah.decompress_device(d_in, c, d_out, cap, d_info, ws)
     info = d_info.cpu().tolist()
-    return to_host(d_out[: min(info[0], cap)]), info
+    assert info[2] == 0, f"decode status {info[2]:#x}"
+    return to_host(d_out[: min(info[0], cap)]), info[:2]
 
 
 def _cases():
@@ -142,7 +143,7 @@ def test_output_capacity_is_respected():
     assert (d_out[cap:] == -1).all()                           # nothing past the capacity
     dec_cap = 3 * TW + 11
     d_dec = torch.full((dec_cap + 64,), -1, dtype=torch.int32, device="cuda")
-    d_info = torch.zeros(2, dtype=torch.int64, device="cuda")
+    d_info = torch.zeros(3, dtype=torch.int64, device="cuda")
     wah.decompress_device(to_dev(want), want.size, d_dec, dec_cap, d_info, wah.Workspace.for_decompress(want.size, dec_cap))
     assert d_info.cpu().tolist()[0] == n
     assert np.array_equal(to_host(d_dec[:dec_cap]), data[:dec_cap])
@@ -168,18 +169,19 @@ def test_batch_columns(mode):
     assert np.array_equal(got_offs, offs)
     assert np.array_equal(to_host(d_out[: int(offs[-1])]), want)
 
-    # and back: every column decoded to its own slot (the streams start at arbitrary word offsets)
+    # and back, ONE launch: every column decoded to its own slot (the streams start at arbitrary word offsets)
     stride = (wpc + 1 + 3) // 4 * 4
     d_back = torch.full((n_cols * stride,), -1, dtype=torch.int32, device="cuda")
-    d_info = torch.full((2 * n_cols,), -1, dtype=torch.int64, device="cuda")
-    lens = np.diff(offs.astype(np.int64))
-    wsd = wah.Workspace.for_decompress_batch(int(lens.max()), wpc + 1)
-    wah.decompress_batch_device(d_out, [int(v) for v in offs], d_back, stride, wpc + 1, d_info, wsd)
+    d_info = torch.full((3,), -1, dtype=torch.int64, device="cuda")
+    c_total = int(offs[-1])
+    wsd = wah.Workspace.for_decompress_batch(n_cols, c_total, wpc)
+    wah.decompress_batch_device(d_out, c_total, n_cols, wpc, d_back, stride, wpc + 1, d_info, wsd)
     back = to_host(d_back).reshape(n_cols, stride)
-    info = d_info.cpu().numpy().reshape(n_cols, 2)
+    info = d_info.cpu().tolist()
+    assert info == [orc.decoded_words(orc.num_groups(wpc)), orc.num_groups(wpc) * n_cols, 0]
     for j in range(n_cols):
-        assert info[j, 1] == orc.num_groups(wpc) and info[j, 0] == orc.decoded_words(orc.num_groups(wpc))
         assert np.array_equal(back[j, :wpc], cols[j]), j
+        assert (back[j, wpc + 1:] == 0xFFFFFFFF).all()         # nothing past out_col_words
 
 
 def test_host_entry_points_mirror_the_reference():
@@ -329,10 +331,11 @@ def test_large_clustered_round_trip(n, density, mode):
     assert c == want.size
     assert np.array_equal(to_host(out[:c]), want)
     dec = torch.full((n + 32,), -1, dtype=torch.int32, device="cuda")
-    info = torch.zeros(2, dtype=torch.int64, device="cuda")
+    info = torch.full((3,), -1, dtype=torch.int64, device="cuda")
     wd = wah.Workspace.for_decompress(c, n + 32)
     wah.decompress_device(out, c, dec, n + 32, info, wd)
-    words, groups = info.tolist()
+    words, groups, status = info.tolist()
+    assert status == 0
     assert groups == orc.num_groups(n) and words == orc.decoded_words(groups)
     assert torch.equal(dec[:n], x)
     assert not bool(dec[n:words].any())
@@ -381,14 +384,18 @@ def test_zero_length_fills_are_counted_and_rejected(n_words, n_bad):
     pos = rng.choice(n_words, size=n_bad, replace=False)
     cw[pos] = np.where(rng.random(n_bad) < 0.5, np.uint32(0x80000000), np.uint32(0xC0000000))
     d_in = to_dev(cw)
-    d_info = torch.zeros(2, dtype=torch.int64, device="cuda")
+    d_info = torch.full((3,), -1, dtype=torch.int64, device="cuda")
     ws = wah.Workspace.for_decompress(n_words, 0)
     wah.decoded_size_device(d_in, n_words, d_info, ws)
-    torch.cuda.synchronize()
-    hdr = ws.buf[:32].cpu().numpy()
-    assert int(hdr[24:28].view(np.uint32)[0]) == n_bad          # DecodeHeader.bad_words
     good = np.delete(cw, pos)
-    assert d_info.tolist()[1] == orc.decoded_groups(good)        # zero-length fills add no groups
+    assert d_info.tolist()[1:] == [orc.decoded_groups(good), n_bad]   # zero-length fills add no groups; status = their number
+    # the same through the full decoder of the device API: the caller is told, whatever it does with the words
+    words = orc.decoded_words(orc.decoded_groups(good))
+    d_out = torch.empty(words + 8, dtype=torch.int32, device="cuda")
+    d_info.fill_(-1)
+    wah.decompress_device(d_in, n_words, d_out, words + 8, d_info, wah.Workspace.for_decompress(n_words, words + 8))
+    assert d_info.tolist() == [words, orc.decoded_groups(good), n_bad]
+    assert np.array_equal(to_host(d_out[:words]), orc.decompress(good))
     if n_bad:
         with pytest.raises(wah.WahError) as e:
             wah.decompress(cw)
@@ -436,43 +443,52 @@ def _popcount_stream(cw):
 
 
 @pytest.mark.parametrize("name,n,gen,density,mode", [
+    ("C1_uniform_32mbit", 1 << 20, "uniform", 0.5, 0),
+    ("C1_uniform_32mbit_canonical", 1 << 20, "uniform", 0.5, 1),
     ("C2_sparse_1gbit", 1 << 25, "uniform", 0.001, 0),
     ("C2_sparse_1gbit_canonical", 1 << 25, "uniform", 0.001, 1),
-    ("C3_clustered_16gbit", 1 << 29, "clustered", 0.01, 0),
-    ("C3_clustered_16gbit_d05_canonical", 1 << 29, "clustered", 0.5, 1),
+] + [(f"C3_clustered_16gbit_d{d}_{'canonical' if m else 'block1024'}", 1 << 29, "clustered", d, m)
+     for d in (0.0001, 0.001, 0.01, 0.1, 0.25, 0.5) for m in (0, 1)] + [
     ("C5_128gbit_single_vector", 1 << 32, "clustered", 0.001, 0),
     ("C5_128gbit_single_vector_canonical", 1 << 32, "clustered", 0.1, 1),
 ])
 def test_full_size_configs(name, n, gen, density, mode):
     x = (wah.gen_uniform_device(n, density, 4711) if gen == "uniform"
          else wah.gen_clustered_device(n, density, 1000.0, 4711))
-    # room for the stream: these vectors compress at least 4 : 1 (the capacity is enforced by the kernel anyway)
-    cap = n // 4 + 1024
+    # room for the stream: the clustered / sparse vectors compress at least 4 : 1 (the capacity is enforced by the
+    # kernel anyway); the uniform d = 0.5 vector of configs[0] does not compress at all
+    cap = wah.max_compressed_words(n) if density == 0.5 and gen == "uniform" else n // 4 + 1024
     out = torch.empty(cap, dtype=torch.int32, device="cuda")
     cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
     wah.compress_device(x, n, out, cap, cnt, wah.Workspace.for_compress(n), mode)
     c = int(cnt.item())
     assert 0 < c <= cap, (c, cap)
-    # (3) the oracle on the first 2^21 words (a multiple of 992 words = whole blocks: 2114 * 992)
-    k = 2114 * 992
-    want = orc.compress(to_host(x[:k]), 0)
-    if mode == 0:
-        assert np.array_equal(to_host(out[:want.size]), want)
+    # (3) the oracle on the first 2^21 words (a multiple of 992 words = whole blocks: 2114 * 992), or on all of a
+    #     small vector.  BLOCK1024: blocks are independent, the prefix's stream is a prefix of the stream.  CANONICAL:
+    #     the same up to the prefix's last word, which may be a run that goes on behind the prefix.
+    k = min(n, 2114 * 992)
+    want = orc.compress(to_host(x[:k]), mode)
+    keep = want.size if (mode == 0 or k == n) else want.size - 1
+    assert np.array_equal(to_host(out[:keep]), want[:keep])
+    if k == n:
+        assert c == want.size
     # (2) checksum of checksums
     bits = _popcount_words(x)
     assert _popcount_stream(out[:c]) == bits
     # (1) + (4) round trip
     dec = torch.empty(n + 4, dtype=torch.int32, device="cuda")
-    info = torch.zeros(2, dtype=torch.int64, device="cuda")
+    info = torch.full((3,), -1, dtype=torch.int64, device="cuda")
     wah.decompress_device(out, c, dec, n + 4, info, wah.Workspace.for_decompress(c, n + 4))
-    words, groups = info.tolist()
+    words, groups, status = info.tolist()
+    assert status == 0
     assert groups == orc.num_groups(n) and words == orc.decoded_words(groups)
     assert torch.equal(dec[:n], x)
     assert not bool(dec[n:words].any())
 
 
 def test_full_size_bitmap_index_columns():
-    """BASELINE configs[3]: 1024 columns x 64 Mbit, one batched launch; every column a stream of its own."""
+    """BASELINE configs[3]: 1024 columns x 64 Mbit: one batched compress launch and ONE batched decode launch; every
+    column a stream of its own."""
     n_cols, wpc = 1024, 1 << 21
     x = wah.gen_clustered_device(n_cols * wpc, 0.02, 1000.0, 99)
     cap = n_cols * wpc // 4 + 4096
@@ -485,16 +501,114 @@ def test_full_size_bitmap_index_columns():
     for j in (0, 511, 1023):
         want = orc.compress(to_host(x[j * wpc:(j + 1) * wpc]), 0)
         assert np.array_equal(to_host(out[h_offs[j]:h_offs[j + 1]]), want), j
-    assert _popcount_stream(out[: int(h_offs[-1])]) == _popcount_words(x)
+    c_total = int(h_offs[-1])
+    assert _popcount_stream(out[:c_total]) == _popcount_words(x)
     # and back
     stride = wpc + 4
-    back = torch.empty(n_cols * stride, dtype=torch.int32, device="cuda")
-    info = torch.zeros(2 * n_cols, dtype=torch.int64, device="cuda")
-    lens = np.diff(h_offs)
-    wsd = wah.Workspace.for_decompress_batch(int(lens.max()), wpc + 1)
-    wah.decompress_batch_device(out, [int(v) for v in h_offs], back, stride, wpc + 1, info, wsd)
+    back = torch.full((n_cols * stride,), -1, dtype=torch.int32, device="cuda")
+    info = torch.full((3,), -1, dtype=torch.int64, device="cuda")
+    wsd = wah.Workspace.for_decompress_batch(n_cols, c_total, wpc)
+    wah.decompress_batch_device(out, c_total, n_cols, wpc, back, stride, wpc + 1, info, wsd)
+    assert info.tolist() == [orc.decoded_words(orc.num_groups(wpc)), orc.num_groups(wpc) * n_cols, 0]
     assert torch.equal(back.view(n_cols, stride)[:, :wpc], x.view(n_cols, wpc))
-    assert (info.view(n_cols, 2)[:, 1] == orc.num_groups(wpc)).all()
+    assert not bool(back.view(n_cols, stride)[:, wpc].any())          # the padding word of every column
+    assert bool((back.view(n_cols, stride)[:, wpc + 1:] == -1).all())  # nothing past out_col_words
+
+
+@pytest.mark.parametrize("mode", MODES)
+@pytest.mark.parametrize("n_cols,wpc,kind", [
+    (5, 31, "mixed"), (64, 992, "zeros"), (33, 7936, "mixed"), (9, 8192 * 3 + 17, "mixed"), (300, 1000, "ones"),
+    (17, 3 * 7936, "dense"), (2000, 40, "zeros"), (3, 1 << 18, "mixed"),
+])
+def test_batch_decode_column_shapes(n_cols, wpc, kind, mode):
+    """One decode launch over columns of every shape: shorter than a tile, whole tiles, ragged ends; columns that
+    compress to a single word (hundreds of columns inside one scan pack); all-literal columns."""
+    rng = np.random.default_rng(n_cols * 1000 + wpc)
+    cols = np.zeros((n_cols, wpc), dtype=np.uint32)
+    for j in range(n_cols):
+        pick = kind if kind != "mixed" else ("zeros", "ones", "sparse", "dense", "clustered")[int(rng.integers(0, 5))]
+        if pick == "ones":
+            cols[j] = 0xFFFFFFFF
+        elif pick == "sparse":
+            cols[j] = datagen.uniform(wpc, 0.002, 100 + j)
+        elif pick == "dense":
+            cols[j] = datagen.uniform(wpc, 0.5, 200 + j)
+        elif pick == "clustered":
+            cols[j] = datagen.clustered(wpc, 0.3, 300, 300 + j)
+    want, offs = orc.compress_batch(cols, mode)
+    c_total = int(offs[-1])
+    stride = (wpc + 1 + 3) // 4 * 4
+    d_back = torch.full((n_cols * stride,), -1, dtype=torch.int32, device="cuda")
+    d_info = torch.full((3,), -1, dtype=torch.int64, device="cuda")
+    wsd = wah.Workspace.for_decompress_batch(n_cols, c_total, wpc)
+    wah.decompress_batch_device(to_dev(want), c_total, n_cols, wpc, d_back, stride, wpc + 1, d_info, wsd)
+    assert d_info.tolist() == [orc.decoded_words(orc.num_groups(wpc)), orc.num_groups(wpc) * n_cols, 0]
+    back = to_host(d_back).reshape(n_cols, stride)
+    assert np.array_equal(back[:, :wpc], cols)
+    # a stream that does not hold n_cols equal columns is reported
+    if n_cols > 1:
+        d_info.fill_(-1)
+        wsd = wah.Workspace.for_decompress_batch(n_cols - 1, c_total, wpc)
+        wah.decompress_batch_device(to_dev(want), c_total, n_cols - 1, wpc, d_back, stride, wpc + 1, d_info, wsd)
+        assert d_info.tolist()[2] == wah.WAH_STATUS_BATCH_LENGTH
+
+
+# --------------------------------------------------------------------------- errors instead of hangs
+
+def test_poisoned_counter_slot_times_out_and_heals():
+    """What a launch that was killed half way leaves in the decode kernel's counters must not hang the next launch:
+    it gives up after about two seconds with WAH_STATUS_TIMEOUT, and -- every launch zeroes its successor's slot --
+    the launch after it works again."""
+    data = datagen.uniform(40 * TW + 3, 0.01, 77)
+    cw = orc.compress(data, 0)
+    got, _ = gpu_decompress(cw)                      # the library's slot array exists now
+    assert np.array_equal(got[: data.size], data)
+    assert wah.lib.wah_test_poison_counter_slots() == 0
+    d_in = to_dev(cw)
+    d_out = torch.empty(data.size + 8, dtype=torch.int32, device="cuda")
+    d_info = torch.full((3,), -1, dtype=torch.int64, device="cuda")
+    ws = wah.Workspace.for_decompress(cw.size, data.size + 8)
+    wah.decompress_device(d_in, cw.size, d_out, data.size + 8, d_info, ws)
+    torch.cuda.synchronize()
+    assert d_info.tolist()[2] & wah.WAH_STATUS_TIMEOUT
+    with pytest.raises(wah.WahError) as e:           # the host entry point turns it into an error code
+        wah.lib.wah_test_poison_counter_slots()
+        wah.decompress(cw)
+    assert e.value.code == 2                         # WAH_ERR_CUDA
+    got, _ = gpu_decompress(cw)                      # healed
+    assert np.array_equal(got[: data.size], data)
+    assert np.array_equal(wah.decompress(cw)[: data.size], data)
+
+
+def test_launches_on_different_streams_are_ordered():
+    """Both kernels are persistent grids that need the whole GPU; launches on different streams (and the host entry
+    points' private stream) must not overlap.  The library orders them itself: results stay correct and nothing
+    hangs when several streams issue launches back to back."""
+    n = 64 * TW + 5
+    xs = [wah.gen_uniform_device(n, 0.01 * (i + 1), 900 + i) for i in range(4)]
+    streams = [torch.cuda.Stream() for _ in range(4)]
+    cap = wah.max_compressed_words(n)
+    outs = [torch.empty(cap, dtype=torch.int32, device="cuda") for _ in range(4)]
+    cnts = [torch.zeros(1, dtype=torch.int64, device="cuda") for _ in range(4)]
+    decs = [torch.empty(n + 8, dtype=torch.int32, device="cuda") for _ in range(4)]
+    infos = [torch.full((3,), -1, dtype=torch.int64, device="cuda") for _ in range(4)]
+    wcs = [wah.Workspace.for_compress(n) for _ in range(4)]
+    wds = [wah.Workspace.for_decompress(cap, n + 8) for _ in range(4)]
+    torch.cuda.synchronize()
+    for rep in range(3):
+        for i, st in enumerate(streams):
+            wah.compress_device(xs[i], n, outs[i], cap, cnts[i], wcs[i], rep & 1, stream=st)
+        for i, st in enumerate(streams):
+            # (the stream's length is only known on the device: decode the capacity, fills of 0 groups behind the end)
+            st.synchronize()
+            c = int(cnts[i].item())
+            wah.decompress_device(outs[i], c, decs[i], n + 8, infos[i], wds[i], stream=st)
+        host = wah.decompress(wah.compress(to_host(xs[0])))   # the host path's own stream in between
+        assert np.array_equal(host[:n], to_host(xs[0]))
+    torch.cuda.synchronize()
+    for i in range(4):
+        assert infos[i].tolist()[2] == 0
+        assert torch.equal(decs[i][:n], xs[i])
 
 
 # --------------------------------------------------------------------------- query operators (SURVEY.md 8f-1)

@@ -459,7 +459,10 @@ def run_single(args):
                             "l2": "4 distinct vectors rotated (a step touches 272 MiB > 126 MB L2); launch durations from batches of 10 consecutive launches",
                             **kernel_entry(bc, bd, nw, ca, peak)}
             del vs
-        extras["bitmap_index"] = bitmap_block(wah, orc, np, torch, dev, stream, args, 0, 1, peak, None)
+        bm = bitmap_block(wah, orc, np, torch, dev, stream, args, 0, 1, peak, None)
+        for k in ("_x", "_mode", "_total_ms"):
+            bm.pop(k)
+        extras["bitmap_index"] = bm
 
     # ---- end to end through the reference-facing host entry points
     e2e = None

@@ -421,17 +421,6 @@ extern "C" int wah_test_poison_counter_slots(void)
 
 // ----------------------------------------------------------------- range sharding
 
-namespace {
-struct DevBuf {
-    void *p = nullptr;
-    ~DevBuf()
-    {
-        if (p) cudaFree(p);
-    }
-    cudaError_t alloc(size_t bytes) { return cudaMalloc(&p, bytes ? bytes : 16); }
-};
-}  // namespace
-
 extern "C" int wah_shard_record_device(const uint32_t *d_shard, uint64_t words, uint64_t groups,
                                        wah_shard_record *h_record, void *stream_)
 {
@@ -442,11 +431,18 @@ extern "C" int wah_shard_record_device(const uint32_t *d_shard, uint64_t words, 
     h_record->groups = groups;
     if (words == 0) return WAH_OK;
     if (!d_shard) return fail(WAH_ERR_INVALID, "d_shard is null");
-    DevBuf d_res;
-    CUDA_TRY(d_res.alloc(8 * sizeof(uint64_t)));
-    CUDA_TRY(launch_shard_probe(d_shard, words, (uint64_t *)d_res.p, stream));
+    // 64 bytes of device scratch per device, allocated once (a cudaMalloc / cudaFree pair per call costs more than
+    // the probe); calls on one device are serialised by the lock
+    static std::mutex mu;
+    static void *scratch[64] = {};
+    int dev = 0;
+    CUDA_TRY(cudaGetDevice(&dev));
+    if (dev < 0 || dev >= 64) return fail(WAH_ERR_INVALID, "device ordinal %d not supported", dev);
+    std::lock_guard<std::mutex> g(mu);
+    if (!scratch[dev]) CUDA_TRY(cudaMalloc(&scratch[dev], 8 * sizeof(uint64_t)));
+    CUDA_TRY(launch_shard_probe(d_shard, words, (uint64_t *)scratch[dev], stream));
     uint64_t r[5];
-    CUDA_TRY(cudaMemcpyAsync(r, d_res.p, sizeof(r), cudaMemcpyDeviceToHost, stream));
+    CUDA_TRY(cudaMemcpyAsync(r, scratch[dev], sizeof(r), cudaMemcpyDeviceToHost, stream));
     CUDA_TRY(cudaStreamSynchronize(stream));
     h_record->lead_groups = r[0];
     h_record->lead_words = r[1];

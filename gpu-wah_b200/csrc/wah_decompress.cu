@@ -11,10 +11,10 @@
 //                 tile boundary that falls into it, which compressed word covers it.
 //   expand phase  output-centric, hence load balanced whatever the fill lengths are.  The grid walks output tiles
 //                 of 8192 groups = 7936 words; a tile waits only for its own two boundary entries.  A tile is
-//                 assembled as a bit image in SHARED memory -- a literal ORs its 31 bits in, a one-fill ORs its two
-//                 partial words in and marks its whole words in a 248-bit-per-warp coverage map, which one
-//                 prefix-XOR per warp turns into 128-bit stores of ones; zero fills cost nothing -- and leaves
-//                 through a TMA bulk store.  All-literal tiles are repacked in registers with one shuffle per word;
+//                 assembled as a bit image in SHARED memory -- a literal ORs its 31 bits in, a one-fill ORs its ends in
+//                 and marks its whole 16-byte units in a coverage map, which a prefix XOR turns into one 128-bit
+//                 store of ones per thread and eight units; zero fills cost nothing -- and leaves through a TMA bulk
+//                 store.  All-literal tiles are repacked in registers with one shuffle per word;
 //                 tiles with more than 4096 words go through the reference's one-group-per-int array
 //                 (kernels.cu:321-359), kept in shared memory, and the 32 -> 31 repack of mergeWords (kernels.cu:375).
 // Output tiles are aligned in group space to multiples of 32 groups = 31 words, so no output word is shared
@@ -576,10 +576,7 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
 
 constexpr int SPARSE_MAX_WORDS = 4096;          // output tiles covered by at most this many compressed words take the scatter path
 constexpr int SC_ROUND = EXPAND_THREADS * 4;    // compressed words per scatter round (one 16-byte pack per thread)
-constexpr int COV_WORDS = EXPAND_TILE_WORDS / 32;   // 248: one coverage bit per word of the tile image
-constexpr int COV_PER_WARP = COV_WORDS / (EXPAND_THREADS / 32);   // 31 coverage words = 992 image words per warp
-static_assert(COV_PER_WARP * (EXPAND_THREADS / 32) == COV_WORDS && COV_PER_WARP <= 31, "coverage map: one word per lane");
-constexpr uint32_t FILL_DIRECT_WORDS = 2;       // whole words of a one-fill its owner writes itself
+constexpr int COV_WORDS = 64;                   // coverage map: one bit per 16-byte unit of the tile image (1984) and one for its end
 
 // how a tile is expanded (decided by thread 0, which has the numbers in registers)
 enum : uint32_t { PATH_STOP = 0, PATH_SKIP, PATH_CONST, PATH_UNIT, PATH_SCATTER, PATH_GENERAL };
@@ -589,7 +586,6 @@ enum : uint32_t { PATH_STOP = 0, PATH_SKIP, PATH_CONST, PATH_UNIT, PATH_SCATTER,
 struct TileRes {
     uint64_t ws;        // first compressed word of the tile
     uint64_t dst;       // word offset of the tile's first output word in p.out
-    uint64_t next;      // the tile this CTA expands three iterations from now
     uint64_t next_ws;   // first compressed word of the CTA's next tile, ~0 = not known yet
     uint32_t nw;        // words (ws & ~3) .. we, the tile's last word
     uint32_t skip;      // groups of word ws that belong to earlier tiles
@@ -618,10 +614,9 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     extern __shared__ __align__(16) uint32_t smem[];
     uint32_t *s_grp = smem;                  // GRP_WORDS: one group per int, rows of 32 padded to 33 / tile image 1
     uint32_t *s_stage = smem + GRP_WORDS;    // EXPAND_TILE_WORDS output words / tile image 0
-    uint32_t *s_cov = smem + EXPAND_TILE_WORDS;   // 256 words behind image 1 (inside s_grp's padding): the coverage map
-    static_assert(GRP_WORDS - EXPAND_TILE_WORDS >= 256, "coverage map lives behind tile image 1");
     __shared__ uint32_t s_wsum[2][NW];
     __shared__ uint2 s_list[EXP_LIST];
+    __shared__ __align__(16) uint32_t s_cov[COV_WORDS];
     __shared__ uint32_t s_nlist;
     __shared__ uint32_t s_marks;
     __shared__ TileRes s_res[2];
@@ -644,40 +639,28 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         load_entry(p.starts + ot_, p.epoch, r.sx, r.sy);
         load_entry(p.starts + ot_ + 1, p.epoch, r.ex, ey);
     };
-    // The same two entries, requested but not looked at (thread 0 only).  The epoch check of load_entry() consumes
-    // the loaded words on the spot, i.e. waits out the L2 round trip.  Here the registers are only written (a
-    // predicated load with read-write operands, so that no copy -- no wait -- follows it); they are decoded when the
-    // tile comes up, a tile or two later.
-    struct RawPeek {
-        uint64_t ax, ay, bx;   // entry ot: x, y; entry ot + 1: x
-        uint32_t by_hi;        // ... and the upper half of its y (its epoch tag; the offset below it is not needed)
+    // The same two entries, requested but not looked at: thread 0 has them copied into shared memory (cp.async, no
+    // register waits for them) two tiles ahead and decodes them when the tile comes up.  x and y each carry half of
+    // the epoch, so an entry the scan had not written yet when it was fetched reads as unpublished and is fetched
+    // again then.
+    __shared__ __align__(16) ulonglong2 s_peek[4][2];
+    auto request = [&](uint64_t ot_, uint32_t slot) {   // (thread 0)
+        if (ot_ < n_total) {
+            cp_async16((uint32_t)__cvta_generic_to_shared(&s_peek[slot][0]), p.starts + ot_, 16u);
+            cp_async16((uint32_t)__cvta_generic_to_shared(&s_peek[slot][1]), p.starts + ot_ + 1, 16u);
+        }
+        cp_async_commit();   // (an empty group if there is no such tile: the groups are counted)
     };
-    // (x and y each carry half of the epoch, so an entry read in pieces is either complete or reads as unpublished;
-    //  every register is loaded exactly as wide as it is used -- the compiler copies the live part of a partly dead
-    //  register right behind the load, which is a wait)
-    auto request = [&](uint64_t ot_, RawPeek &r) {
-        r.ax = r.ay = r.bx = 0;
-        r.by_hi = 0;
-        const uint32_t go = tid == 0 && ot_ < n_total;
-        asm volatile(
-            "{\n\t"
-            ".reg .pred q;\n\t"
-            "setp.ne.u32 q, %5, 0;\n\t"
-            "@q ld.volatile.global.v2.u64 {%0, %1}, [%4];\n\t"
-            "@q ld.volatile.global.u64 %2, [%4+16];\n\t"
-            "@q ld.volatile.global.u32 %3, [%4+28];\n\t"
-            "}"
-            : "+l"(r.ax), "+l"(r.ay), "+l"(r.bx), "+r"(r.by_hi)
-            : "l"(p.starts + (go ? ot_ : 0)), "r"(go)
-            : "memory");
-    };
-    auto decode_peek = [&](const RawPeek &r, Raw &o) {
+    auto decode_peek = [&](uint32_t slot, Raw &o) {
         const uint32_t e_lo = p.epoch & 0xFFFFu, e_hi = p.epoch >> 16;
-        const bool oka = (uint32_t)(r.ax >> 48) == e_lo && (uint32_t)(r.ay >> 48) == e_hi;
-        const bool okb = (uint32_t)(r.bx >> 48) == e_lo && (r.by_hi >> 16) == e_hi;
-        o.sx = oka ? (r.ax & ENTRY_MASK) : 0ull;
-        o.sy = r.ay & ENTRY_MASK;
-        o.ex = okb ? (r.bx & ENTRY_MASK) : 0ull;
+        ulonglong2 ea, eb;   // (written by the copy engine behind the compiler's back)
+        asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(ea.x), "=l"(ea.y) : "r"((uint32_t)__cvta_generic_to_shared(&s_peek[slot][0])) : "memory");
+        asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(eb.x), "=l"(eb.y) : "r"((uint32_t)__cvta_generic_to_shared(&s_peek[slot][1])) : "memory");
+        const bool oka = (uint32_t)(ea.x >> 48) == e_lo && (uint32_t)(ea.y >> 48) == e_hi;
+        const bool okb = (uint32_t)(eb.x >> 48) == e_lo && (uint32_t)(eb.y >> 48) == e_hi;
+        o.sx = oka ? (ea.x & ENTRY_MASK) : 0ull;
+        o.sy = ea.y & ENTRY_MASK;
+        o.ex = okb ? (eb.x & ENTRY_MASK) : 0ull;
     };
     auto header_known = [&]() -> bool {
         if (*reinterpret_cast<const volatile uint32_t *>(&p.hdr->valid) != p.epoch) return false;
@@ -697,7 +680,6 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     };
 
     uint32_t w[8];
-    RawPeek rq0, rq1, rq2;   // thread 0: the entries of this tile and the next two, as requested
     uint4 xpre = make_uint4(0, 0, 0, 0), xpre_n = make_uint4(0, 0, 0, 0);
     uint64_t xpre_ws = ~0ull, xpre_n_ws = ~0ull;   // which tile start the prefetched words belong to
     // a finished tile image whose bulk store has not been issued yet: thread 0 issues it behind the NEXT tile's first
@@ -709,16 +691,17 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     // known before the scan phase is over); after that a CTA draws a ticket whenever it starts a tile -- the tile it
     // will expand four iterations later, so that the ticket, the tile's bookkeeping and its first words are all on
     // their way long before they are needed.  Tiles differ in cost and SMs in speed: with a fixed deal the slowest CTA
-    // finished 5 us (of 36) after the median one.
+    // finished 5 us (of 36) after the median one.  All of this is thread 0's business.
     const uint64_t GD = gridDim.x;
     const bool tickets = p.dynamic_tiles != 0u;
-    uint64_t ot = blockIdx.x, ot1 = ot + GD, ot2 = ot + 2ull * GD, ot3 = 0;
+    uint64_t ot = blockIdx.x, ot1 = ot + GD, ot2 = ot + 2ull * GD;   // (thread 0) this tile and the CTA's next two
     uint32_t tk_prev = 0, tk_new = 0;   // thread 0: tickets drawn one / zero iterations ago
     uint32_t it = 0;
-    request(ot, rq0);
-    request(ot1, rq1);
-    for (;; ot = ot1, ot1 = ot2, ot2 = ot3, it++, rq0 = rq1, rq1 = rq2, xpre = xpre_n, xpre_ws = xpre_n_ws) {
-        request(ot2, rq2);
+    if (tid == 0) {
+        request(ot, 0);
+        request(ot1, 1);
+    }
+    for (;; it++, xpre = xpre_n, xpre_ws = xpre_n_ws) {
         {
             // Thread 0 draws a ticket.  (ptxas wraps an atom.add on a provably uniform address in its warp-aggregation
             // idiom, whose shuffle waits for the result on the spot, and a draw inside a branch is copied -- i.e.
@@ -732,7 +715,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 "@q atom.relaxed.gpu.global.add.u32 %0, [%1], 1;\n\t"
                 "}"
                 : "+r"(tk_new)
-                : "l"(&p.ctr->ticket + (size_t)lane * p.zero), "r"((uint32_t)(tickets && tid == 0 && ot < n_total))
+                : "l"(&p.ctr->ticket + (size_t)lane * p.zero), "r"((uint32_t)(tickets && tid == 0))
                 : "memory");
         }
 
@@ -745,7 +728,9 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             r.nw = r.skip = r.nout = r.first = 0;
             r.tg = EXPAND_TILE_GROUPS;
             r.next_ws = ~0ull;
-            r.next = (!tickets || it == 0u) ? ot2 + GD : (uint64_t)EXPAND_STATIC_ROUNDS * GD + tk_prev;
+            request(ot2, (it + 2u) & 3u);
+            cp_async_wait<1>();   // the entries of this tile and the next have arrived (only the request above may be pending)
+            const uint64_t ot3 = (!tickets || it == 0u) ? ot2 + GD : (uint64_t)EXPAND_STATIC_ROUNDS * GD + tk_prev;
             if (ot < n_total) {
                 // where the tile starts in the stream's group numbering, and how many groups it holds
                 uint32_t j = 0, k = (uint32_t)ot;
@@ -761,8 +746,8 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 const uint64_t g_end = g_start + tg;   // where the next tile starts
                 bool stop = false, last = false, hdr = false;
                 Raw cur, nx1;
-                decode_peek(rq0, cur);   // requested two tiles ago
-                decode_peek(rq1, nx1);   // requested one tile ago
+                decode_peek(it & 3u, cur);          // requested two tiles ago
+                decode_peek((it + 1u) & 3u, nx1);   // requested one tile ago
                 r.next_ws = nx1.sx != 0ull ? nx1.sx - 1ull : ~0ull;
                 while (cur.sx == 0ull) {
                     if (!hdr) hdr = header_known();
@@ -830,6 +815,9 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             }
             if (r.path == PATH_SCATTER || r.path == PATH_GENERAL || r.path == PATH_STOP) bulk_wait_read<0>();   // the image this tile is built in is no longer being read
             s_res[it & 1u] = r;
+            ot = ot1;
+            ot1 = ot2;
+            ot2 = ot3;
         }
         __syncthreads();
         if (tid == 0 && pend_bytes != 0u) {
@@ -839,7 +827,6 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         const TileRes &res = s_res[it & 1u];
         const uint32_t path = res.path;
         if (path == PATH_STOP) break;
-        ot3 = res.next;
         xpre_n_ws = res.next_ws;
         if (xpre_n_ws != ~0ull) pack_at((xpre_n_ws & ~3ull) + 4ull * tid, xpre_n);   // the next tile's first words, a tile ahead
         if (path == PATH_SKIP) continue;
@@ -856,7 +843,6 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         if (p.trace && tid == 0) {
             const uint64_t k = it;
             if (k < 40) p.trace[(uint64_t)blockIdx.x * 64u + 8u + k] = (uint64_t)clock64();
-            p.trace[(uint64_t)blockIdx.x * 64u + 58u] = ot;
             p.trace[(uint64_t)blockIdx.x * 64u + 59u] = ((uint64_t)path << 32) | (uint64_t)nw;
         }
 #endif
@@ -887,131 +873,125 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         }
 
         if (path == PATH_SCATTER) {
-            // ================= scatter path =================
-            // The tile image (7936 words) is cleared in shared memory; every literal ORs its 31 bits into the one or
-            // two words it touches; a one-fill ORs the partial words at its two ends in and marks the whole words in
-            // between in the coverage map (bit i = image word i): a toggle where they begin, a toggle where they
-            // end.  A prefix XOR over the map -- 31 words per warp, one per lane -- then tells every word of the
-            // image whether it lies inside a one-fill, and the warp writes those words 128 bits at a time.  Zero
-            // fills cost nothing.  Whatever the mix of runs, the work is spread evenly over the threads (the owner of
-            // a long one-fill used to write all of it himself while 255 threads waited at the next barrier).
-            // Shared-memory atomics (two per literal) keep this free of ordering constraints between threads.
+            // ================= scatter path (up to 4096 compressed words in the tile) =================
+            // The tile image (7936 words) is cleared in shared memory; the tile's words are scanned in rounds of 1024
+            // (four per thread; warps beyond the last word idle).  A literal ORs its 31 bits into the one or two words
+            // it touches.  A one-fill ORs the partial words at its two ends in, writes the up to three whole words
+            // between each end and the next 16-byte boundary itself, and marks the whole 16-byte units in between in a
+            // coverage map (bit u = unit u of the image): a toggle where they begin, a toggle where they end.  A prefix
+            // XOR over the map (62 words: every warp does it for itself, two words per lane) then tells every unit
+            // whether it lies inside a one-fill, and the CTA writes those units, one 128-bit store per thread and
+            // eight units -- whatever the mix of runs, that part of the work is spread evenly over the threads (the
+            // owner of a long one-fill used to write all of it himself while 255 threads waited at the next barrier).
+            // Zero fills cost nothing.  Shared-memory atomics keep the scatter free of ordering between threads.
             uint32_t *img = (n_img & 1u) ? s_grp : s_stage;
             n_img++;
             {
                 uint4 *z = reinterpret_cast<uint4 *>(img);
                 for (uint32_t i = tid; i < (uint32_t)EXPAND_TILE_WORDS / 4; i += EXPAND_THREADS) z[i] = make_uint4(0, 0, 0, 0);
-                if (tid < 64u) reinterpret_cast<uint4 *>(s_cov)[tid] = make_uint4(0, 0, 0, 0);
+                if (tid < (uint32_t)COV_WORDS / 4) reinterpret_cast<uint4 *>(s_cov)[tid] = make_uint4(0, 0, 0, 0);
                 if (tid == 0) s_marks = 0;
             }
             uint32_t running = 0;   // group offset (tile relative) of the round's first word
             uint4 xc = xpre;
-            if (xpre_ws != ws) pack_at(wa + 4ull * tid, xc);
+            if (xpre_ws != ws && 128u * warp < nw) pack_at(wa + 4ull * tid, xc);
             uint4 xn = xc;
             uint32_t rnd = 0;
             for (uint32_t c0 = 0; c0 < nw; c0 += SC_ROUND, rnd++) {
-                const uint32_t r0 = c0 + 4u * tid;   // my four consecutive words, relative to wa
-                if (c0 + SC_ROUND < nw) pack_at(wa + r0 + SC_ROUND, xn);   // the next round's words, a round ahead
-                const uint32_t x[4] = {xc.x, xc.y, xc.z, xc.w};
-                xc = xn;
-                uint32_t c[4];
-                uint32_t tsum = 0;
+                const bool active = c0 + 128u * warp < nw;   // words for my warp in this round
+                uint32_t x[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
+                uint32_t tsum = 0, incl = 0;
+                if (active) {
+                    const uint32_t r0 = c0 + 4u * tid;   // my four consecutive words, relative to wa
+                    if (c0 + SC_ROUND + 128u * warp < nw) pack_at(wa + r0 + SC_ROUND, xn);   // the next round's words, a round ahead
+                    x[0] = xc.x; x[1] = xc.y; x[2] = xc.z; x[3] = xc.w;
+                    xc = xn;
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    const uint32_t ri = r0 + i;
-                    uint32_t v = word_groups(x[i]);
-                    if (ri < w_beg || ri > w_end) v = 0;   // outside this tile's word range
-                    else if (ri == w_beg) v -= skip;       // part of the first word belongs to earlier tiles
-                    c[i] = v > EXP_CLAMP ? EXP_CLAMP : v;
-                    tsum += c[i];
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t ri = r0 + i;
+                        uint32_t v = word_groups(x[i]);
+                        if (ri < w_beg || ri > w_end) v = 0;   // outside this tile's word range
+                        else if (ri == w_beg) v -= skip;       // part of the first word belongs to earlier tiles
+                        c[i] = v > EXP_CLAMP ? EXP_CLAMP : v;
+                        tsum += c[i];
+                    }
+                    incl = warp_incl_scan(tsum);
                 }
-                const uint32_t incl = warp_incl_scan(tsum);
-                if (lane == 31) s_wsum[rnd & 1u][warp] = incl;
+                if (lane == 31) s_wsum[rnd & 1u][warp] = incl;   // (0 from an idle warp)
                 __syncthreads();   // the warp sums are there (first round: and the image is cleared)
                 uint32_t off = running + (incl - tsum);
-                uint32_t round_sum = 0;
 #pragma unroll
                 for (int k = 0; k < NW; k++) {
                     const uint32_t sv = s_wsum[rnd & 1u][k];
                     if (k < (int)warp) off += sv;
-                    round_sum += sv;
+                    running += sv;
                 }
-                running += round_sum;
+                if (active) {
 #pragma unroll
-                for (int i = 0; i < 4; i++) {
-                    if (c[i] != 0u && off < tg) {
-                        const uint32_t wv = x[i];
-                        if (!is_fill(wv)) {   // kernels.cu:351-354, packed at once (kernels.cu:375)
-                            const uint32_t bit = 31u * off, wi = bit >> 5, sh = bit & 31u;
-                            DCHK(wi < (uint32_t)EXPAND_TILE_WORDS, 1, wi);
-                            atomicOr(img + wi, wv << sh);
-                            if (sh > 1u) atomicOr(img + wi + 1, wv >> (32u - sh));
-                        } else if (wv & BIT30) {   // one-fill, kernels.cu:337-348
-                            uint32_t g1 = off + c[i];
-                            if (g1 > tg) g1 = tg;
-                            const uint32_t b0 = 31u * off, b1 = 31u * g1;
-                            DCHK(b1 > b0 && b1 <= 31u * EXPAND_TILE_GROUPS, 2, ((uint64_t)b0 << 24) | b1);
-                            const uint32_t w0 = b0 >> 5, w1 = (b1 - 1u) >> 5;
-                            const uint32_t m0 = 0xFFFFFFFFu << (b0 & 31u), m1 = 0xFFFFFFFFu >> (31u - ((b1 - 1u) & 31u));
-                            if (w0 == w1) {
-                                atomicOr(img + w0, m0 & m1);
-                            } else {
-                                atomicOr(img + w0, m0);
-                                atomicOr(img + w1, m1);
-                                const uint32_t inner = w1 - w0 - 1u;   // whole words w0 + 1 .. w1 - 1: this run's alone
-                                if (inner > FILL_DIRECT_WORDS) {
-                                    atomicXor(s_cov + ((w0 + 1u) >> 5), 1u << ((w0 + 1u) & 31u));
-                                    atomicXor(s_cov + (w1 >> 5), 1u << (w1 & 31u));
-                                    s_marks = 1;
-                                } else if (inner != 0u) {
-                                    img[w0 + 1u] = 0xFFFFFFFFu;
-                                    if (inner == 2u) img[w0 + 2u] = 0xFFFFFFFFu;
+                    for (int i = 0; i < 4; i++) {
+                        if (c[i] != 0u && off < tg) {
+                            const uint32_t wv = x[i];
+                            const uint32_t b0 = 31u * off, w0 = b0 >> 5, sh = b0 & 31u;
+                            DCHK(w0 < (uint32_t)EXPAND_TILE_WORDS, 1, w0);
+                            if (!is_fill(wv)) {   // kernels.cu:351-354, packed at once (kernels.cu:375)
+                                atomicOr(img + w0, wv << sh);
+                                if (sh > 1u) atomicOr(img + w0 + 1, wv >> (32u - sh));
+                            } else if (wv & BIT30) {   // one-fill, kernels.cu:337-348
+                                uint32_t g1 = off + c[i];
+                                if (g1 > tg) g1 = tg;
+                                const uint32_t b1 = 31u * g1;
+                                DCHK(b1 > b0 && b1 <= 31u * EXPAND_TILE_GROUPS, 2, ((uint64_t)b0 << 24) | b1);
+                                const uint32_t w1 = (b1 - 1u) >> 5;
+                                const uint32_t m0 = 0xFFFFFFFFu << sh, m1 = 0xFFFFFFFFu >> (31u - ((b1 - 1u) & 31u));
+                                if (w0 == w1) {
+                                    atomicOr(img + w0, m0 & m1);
+                                } else {
+                                    atomicOr(img + w0, m0);
+                                    atomicOr(img + w1, m1);
+                                    // whole words a .. w1 - 1 are this run's alone; whole 16-byte units [ua, ub) of them
+                                    const uint32_t a = w0 + 1u, ua = (a + 3u) >> 2, ub = w1 >> 2;
+                                    const bool units = ub > ua;
+                                    const uint32_t head_end = units ? 4u * ua : w1;   // words a .. head_end - 1: at most 3 (6 if no unit)
+#pragma unroll
+                                    for (uint32_t k = 0; k < 6u; k++)
+                                        if (a + k < head_end) img[a + k] = 0xFFFFFFFFu;
+                                    if (units) {
+#pragma unroll
+                                        for (uint32_t k = 0; k < 3u; k++)
+                                            if (4u * ub + k < w1) img[4u * ub + k] = 0xFFFFFFFFu;
+                                        atomicXor(s_cov + (ua >> 5), 1u << (ua & 31u));
+                                        atomicXor(s_cov + (ub >> 5), 1u << (ub & 31u));
+                                        s_marks = 1;
+                                    }
                                 }
                             }
                         }
+                        off += c[i];
                     }
-                    off += c[i];
                 }
                 if (running >= tg) break;   // uniform: the tile is covered
             }
             __syncthreads();   // every mark is in the coverage map
             if (s_marks != 0u) {
-                // prefix XOR over the map: my warp's 31 words (lane 31 idles), then the parity of everything below
-                // them, which every warp works out for itself (8 loads per lane) rather than wait for the others
-                const uint32_t cbase = (uint32_t)COV_PER_WARP * warp;
-                uint32_t below = 0;
-#pragma unroll
-                for (int k = 0; k < COV_WORDS / 32 + 1; k++) {
-                    const uint32_t idx = lane + 32u * k;
-                    if (idx < cbase) below ^= s_cov[idx];
+                // prefix XOR over the 64 words of the map, two per lane
+                const uint2 cv = reinterpret_cast<const uint2 *>(s_cov)[lane];
+                uint32_t pa = cv.x, pb = cv.y;
+                pa ^= pa << 1; pa ^= pa << 2; pa ^= pa << 4; pa ^= pa << 8; pa ^= pa << 16;
+                pb ^= pb << 1; pb ^= pb << 2; pb ^= pb << 4; pb ^= pb << 8; pb ^= pb << 16;
+                if (pa >> 31) pb = ~pb;
+                const uint32_t tops = __ballot_sync(0xffffffffu, (pb >> 31) != 0u);
+                if (__popc(tops & lanemask_lt()) & 1u) {
+                    pa = ~pa;
+                    pb = ~pb;
                 }
-                below = __reduce_xor_sync(0xffffffffu, below);
-                uint32_t cv = lane < (uint32_t)COV_PER_WARP ? s_cov[cbase + lane] : 0u;
-                cv ^= cv << 1;
-                cv ^= cv << 2;
-                cv ^= cv << 4;
-                cv ^= cv << 8;
-                cv ^= cv << 16;
-                const uint32_t tops = __ballot_sync(0xffffffffu, (cv >> 31) != 0u);
-                if ((__popc(below) + __popc(tops & lanemask_lt())) & 1u) cv = ~cv;
-                if (lane >= (uint32_t)COV_PER_WARP) cv = 0;
-                if (__any_sync(0xffffffffu, cv != 0u)) {
-                    // bit i of lane l's word: image word 992 warp + 32 l + i lies inside a one-fill.  128-bit stores,
-                    // lane after lane: 16-byte unit u of the warp's part takes its 4 bits from lane u / 8.
-                    uint32_t *part = img + 992u * warp;
+                // unit u = 256 r + tid: bit `lane` of map word 8 r + warp, which lane (8 r + warp) / 2 holds
+                const uint32_t mine = (warp & 1u) ? pb : pa;
+                uint4 *img4 = reinterpret_cast<uint4 *>(img);
 #pragma unroll
-                    for (uint32_t r8 = 0; r8 < 8u; r8++) {
-                        const uint32_t u = r8 * 32u + lane;
-                        const uint32_t nib = (__shfl_sync(0xffffffffu, cv, u >> 3) >> ((u & 7u) * 4u)) & 0xFu;
-                        if (nib == 0xFu) {
-                            reinterpret_cast<uint4 *>(part)[u] = make_uint4(~0u, ~0u, ~0u, ~0u);
-                        } else if (nib != 0u) {
-                            if (nib & 1u) part[4u * u] = 0xFFFFFFFFu;
-                            if (nib & 2u) part[4u * u + 1u] = 0xFFFFFFFFu;
-                            if (nib & 4u) part[4u * u + 2u] = 0xFFFFFFFFu;
-                            if (nib & 8u) part[4u * u + 3u] = 0xFFFFFFFFu;
-                        }
-                    }
+                for (uint32_t r8 = 0; r8 < 8u; r8++) {
+                    const uint32_t v = __shfl_sync(0xffffffffu, mine, r8 * 4u + (warp >> 1));
+                    const uint32_t u = r8 * 256u + tid;
+                    if (((v >> lane) & 1u) != 0u && u < (uint32_t)EXPAND_TILE_WORDS / 4) img4[u] = make_uint4(~0u, ~0u, ~0u, ~0u);
                 }
             }
             if (nout == (uint32_t)EXPAND_TILE_WORDS) {

@@ -9,7 +9,7 @@ Two workloads shard:
   56-byte record per rank lets every rank compute where its segment lands in the global
   stream and how the fill runs that cross a range boundary are merged (CANONICAL mode; in
   BLOCK1024 mode plain concatenation is already bit-exact).  ``gather_stream`` then
-  all-gathers the segments themselves over NCCL/NVLink.
+  all-gathers the segments themselves (all-gather-v: grouped sends / receives over NCCL/NVLink).
 
 The local compressor is injected (``backend``) so the host logic runs unchanged over gloo on
 CPU tensors in the tests; the default backend is the CUDA library.
@@ -42,20 +42,28 @@ def word_range(n_words: int, rank: int, world: int) -> tuple[int, int]:
 
 
 class CudaBackend:
-    """Local compress / record on the rank's GPU through the C ABI."""
+    """Local compress / record on the rank's GPU through the C ABI.  The output buffer, the length word and the
+    workspace are kept between calls: the segment ``compress`` returns is a view of that buffer, valid until the next
+    ``compress`` of this backend."""
 
     def __init__(self, device=None):
         self.device = device if device is not None else torch.device("cuda", torch.cuda.current_device())
+        self._n = -1
+        self._out = self._cnt = self._ws = None
 
     def compress(self, local: torch.Tensor, mode: int):
         n = local.numel()
-        cap = wah.max_compressed_words(n)
-        out = torch.empty(max(cap, 1), dtype=torch.int32, device=self.device)
-        cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
-        ws = wah.Workspace.for_compress(n, self.device)
-        wah.compress_device(local, n, out, cap, cnt, ws, mode)
-        c = int(cnt.item())
-        return out[:c]
+        if n != self._n:
+            cap = wah.max_compressed_words(n)
+            self._out = torch.empty(max(cap, 1), dtype=torch.int32, device=self.device)
+            self._cnt = torch.zeros(1, dtype=torch.int64, device=self.device)
+            self._ws = wah.Workspace.for_compress(n, self.device)
+            self._n = n
+        wah.compress_device(local, n, self._out, self._out.numel(), self._cnt, self._ws, mode)
+        c = int(self._cnt.item())
+        if c < 0 or c > self._out.numel():
+            raise wah.WahError(2, "the compress kernel reported a failed launch")
+        return self._out[:c]
 
     def record(self, seg: torch.Tensor, groups: int):
         return wah.shard_record_device(seg, seg.numel(), groups)
@@ -78,11 +86,13 @@ class ShardedStream:
 
 
 def _all_gather_records(rec, group, device):
+    """ONE all-gather of 7 x int64 per rank, one device -> host copy of the result"""
     world = dist.get_world_size(group)
     mine = torch.tensor(rec.as_list(), dtype=torch.int64, device=device)
-    gathered = [torch.empty_like(mine) for _ in range(world)]
-    dist.all_gather(gathered, mine, group=group)
-    return [wah.ShardRecord.from_list(t.tolist()) for t in gathered]
+    gathered = torch.empty(world * mine.numel(), dtype=torch.int64, device=device)
+    dist.all_gather_into_tensor(gathered, mine, group=group)
+    rows = gathered.view(world, mine.numel()).cpu().tolist()
+    return [wah.ShardRecord.from_list(r) for r in rows]
 
 
 def compress_range_sharded(local: torch.Tensor, mode: int = wah.WAH_BLOCK1024, group=None, backend=None) -> ShardedStream:
@@ -99,31 +109,46 @@ def compress_range_sharded(local: torch.Tensor, mode: int = wah.WAH_BLOCK1024, g
     return ShardedStream(segment=seg, records=records, plan=plan, mode=mode, rank=rank, world=world)
 
 
-def gather_stream(ss: ShardedStream, group=None) -> torch.Tensor:
-    """All-gather the compressed segments and assemble the global stream on every rank.
+def gather_stream(ss: ShardedStream, group=None, out: torch.Tensor | None = None) -> torch.Tensor:
+    """All-gather-v of the compressed segments: every rank ends up with the global stream.
 
-    Segments are padded to the longest one so a single ``all_gather_into_tensor`` (NCCL over
-    NVLink on GPUs) moves them; seams are then patched from the plan."""
-    world = ss.world
+    Every rank sends the part of its segment that survives the seam merge straight to its place ``dst[r]`` in every
+    other rank's copy of the stream -- one grouped batch of sends and receives (``ncclGroupStart`` / ``ncclSend`` /
+    ``ncclRecv`` over NVLink on GPUs), sum of the segment lengths on the wire, nothing padded -- then the few seam
+    words of the plan are patched in by one indexed store."""
+    world, rank = ss.world, ss.rank
     dev = ss.segment.device
-    lens = [int(r.words) for r in ss.records]
-    pad = max(max(lens), 1)
-    mine = torch.zeros(pad, dtype=torch.int32, device=dev)
-    mine[: ss.segment.numel()] = ss.segment
-    allseg = torch.empty(world * pad, dtype=torch.int32, device=dev)
-    dist.all_gather_into_tensor(allseg, mine, group=group)
-    out = torch.empty(max(ss.total_words, 1), dtype=torch.int32, device=dev)
     plan = ss.plan
+    lens = [int(r.words) for r in ss.records]
+    total = ss.total_words
+    if out is None or out.numel() < total:
+        out = torch.empty(max(total, 1), dtype=torch.int32, device=dev)
+    peer = (lambda r: r) if group is None else (lambda r: dist.get_global_rank(group, r))
+    mine = ss.segment[plan["skip"][rank]: lens[rank]]
+    ops = []
     for r in range(world):
-        skip, body = plan["skip"][r], lens[r] - plan["skip"][r]
-        if body > 0:
-            out[plan["dst"][r]: plan["dst"][r] + body] = allseg[r * pad + skip: r * pad + lens[r]]
-    for r in range(world):   # in rank order: a seam may overwrite the previous seam's last word
-        sw = plan["seam_words"][r]
-        if sw:
-            vals = torch.tensor([w - (1 << 32) if w >= (1 << 31) else w for w in sw], dtype=torch.int32, device=dev)
-            out[plan["seam_offset"][r]: plan["seam_offset"][r] + len(sw)] = vals
-    return out[: ss.total_words]
+        body = lens[r] - plan["skip"][r]
+        if body <= 0:
+            continue
+        view = out[plan["dst"][r]: plan["dst"][r] + body]
+        if r == rank:
+            view.copy_(mine)
+        else:
+            ops.append(dist.P2POp(dist.irecv, view, peer(r), group))
+    if mine.numel() > 0:
+        ops += [dist.P2POp(dist.isend, mine, peer(r), group) for r in range(world) if r != rank]
+    if ops:
+        for work in dist.batch_isend_irecv(ops):
+            work.wait()
+    # seam words, applied in rank order on the host (a seam may rewrite the previous seam's last word), one store
+    patch = {}
+    for r in range(world):
+        for i, w in enumerate(plan["seam_words"][r]):
+            patch[plan["seam_offset"][r] + i] = w - (1 << 32) if w >= (1 << 31) else w
+    if patch:
+        idx = torch.tensor(list(patch.keys()), dtype=torch.int64, device=dev)
+        out[idx] = torch.tensor(list(patch.values()), dtype=torch.int32, device=dev)
+    return out[:total]
 
 
 def compress_columns_sharded(local_cols: torch.Tensor, mode: int = wah.WAH_BLOCK1024, group=None,

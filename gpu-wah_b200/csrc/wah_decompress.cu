@@ -44,8 +44,8 @@ __device__ __forceinline__ bool cell_load(const ulonglong2 *c, uint32_t epoch, u
     return e == (uint64_t)epoch;
 }
 constexpr uint64_t ENTRY_MASK = (1ull << 48) - 1ull;   // output-tile table: low 48 bits value, high 16 bits half of the epoch
-constexpr uint32_t TG_SHIFT = 13;
-static_assert((1u << TG_SHIFT) == (uint32_t)EXPAND_TILE_GROUPS, "output tile must be 8192 groups");
+constexpr uint32_t TG_SHIFT = 10;
+static_assert((1u << TG_SHIFT) == (uint32_t)EXPAND_TILE_GROUPS, "output tile must be 1024 groups");
 
 // A CTA that waits for another CTA of the grid polls politely and not for ever: after SPIN_LIMIT polls (about 2 s) it
 // flags the launch as failed and carries on with whatever it has; the launch then ends with STATUS_TIMEOUT in
@@ -156,6 +156,26 @@ __device__ __noinline__ void record_boundaries(ulonglong2 *starts, uint32_t epoc
         }
         off += c[j];
     }
+}
+
+// The common case inline: a single stream and ONE boundary in the pack (with 1024-group output tiles every few packs of
+// a fill-dominated stream hold one) -- find the word that covers it and record it; everything else out of line.
+__device__ __forceinline__ void note_boundaries(ulonglong2 *starts, uint32_t epoch, const BoundaryGeom &g, const ColumnCursor &cur,
+                                                bool batch, uint64_t kf, uint64_t ke, uint64_t wi, uint64_t off, const uint4 &x,
+                                                ulonglong4 *s_heavy, uint32_t *s_nheavy)
+{
+    const uint32_t c0 = word_groups(x.x), c1 = word_groups(x.y), c2 = word_groups(x.z);
+    if (!batch && ke - kf == 1ull) {
+        if (kf < g.k_lim) {
+            const uint32_t d = (uint32_t)((kf << TG_SHIFT) - off);   // the boundary's distance from the pack's first group (< 2^32)
+            const uint32_t s1 = c0 + c1, s2 = s1 + c2;
+            const uint32_t jj = (c0 <= d ? 1u : 0u) + (s1 <= d ? 1u : 0u) + (s2 <= d ? 1u : 0u);   // the word that covers it
+            const uint32_t before = jj == 0u ? 0u : (jj == 1u ? c0 : (jj == 2u ? s1 : s2));
+            store_entry(starts + kf, wi + jj + 1ull, off + before, epoch);
+        }
+        return;
+    }
+    record_boundaries(starts, epoch, g, cur, wi, off, make_uint4(c0, c1, c2, word_groups(x.w)), s_heavy, s_nheavy);
 }
 
 // 16 bytes global -> shared without passing through registers (LDGSTS): `bytes` (0..16) are read, the rest of the
@@ -465,10 +485,10 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
                 const uint64_t off = excl + s_loc[v * SCAN_THREADS + tid];
                 col_seek(cur, off, geo.cg);
                 const uint64_t rel = off - cur.base;
-                if (((rel + TGM) >> TG_SHIFT) != ((rel + sl + TGM) >> TG_SHIFT) || rel + sl > geo.cg)   // rare: a boundary in my 4 words
-                    record_boundaries(p.starts, p.epoch, geo, cur, seg_begin + (uint64_t)(v * 32u + lane) * 4u, off,
-                                      make_uint4(word_groups(x.x), word_groups(x.y), word_groups(x.z), word_groups(x.w)),
-                                      s_heavy, &s_nheavy);
+                const uint64_t kf = (rel + TGM) >> TG_SHIFT, ke = (rel + sl + TGM) >> TG_SHIFT;
+                if (kf != ke || rel + sl > geo.cg)   // a boundary in my 4 words
+                    note_boundaries(p.starts, p.epoch, geo, cur, batch, kf, ke, seg_begin + (uint64_t)(v * 32u + lane) * 4u, off, x,
+                                    s_heavy, &s_nheavy);
             }
 #ifdef WAH_TRACE
             if (p.trace && lane == 0) p.trace[(uint64_t)blockIdx.x * 64u + 50u + warp] = (uint64_t)clock64();
@@ -508,10 +528,10 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
                     const uint64_t off = row_base + incl - sl;
                     col_seek(cur, off, geo.cg);
                     const uint64_t rel = off - cur.base;
-                    if (((rel + TGM) >> TG_SHIFT) != ((rel + sl + TGM) >> TG_SHIFT) || rel + sl > geo.cg)   // rare: a boundary in my 4 words
-                        record_boundaries(p.starts, p.epoch, geo, cur, seg_begin + (uint64_t)(v * 32u + lane) * 4u, off,
-                                          make_uint4(word_groups(x.x), word_groups(x.y), word_groups(x.z), word_groups(x.w)),
-                                          s_heavy, &s_nheavy);
+                    const uint64_t kf = (rel + TGM) >> TG_SHIFT, ke = (rel + sl + TGM) >> TG_SHIFT;
+                    if (kf != ke || rel + sl > geo.cg)   // a boundary in my 4 words
+                        note_boundaries(p.starts, p.epoch, geo, cur, batch, kf, ke, seg_begin + (uint64_t)(v * 32u + lane) * 4u, off, x,
+                                        s_heavy, &s_nheavy);
                     row_base += __shfl_sync(0xffffffffu, incl, 31);
                 }
             }
@@ -539,13 +559,96 @@ __global__ void __launch_bounds__(SCAN_THREADS) wah_scan_kernel(const ScanParams
 }
 
 // ---------------------------------------------------------------- expand phase
+//
+// WARP autonomous: an output tile is 1024 groups = 992 words (3968 bytes, a multiple of 128), one warp expands it from
+// start to finish -- its own slice of shared memory, __syncwarp() only, no CTA barrier anywhere in the phase.  (The
+// first version of this phase gave a tile of 8192 groups to the CTA: thread 0 resolved the tile while 255 threads
+// waited, the low warps scanned the tile's few words while the high warps waited, ...: ncu put 20 - 40 % of all issue
+// slots into barrier stalls.)  Tiles are dealt in chunks of 8 consecutive tiles (31 KB of output), the first rounds
+// round robin, later chunks by ticket.
 
-constexpr int EXP_CHUNK = EXPAND_THREADS * 8;          // compressed words scanned per round of the general path
-constexpr int GRP_WORDS = EXPAND_TILE_GROUPS + EXPAND_TILE_GROUPS / 32;   // rows of 32 groups padded to 33
-constexpr int EXP_LIST = 512;                          // long one-fills deferred to a warp-wide store loop
+constexpr int CHUNK_TILES = 8;                                                // tiles per chunk (unit of work distribution)
+constexpr int CW_WORDS = EXPAND_TILE_GROUPS + EXPAND_TILE_GROUPS / 32 + 8;   // a tile's words by rank (0 .. 1025), rows of 32 padded to 33
+constexpr int FLAG_WORDS = EXPAND_TILE_GROUPS / 32 + 4;                       // bit g: a word starts at group g of the tile (+ a word for g = 1024)
+constexpr int WARP_SMEM_WORDS = CW_WORDS + EXPAND_TILE_WORDS + FLAG_WORDS;    // 8368 bytes per warp
+static_assert(EXPAND_TILE_GROUPS + 1 + ((EXPAND_TILE_GROUPS + 1) >> 5) < CW_WORDS, "s_cw too small");
+static_assert((CW_WORDS * 4) % 16 == 0 && (WARP_SMEM_WORDS * 4) % 16 == 0, "the tile image must be 16-byte aligned (bulk store)");
 constexpr uint32_t EXP_CLAMP = 2u * EXPAND_TILE_GROUPS;   // any count >= the tile span behaves the same
+// the packed warp scan of the window path: groups in the low 20 bits (a round's 128 words x EXP_CLAMP fit), words above
+constexpr uint32_t RANK_SHIFT = 20, RANK_ONE = 1u << RANK_SHIFT, GROUP_MASK = RANK_ONE - 1u;
+static_assert(128u * EXP_CLAMP <= GROUP_MASK, "packed warp scan overflows");
 
-__device__ __forceinline__ uint32_t grp_pos(uint32_t g) { return g + (g >> 5); }
+// where the tile's word of rank r is parked: neighbouring lanes of the window walk read words about 32 ranks apart
+// when the tile is literal dense -- the padding keeps those reads on different banks
+__device__ __forceinline__ uint32_t cw_pos(uint32_t r) { return r + (r >> 5); }
+// the 31 bits of a group that word x holds (kernels.cu:337-354)
+__device__ __forceinline__ uint32_t group_bits(uint32_t x)
+{
+    const uint32_t f = (uint32_t)((int32_t)(x << 1) >> 31) & ONES31;   // fill: all ones or all zeros
+    return is_fill(x) ? f : x;
+}
+
+// how a tile is expanded (decided once per chunk by the lane that holds the tile's table entry)
+enum : uint32_t { PATH_STOP = 0, PATH_SKIP, PATH_CONST, PATH_UNIT, PATH_WINDOW };
+
+// W consecutive compressed words for a lane, the first at src[i0]; `room` = words from src to the end of the stream
+// (words behind it read as fills of 0 groups).  src is 16-byte aligned and i0 a multiple of W.
+template <int W>
+__device__ __forceinline__ void load_words(const uint32_t *src, uint32_t i0, uint64_t room, uint32_t (&x)[W])
+{
+    if ((uint64_t)i0 + W <= room) {
+        if (W == 4) {
+            const uint4 v = *reinterpret_cast<const uint4 *>(src + i0);
+            x[0] = v.x; x[1 % W] = v.y; x[2 % W] = v.z; x[3 % W] = v.w;
+        } else if (W == 2) {
+            const uint2 v = *reinterpret_cast<const uint2 *>(src + i0);
+            x[0] = v.x; x[1 % W] = v.y;
+        } else {
+            x[0] = src[i0];
+        }
+    } else {
+#pragma unroll
+        for (int i = 0; i < W; i++) x[i] = (uint64_t)i0 + i < room ? src[i0 + i] : BIT31;
+    }
+}
+
+// Word phase of the window path, one round: my W consecutive words x[], the first at index r0 from the tile's aligned
+// start.  w_beg = index of the tile's first word there, w_span = index of its last word among the tile's words.
+template <int W>
+__device__ __forceinline__ void park_words(const uint32_t (&x)[W], uint32_t r0, uint32_t w_beg, uint32_t w_span, uint32_t skip,
+                                           uint32_t tg, uint32_t &running, uint32_t &rk_run, uint32_t *s_cw, uint32_t *s_flag)
+{
+    uint32_t c[W];
+    uint32_t tsum = 0;   // groups in the low 20 bits, words that hold a group above
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        const uint32_t rel = r0 + i - w_beg;   // index among the tile's words (wraps for the up to 3 words before it)
+        uint32_t v = word_groups(x[i]);
+        if (rel > w_span) v = 0;               // outside this tile's word range
+        if (rel == 0u) v -= skip;              // part of the first word belongs to earlier tiles
+        v = v > EXP_CLAMP ? EXP_CLAMP : v;
+        c[i] = v;
+        tsum += v + (v != 0u ? RANK_ONE : 0u);
+    }
+    const uint32_t incl = warp_incl_scan(tsum);
+    const uint32_t excl = incl - tsum;
+    uint32_t off = running + (excl & GROUP_MASK);
+    uint32_t rk = rk_run + (excl >> RANK_SHIFT);
+    const uint32_t tot = __shfl_sync(0xffffffffu, incl, 31);
+    running += tot & GROUP_MASK;
+    rk_run += tot >> RANK_SHIFT;
+#pragma unroll
+    for (int i = 0; i < W; i++) {
+        // (the tile's last word may start exactly where the tile ends: it is parked like the others -- the ranks stay
+        //  consecutive -- but reads as zeros: behind a short tile lies padding)
+        if (c[i] != 0u && off <= tg) {
+            s_cw[cw_pos(rk)] = off < tg ? group_bits(x[i]) : 0u;
+            atomicOr(s_flag + (off >> 5), 1u << (off & 31u));
+        }
+        rk += c[i] != 0u ? 1u : 0u;
+        off += c[i];
+    }
+}
 
 // ---- bulk (TMA) store of a finished tile, shared -> global
 __device__ __forceinline__ void bulk_s2g(void *dst, uint32_t src_smem, uint32_t bytes)
@@ -574,557 +677,309 @@ __device__ __forceinline__ void fence_async_smem() { asm volatile("fence.proxy.a
     } while (0)
 #endif
 
-constexpr int SPARSE_MAX_WORDS = 4096;          // output tiles covered by at most this many compressed words take the scatter path
-constexpr int SC_ROUND = EXPAND_THREADS * 4;    // compressed words per scatter round (one 16-byte pack per thread)
-constexpr int COV_WORDS = 64;                   // coverage map: one bit per 16-byte unit of the tile image (1984) and one for its end
-
-// how a tile is expanded (decided by thread 0, which has the numbers in registers)
-enum : uint32_t { PATH_STOP = 0, PATH_SKIP, PATH_CONST, PATH_UNIT, PATH_SCATTER, PATH_GENERAL };
-
-// Thread 0 resolves a tile (it may have to wait for the scan) and publishes the result in shared memory, so that
-// the whole CTA works from the same numbers -- every path below has CTA barriers.
-struct TileRes {
-    uint64_t ws;        // first compressed word of the tile
-    uint64_t dst;       // word offset of the tile's first output word in p.out
-    uint64_t next_ws;   // first compressed word of the CTA's next tile, ~0 = not known yet
-    uint32_t nw;        // words (ws & ~3) .. we, the tile's last word
-    uint32_t skip;      // groups of word ws that belong to earlier tiles
-    uint32_t tg;        // groups in the tile: 8192, fewer at the end of a column / of the stream
-    uint32_t nout;      // output words to write
-    uint32_t path;
-    uint32_t first;     // PATH_CONST: the fill word the tile lies in
-};
-
-__device__ __forceinline__ void load8(const ExpandParams &p, uint64_t i0, uint32_t (&w)[8])
-{
-    if (i0 + 8 <= p.c_words) {
-        const uint4 *src = reinterpret_cast<const uint4 *>(p.in + i0);
-        const uint4 a = ld_stream_v4(src), b = ld_stream_v4(src + 1);
-        w[0] = a.x; w[1] = a.y; w[2] = a.z; w[3] = a.w;
-        w[4] = b.x; w[5] = b.y; w[6] = b.z; w[7] = b.w;
-    } else {
-#pragma unroll
-        for (int i = 0; i < 8; i++) w[i] = (i0 + i < p.c_words) ? ld_stream_u32(p.in + i0 + i) : BIT31;
-    }
-}
-
 __device__ __forceinline__ void expand_body(const ExpandParams &p)
 {
     constexpr int NW = EXPAND_THREADS / 32;
+    constexpr uint32_t TG = (uint32_t)EXPAND_TILE_GROUPS, TW = (uint32_t)EXPAND_TILE_WORDS;
     extern __shared__ __align__(16) uint32_t smem[];
-    uint32_t *s_grp = smem;                  // GRP_WORDS: one group per int, rows of 32 padded to 33 / tile image 1
-    uint32_t *s_stage = smem + GRP_WORDS;    // EXPAND_TILE_WORDS output words / tile image 0
-    __shared__ uint32_t s_wsum[2][NW];
-    __shared__ uint2 s_list[EXP_LIST];
-    __shared__ __align__(16) uint32_t s_cov[COV_WORDS];
-    __shared__ uint32_t s_nlist;
-    __shared__ uint32_t s_marks;
-    __shared__ TileRes s_res[2];
-    uint32_t n_img = 0;   // scatter tiles so far: they alternate between the two tile images
-
     const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    uint32_t *s_cw = smem + warp * WARP_SMEM_WORDS;   // the tile's words that hold a group, by rank: what a group of theirs decodes to
+    uint32_t *s_stage = s_cw + CW_WORDS;              // the tile image: 992 output words
+    uint32_t *s_flag = s_stage + TW;                  // bit g: a word starts at group g of the tile
+    const uint32_t stage_addr = (uint32_t)__cvta_generic_to_shared(s_stage);
+
     const bool batch = p.col_groups != ~0ull;
-    const uint32_t tpc = (uint32_t)p.max_out_tiles;
-    const uint64_t n_total = batch ? (uint64_t)p.n_cols * tpc : p.max_out_tiles;
-
-    // An output tile can be expanded as soon as the scan has recorded where it starts and where the next one
-    // starts (starts[k].x = word index + 1, 0 = not recorded yet) -- the offsets of the low tiles are known long
-    // before a straggling scan tile at the far end of the stream is done.  The decoded size (the header) is only
-    // needed to recognise the stream's last tile.
-    struct Raw {
-        uint64_t sx, sy, ex;
-    };
-    auto peek = [&](uint64_t ot_, Raw &r) {   // non-blocking
-        uint64_t ey;
-        load_entry(p.starts + ot_, p.epoch, r.sx, r.sy);
-        load_entry(p.starts + ot_ + 1, p.epoch, r.ex, ey);
-    };
-    // The same two entries, requested but not looked at: thread 0 has them copied into shared memory (cp.async, no
-    // register waits for them) two tiles ahead and decodes them when the tile comes up.  x and y each carry half of
-    // the epoch, so an entry the scan had not written yet when it was fetched reads as unpublished and is fetched
-    // again then.
-    __shared__ __align__(16) ulonglong2 s_peek[4][2];
-    auto request = [&](uint64_t ot_, uint32_t slot) {   // (thread 0)
-        if (ot_ < n_total) {
-            cp_async16((uint32_t)__cvta_generic_to_shared(&s_peek[slot][0]), p.starts + ot_, 16u);
-            cp_async16((uint32_t)__cvta_generic_to_shared(&s_peek[slot][1]), p.starts + ot_ + 1, 16u);
-        }
-        cp_async_commit();   // (an empty group if there is no such tile: the groups are counted)
-    };
-    auto decode_peek = [&](uint32_t slot, Raw &o) {
-        const uint32_t e_lo = p.epoch & 0xFFFFu, e_hi = p.epoch >> 16;
-        ulonglong2 ea, eb;   // (written by the copy engine behind the compiler's back)
-        asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(ea.x), "=l"(ea.y) : "r"((uint32_t)__cvta_generic_to_shared(&s_peek[slot][0])) : "memory");
-        asm volatile("ld.volatile.shared.v2.u64 {%0, %1}, [%2];" : "=l"(eb.x), "=l"(eb.y) : "r"((uint32_t)__cvta_generic_to_shared(&s_peek[slot][1])) : "memory");
-        const bool oka = (uint32_t)(ea.x >> 48) == e_lo && (uint32_t)(ea.y >> 48) == e_hi;
-        const bool okb = (uint32_t)(eb.x >> 48) == e_lo && (uint32_t)(eb.y >> 48) == e_hi;
-        o.sx = oka ? (ea.x & ENTRY_MASK) : 0ull;
-        o.sy = ea.y & ENTRY_MASK;
-        o.ex = okb ? (eb.x & ENTRY_MASK) : 0ull;
-    };
-    auto header_known = [&]() -> bool {
-        if (*reinterpret_cast<const volatile uint32_t *>(&p.hdr->valid) != p.epoch) return false;
-        __threadfence();
-        return true;
-    };
-    // the 16-byte pack a thread handles in the first round of the scatter path
-    auto pack_at = [&](uint64_t i0, uint4 &x) {
-        if (i0 + 4 <= p.c_words) {
-            x = *reinterpret_cast<const uint4 *>(p.in + i0);
-        } else {
-            x.x = i0 < p.c_words ? p.in[i0] : BIT31;
-            x.y = i0 + 1 < p.c_words ? p.in[i0 + 1] : BIT31;
-            x.z = i0 + 2 < p.c_words ? p.in[i0 + 2] : BIT31;
-            x.w = BIT31;
-        }
-    };
-
-    uint32_t w[8];
-    uint4 xpre = make_uint4(0, 0, 0, 0), xpre_n = make_uint4(0, 0, 0, 0);
-    uint64_t xpre_ws = ~0ull, xpre_n_ws = ~0ull;   // which tile start the prefetched words belong to
-    // a finished tile image whose bulk store has not been issued yet: thread 0 issues it behind the NEXT tile's first
-    // barrier, which is the one that orders every thread's writes to the image before it
-    uint32_t pend_bytes = 0, pend_src = 0;
-    uint32_t *pend_dst = nullptr;
-    uint32_t budget = SPIN_LIMIT;
-    // Which tiles a CTA expands: the first EXPAND_STATIC_ROUNDS rounds are dealt round robin (no communication, and
-    // known before the scan phase is over); after that a CTA draws a ticket whenever it starts a tile -- the tile it
-    // will expand four iterations later, so that the ticket, the tile's bookkeeping and its first words are all on
-    // their way long before they are needed.  Tiles differ in cost and SMs in speed: with a fixed deal the slowest CTA
-    // finished 5 us (of 36) after the median one.  All of this is thread 0's business.
-    const uint64_t GD = gridDim.x;
+    const uint32_t tpc = (uint32_t)p.max_out_tiles;                   // tiles per column (single stream: tiles the capacity has room for)
+    const uint32_t cpc = (tpc + CHUNK_TILES - 1u) / CHUNK_TILES;      // chunks per column
+    const uint64_t n_chunks = (uint64_t)(batch ? p.n_cols : 1u) * cpc;
+    const uint64_t GW = (uint64_t)gridDim.x * NW, gw = (uint64_t)blockIdx.x * NW + warp;
     const bool tickets = p.dynamic_tiles != 0u;
-    uint64_t ot = blockIdx.x, ot1 = ot + GD, ot2 = ot + 2ull * GD;   // (thread 0) this tile and the CTA's next two
-    uint32_t tk_prev = 0, tk_new = 0;   // thread 0: tickets drawn one / zero iterations ago
-    uint32_t it = 0;
-    if (tid == 0) {
-        request(ot, 0);
-        request(ot1, 1);
-    }
-    for (;; it++, xpre = xpre_n, xpre_ws = xpre_n_ws) {
+
+    // Chunk c = tiles k0 .. k0 + 7 of column j (a single stream is one column).  Lane l <= 8 holds the table entry
+    // of tile k0 + l: {index + 1 of the compressed word that covers the tile's first group (0 = not recorded), that
+    // word's group offset}; the entry behind a column's last tile is the next column's first.
+    auto where = [&](uint64_t c, uint32_t &j, uint32_t &k0) {
+        j = batch ? (uint32_t)(c / cpc) : 0u;
+        k0 = (uint32_t)(c - (uint64_t)j * cpc) * CHUNK_TILES;
+    };
+    auto fetch = [&](uint64_t c, uint64_t &x, uint64_t &y) {
+        x = 0;
+        y = 0;
+        if (c < n_chunks && lane <= (uint32_t)CHUNK_TILES) {
+            uint32_t j, k0;
+            where(c, j, k0);
+            if (k0 + lane <= tpc) load_entry(p.starts + (uint64_t)j * tpc + k0 + lane, p.epoch, x, y);
+        }
+    };
+    uint32_t budget = SPIN_LIMIT;
+    bool hdr = false;                  // the decoded size is known (only needed where the stream ends)
+    uint64_t G = ~0ull, Gwords = ~0ull;
+    // Software pipeline over a warp's chunks -- nothing a tile needs is asked for when it is needed:
+    //   chunk i + 2   its table entries are requested                      (fetch)
+    //   chunk i + 1   the first word of each of its tiles is requested     (needs the entries)
+    //   chunk i       is resolved (needs the first words) and expanded; tile s + 1's words are requested before
+    //                 tile s is expanded.
+    // The first EXPAND_STATIC_ROUNDS rounds of chunks are dealt round robin (known before the scan phase is over);
+    // after that a warp draws a ticket three chunks ahead of the chunk it is for.
+    static_assert(EXPAND_STATIC_ROUNDS >= 3, "the first three chunks of a warp are dealt statically");
+    uint64_t c0 = gw, c1 = gw + GW, c2 = gw + 2ull * GW;
+    uint64_t e0x, e0y, e1x, e1y, e2x, e2y;
+    fetch(c0, e0x, e0y);
+    fetch(c1, e1x, e1y);
+    auto first_word = [&](uint64_t x) -> uint32_t { return (lane <= (uint32_t)CHUNK_TILES && x != 0ull) ? ld_stream_u32(p.in + (x - 1ull)) : 0u; };
+    uint32_t first0 = first_word(e0x), first1;
+    bool stop = false;
+    for (uint32_t it = 0; !stop && c0 < n_chunks; it++) {
+        uint32_t tk = 0;
+        if (tickets && it + 3u >= (uint32_t)EXPAND_STATIC_ROUNDS && lane == 0) tk = atomicAdd(&p.ctr->ticket, 1u);
+        fetch(c2, e2x, e2y);
+        first1 = first_word(e1x);
+
+        uint32_t j, k0;
+        where(c0, j, k0);
+        const uint32_t nt = tpc - k0 < (uint32_t)CHUNK_TILES ? tpc - k0 : (uint32_t)CHUNK_TILES;   // tiles in the chunk
+        const uint64_t col_g0 = batch ? (uint64_t)j * p.col_groups : 0ull;
+        // the group where my entry's tile starts (the entry behind a column's last tile: where the column ends)
+        const uint64_t my_g = (batch && k0 + lane >= tpc) ? col_g0 + p.col_groups : col_g0 + ((uint64_t)(k0 + lane) << TG_SHIFT);
+
+        // ---- the chunk's entries must have been recorded by the scan -- or lie behind the end of the stream
+        if (__any_sync(0xffffffffu, lane <= nt && e0x == 0ull)) {
+            const bool had = e0x != 0ull;
+            for (;;) {
+                const bool missing = lane <= nt && e0x == 0ull && !(hdr && my_g >= G);
+                if (!__any_sync(0xffffffffu, missing)) break;
+                if (!hdr) {
+                    if (*reinterpret_cast<const volatile uint32_t *>(&p.hdr->valid) == p.epoch) {
+                        __threadfence();
+                        G = *reinterpret_cast<const volatile uint64_t *>(&p.hdr->groups);
+                        Gwords = *reinterpret_cast<const volatile uint64_t *>(&p.hdr->words);
+                        hdr = true;
+                        continue;
+                    }
+                }
+                bool ok = true;
+                if (lane == 0) ok = spin_ok(budget, p.hdr_rw, p.epoch);
+                if (!__shfl_sync(0xffffffffu, ok, 0)) {
+                    stop = true;
+                    break;
+                }
+                __nanosleep(256);   // polite polling, see scan_body
+                if (missing) load_entry(p.starts + (uint64_t)j * tpc + k0 + lane, p.epoch, e0x, e0y);
+            }
+            if (stop) break;
+            if (!had) first0 = first_word(e0x);
+        }
+
+        // ---- resolve the chunk's tiles, lane l its tile l (the arithmetic once per chunk and in parallel instead of
+        //      once per tile and uniform); what the tile loop needs comes back by shuffle, 32 bits at a time
+        uint64_t my_ws = 0;
+        uint32_t my_nw = 0, my_skip = 0, my_meta = PATH_STOP;
         {
-            // Thread 0 draws a ticket.  (ptxas wraps an atom.add on a provably uniform address in its warp-aggregation
-            // idiom, whose shuffle waits for the result on the spot, and a draw inside a branch is copied -- i.e.
-            // waited for -- at the branch's end: hence an address the compiler cannot prove uniform (p.zero is 0) and a
-            // predicated instruction.  The result is first used an iteration later.)
-            tk_prev = tk_new;
-            asm volatile(
-                "{\n\t"
-                ".reg .pred q;\n\t"
-                "setp.ne.u32 q, %2, 0;\n\t"
-                "@q atom.relaxed.gpu.global.add.u32 %0, [%1], 1;\n\t"
-                "}"
-                : "+r"(tk_new)
-                : "l"(&p.ctr->ticket + (size_t)lane * p.zero), "r"((uint32_t)(tickets && tid == 0))
-                : "memory");
-        }
-
-        // ---- resolve the tile (thread 0, blocking)
-        if (tid == 0) {
-            TileRes r;
-            r.path = PATH_STOP;
-            r.ws = 0;
-            r.dst = 0;
-            r.nw = r.skip = r.nout = r.first = 0;
-            r.tg = EXPAND_TILE_GROUPS;
-            r.next_ws = ~0ull;
-            request(ot2, (it + 2u) & 3u);
-            cp_async_wait<1>();   // the entries of this tile and the next have arrived (only the request above may be pending)
-            const uint64_t ot3 = (!tickets || it == 0u) ? ot2 + GD : (uint64_t)EXPAND_STATIC_ROUNDS * GD + tk_prev;
-            if (ot < n_total) {
-                // where the tile starts in the stream's group numbering, and how many groups it holds
-                uint32_t j = 0, k = (uint32_t)ot;
-                uint64_t g_start = ot << TG_SHIFT;
-                uint32_t tg = EXPAND_TILE_GROUPS;
-                if (batch) {
-                    j = (uint32_t)ot / tpc;
-                    k = (uint32_t)ot - j * tpc;
-                    const uint64_t in_col = (uint64_t)k << TG_SHIFT;
-                    g_start = (uint64_t)j * p.col_groups + in_col;
-                    if (p.col_groups - in_col < (uint64_t)EXPAND_TILE_GROUPS) tg = (uint32_t)(p.col_groups - in_col);
-                }
-                const uint64_t g_end = g_start + tg;   // where the next tile starts
-                bool stop = false, last = false, hdr = false;
-                Raw cur, nx1;
-                decode_peek(it & 3u, cur);          // requested two tiles ago
-                decode_peek((it + 1u) & 3u, nx1);   // requested one tile ago
-                r.next_ws = nx1.sx != 0ull ? nx1.sx - 1ull : ~0ull;
-                while (cur.sx == 0ull) {
-                    if (!hdr) hdr = header_known();
-                    if (hdr && g_start >= p.hdr->groups) {
-                        stop = true;   // the stream ends before this tile
-                        break;
-                    }
-                    if (!spin_ok(budget, p.hdr_rw, p.epoch)) {
-                        stop = true;
-                        break;
-                    }
-                    __nanosleep(128);   // polite polling, see scan_body
-                    peek(ot, cur);
-                }
-                while (!stop && cur.ex == 0ull) {
-                    if (!hdr) hdr = header_known();
-                    if (hdr && g_end >= p.hdr->groups) {
-                        last = true;   // the stream's last tile: it ends with the last compressed word
-                        break;
-                    }
-                    if (!spin_ok(budget, p.hdr_rw, p.epoch)) {
-                        stop = true;
-                        break;
-                    }
-                    __nanosleep(128);
-                    peek(ot, cur);
-                }
-                // room for the tile's words
-                uint64_t w_lo = (uint64_t)k * EXPAND_TILE_WORDS;   // word offset in the column / the stream
-                uint64_t total_words = p.out_cap;                  // single stream: capacity; batch: words per column
+            const uint64_t nxt = __shfl_down_sync(0xffffffffu, e0x, 1);
+            if (lane < nt && e0x != 0ull) {
+                const uint32_t k = k0 + lane;
+                const uint64_t in_col = (uint64_t)k << TG_SHIFT;
+                const uint64_t g_start = col_g0 + in_col;
+                uint32_t tg = TG;   // groups in the tile: fewer at the end of a column / of the stream
+                if (batch && p.col_groups - in_col < (uint64_t)TG) tg = (uint32_t)(p.col_groups - in_col);
+                const bool last = nxt == 0ull;   // the stream's last tile: it ends with the last compressed word
+                const uint64_t w_lo = (uint64_t)k * TW;   // word offset in the column / the stream
+                uint64_t total_words = p.out_cap;         // single stream: capacity; batch: words per column
                 if (last) {
-                    const uint64_t G = p.hdr->groups;
                     if (G - g_start < (uint64_t)tg) tg = (uint32_t)(G - g_start);
-                    if (!batch && p.hdr->words < total_words) total_words = p.hdr->words;
+                    if (!batch && Gwords < total_words) total_words = Gwords;
                 }
-                if (!stop) {
-                    const uint64_t avail = w_lo < total_words ? total_words - w_lo : 0ull;
-                    const uint32_t nout = avail < (uint64_t)EXPAND_TILE_WORDS ? (uint32_t)avail : (uint32_t)EXPAND_TILE_WORDS;
-                    const uint64_t ws = cur.sx - 1ull;
-                    const uint64_t we = last ? p.c_words - 1ull : cur.ex - 1ull;
-                    const uint64_t span = we - (ws & ~3ull) + 1ull;
-                    r.ws = ws;
-                    r.dst = (uint64_t)j * p.col_stride + w_lo;
-                    r.nw = span > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)span;
-                    r.skip = (uint32_t)(g_start - cur.sy);   // groups of word ws that belong to earlier tiles
-                    r.tg = tg;
-                    r.nout = nout;
-                    DCHK(ws < p.c_words && we < p.c_words && we >= ws, 4, ((uint64_t)(ws & 0xFFFFFF) << 24) | (we & 0xFFFFFF));
-                    DCHK(g_start >= cur.sy, 5, ot);
-                    if (nout == 0u) {
-                        // no room: a single stream is cut short by the capacity here and for good, a column only here
-                        r.path = batch ? PATH_SKIP : PATH_STOP;
-                    } else if (ws == we) {
-                        // the tile lies inside ONE word: written without decoding if that is a fill (the stream's
-                        // last tile may end in a partly padded group: a one-fill there is expanded like any other tile)
-                        r.first = p.in[ws];
-                        r.path = (is_fill(r.first) && (!last || !(r.first & BIT30))) ? PATH_CONST : PATH_SCATTER;
-                    } else if (!last && r.skip == 0u && we - ws == (uint64_t)EXPAND_TILE_GROUPS && tg == (uint32_t)EXPAND_TILE_GROUPS &&
-                               nout == (uint32_t)EXPAND_TILE_WORDS) {
-                        r.path = PATH_UNIT;   // 8192 groups from 8192 words: every word is one group
-                    } else {
-                        r.path = r.nw <= (uint32_t)SPARSE_MAX_WORDS ? PATH_SCATTER : PATH_GENERAL;
-                    }
-                }
+                const uint64_t avail = w_lo < total_words ? total_words - w_lo : 0ull;
+                const uint32_t nout = avail < (uint64_t)TW ? (uint32_t)avail : TW;
+                const uint64_t ws = e0x - 1ull;
+                const uint64_t we = last ? p.c_words - 1ull : nxt - 1ull;
+                const uint64_t span = we - (ws & ~3ull) + 1ull;
+                DCHK(ws < p.c_words && we < p.c_words && we >= ws, 4, ((uint64_t)(ws & 0xFFFFFF) << 24) | (we & 0xFFFFFF));
+                DCHK(g_start >= e0y, 5, c0);
+                my_ws = ws;
+                my_nw = span > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)span;   // words (ws & ~3) .. we
+                my_skip = (uint32_t)(g_start - e0y);                           // groups of word ws that belong to earlier tiles
+                uint32_t path;
+                if (nout == 0u)
+                    path = batch ? PATH_SKIP : PATH_STOP;   // no room: a single stream is cut short by the capacity here and for good, a column only here
+                else if (ws == we && is_fill(first0) && (!last || !(first0 & BIT30)))
+                    path = PATH_CONST;    // inside ONE fill word (the stream's last tile may end in a partly padded group: a one-fill there is expanded like any other tile)
+                else if (!last && my_skip == 0u && we - ws == (uint64_t)TG && tg == TG && nout == TW)
+                    path = PATH_UNIT;     // 1024 groups from 1024 words: every word is one group
+                else
+                    path = PATH_WINDOW;
+                my_meta = path | (tg << 4) | (nout << 16);
             }
-            if (r.path == PATH_SCATTER || r.path == PATH_GENERAL || r.path == PATH_STOP) bulk_wait_read<0>();   // the image this tile is built in is no longer being read
-            s_res[it & 1u] = r;
-            ot = ot1;
-            ot1 = ot2;
-            ot2 = ot3;
         }
-        __syncthreads();
-        if (tid == 0 && pend_bytes != 0u) {
-            bulk_s2g(pend_dst, pend_src, pend_bytes);   // (every thread fenced its writes to the image before the barrier)
-            pend_bytes = 0;
-        }
-        const TileRes &res = s_res[it & 1u];
-        const uint32_t path = res.path;
-        if (path == PATH_STOP) break;
-        xpre_n_ws = res.next_ws;
-        if (xpre_n_ws != ~0ull) pack_at((xpre_n_ws & ~3ull) + 4ull * tid, xpre_n);   // the next tile's first words, a tile ahead
-        if (path == PATH_SKIP) continue;
-        const uint64_t ws = res.ws;
-        const uint32_t skip = res.skip, tg = res.tg, nout = res.nout;
-        uint32_t *dst = p.out + res.dst;
-        uint4 *dst4 = reinterpret_cast<uint4 *>(dst);
-        const uint32_t nvec = nout >> 2;
-        const uint64_t wa = ws & ~3ull;   // 16-byte aligned start; words before ws are ignored
-        const uint32_t nw = res.nw;       // words wa .. we
-        const uint32_t w_end = nw - 1u;   // index of we relative to wa
-        const uint32_t w_beg = (uint32_t)(ws - wa);
-#ifdef WAH_TRACE
-        if (p.trace && tid == 0) {
-            const uint64_t k = it;
-            if (k < 40) p.trace[(uint64_t)blockIdx.x * 64u + 8u + k] = (uint64_t)clock64();
-            p.trace[(uint64_t)blockIdx.x * 64u + 59u] = ((uint64_t)path << 32) | (uint64_t)nw;
-        }
-#endif
+        uint32_t *dst_chunk = p.out + (uint64_t)j * p.col_stride + (uint64_t)k0 * TW;
 
-        if (path == PATH_CONST) {
-            const uint32_t f = (res.first & BIT30) ? 0xFFFFFFFFu : 0u;
-            const uint4 v = make_uint4(f, f, f, f);
-            for (uint32_t i = tid; i < nvec; i += EXPAND_THREADS) st_stream_v4(dst4 + i, v);
-            for (uint32_t i = (nvec << 2) + tid; i < nout; i += EXPAND_THREADS) dst[i] = f;
-            continue;
-        }
+        // what the tile at hand needs (uniform), and the first 128 words of a window-path tile, four per lane
+        uint32_t meta = __shfl_sync(0xffffffffu, my_meta, 0);
+        uint64_t ws = __shfl_sync(0xffffffffu, my_ws, 0);
+        uint32_t nw = __shfl_sync(0xffffffffu, my_nw, 0);
+        uint32_t xp[4] = {BIT31, BIT31, BIT31, BIT31};
+        if ((meta & 15u) == PATH_WINDOW && 4u * lane < nw) load_words<4>(p.in + (ws & ~3ull), 4u * lane, p.c_words - (ws & ~3ull), xp);
 
-        if (path == PATH_UNIT) {
-            // ================= unit path (literal dominated data) =================
-            // 8192 groups from 8192 words: every word is one group (a literal, or a fill of length 1).  A warp
-            // takes 32 rows of 32 words with coalesced loads; output word j of a row needs groups j and j + 1
-            // (kernels.cu:375), i.e. the neighbouring lane's word.  No shared memory, no barrier.
-            const uint32_t *src = p.in + ws + 1024u * warp;
-            uint32_t *o = dst + 992u * warp;
+        for (uint32_t s = 0; s < nt; s++) {
+            const uint32_t path = meta & 15u, tg = (meta >> 4) & 0xFFFu, nout = meta >> 16;
+            const uint64_t ws_t = ws;
+            const uint32_t nw_t = nw;
+            uint32_t xc[4] = {xp[0], xp[1], xp[2], xp[3]};
+            // the next tile's numbers and first words: on their way while this tile is expanded
+            meta = __shfl_sync(0xffffffffu, my_meta, s + 1u);
+            if (s + 1u >= nt) meta = PATH_STOP;
+            if ((meta & 15u) >= PATH_UNIT) {
+                ws = __shfl_sync(0xffffffffu, my_ws, s + 1u);
+                nw = __shfl_sync(0xffffffffu, my_nw, s + 1u);
+                if ((meta & 15u) == PATH_WINDOW && 4u * lane < nw) load_words<4>(p.in + (ws & ~3ull), 4u * lane, p.c_words - (ws & ~3ull), xp);
+            }
+            if (path == PATH_STOP) {   // the stream (or the room for it) ends before this tile, and before every later one
+                stop = true;
+                break;
+            }
+            if (path == PATH_SKIP) continue;
+            uint32_t *dst = dst_chunk + s * TW;
+            uint4 *dst4 = reinterpret_cast<uint4 *>(dst);
+            const uint32_t nvec = nout >> 2;
+
+            if (path == PATH_CONST) {
+                // ================= the tile lies inside ONE fill word: written without decoding =================
+                const uint32_t first = __shfl_sync(0xffffffffu, first0, s);
+                const uint32_t f = (first & BIT30) ? 0xFFFFFFFFu : 0u;
+                const uint4 v = make_uint4(f, f, f, f);
+                for (uint32_t i = lane; i < nvec; i += 32u) st_stream_v4(dst4 + i, v);
+                for (uint32_t i = (nvec << 2) + lane; i < nout; i += 32u) dst[i] = f;
+                continue;
+            }
+
+            if (path == PATH_UNIT) {
+                // ================= unit path (literal dominated data) =================
+                // 1024 groups from 1024 words: every word is one group (a literal, or a fill of length 1).  32 rows of 32
+                // words with coalesced loads; output word j of a row needs groups j and j + 1 (kernels.cu:375), i.e.
+                // the neighbouring lane's word.  No shared memory.
+                const uint32_t *src = p.in + ws_t;
 #pragma unroll 8
-            for (uint32_t k = 0; k < 32u; k++) {
-                const uint32_t x = ld_stream_u32(src + 32u * k + lane);
-                const uint32_t v = is_fill(x) ? ((x & BIT30) ? ONES31 : 0u) : x;
-                const uint32_t nx = __shfl_down_sync(0xffffffffu, v, 1);
-                if (lane < 31u) st_stream_u32(o + 31u * k + lane, (v >> lane) | (nx << (31u - lane)));
+                for (uint32_t r = 0; r < 32u; r++) {
+                    const uint32_t x = ld_stream_u32(src + 32u * r + lane);
+                    const uint32_t v = group_bits(x);
+                    const uint32_t nv = __shfl_down_sync(0xffffffffu, v, 1);
+                    if (lane < 31u) st_stream_u32(dst + 31u * r + lane, (v >> lane) | (nv << (31u - lane)));
+                }
+                continue;
             }
-            continue;
-        }
 
-        if (path == PATH_SCATTER) {
-            // ================= scatter path (up to 4096 compressed words in the tile) =================
-            // The tile image (7936 words) is cleared in shared memory; the tile's words are scanned in rounds of 1024
-            // (four per thread; warps beyond the last word idle).  A literal ORs its 31 bits into the one or two words
-            // it touches.  A one-fill ORs the partial words at its two ends in, writes the up to three whole words
-            // between each end and the next 16-byte boundary itself, and marks the whole 16-byte units in between in a
-            // coverage map (bit u = unit u of the image): a toggle where they begin, a toggle where they end.  A prefix
-            // XOR over the map (62 words: every warp does it for itself, two words per lane) then tells every unit
-            // whether it lies inside a one-fill, and the CTA writes those units, one 128-bit store per thread and
-            // eight units -- whatever the mix of runs, that part of the work is spread evenly over the threads (the
-            // owner of a long one-fill used to write all of it himself while 255 threads waited at the next barrier).
-            // Zero fills cost nothing.  Shared-memory atomics keep the scatter free of ordering between threads.
-            uint32_t *img = (n_img & 1u) ? s_grp : s_stage;
-            n_img++;
-            {
-                uint4 *z = reinterpret_cast<uint4 *>(img);
-                for (uint32_t i = tid; i < (uint32_t)EXPAND_TILE_WORDS / 4; i += EXPAND_THREADS) z[i] = make_uint4(0, 0, 0, 0);
-                if (tid < (uint32_t)COV_WORDS / 4) reinterpret_cast<uint4 *>(s_cov)[tid] = make_uint4(0, 0, 0, 0);
-                if (tid == 0) s_marks = 0;
-            }
+            // ================= window path (every other tile) =================
+            // Step 1, word centric: the tile's compressed words are taken 32, 64 or (in rounds) 128 at a time, one, two or
+            //   four per lane.  One packed warp scan gives every word its tile-relative group offset AND its rank among
+            //   the words that hold at least one group; the 31 bits its groups decode to (the literal; all ones or all
+            //   zeros for a fill, kernels.cu:337-354) are parked at s_cw[rank], and bit `offset` of a 1024-bit flag map is
+            //   set ("a word starts at this group").  Nothing else is done per word -- no branch on what kind it is.
+            // Step 2, output centric: lane t owns window t = groups 32 t .. 32 t + 31 = output words 31 t .. 31 t + 30
+            //   (no word is shared between lanes).  The number of flags below the window is the rank of the word that
+            //   covers its first group; walking the 32 flag bits, the lane steps to the next word wherever a flag is set
+            //   and emits output word j = group j >> j | group j+1 << (31 - j) (mergeWords, kernels.cu:375) into the
+            //   tile image.  Straight-line code, the same 9 instructions per group whatever the mix of fills and
+            //   literals; if all 32 windows lie inside fills the constants are written without the walk.
+            // The image leaves through one TMA bulk store.
+            const uint32_t skip = __shfl_sync(0xffffffffu, my_skip, s);
+            const uint32_t w_beg = (uint32_t)ws_t & 3u;                   // words before ws are ignored
+            const uint32_t w_span = nw_t - 1u - w_beg;                    // index of we among the tile's words
+            s_flag[lane] = 0;
+            if (lane == 0) s_flag[32] = 0;
+            __syncwarp();
             uint32_t running = 0;   // group offset (tile relative) of the round's first word
-            uint4 xc = xpre;
-            if (xpre_ws != ws && 128u * warp < nw) pack_at(wa + 4ull * tid, xc);
-            uint4 xn = xc;
-            uint32_t rnd = 0;
-            for (uint32_t c0 = 0; c0 < nw; c0 += SC_ROUND, rnd++) {
-                const bool active = c0 + 128u * warp < nw;   // words for my warp in this round
-                uint32_t x[4] = {0, 0, 0, 0}, c[4] = {0, 0, 0, 0};
-                uint32_t tsum = 0, incl = 0;
-                if (active) {
-                    const uint32_t r0 = c0 + 4u * tid;   // my four consecutive words, relative to wa
-                    if (c0 + SC_ROUND + 128u * warp < nw) pack_at(wa + r0 + SC_ROUND, xn);   // the next round's words, a round ahead
-                    x[0] = xc.x; x[1] = xc.y; x[2] = xc.z; x[3] = xc.w;
-                    xc = xn;
+            uint32_t rk_run = 0;    // words of earlier rounds that hold at least one group
+            if (nw_t <= 32u) {
+                // word `lane`: component lane & 3 of lane (lane >> 2)'s pack
+                uint32_t x[1];
+                const uint32_t a = __shfl_sync(0xffffffffu, xc[0], lane >> 2), b = __shfl_sync(0xffffffffu, xc[1], lane >> 2);
+                const uint32_t c = __shfl_sync(0xffffffffu, xc[2], lane >> 2), d = __shfl_sync(0xffffffffu, xc[3], lane >> 2);
+                x[0] = (lane & 2u) ? ((lane & 1u) ? d : c) : ((lane & 1u) ? b : a);
+                park_words<1>(x, lane, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
+            } else if (nw_t <= 64u) {
+                // words 2 lane, 2 lane + 1: a half of lane (lane >> 1)'s pack
+                uint32_t x[2];
+                const uint32_t a = __shfl_sync(0xffffffffu, xc[0], lane >> 1), b = __shfl_sync(0xffffffffu, xc[1], lane >> 1);
+                const uint32_t c = __shfl_sync(0xffffffffu, xc[2], lane >> 1), d = __shfl_sync(0xffffffffu, xc[3], lane >> 1);
+                x[0] = (lane & 1u) ? c : a;
+                x[1] = (lane & 1u) ? d : b;
+                park_words<2>(x, 2u * lane, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
+            } else {
+                const uint32_t *src = p.in + (ws_t & ~3ull);              // 16-byte aligned start
+                const uint64_t room = p.c_words - (ws_t & ~3ull);         // words from there to the end of the stream
+                uint32_t xn[4] = {BIT31, BIT31, BIT31, BIT31};
+#pragma unroll 1
+                for (uint32_t r0 = 4u * lane;; r0 += 128u) {   // my four consecutive words, relative to the aligned start
+                    const bool more = r0 - 4u * lane + 128u < nw_t;
+                    if (more && r0 + 128u < nw_t) load_words<4>(src, r0 + 128u, room, xn);   // the next round's words, a round ahead
+                    park_words<4>(xc, r0, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
 #pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        const uint32_t ri = r0 + i;
-                        uint32_t v = word_groups(x[i]);
-                        if (ri < w_beg || ri > w_end) v = 0;   // outside this tile's word range
-                        else if (ri == w_beg) v -= skip;       // part of the first word belongs to earlier tiles
-                        c[i] = v > EXP_CLAMP ? EXP_CLAMP : v;
-                        tsum += c[i];
-                    }
-                    incl = warp_incl_scan(tsum);
-                }
-                if (lane == 31) s_wsum[rnd & 1u][warp] = incl;   // (0 from an idle warp)
-                __syncthreads();   // the warp sums are there (first round: and the image is cleared)
-                uint32_t off = running + (incl - tsum);
-#pragma unroll
-                for (int k = 0; k < NW; k++) {
-                    const uint32_t sv = s_wsum[rnd & 1u][k];
-                    if (k < (int)warp) off += sv;
-                    running += sv;
-                }
-                if (active) {
-#pragma unroll
-                    for (int i = 0; i < 4; i++) {
-                        if (c[i] != 0u && off < tg) {
-                            const uint32_t wv = x[i];
-                            const uint32_t b0 = 31u * off, w0 = b0 >> 5, sh = b0 & 31u;
-                            DCHK(w0 < (uint32_t)EXPAND_TILE_WORDS, 1, w0);
-                            if (!is_fill(wv)) {   // kernels.cu:351-354, packed at once (kernels.cu:375)
-                                atomicOr(img + w0, wv << sh);
-                                if (sh > 1u) atomicOr(img + w0 + 1, wv >> (32u - sh));
-                            } else if (wv & BIT30) {   // one-fill, kernels.cu:337-348
-                                uint32_t g1 = off + c[i];
-                                if (g1 > tg) g1 = tg;
-                                const uint32_t b1 = 31u * g1;
-                                DCHK(b1 > b0 && b1 <= 31u * EXPAND_TILE_GROUPS, 2, ((uint64_t)b0 << 24) | b1);
-                                const uint32_t w1 = (b1 - 1u) >> 5;
-                                const uint32_t m0 = 0xFFFFFFFFu << sh, m1 = 0xFFFFFFFFu >> (31u - ((b1 - 1u) & 31u));
-                                if (w0 == w1) {
-                                    atomicOr(img + w0, m0 & m1);
-                                } else {
-                                    atomicOr(img + w0, m0);
-                                    atomicOr(img + w1, m1);
-                                    // whole words a .. w1 - 1 are this run's alone; whole 16-byte units [ua, ub) of them
-                                    const uint32_t a = w0 + 1u, ua = (a + 3u) >> 2, ub = w1 >> 2;
-                                    const bool units = ub > ua;
-                                    const uint32_t head_end = units ? 4u * ua : w1;   // words a .. head_end - 1: at most 3 (6 if no unit)
-#pragma unroll
-                                    for (uint32_t k = 0; k < 6u; k++)
-                                        if (a + k < head_end) img[a + k] = 0xFFFFFFFFu;
-                                    if (units) {
-#pragma unroll
-                                        for (uint32_t k = 0; k < 3u; k++)
-                                            if (4u * ub + k < w1) img[4u * ub + k] = 0xFFFFFFFFu;
-                                        atomicXor(s_cov + (ua >> 5), 1u << (ua & 31u));
-                                        atomicXor(s_cov + (ub >> 5), 1u << (ub & 31u));
-                                        s_marks = 1;
-                                    }
-                                }
-                            }
-                        }
-                        off += c[i];
-                    }
-                }
-                if (running >= tg) break;   // uniform: the tile is covered
-            }
-            __syncthreads();   // every mark is in the coverage map
-            if (s_marks != 0u) {
-                // prefix XOR over the 64 words of the map, two per lane
-                const uint2 cv = reinterpret_cast<const uint2 *>(s_cov)[lane];
-                uint32_t pa = cv.x, pb = cv.y;
-                pa ^= pa << 1; pa ^= pa << 2; pa ^= pa << 4; pa ^= pa << 8; pa ^= pa << 16;
-                pb ^= pb << 1; pb ^= pb << 2; pb ^= pb << 4; pb ^= pb << 8; pb ^= pb << 16;
-                if (pa >> 31) pb = ~pb;
-                const uint32_t tops = __ballot_sync(0xffffffffu, (pb >> 31) != 0u);
-                if (__popc(tops & lanemask_lt()) & 1u) {
-                    pa = ~pa;
-                    pb = ~pb;
-                }
-                // unit u = 256 r + tid: bit `lane` of map word 8 r + warp, which lane (8 r + warp) / 2 holds
-                const uint32_t mine = (warp & 1u) ? pb : pa;
-                uint4 *img4 = reinterpret_cast<uint4 *>(img);
-#pragma unroll
-                for (uint32_t r8 = 0; r8 < 8u; r8++) {
-                    const uint32_t v = __shfl_sync(0xffffffffu, mine, r8 * 4u + (warp >> 1));
-                    const uint32_t u = r8 * 256u + tid;
-                    if (((v >> lane) & 1u) != 0u && u < (uint32_t)EXPAND_TILE_WORDS / 4) img4[u] = make_uint4(~0u, ~0u, ~0u, ~0u);
+                    for (int i = 0; i < 4; i++) xc[i] = xn[i];
+                    if (!more || running >= tg) break;   // uniform: the tile is covered
                 }
             }
-            if (nout == (uint32_t)EXPAND_TILE_WORDS) {
+            if (lane == 0) {
+                if (tg < TG) {
+                    // a short tile (the end of a column / of the stream): what lies behind it reads as a zero fill
+                    s_cw[cw_pos(rk_run <= TG ? rk_run : TG + 1u)] = 0u;
+                    atomicOr(s_flag + (tg >> 5), 1u << (tg & 31u));
+                }
+                bulk_wait_read<0>();   // the previous tile's bulk store has read the image
+            }
+            __syncwarp();   // words parked, flags set, image free
+
+            const uint32_t F = s_flag[lane];
+            const uint32_t pc = __popc(F);
+            uint32_t r = warp_incl_scan(pc) - pc + (F & 1u) - 1u;   // rank of the word that covers my first group
+            DCHK(r <= TG + 1u, 2, r);
+            uint32_t *o = s_stage + 31u * lane;
+            uint32_t v = s_cw[cw_pos(r)];
+            if (__any_sync(0xffffffffu, (F >> 1) != 0u)) {
+#pragma unroll
+                for (int jj = 1; jj < 32; jj++) {
+                    r += (F >> jj) & 1u;
+                    const uint32_t nv = s_cw[cw_pos(r)];
+                    o[jj - 1] = __funnelshift_r(v << 1, nv, jj);
+                    v = nv;
+                }
+            } else {
+                // every window lies inside one word (a fill, or the zeros behind a short tile)
+                const uint32_t v1 = v << 1;
+#pragma unroll
+                for (int jj = 1; jj < 32; jj++) o[jj - 1] = __funnelshift_r(v1, v, jj);
+            }
+            if (nout == TW) {
                 fence_async_smem();   // my writes to the image, visible to the bulk copy engine
-                if (tid == 0) {       // issued behind the next tile's first barrier
-                    pend_bytes = EXPAND_TILE_WORDS * 4u;
-                    pend_src = (uint32_t)__cvta_generic_to_shared(img);
-                    pend_dst = dst;
-                }
+                __syncwarp();
+                if (lane == 0) bulk_s2g(dst, stage_addr, TW * 4u);
             } else {
                 // the last tile of a column or of the stream, or one cut short by the output capacity: the part that
                 // exists, by hand
-                __syncthreads();
-                const uint4 *src4 = reinterpret_cast<const uint4 *>(img);
-                for (uint32_t i = tid; i < nvec; i += EXPAND_THREADS) st_stream_v4(dst4 + i, src4[i]);
-                for (uint32_t i = (nvec << 2) + tid; i < nout; i += EXPAND_THREADS) dst[i] = img[i];
-            }
-            continue;
-        }
-
-        // ================= general path (more than 4096 words in the tile) =================
-        // uses both images as scratch: the bulk store issued above may still be reading one of them
-        if (n_img != 0u) {
-            if (tid == 0) bulk_wait_read<0>();
-            __syncthreads();
-        }
-
-        // ---- 1. clear the group array
-        {
-            uint4 *z = reinterpret_cast<uint4 *>(s_grp);
-            for (uint32_t i = tid; i < GRP_WORDS / 4; i += EXPAND_THREADS) z[i] = make_uint4(0, 0, 0, 0);
-            if (tid == 0) s_nlist = 0;
-        }
-        __syncthreads();
-
-        // ---- 2. scan the compressed words of the tile in rounds of EXP_CHUNK and scatter them
-        uint32_t running = 0;                           // group offset (tile relative) of the round's first word
-        for (uint32_t c0 = 0; c0 < nw; c0 += EXP_CHUNK) {
-            const uint32_t r0 = c0 + 8u * tid;          // my 8 consecutive words, relative to wa
-            load8(p, wa + r0, w);
-            uint32_t c[8];
-            uint32_t tsum = 0;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                const uint32_t ri = r0 + i;
-                uint32_t x = word_groups(w[i]);
-                if (ri < w_beg || ri > w_end) x = 0;     // outside this tile's word range
-                else if (ri == w_beg) x -= skip;         // part of the first word belongs to earlier tiles
-                c[i] = x > EXP_CLAMP ? EXP_CLAMP : x;
-                tsum += c[i];
-            }
-            const uint32_t incl = warp_incl_scan(tsum);
-            if (c0 != 0) __syncthreads();   // previous round's s_wsum consumed
-            if (lane == 31) s_wsum[0][warp] = incl;
-            __syncthreads();
-            uint32_t off = running + (incl - tsum);
-            uint32_t round_sum = 0;
-#pragma unroll
-            for (int k = 0; k < NW; k++) {
-                const uint32_t sv = s_wsum[0][k];
-                if (k < (int)warp) off += sv;
-                round_sum += sv;
-            }
-            running += round_sum;
-#pragma unroll
-            for (int i = 0; i < 8; i++) {
-                if (c[i] != 0u && off < tg) {
-                    const uint32_t wv = w[i];
-                    if (!is_fill(wv)) {
-                        s_grp[grp_pos(off)] = wv;                                 // kernels.cu:351-354
-                    } else if (wv & BIT30) {                                      // one-fill, kernels.cu:337-348
-                        const uint32_t lo = off;
-                        uint32_t hi = lo + c[i];
-                        if (hi > tg) hi = tg;
-                        if (hi - lo <= 8u) {
-                            for (uint32_t g = lo; g < hi; g++) s_grp[grp_pos(g)] = ONES31;
-                        } else {
-                            const uint32_t e = atomicAdd(&s_nlist, 1u);
-                            if (e < EXP_LIST) s_list[e] = make_uint2(lo, hi);
-                            else for (uint32_t g = lo; g < hi; g++) s_grp[grp_pos(g)] = ONES31;
-                        }
-                    }
-                }
-                off += c[i];
-            }
-            if (running >= tg) break;   // uniform: the tile is covered
-        }
-        __syncthreads();
-
-        // ---- 3. long one-fills: a warp per run
-        {
-            const uint32_t nl = s_nlist < (uint32_t)EXP_LIST ? s_nlist : (uint32_t)EXP_LIST;
-            for (uint32_t e = warp; e < nl; e += NW) {
-                const uint2 r = s_list[e];
-                for (uint32_t g = r.x + lane; g < r.y; g += 32) s_grp[grp_pos(g)] = ONES31;
-            }
-            if (nl) __syncthreads();
-        }
-
-        // ---- 4. my 32 groups -> 31 output words (mergeWords, kernels.cu:375:
-        //         word j = group[j] >> j | group[j+1] << (31-j)); rows padded to 33 = conflict free
-        if (32u * tid < tg) {
-            const uint32_t *r = s_grp + 33u * tid;
-            uint32_t *o = s_stage + 31u * tid;
-            uint32_t a = r[0];
-#pragma unroll
-            for (int j = 0; j < 31; j++) {
-                const uint32_t b = r[j + 1];
-                o[j] = __funnelshift_r(a << 1, b, j + 1);
-                a = b;
+                __syncwarp();
+                const uint4 *src4 = reinterpret_cast<const uint4 *>(s_stage);
+                for (uint32_t i = lane; i < nvec; i += 32u) st_stream_v4(dst4 + i, src4[i]);
+                for (uint32_t i = (nvec << 2) + lane; i < nout; i += 32u) dst[i] = s_stage[i];
+                __syncwarp();
             }
         }
-        __syncthreads();
 
-        // ---- 5. coalesced 128-bit write of the tile
-        {
-            const uint4 *src4 = reinterpret_cast<const uint4 *>(s_stage);
-            for (uint32_t i = tid; i < nvec; i += EXPAND_THREADS) st_stream_v4(dst4 + i, src4[i]);
-            for (uint32_t i = (nvec << 2) + tid; i < nout; i += EXPAND_THREADS) dst[i] = s_stage[i];
-        }
-        // no barrier here: whatever the next tile does to shared memory happens behind its first barrier
+        // ---- shift the pipeline
+        c0 = c1;
+        e0x = e1x;
+        e0y = e1y;
+        first0 = first1;
+        c1 = c2;
+        e1x = e2x;
+        e1y = e2y;
+        c2 = it + 3u < (uint32_t)EXPAND_STATIC_ROUNDS || !tickets ? gw + (uint64_t)(it + 3u) * GW
+                                                                  : (uint64_t)EXPAND_STATIC_ROUNDS * GW + __shfl_sync(0xffffffffu, tk, 0);
     }
-#ifdef WAH_TRACE
-    if (p.trace && tid == 0) p.trace[(uint64_t)blockIdx.x * 64u + 60u] = (uint64_t)clock64();
-#endif
-    if (tid == 0) bulk_wait_read<0>();   // shared memory must outlive the bulk stores that read it
-#ifdef WAH_TRACE
-    if (p.trace && tid == 0) p.trace[(uint64_t)blockIdx.x * 64u + 61u] = (uint64_t)clock64();
-#endif
+    if (lane == 0) bulk_wait_read<0>();   // shared memory must outlive the bulk stores that read it
+    __syncthreads();
     if (p.ctr != nullptr && tid == 0) {
         // The last CTA to leave reports the launch's status and zeroes the counters for the next launch -- all of them,
         // so that a launch that went wrong (a CTA gave up waiting) still leaves its slot clean.  (My own draws are
-        // performed before that: the fence orders them before my `done`.)
+        // performed before that: the barrier and the fence order them before my `done`.)
         // (a CTA that saw the launch fail says so itself: with poisoned counters there may be no "last CTA")
         if (p.out_info && *reinterpret_cast<volatile uint32_t *>(&p.hdr_rw->error) == p.epoch) p.out_info[2] = STATUS_TIMEOUT;
         __threadfence();
@@ -1147,7 +1002,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
 // Both phases in one persistent launch: every CTA first takes its share of the scan tiles, then its share of the
 // output tiles, each of which waits only for its own two `starts` entries.  Saves a launch, the idle tail / ramp
 // between two kernels, and the wait for the slowest scan tile.
-static_assert(2 * SCAN_SUB_WORDS <= GRP_WORDS + EXPAND_TILE_WORDS, "the scan phase's two sub-tile buffers live in the expand phase's shared memory");
+static_assert(2 * SCAN_SUB_WORDS <= (EXPAND_THREADS / 32) * WARP_SMEM_WORDS, "the scan phase's two sub-tile buffers live in the expand phase's shared memory");
 static_assert(SCAN_THREADS == EXPAND_THREADS, "the fused kernel runs both phases with one CTA shape");
 #ifdef WAH_TRACE
 #define DTRACE(slot, val)                                                                      \
@@ -1187,7 +1042,7 @@ __global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_decode_kernel(const Sca
 
 size_t expand_smem_bytes()
 {
-    return (size_t)(GRP_WORDS + EXPAND_TILE_WORDS) * sizeof(uint32_t);
+    return (size_t)(EXPAND_THREADS / 32) * WARP_SMEM_WORDS * sizeof(uint32_t);
 }
 
 // ---- launch geometry, per device (a process may drive several devices: SM count, occupancy and the >48 KB dynamic

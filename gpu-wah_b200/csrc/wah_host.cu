@@ -6,10 +6,10 @@
 // synchronously.  Here a process-wide context keeps the device buffers, a ring of pinned bounce
 // buffers and a small pool of copy threads alive between calls:
 //   * a host buffer that is already page locked is DMAed directly;
-//   * a pageable buffer moves in 4 MiB chunks through the pinned ring, the copy threads moving
+//   * a pageable buffer moves in 16 MiB chunks through the pinned ring, the copy threads moving
 //     chunk k+1 between user memory and the ring while the DMA engine moves chunk k;
-//   * the result is malloc()ed because the reference's callers free() it (compress.cu:181,208);
-//     the copy threads touch it in parallel, so its first-touch page faults are spread over cores.
+//   * the result comes from calloc() because the reference's callers free() it (compress.cu:181,208); the copy
+//     threads fill it in parallel and skip the 4 KiB blocks that are all zero, whose pages are then never touched.
 #include "../../include/wah_b200.h"
 #include "wah_kernels.h"
 
@@ -72,6 +72,22 @@ inline void stream_copy(void *dst, const void *src, size_t bytes)
     memcpy(d, s, bytes & 15);
 }
 
+inline bool all_zero(const char *p, size_t bytes)
+{
+    size_t i = 0;
+    for (; i < bytes && ((uintptr_t)(p + i) & 15); i++)
+        if (p[i]) return false;
+    for (; i + 64 <= bytes; i += 64) {
+        const __m128i a = _mm_load_si128((const __m128i *)(p + i)), b = _mm_load_si128((const __m128i *)(p + i + 16));
+        const __m128i c = _mm_load_si128((const __m128i *)(p + i + 32)), d = _mm_load_si128((const __m128i *)(p + i + 48));
+        const __m128i o = _mm_or_si128(_mm_or_si128(a, b), _mm_or_si128(c, d));
+        if (_mm_movemask_epi8(_mm_cmpeq_epi8(o, _mm_setzero_si128())) != 0xFFFF) return false;
+    }
+    for (; i < bytes; i++)
+        if (p[i]) return false;
+    return true;
+}
+
 class CopyPool {
    public:
     explicit CopyPool(int n) : n_(n)
@@ -130,8 +146,12 @@ class CopyPool {
         });
     }
 
-    // Populate the page tables of a freshly malloc()ed buffer, every thread its own contiguous part, with one
-    // madvise(MADV_POPULATE_WRITE) per part (Linux >= 5.14) instead of one page fault per 4 KiB; falls back to
+    // The same into a destination that is known to hold zeros already (a fresh calloc() block): 4 KiB blocks of the
+    // source that are all zero are not written at all.  A decoded bitvector of the fill-dominated kind is mostly such
+    // blocks; their pages of the result are never touched, i.e. never faulted in and zeroed by the kernel either --
+    // they stay the shared zero page until the caller writes to them.
+    // Populate the page tables of a freshly allocated buffer, every thread its own contiguous part, with one
+    // madvise(MADV_POPULATE_WRITE) per part (Linux >= 5.14) instead of one page fault per page; falls back to
     // touching the pages.
     void prefault(void *p, size_t bytes)
     {
@@ -146,6 +166,29 @@ class CopyPool {
 #endif
             for (uintptr_t o = a; o < b; o += 4096) *(volatile char *)o = 0;
         });
+    }
+
+    void copy_into_zeroed(void *dst, const void *src, size_t bytes)
+    {
+        constexpr uintptr_t BLK = 4096;
+        const uintptr_t d0 = (uintptr_t)dst, d1 = d0 + bytes;
+        const uintptr_t first = d0 & ~(BLK - 1);
+        const size_t nblk = (d1 - first + BLK - 1) / BLK;
+        auto work = [&](int i) {
+            // contiguous runs of blocks per thread (16 blocks at a time), dealt round robin
+            for (size_t b0 = (size_t)i * 16; b0 < nblk; b0 += (size_t)n_ * 16) {
+                for (size_t b = b0; b < b0 + 16 && b < nblk; b++) {
+                    const uintptr_t a = std::max(first + b * BLK, d0), e = std::min(first + (b + 1) * BLK, d1);
+                    const char *sp = (const char *)src + (a - d0);
+                    if (!all_zero(sp, e - a)) stream_copy((void *)a, sp, e - a);
+                }
+            }
+        };
+        if (bytes < (256u << 10) || n_ == 1) {
+            for (int i = 0; i < n_; i++) work(i);
+            return;
+        }
+        parallel(work);
     }
 
    private:
@@ -299,8 +342,20 @@ int upload(HostCtx &c, void *d_dst, const void *h_src, size_t bytes)
     return WAH_OK;
 }
 
+// How a result buffer is allocated and filled (WAH_B200_RESULT): 0 malloc + parallel copy; 1 malloc, advised towards
+// huge pages, page tables populated by the copy threads while the first chunks are in flight; 2 calloc + zero blocks
+// skipped; 3 = 2 with the huge-page advice.
+int result_strategy()
+{
+    static const int st = [] {
+        const char *e = getenv("WAH_B200_RESULT");
+        return e ? atoi(e) : 2;
+    }();
+    return st;
+}
+
 // device -> host; returns with the data in place
-int download(HostCtx &c, void *h_dst, const void *d_src, size_t bytes, bool fresh)
+int download(HostCtx &c, void *h_dst, const void *d_src, size_t bytes, bool zeroed)
 {
     if (bytes == 0) return WAH_OK;
     if (is_pinned(h_dst)) {
@@ -317,28 +372,32 @@ int download(HostCtx &c, void *h_dst, const void *d_src, size_t bytes, bool fres
         return cudaEventRecord(c.slot_ev[s], c.stream);
     };
     for (size_t k = 0; k < n && k < NSLOT; k++) CUDA_TRY(issue(k));
-    static const bool do_prefault = [] {
-        const char *e = getenv("WAH_B200_PREFAULT");
-        return e ? e[0] == '1' : true;
-    }();
-    if (fresh && do_prefault && bytes >= (4u << 20)) c.pool->prefault(h_dst, bytes);   // while the first chunks are in flight
+    if (zeroed && result_strategy() == 1 && bytes >= (4u << 20)) c.pool->prefault(h_dst, bytes);   // while the first chunks are in flight
+    if (result_strategy() < 2) zeroed = false;
+    // `zeroed`: the destination is a fresh calloc() block: blocks of zeros are not written (nor their pages faulted in)
     for (size_t k = 0; k < n; k++) {
         const int s = (int)(k % NSLOT);
         const size_t off = k * CHUNK, len = std::min(CHUNK, bytes - off);
         CUDA_TRY(cudaEventSynchronize(c.slot_ev[s]));
-        c.pool->copy((char *)h_dst + off, c.pin + s * CHUNK, len);
+        if (zeroed)
+            c.pool->copy_into_zeroed((char *)h_dst + off, c.pin + s * CHUNK, len);
+        else
+            c.pool->copy((char *)h_dst + off, c.pin + s * CHUNK, len);
         if (k + NSLOT < n) CUDA_TRY(issue(k + NSLOT));
     }
     return WAH_OK;
 }
 
-// malloc for a result the caller will free(); large blocks are advised towards huge pages so that
-// their first touch costs one fault per 2 MiB where the kernel allows it
+// A result the caller will free() (the reference's contract: compress.cu:181,208, decompress.cu:127,140).  calloc():
+// a block this size comes straight from mmap, i.e. it IS zero without anybody writing to it, and the copy threads
+// leave the parts of it that stay zero alone (CopyPool::copy_into_zeroed).
 uint32_t *alloc_result(uint64_t words)
 {
     const size_t bytes = (size_t)(words ? words : 1) * 4;
-    char *p = (char *)malloc(bytes);
-    if (p && bytes >= (8u << 20)) {
+    const int st = result_strategy();
+    char *p = (char *)(st >= 2 ? calloc(bytes, 1) : malloc(bytes));
+    if (p && (st == 1 || st == 3) && bytes >= (8u << 20)) {
+        // large blocks are advised towards huge pages: their first touch costs one fault per 2 MiB where the kernel allows it
         const uintptr_t lo = ((uintptr_t)p + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1);
         const uintptr_t hi = ((uintptr_t)p + bytes) & ~(uintptr_t)((2u << 20) - 1);
         if (hi > lo) madvise((void *)lo, hi - lo, MADV_HUGEPAGE);

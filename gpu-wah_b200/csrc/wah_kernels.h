@@ -51,8 +51,8 @@ constexpr int SCAN_THREADS = 256;
 constexpr int SCAN_TILE_WORDS = SCAN_THREADS * 8;              // 2048: smallest scan tile, the unit the workspace is sized by
 
 constexpr int EXPAND_THREADS = 256;
-constexpr int EXPAND_TILE_GROUPS = EXPAND_THREADS * 32;        // 8192 groups per output tile
-constexpr int EXPAND_TILE_WORDS = EXPAND_THREADS * 31;         // 7936 output words
+constexpr int EXPAND_TILE_GROUPS = 1024;                       // groups per output tile: a warp's tile, and the grain of the boundary table
+constexpr int EXPAND_TILE_WORDS = 992;                         // = 31 x 32 output words (3968 bytes)
 
 // header written by the scan kernel, read by the expand kernel and the host
 struct DecodeHeader {

@@ -301,7 +301,7 @@ def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0):
 
 SCAN_THREADS, SCAN_ITEMS = 256, 8
 SCAN_TILE = SCAN_THREADS * SCAN_ITEMS
-TG, TWO = 8192, 7936
+TG, TWO = 1024, 992
 
 
 def scan_model(cw, max_out_tiles):
@@ -332,84 +332,35 @@ def scan_model(cw, max_out_tiles):
     return G, words, (G + TG - 1) // TG, starts
 
 
-def grp_pos(g):
-    return g + (g >> 5)
-
-
 def expand_model(cw, out_cap=None):
-    """Mirror of the general path of wah_decode_kernel's expand phase: per output tile, scatter the compressed words into a padded
-    one-group-per-int array, then repack rows of 32 groups into 31 words."""
+    """Mirror of wah_decode_kernel's expand phase for a single stream: per output tile (1024 groups = 992 words, one warp)
+    the table entries of the tile and of the next one give the tile's word range; a tile inside one fill word is written
+    as a constant, every other tile goes through the window path (window_tile_model).  `out_cap` = capacity of the output
+    in words (the table then has room for ceil(out_cap / 992) tiles and the last tile may be cut short)."""
     c = len(cw)
-    CLAMP = 2 * TG
-    CHUNK = 2048
     G, words, real_tiles, starts = scan_model(cw, 1 << 40 if out_cap is None else (out_cap + TWO - 1) // TWO)
     total_words = words if out_cap is None else min(words, out_cap)
     out = [None] * total_words
     n_tiles = real_tiles if out_cap is None else min(real_tiles, (out_cap + TWO - 1) // TWO)
     for ot in range(n_tiles):
         ws, g0 = starts[ot]
-        we = starts[ot + 1][0] if ot + 1 < real_tiles else c - 1
+        last = ot + 1 >= real_tiles            # the entry of the next tile is never recorded: it lies behind the stream
+        we = c - 1 if last else starts[ot + 1][0]
         g_lo = ot * TG
         skip = g_lo - g0
+        tg = min(TG, G - g_lo) if last else TG
         w_lo = ot * TWO
         if w_lo >= total_words:
             continue
         nout = min(TWO, total_words - w_lo)
         first = cw[ws]
-        if ws == we and (first & BIT31) and (ot + 1 < real_tiles or not (first & BIT30)):
+        if ws == we and (first & BIT31) and (not last or not (first & BIT30)):
             f = M32 if (first & BIT30) else 0
             for i in range(nout):
                 out[w_lo + i] = f
             continue
-        grp = [0] * (TG + TG // 32)
-        wa = ws & ~3
-        nw = we - wa + 1
-        running = 0
-        long_list = []
-        for c0 in range(0, nw, CHUNK):
-            offs = running
-            for tid in range(256):
-                i0 = wa + c0 + 8 * tid
-                for i in range(8):
-                    gi = i0 + i
-                    w = cw[gi] if gi < c else BIT31
-                    x = word_groups(w)
-                    if gi < ws or gi > we:
-                        x = 0
-                    elif gi == ws:
-                        x -= skip
-                    x = min(x, CLAMP)
-                    off = offs
-                    if x != 0 and off < TG:
-                        if not (w & BIT31):
-                            grp[grp_pos(off)] = w
-                        elif w & BIT30:
-                            lo, hi = off, min(off + x, TG)
-                            if hi - lo <= 8:
-                                for g in range(lo, hi):
-                                    grp[grp_pos(g)] = ONES31
-                            else:
-                                long_list.append((lo, hi))
-                    offs += x
-            running = offs
-            if running >= TG:
-                break
-        for lo, hi in long_list:
-            for g in range(lo, hi):
-                grp[grp_pos(g)] = ONES31
-        stage = [None] * TWO
-        for tid in range(256):
-            if not (g_lo + 32 * tid < G):
-                continue
-            r = grp[33 * tid: 33 * tid + 32]
-            a = r[0]
-            for j in range(31):
-                b = r[j + 1]
-                stage[31 * tid + j] = funnelshift_r((a << 1) & M32, b, j + 1)
-                a = b
-        for i in range(nout):
-            assert stage[i] is not None
-            out[w_lo + i] = stage[i]
+        img = window_tile_model([int(x) for x in cw[ws:we + 1]], skip, tg)
+        out[w_lo:w_lo + nout] = img[:nout]
     assert all(w is not None for w in out)
     return out, words, G
 
@@ -464,4 +415,93 @@ def scan_geometry_model(cw, skip_words=0, grid=444):
                             zero_fills += (w & ~BIT30 & 0xFFFFFFFF) == BIT31
         out.append((groups, zero_fills - padding, w_last > w_first and groups == w_last - w_first))
     assert (seen == 1).all()
+    return out
+
+
+# ---------------------------------------------------------------- window path of the expand phase (wah_decompress.cu)
+
+RANK_SHIFT = 20
+GROUP_MASK = (1 << RANK_SHIFT) - 1
+
+
+def group_bits(x):
+    if x & BIT31:
+        return ONES31 if x & BIT30 else 0
+    return x
+
+
+def cw_pos(r):
+    return r + (r >> 5)
+
+
+def window_tile_model(words, skip, tg):
+    """Mirror of PATH_WINDOW for ONE output tile: `words` = the compressed words ws .. we of the tile, `skip` = groups of
+    the first word that belong to earlier tiles, `tg` = groups in the tile.  Step 1 (word centric): a packed scan gives
+    every word its group offset (low 22 bits) and its rank among the words that hold a group (bits above); the word's
+    group bits are parked by rank and a flag is set where it starts.  Step 2 (output centric): window t = groups
+    32 t .. 32 t + 31 finds the rank of the word covering its first group from the number of flags below it, walks its
+    32 flag bits and emits output words 31 t .. 31 t + 30.  Returns the 992-word image."""
+    s_cw = [None] * (TG + TG // 32 + 8)
+    s_flag = [0] * (TG // 32 + 8)
+    packed = 0
+    for i, wv in enumerate(words):
+        c = word_groups(wv)
+        if i == 0:
+            c -= skip
+        c = min(c, 2 * TG)
+        off, rk = packed & GROUP_MASK, packed >> RANK_SHIFT
+        if c != 0 and off <= tg:   # (the last word may start exactly where the tile ends: parked, but reads as zeros)
+            s_cw[cw_pos(rk)] = group_bits(wv) if off < tg else 0
+            s_flag[off >> 5] |= 1 << (off & 31)
+        packed += c + ((1 << RANK_SHIFT) if c else 0)
+        if (packed & GROUP_MASK) >= tg:   # (the kernel leaves at the end of a round of 1024 words; later words hold nothing)
+            packed = (packed >> RANK_SHIFT << RANK_SHIFT) | min(packed & GROUP_MASK, GROUP_MASK)
+    if tg < TG:
+        s_cw[cw_pos(min(packed >> RANK_SHIFT, TG + 1))] = 0
+        s_flag[tg >> 5] |= 1 << (tg & 31)
+    img = [0] * TWO
+    below = 0
+    for t in range(TG // 32):
+        F = s_flag[t]
+        r = below + (F & 1) - 1
+        assert r >= 0
+        v = s_cw[cw_pos(r)]
+        for j in range(1, 32):
+            r += (F >> j) & 1
+            nv = s_cw[cw_pos(r)]
+            img[31 * t + j - 1] = funnelshift_r((v << 1) & M32, nv, j)
+            v = nv
+        below += popc(F)
+    return img
+
+
+def expand_model_window(cw, n_cols=1, col_groups=None):
+    """The expand phase with every tile on the window path; with n_cols > 1 the stream is a batch of columns of
+    col_groups groups each (output tile k of column j starts at group j * col_groups + k * 1024).  Returns the list of
+    decoded columns (each a list of ceil(31 * groups / 32) words)."""
+    c = len(cw)
+    offs = [0]
+    for w in cw:
+        offs.append(offs[-1] + word_groups(w))
+    G = offs[-1]
+    if col_groups is None:
+        col_groups = G
+    assert G == n_cols * col_groups
+    import bisect
+
+    out = []
+    for j in range(n_cols):
+        words_out = (col_groups * 31 + 31) // 32
+        col = [0] * words_out
+        for k in range((col_groups + TG - 1) // TG):
+            g_start = j * col_groups + k * TG
+            tg = min(TG, col_groups - k * TG)
+            # the word that covers group g_start: the last one that starts at or before it and holds at least a group
+            ws = bisect.bisect_right(offs, g_start) - 1
+            g_end = g_start + tg
+            we = bisect.bisect_right(offs, g_end) - 1 if g_end < G else c - 1
+            img = window_tile_model([int(x) for x in cw[ws:we + 1]], g_start - offs[ws], tg)
+            nout = min(TWO, words_out - k * TWO)
+            col[k * TWO:k * TWO + nout] = img[:nout]
+        out.append(col)
     return out

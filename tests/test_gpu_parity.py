@@ -642,3 +642,30 @@ def test_logical_operators_and_popcount(name, n, gen_a, gen_b, mode):
         assert np.array_equal(to_host(d_out[:c]), want), (name, op)
         wah.popcount_device(d_out, c, d_bits)
         assert int(d_bits.item()) == int(np.unpackbits(want_vec.view(np.uint8)).sum()), (name, op)
+
+
+def test_results_txt_has_the_reference_columns(tmp_path):
+    """scripts/results_txt.py writes the rows of the reference's benchmark main (source.cpp:38-48 header,
+    source.cpp:128-138 one row per size x density): 11 comma-separated columns, sizes in words, the density index,
+    the ratio, the three timers of compress() and of decompress()."""
+    import subprocess
+    import sys
+
+    out = tmp_path / "results.txt"
+    subprocess.run([sys.executable, os.path.join(ROOT, "scripts", "results_txt.py"), "--sizes", "1", "--densities", "1,10",
+                    "--reps", "1", "--out", str(out)], check=True, timeout=600, capture_output=True)
+    lines = out.read_text().strip().split("\n")
+    assert len(lines) == 3
+    header = [h.strip() for h in lines[0].split(",")]
+    assert header == ["Original size [Int]", "Compressed size [Int]", "Decompressed size [Int]", "Density", "Compression Ratio",
+                      "Compression transfer to device [ms]", "Compression time [ms]", "Compression transfer from device [ms]",
+                      "Decompression transfer to device [ms]", "Decompression time [ms]", "Decompression transfer from device [ms]"]
+    n = 1024 * 31 * 32                                                 # dataSize for s = 1 (source.cpp:54-57)
+    for line, dens in zip(lines[1:], (1, 10)):
+        cols = [c.strip() for c in line.split(",")]
+        assert len(cols) == 11
+        assert int(cols[0]) == n and int(cols[2]) == n and int(cols[3]) == dens
+        data = to_host(wah.gen_uniform_device(n, 1.0 / (1 << dens), 1337 + dens))
+        assert int(cols[1]) == orc.compress(data, 0).size              # the compressed size is the reference encoder's
+        assert abs(float(cols[4]) - int(cols[1]) / n) < 1e-4
+        assert all(float(c) >= 0.0 for c in cols[5:])

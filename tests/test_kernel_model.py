@@ -99,6 +99,37 @@ def test_expand_model_matches_oracle(name, cw, data):
         assert not want[data.size:].any()
 
 
+@pytest.mark.parametrize("name,cw,data", list(_streams()), ids=[c[0] for c in _streams()])
+def test_window_path_model_matches_oracle(name, cw, data):
+    """The window path's arithmetic -- the packed offset / rank scan, the flag map, the end marker of a short tile, the
+    rank of the word that covers a window's first group, the 32 -> 31 repack -- for every tile of the stream
+    (wah_decompress.cu PATH_WINDOW)."""
+    want = orc.decompress(cw)
+    (got,) = km.expand_model_window([int(x) for x in cw])
+    assert np.array_equal(np.array(got, dtype=np.uint32), want)
+
+
+@pytest.mark.parametrize("n_cols,wpc", [(3, 31), (5, 992), (4, 7936 + 17), (2, 3 * 7936), (7, 100)])
+def test_window_path_model_on_a_batch_of_columns(n_cols, wpc):
+    """One stream holding several columns: tile k of column j starts at group j * col_groups + k * 8192 and its last
+    tile holds fewer than 8192 groups (wah_decompress.cu: ColumnCursor, TileRes::tg)."""
+    import datagen
+
+    rng = np.random.default_rng(n_cols * 100 + wpc)
+    cols = []
+    for j in range(n_cols):
+        kind = int(rng.integers(0, 4))
+        cols.append([np.zeros(wpc, dtype=np.uint32), np.full(wpc, 0xFFFFFFFF, dtype=np.uint32),
+                     datagen.uniform(wpc, 0.3, j), datagen.clustered(wpc, 0.4, 200, j)][kind])
+    cols = np.stack(cols)
+    for mode in (0, 1):
+        cw, _ = orc.compress_batch(cols, mode)
+        got = km.expand_model_window([int(x) for x in cw], n_cols, orc.num_groups(wpc))
+        for j in range(n_cols):
+            assert np.array_equal(np.array(got[j][:wpc], dtype=np.uint32), cols[j]), (mode, j)
+            assert not any(got[j][wpc:])
+
+
 @pytest.mark.parametrize("c_words,skip,n_bad,grid", [
     (1, 0, 0, 444), (1000, 0, 2, 444), (2048, 3, 0, 444), (2049, 0, 1, 444), (200_001, 2, 5, 444),
     (6 * 8192 + 17, 0, 3, 6),        # (a grid of 6 CTAs:) tiles of two sub-tiles, the second one row long

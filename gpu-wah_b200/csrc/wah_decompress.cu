@@ -567,7 +567,7 @@ __global__ void __launch_bounds__(SCAN_THREADS) wah_scan_kernel(const ScanParams
 // slots into barrier stalls.)  Tiles are dealt in chunks of 8 consecutive tiles (31 KB of output), the first rounds
 // round robin, later chunks by ticket.
 
-constexpr int CHUNK_TILES = 8;                                                // tiles per chunk (unit of work distribution)
+constexpr int MAX_CHUNK_TILES = 8;                                            // tiles per chunk (the unit of work distribution): 8, fewer for short streams
 constexpr int CW_WORDS = EXPAND_TILE_GROUPS + EXPAND_TILE_GROUPS / 32 + 8;   // a tile's words by rank (0 .. 1025), rows of 32 padded to 33
 constexpr int FLAG_WORDS = EXPAND_TILE_GROUPS / 32 + 4;                       // bit g: a word starts at group g of the tile (+ a word for g = 1024)
 constexpr int WARP_SMEM_WORDS = CW_WORDS + EXPAND_TILE_WORDS + FLAG_WORDS;    // 8368 bytes per warp
@@ -614,7 +614,7 @@ __device__ __forceinline__ void load_words(const uint32_t *src, uint32_t i0, uin
 
 // Word phase of the window path, one round: my W consecutive words x[], the first at index r0 from the tile's aligned
 // start.  w_beg = index of the tile's first word there, w_span = index of its last word among the tile's words.
-template <int W>
+template <int W, bool PAD>
 __device__ __forceinline__ void park_words(const uint32_t (&x)[W], uint32_t r0, uint32_t w_beg, uint32_t w_span, uint32_t skip,
                                            uint32_t tg, uint32_t &running, uint32_t &rk_run, uint32_t *s_cw, uint32_t *s_flag)
 {
@@ -642,11 +642,41 @@ __device__ __forceinline__ void park_words(const uint32_t (&x)[W], uint32_t r0, 
         // (the tile's last word may start exactly where the tile ends: it is parked like the others -- the ranks stay
         //  consecutive -- but reads as zeros: behind a short tile lies padding)
         if (c[i] != 0u && off <= tg) {
-            s_cw[cw_pos(rk)] = off < tg ? group_bits(x[i]) : 0u;
+            const uint32_t gb = off < tg ? group_bits(x[i]) : 0u;
+            if (PAD)
+                s_cw[cw_pos(rk)] = gb;
+            else
+                reinterpret_cast<uint2 *>(s_cw)[rk] = make_uint2(gb << 1, gb);   // both operand forms of the repack, one 8-byte load in the walk
             atomicOr(s_flag + (off >> 5), 1u << (off & 31u));
         }
         rk += c[i] != 0u ? 1u : 0u;
         off += c[i];
+    }
+}
+
+// The walk of the window path over words parked 8 bytes apart as {bits << 1, bits}: group JJ of the lane's window.  Where
+// the flag map says a word starts, the address steps to it and one 8-byte load brings both operand forms -- both under
+// the flag's predicate: a lane inside a fill issues no load at all, so a shared-memory request serves the two or three
+// lanes that change word at this step instead of all 32 (measured: the unconditional load kept the shared-memory pipe
+// 70 % busy, two wavefronts per request plus bank conflicts).  One funnel shift makes output word
+// JJ - 1 = group JJ-1 >> (JJ-1) | group JJ << (32-JJ) (kernels.cu:375).
+template <int JJ>
+__device__ __forceinline__ void walk_from(uint32_t a, uint32_t F, uint32_t lo, uint32_t cx, uint32_t cy, uint32_t *o)
+{
+    if constexpr (JJ < 32) {
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q;\n\t"
+            ".reg .b32 t;\n\t"
+            "and.b32 t, %3, %4;\n\t"
+            "setp.ne.u32 q, t, 0;\n\t"
+            "@q add.u32 %0, %0, 8;\n\t"
+            "@q ld.shared.v2.u32 {%1, %2}, [%0];\n\t"
+            "}"
+            : "+r"(a), "+r"(cx), "+r"(cy)
+            : "r"(F), "n"(1u << JJ));
+        o[JJ - 1] = __funnelshift_r(lo, cy, JJ);
+        walk_from<JJ + 1>(a, F, cx, cx, cy, o);
     }
 }
 
@@ -690,7 +720,10 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
 
     const bool batch = p.col_groups != ~0ull;
     const uint32_t tpc = (uint32_t)p.max_out_tiles;                   // tiles per column (single stream: tiles the capacity has room for)
-    const uint32_t cpc = (tpc + CHUNK_TILES - 1u) / CHUNK_TILES;      // chunks per column
+    // tiles per chunk: 8 (31 KB of output per draw), fewer when the stream is so short that 8 would leave warps without
+    // work or with twice the work of their neighbours (launch_decode picks it from the number of tiles and warps)
+    const uint32_t CT = p.chunk_tiles;
+    const uint32_t cpc = (tpc + CT - 1u) / CT;                        // chunks per column
     const uint64_t n_chunks = (uint64_t)(batch ? p.n_cols : 1u) * cpc;
     const uint64_t GW = (uint64_t)gridDim.x * NW, gw = (uint64_t)blockIdx.x * NW + warp;
     const bool tickets = p.dynamic_tiles != 0u;
@@ -700,12 +733,12 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     // word's group offset}; the entry behind a column's last tile is the next column's first.
     auto where = [&](uint64_t c, uint32_t &j, uint32_t &k0) {
         j = batch ? (uint32_t)(c / cpc) : 0u;
-        k0 = (uint32_t)(c - (uint64_t)j * cpc) * CHUNK_TILES;
+        k0 = (uint32_t)(c - (uint64_t)j * cpc) * CT;
     };
     auto fetch = [&](uint64_t c, uint64_t &x, uint64_t &y) {
         x = 0;
         y = 0;
-        if (c < n_chunks && lane <= (uint32_t)CHUNK_TILES) {
+        if (c < n_chunks && lane <= CT) {
             uint32_t j, k0;
             where(c, j, k0);
             if (k0 + lane <= tpc) load_entry(p.starts + (uint64_t)j * tpc + k0 + lane, p.epoch, x, y);
@@ -726,7 +759,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     uint64_t e0x, e0y, e1x, e1y, e2x, e2y;
     fetch(c0, e0x, e0y);
     fetch(c1, e1x, e1y);
-    auto first_word = [&](uint64_t x) -> uint32_t { return (lane <= (uint32_t)CHUNK_TILES && x != 0ull) ? ld_stream_u32(p.in + (x - 1ull)) : 0u; };
+    auto first_word = [&](uint64_t x) -> uint32_t { return (lane <= CT && x != 0ull) ? ld_stream_u32(p.in + (x - 1ull)) : 0u; };
     uint32_t first0 = first_word(e0x), first1;
     bool stop = false;
     for (uint32_t it = 0; !stop && c0 < n_chunks; it++) {
@@ -737,7 +770,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
 
         uint32_t j, k0;
         where(c0, j, k0);
-        const uint32_t nt = tpc - k0 < (uint32_t)CHUNK_TILES ? tpc - k0 : (uint32_t)CHUNK_TILES;   // tiles in the chunk
+        const uint32_t nt = tpc - k0 < CT ? tpc - k0 : CT;   // tiles in the chunk
         const uint64_t col_g0 = batch ? (uint64_t)j * p.col_groups : 0ull;
         // the group where my entry's tile starts (the entry behind a column's last tile: where the column ends)
         const uint64_t my_g = (batch && k0 + lane >= tpc) ? col_g0 + p.col_groups : col_g0 + ((uint64_t)(k0 + lane) << TG_SHIFT);
@@ -887,6 +920,9 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             s_flag[lane] = 0;
             if (lane == 0) s_flag[32] = 0;
             __syncwarp();
+            // a tile of many words is literal dense: neighbouring lanes of the walk then read words about 32 ranks apart, and
+            // the words are parked in rows of 32 padded to 33 (cw_pos) to keep those reads on different banks
+            const bool pad = nw_t > 256u;   // (unpadded: 8 bytes per word, ranks 0 .. 259)
             uint32_t running = 0;   // group offset (tile relative) of the round's first word
             uint32_t rk_run = 0;    // words of earlier rounds that hold at least one group
             if (nw_t <= 32u) {
@@ -895,7 +931,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 const uint32_t a = __shfl_sync(0xffffffffu, xc[0], lane >> 2), b = __shfl_sync(0xffffffffu, xc[1], lane >> 2);
                 const uint32_t c = __shfl_sync(0xffffffffu, xc[2], lane >> 2), d = __shfl_sync(0xffffffffu, xc[3], lane >> 2);
                 x[0] = (lane & 2u) ? ((lane & 1u) ? d : c) : ((lane & 1u) ? b : a);
-                park_words<1>(x, lane, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
+                park_words<1, false>(x, lane, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
             } else if (nw_t <= 64u) {
                 // words 2 lane, 2 lane + 1: a half of lane (lane >> 1)'s pack
                 uint32_t x[2];
@@ -903,7 +939,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 const uint32_t c = __shfl_sync(0xffffffffu, xc[2], lane >> 1), d = __shfl_sync(0xffffffffu, xc[3], lane >> 1);
                 x[0] = (lane & 1u) ? c : a;
                 x[1] = (lane & 1u) ? d : b;
-                park_words<2>(x, 2u * lane, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
+                park_words<2, false>(x, 2u * lane, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
             } else {
                 const uint32_t *src = p.in + (ws_t & ~3ull);              // 16-byte aligned start
                 const uint64_t room = p.c_words - (ws_t & ~3ull);         // words from there to the end of the stream
@@ -912,7 +948,10 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 for (uint32_t r0 = 4u * lane;; r0 += 128u) {   // my four consecutive words, relative to the aligned start
                     const bool more = r0 - 4u * lane + 128u < nw_t;
                     if (more && r0 + 128u < nw_t) load_words<4>(src, r0 + 128u, room, xn);   // the next round's words, a round ahead
-                    park_words<4>(xc, r0, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
+                    if (pad)
+                        park_words<4, true>(xc, r0, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
+                    else
+                        park_words<4, false>(xc, r0, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
 #pragma unroll
                     for (int i = 0; i < 4; i++) xc[i] = xn[i];
                     if (!more || running >= tg) break;   // uniform: the tile is covered
@@ -921,7 +960,11 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             if (lane == 0) {
                 if (tg < TG) {
                     // a short tile (the end of a column / of the stream): what lies behind it reads as a zero fill
-                    s_cw[cw_pos(rk_run <= TG ? rk_run : TG + 1u)] = 0u;
+                    const uint32_t re = rk_run <= TG ? rk_run : TG + 1u;
+                    if (pad)
+                        s_cw[cw_pos(re)] = 0u;
+                    else
+                        reinterpret_cast<uint2 *>(s_cw)[re] = make_uint2(0u, 0u);
                     atomicOr(s_flag + (tg >> 5), 1u << (tg & 31u));
                 }
                 bulk_wait_read<0>();   // the previous tile's bulk store has read the image
@@ -933,14 +976,21 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             uint32_t r = warp_incl_scan(pc) - pc + (F & 1u) - 1u;   // rank of the word that covers my first group
             DCHK(r <= TG + 1u, 2, r);
             uint32_t *o = s_stage + 31u * lane;
-            uint32_t v = s_cw[cw_pos(r)];
+            uint32_t v = pad ? s_cw[cw_pos(r)] : reinterpret_cast<const uint2 *>(s_cw)[r].y;
             if (__any_sync(0xffffffffu, (F >> 1) != 0u)) {
+                if (!pad) {
+                    // (the words are parked as {bits << 1, bits}: the two forms in which a group enters the two output words it
+                    //  contributes to -- one 8-byte load per group, no shift; the address advances by predicate)
+                    const uint32_t a = (uint32_t)__cvta_generic_to_shared(s_cw) + 8u * r;
+                    walk_from<1>(a, F, v << 1, v << 1, v, o);
+                } else {
 #pragma unroll
-                for (int jj = 1; jj < 32; jj++) {
-                    r += (F >> jj) & 1u;
-                    const uint32_t nv = s_cw[cw_pos(r)];
-                    o[jj - 1] = __funnelshift_r(v << 1, nv, jj);
-                    v = nv;
+                    for (int jj = 1; jj < 32; jj++) {
+                        r += (F >> jj) & 1u;
+                        const uint32_t nv = s_cw[cw_pos(r)];
+                        o[jj - 1] = __funnelshift_r(v << 1, nv, jj);
+                        v = nv;
+                    }
                 }
             } else {
                 // every window lies inside one word (a fill, or the zeros behind a short tile)
@@ -1136,6 +1186,10 @@ cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStre
     if (e != cudaSuccess) return e;
     ScanParams a = sp;
     ExpandParams b = ep;
+    // every warp should get a dozen chunks or more (the first EXPAND_STATIC_ROUNDS are dealt round robin): 8 tiles per
+    // chunk for long streams, fewer for short ones
+    const uint64_t tiles = ep.max_out_tiles * (uint64_t)(ep.n_cols ? ep.n_cols : 1u), warps = (uint64_t)grid * (EXPAND_THREADS / 32);
+    b.chunk_tiles = tiles >= 96ull * warps ? 8u : (tiles >= 48ull * warps ? 4u : (tiles >= 24ull * warps ? 2u : 1u));
     void *args[] = {&a, &b};
     return launch_pdl((const void *)wah_decode_kernel, grid, EXPAND_THREADS, args, expand_smem_bytes(), stream);
 }

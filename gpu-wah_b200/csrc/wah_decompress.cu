@@ -24,6 +24,8 @@
 // well: group offsets run over the concatenation, output tile k of column j starts at group j * col_groups + k * 8192
 // and lands at out + j * col_stride + k * 7936.
 #include "wah_common.cuh"
+
+#include <stdlib.h>
 #include "wah_kernels.h"
 
 namespace wahb200 {
@@ -198,6 +200,10 @@ constexpr int SCAN_SUB_WORDS = SCAN_MAXV * 4 * SCAN_THREADS;   // 8192 words = 3
 __device__ __forceinline__ uint64_t pack_groups(const uint4 x)
 {
     return (uint64_t)word_groups(x.x) + word_groups(x.y) + word_groups(x.z) + word_groups(x.w);
+}
+__device__ __forceinline__ uint32_t pack_groups32(const uint4 x)   // (four counts below 2^30 each)
+{
+    return word_groups(x.x) + word_groups(x.y) + word_groups(x.z) + word_groups(x.w);
 }
 __device__ __forceinline__ uint32_t zero_fill(uint32_t x) { return (x & ~BIT30) == BIT31; }   // a fill of 0 groups
 
@@ -495,6 +501,11 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
 #endif
         } else if (p.starts != nullptr) {
             uint64_t sub_base = excl;   // group offset of the sub-tile's first word
+            // words that hold under 8 groups on average: most 128-word rows hold no output-tile boundary and are skipped
+            const bool skip_rows = tile_sum < 8ull * (w_last - w_first);
+            ColumnCursor rcur;          // (uniform) the column that holds the row at hand
+            rcur.base = 0;
+            rcur.j = 0;
             fetch_sub(0);
 #pragma unroll 1
             for (uint32_t sub = 0; sub < nsub; sub++) {
@@ -506,33 +517,91 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
                 }
                 geometry(sub);
                 if (ragged) patch_sub(sub);
-                uint64_t lsub = 0;
+                if (!skip_rows) {
+                    // (most rows hold a boundary: every row is scanned, 64-bit)
+                    uint64_t lsub = 0;
 #pragma unroll 2
-                for (uint32_t v = 0; v < nv; v++) lsub += pack_groups(*my_pack(sub & 1u, v));
-                const uint64_t wsub = warp_sum_u64(lsub);
+                    for (uint32_t v = 0; v < nv; v++) lsub += pack_groups(*my_pack(sub & 1u, v));
+                    const uint64_t wsub = warp_sum_u64(lsub);
+                    __syncthreads();   // s_wsum: the previous sub-tile's (or pass 1's) sums have been consumed
+                    if (lane == 0) s_wsum[warp] = wsub;
+                    __syncthreads();
+                    uint64_t row_base = sub_base;   // group offset of the row's first word
+#pragma unroll
+                    for (int k = 0; k < NW; k++) {
+                        const uint64_t sv = s_wsum[k];
+                        if (k < (int)warp) row_base += sv;
+                        sub_base += sv;
+                    }
+#pragma unroll 1
+                    for (uint32_t v = 0; v < nv; v++) {
+                        const uint4 x = *my_pack(sub & 1u, v);
+                        const uint64_t sl = pack_groups(x);
+                        const uint64_t incl = warp_incl_scan_u64(sl);
+                        const uint64_t off = row_base + incl - sl;
+                        col_seek(cur, off, geo.cg);
+                        const uint64_t rel = off - cur.base;
+                        const uint64_t kf = (rel + TGM) >> TG_SHIFT, ke = (rel + sl + TGM) >> TG_SHIFT;
+                        if (kf != ke || rel + sl > geo.cg)   // a boundary in my 4 words
+                            note_boundaries(p.starts, p.epoch, geo, cur, batch, kf, ke, seg_begin + (uint64_t)(v * 32u + lane) * 4u, off, x,
+                                            s_heavy, &s_nheavy);
+                        row_base += __shfl_sync(0xffffffffu, incl, 31);
+                    }
+                    continue;
+                }
+                // the groups of each of my warp's rows (128 words): lane v ends up with row v's.  A pack's four counts fit
+                // 32 bits; two 16-bit halves summed over the warp by redux.sync are exact.
+                uint64_t myrow = 0;
+#pragma unroll 2
+                for (uint32_t v = 0; v < nv; v++) {
+                    const uint32_t s32 = pack_groups32(*my_pack(sub & 1u, v));
+                    const uint32_t lo = __reduce_add_sync(0xffffffffu, s32 & 0xFFFFu), hi = __reduce_add_sync(0xffffffffu, s32 >> 16);
+                    if (lane == v) myrow = ((uint64_t)hi << 16) + lo;
+                }
+                uint64_t rincl = myrow;   // prefix over the rows (lanes 0 .. SCAN_MAXV - 1)
+#pragma unroll
+                for (int dd = 1; dd < SCAN_MAXV; dd <<= 1) {
+                    const uint64_t o = __shfl_up_sync(0xffffffffu, rincl, dd);
+                    if ((int)lane >= dd) rincl += o;
+                }
+                const uint64_t wsub = __shfl_sync(0xffffffffu, rincl, SCAN_MAXV - 1);
                 __syncthreads();   // s_wsum: the previous sub-tile's (or pass 1's) sums have been consumed
                 if (lane == 0) s_wsum[warp] = wsub;
                 __syncthreads();
-                uint64_t row_base = sub_base;   // group offset of the row's first word
+                uint64_t row_base = sub_base;   // group offset of my warp's first row
 #pragma unroll
                 for (int k = 0; k < NW; k++) {
                     const uint64_t sv = s_wsum[k];
                     if (k < (int)warp) row_base += sv;
                     sub_base += sv;
                 }
+                // Only a row that holds an output-tile boundary is looked at word by word (a literal-dense stream has
+                // one in eight rows, a stream of long fills one in hundreds), in 32-bit arithmetic relative to the row
+                // unless the row holds 2^32 groups or more.
 #pragma unroll 1
                 for (uint32_t v = 0; v < nv; v++) {
+                    const uint64_t rsum = __shfl_sync(0xffffffffu, myrow, v);
+                    const uint64_t roff = row_base + __shfl_sync(0xffffffffu, rincl - myrow, v);
+                    col_seek(rcur, roff, geo.cg);
+                    const uint64_t rel0 = roff - rcur.base;
+                    if (((rel0 + TGM) >> TG_SHIFT) == ((rel0 + rsum + TGM) >> TG_SHIFT) && rel0 + rsum <= geo.cg) continue;
                     const uint4 x = *my_pack(sub & 1u, v);
-                    const uint64_t sl = pack_groups(x);
-                    const uint64_t incl = warp_incl_scan_u64(sl);
-                    const uint64_t off = row_base + incl - sl;
+                    uint64_t sl, off;
+                    if (rsum < (1ull << 32)) {
+                        const uint32_t s32 = pack_groups32(x);
+                        sl = s32;
+                        off = roff + (uint64_t)(warp_incl_scan(s32) - s32);
+                    } else {
+                        sl = pack_groups(x);
+                        off = roff + warp_incl_scan_u64(sl) - sl;
+                    }
+                    ColumnCursor cur = rcur;
                     col_seek(cur, off, geo.cg);
                     const uint64_t rel = off - cur.base;
                     const uint64_t kf = (rel + TGM) >> TG_SHIFT, ke = (rel + sl + TGM) >> TG_SHIFT;
                     if (kf != ke || rel + sl > geo.cg)   // a boundary in my 4 words
                         note_boundaries(p.starts, p.epoch, geo, cur, batch, kf, ke, seg_begin + (uint64_t)(v * 32u + lane) * 4u, off, x,
                                         s_heavy, &s_nheavy);
-                    row_base += __shfl_sync(0xffffffffu, incl, 31);
                 }
             }
         }
@@ -890,13 +959,21 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 // 1024 groups from 1024 words: every word is one group (a literal, or a fill of length 1).  32 rows of 32
                 // words with coalesced loads; output word j of a row needs groups j and j + 1 (kernels.cu:375), i.e.
                 // the neighbouring lane's word.  No shared memory.
-                const uint32_t *src = p.in + ws_t;
-#pragma unroll 8
-                for (uint32_t r = 0; r < 32u; r++) {
-                    const uint32_t x = ld_stream_u32(src + 32u * r + lane);
-                    const uint32_t v = group_bits(x);
-                    const uint32_t nv = __shfl_down_sync(0xffffffffu, v, 1);
-                    if (lane < 31u) st_stream_u32(dst + 31u * r + lane, (v >> lane) | (nv << (31u - lane)));
+                // (all of a half tile's loads are in flight before the first is used: the path is bound by the bytes a warp
+                //  keeps in flight, not by its instructions)
+                const uint32_t *src = p.in + ws_t + lane;
+                uint32_t *d = dst + lane;
+#pragma unroll 1
+                for (uint32_t h = 0; h < 2u; h++, src += 512, d += 496) {
+                    uint32_t x[16];
+#pragma unroll
+                    for (int r = 0; r < 16; r++) x[r] = ld_stream_u32(src + 32 * r);
+#pragma unroll
+                    for (int r = 0; r < 16; r++) {
+                        const uint32_t v = group_bits(x[r]);
+                        const uint32_t nv = __shfl_down_sync(0xffffffffu, v, 1);
+                        if (lane < 31u) st_stream_u32(d + 31 * r, (v >> lane) | (nv << (31u - lane)));
+                    }
                 }
                 continue;
             }
@@ -917,6 +994,45 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             const uint32_t skip = __shfl_sync(0xffffffffu, my_skip, s);
             const uint32_t w_beg = (uint32_t)ws_t & 3u;                   // words before ws are ignored
             const uint32_t w_span = nw_t - 1u - w_beg;                    // index of we among the tile's words
+            bool image_done = false;
+            if (nw_t <= 128u) {
+                // A tile of zero fills and literals only (uniformly sparse data): no walk.  The image is cleared and every
+                // literal ORs its 31 bits into the one or two output words they fall into; zero fills cost nothing.
+                bool one_fill = false;
+#pragma unroll
+                for (int i = 0; i < 4; i++) one_fill = one_fill || ((4u * lane + i - w_beg) <= w_span && (xc[i] >> 30) == 3u);
+                if (!__any_sync(0xffffffffu, one_fill)) {
+                    if (lane == 0) bulk_wait_read<0>();   // the previous tile's bulk store has read the image
+                    __syncwarp();
+                    uint4 *z = reinterpret_cast<uint4 *>(s_stage);
+#pragma unroll
+                    for (uint32_t i = 0; i < (TW / 4u + 31u) / 32u; i++)
+                        if (lane + 32u * i < TW / 4u) z[lane + 32u * i] = make_uint4(0u, 0u, 0u, 0u);
+                    uint32_t c[4], tsum = 0;
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        const uint32_t rel = 4u * lane + i - w_beg;
+                        uint32_t v = word_groups(xc[i]);
+                        if (rel > w_span) v = 0;
+                        if (rel == 0u) v -= skip;
+                        c[i] = v > EXP_CLAMP ? EXP_CLAMP : v;
+                        tsum += c[i];
+                    }
+                    uint32_t off = warp_incl_scan(tsum) - tsum;
+                    __syncwarp();   // the image is cleared
+#pragma unroll
+                    for (int i = 0; i < 4; i++) {
+                        if (c[i] != 0u && off < tg && !is_fill(xc[i])) {   // kernels.cu:351-354, packed at once (kernels.cu:375)
+                            const uint32_t b0 = 31u * off, w0 = b0 >> 5, sh = b0 & 31u;
+                            atomicOr(s_stage + w0, xc[i] << sh);
+                            if (sh > 1u) atomicOr(s_stage + w0 + 1u, xc[i] >> (32u - sh));
+                        }
+                        off += c[i];
+                    }
+                    image_done = true;
+                }
+            }
+            if (!image_done) {
             s_flag[lane] = 0;
             if (lane == 0) s_flag[32] = 0;
             __syncwarp();
@@ -998,6 +1114,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
 #pragma unroll
                 for (int jj = 1; jj < 32; jj++) o[jj - 1] = __funnelshift_r(v1, v, jj);
             }
+            }   // (!image_done)
             if (nout == TW) {
                 fence_async_smem();   // my writes to the image, visible to the bulk copy engine
                 __syncwarp();
@@ -1186,10 +1303,16 @@ cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStre
     if (e != cudaSuccess) return e;
     ScanParams a = sp;
     ExpandParams b = ep;
-    // every warp should get a dozen chunks or more (the first EXPAND_STATIC_ROUNDS are dealt round robin): 8 tiles per
-    // chunk for long streams, fewer for short ones
+    // every warp should get several chunks (the first EXPAND_STATIC_ROUNDS are dealt round robin): 8 tiles per chunk for
+    // long streams, fewer for short ones
     const uint64_t tiles = ep.max_out_tiles * (uint64_t)(ep.n_cols ? ep.n_cols : 1u), warps = (uint64_t)grid * (EXPAND_THREADS / 32);
-    b.chunk_tiles = tiles >= 96ull * warps ? 8u : (tiles >= 48ull * warps ? 4u : (tiles >= 24ull * warps ? 2u : 1u));
+    b.chunk_tiles = tiles >= 64ull * warps ? 8u : (tiles >= 24ull * warps ? 4u : 2u);   // (measured: 1 never pays -- the per-chunk work is not amortised)
+    static const int forced = [] {
+        const char *e = getenv("WAH_B200_CHUNK_TILES");   // (experiments)
+        const int v = e ? atoi(e) : 0;
+        return v == 1 || v == 2 || v == 4 || v == 8 ? v : 0;
+    }();
+    if (forced) b.chunk_tiles = (uint32_t)forced;
     void *args[] = {&a, &b};
     return launch_pdl((const void *)wah_decode_kernel, grid, EXPAND_THREADS, args, expand_smem_bytes(), stream);
 }

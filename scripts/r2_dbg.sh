@@ -11,5 +11,5 @@ python scripts/prof_kernels.py --gen uniform --density 0.05 --log2n 27 --reps 5 
 cat gpurun_out/r2_new_c3.jsonl
 [ "$1" = prof ] || exit 0
 for d in 0.5 0.01; do
-ncu --set full --clock-control none --import-source on -k regex:wah_decode -c 1 -f -o gpurun_out/r2j_dec_clu_$d python scripts/prof_kernels.py --density $d --log2n 27 --reps 1 --which decode > gpurun_out/ncu_dec_$d.log 2>&1
+ncu --set full --clock-control none --import-source on -k regex:wah_decode -c 1 -f -o gpurun_out/r2k_dec_clu_$d python scripts/prof_kernels.py --density $d --log2n 27 --reps 1 --which decode > gpurun_out/ncu_dec_$d.log 2>&1
 done

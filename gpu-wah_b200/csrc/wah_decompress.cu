@@ -5,24 +5,23 @@
 // 8-byte count per compressed word and a one-group-per-int intermediate array in
 // HBM and expand every fill with a serial per-thread loop (kernels.cu:346-348).
 //
-// Here: ONE persistent launch (wah_decode_kernel, 3 CTAs per SM), two phases per CTA:
-//   scan phase    one pass over the compressed words, one tile per CTA: per-tile group sums, exchanged through a
-//                 round aggregator, give every tile its group offset; each tile then records, for every OUTPUT
-//                 tile boundary that falls into it, which compressed word covers it.
-//   expand phase  output-centric, hence load balanced whatever the fill lengths are.  The grid walks output tiles
-//                 of 8192 groups = 7936 words; a tile waits only for its own two boundary entries.  A tile is
-//                 assembled as a bit image in SHARED memory -- a literal ORs its 31 bits in, a one-fill ORs its ends in
-//                 and marks its whole 16-byte units in a coverage map, which a prefix XOR turns into one 128-bit
-//                 store of ones per thread and eight units; zero fills cost nothing -- and leaves through a TMA bulk
-//                 store.  All-literal tiles are repacked in registers with one shuffle per word;
-//                 tiles with more than 4096 words go through the reference's one-group-per-int array
-//                 (kernels.cu:321-359), kept in shared memory, and the 32 -> 31 repack of mergeWords (kernels.cu:375).
+// Here: ONE persistent launch (wah_decode_kernel, 3 CTAs of 8 warps per SM), two phases per CTA:
+//   scan phase    one tile of the compressed stream per CTA: per-tile group sums, exchanged through a round aggregator,
+//                 give every tile its group offset; each tile then records, for every OUTPUT tile boundary (a multiple
+//                 of 1024 groups) that falls into it, which compressed word covers it.
+//   expand phase  output centric and WARP autonomous, hence load balanced whatever the fill lengths are and free of CTA
+//                 barriers.  An output tile is 1024 groups = 992 words; a warp waits only for the table entries of its
+//                 own chunk of 8 tiles and expands each tile on its own: constant stores if the tile lies inside one
+//                 fill; a shuffle repack if it is 1024 literals; otherwise the window path -- the tile's words are
+//                 parked by rank in shared memory and flag a 1024-bit map where they start, then every lane walks the
+//                 32 groups of its window and emits 31 output words (the 32 -> 31 repack of mergeWords,
+//                 kernels.cu:375) into a tile image that leaves through a TMA bulk store.
 // Output tiles are aligned in group space to multiples of 32 groups = 31 words, so no output word is shared
-// between threads or tiles and nothing in HBM needs atomics.  wah_scan_kernel is the scan phase alone (size query).
+// between lanes or tiles and nothing in HBM needs atomics.  wah_scan_kernel is the scan phase alone (size query).
 //
 // A bitmap-index batch (n_cols streams back to back, each decoding to the same number of groups) is ONE launch as
-// well: group offsets run over the concatenation, output tile k of column j starts at group j * col_groups + k * 8192
-// and lands at out + j * col_stride + k * 7936.
+// well: group offsets run over the concatenation, output tile k of column j starts at group j * col_groups + k * 1024
+// and lands at out + j * col_stride + k * 992.
 #include "wah_common.cuh"
 
 #include <stdlib.h>
@@ -121,7 +120,26 @@ struct BoundaryGeom {
     uint64_t k_lim;   // table entries per column that may be written (single stream: one more, the end of the last tile)
     uint32_t tpc;     // table indices per column
     uint32_t n_cols;
+    uint32_t ct;      // tiles per chunk of the expand phase (write_fill_entries)
 };
+
+// A long fill: table entries i_first .. i_end - 1 (column base i0) all name word wi at group offset off.  The expand phase
+// asks for the entry of a chunk's first tile (a multiple of `ct` in its column) and, if that word turns out to cover the
+// whole chunk, for nothing else -- so only those are written, and the nine at either end of the range (a chunk that the
+// fill covers in part).  (A 16 Gbit vector of a few thousand fills is half a million entries from a handful of CTAs:
+// writing them all took longer than the expand phase needed to start.)  Thread t of nt.
+__device__ __forceinline__ void write_fill_entries(ulonglong2 *starts, uint32_t epoch, uint64_t wi, uint64_t off, uint64_t i_first,
+                                                   uint64_t i_end, uint64_t i0, uint32_t ct_, uint32_t t, uint32_t nt)
+{
+    const uint64_t ct = ct_ ? ct_ : 1u;
+    const uint64_t head_end = i_first + 9ull < i_end ? i_first + 9ull : i_end;
+    const uint64_t tail_begin = i_end > head_end + 9ull ? i_end - 9ull : head_end;
+    for (uint64_t i = i_first + t; i < head_end; i += nt) store_entry(starts + i, wi + 1ull, off, epoch);
+    for (uint64_t i = tail_begin + t; i < i_end; i += nt) store_entry(starts + i, wi + 1ull, off, epoch);
+    const uint64_t k_mid = (head_end - i0 + ct - 1ull) / ct * ct;   // first chunk start at or behind head_end
+#pragma unroll 1
+    for (uint64_t i = i0 + k_mid + (uint64_t)t * ct; i < tail_begin; i += (uint64_t)nt * ct) store_entry(starts + i, wi + 1ull, off, epoch);
+}
 
 // Four consecutive compressed words, the first at group offset `off`: record every output-tile boundary that falls
 // into one of them (off <= boundary < off + cnt).  A word that covers up to 4 boundaries records them itself; a long
@@ -147,10 +165,11 @@ __device__ __noinline__ void record_boundaries(ulonglong2 *starts, uint32_t epoc
                 const uint64_t i0 = (uint64_t)cur.j * g.tpc;
                 if (k_end - k_first > 4ull) {
                     const uint32_t e = atomicAdd(s_nheavy, 1u);
-                    if (e < (uint32_t)SCAN_HEAVY) {
-                        s_heavy[e] = make_ulonglong4(wi + j, off, i0 + k_first, i0 + k_end);
-                        k_end = k_first;   // queued
-                    }
+                    if (e < (uint32_t)SCAN_HEAVY)
+                        s_heavy[e] = make_ulonglong4(wi + j, off, (i0 + k_first) | ((i0 + k_end) << 32), i0);   // (table indices fit 32 bits)
+                    else
+                        write_fill_entries(starts, epoch, wi + j, off, i0 + k_first, i0 + k_end, i0, g.ct, 0u, 1u);   // (the queue is full)
+                    k_end = k_first;
                 }
 #pragma unroll 1
                 for (uint64_t k = k_first; k < k_end; k++) store_entry(starts + i0 + k, wi + j + 1ull, off, epoch);
@@ -227,6 +246,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
     geo.tpc = batch ? (uint32_t)p.max_out_tiles : 0u;
     geo.k_lim = batch ? p.max_out_tiles : p.max_out_tiles + 1ull;
     geo.n_cols = p.n_cols;
+    geo.ct = p.chunk_tiles;
     // A tile is walked in sub-tiles of up to 8192 words (SCAN_MAXV rows of 128 words per warp), staged in shared
     // memory, two buffers.  A tile of ONE sub-tile -- every stream up to gridDim * 8192 words -- is still there in
     // pass 2; a longer tile is read a second time rather than split into several tiles, because every extra tile per
@@ -611,8 +631,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
 #pragma unroll 1
             for (uint32_t e = 0; e < nh; e++) {
                 const ulonglong4 h = s_heavy[e];
-#pragma unroll 1
-                for (uint64_t k = h.z + tid; k < h.w; k += SCAN_THREADS) store_entry(p.starts + k, h.x + 1ull, h.y, p.epoch);
+                write_fill_entries(p.starts, p.epoch, h.x, h.y, h.z & 0xFFFFFFFFull, h.z >> 32, h.w, p.chunk_tiles, tid, SCAN_THREADS);
             }
         }
         __syncthreads();   // partial sums and the heavy queue are rewritten by the next tile
@@ -793,18 +812,18 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     // work or with twice the work of their neighbours (launch_decode picks it from the number of tiles and warps)
     const uint32_t CT = p.chunk_tiles;
     const uint32_t cpc = (tpc + CT - 1u) / CT;                        // chunks per column
-    const uint64_t n_chunks = (uint64_t)(batch ? p.n_cols : 1u) * cpc;
-    const uint64_t GW = (uint64_t)gridDim.x * NW, gw = (uint64_t)blockIdx.x * NW + warp;
+    const uint32_t n_chunks = (batch ? p.n_cols : 1u) * cpc;   // (the table has fewer than 2^32 entries: wah_capi.cu)
+    const uint32_t GW = gridDim.x * NW, gw = blockIdx.x * NW + warp;
     const bool tickets = p.dynamic_tiles != 0u;
 
     // Chunk c = tiles k0 .. k0 + 7 of column j (a single stream is one column).  Lane l <= 8 holds the table entry
     // of tile k0 + l: {index + 1 of the compressed word that covers the tile's first group (0 = not recorded), that
     // word's group offset}; the entry behind a column's last tile is the next column's first.
-    auto where = [&](uint64_t c, uint32_t &j, uint32_t &k0) {
+    auto where = [&](uint32_t c, uint32_t &j, uint32_t &k0) {
         j = batch ? (uint32_t)(c / cpc) : 0u;
         k0 = (uint32_t)(c - (uint64_t)j * cpc) * CT;
     };
-    auto fetch = [&](uint64_t c, uint64_t &x, uint64_t &y) {
+    auto fetch = [&](uint32_t c, uint64_t &x, uint64_t &y) {
         x = 0;
         y = 0;
         if (c < n_chunks && lane <= CT) {
@@ -814,8 +833,8 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         }
     };
     uint32_t budget = SPIN_LIMIT;
-    bool hdr = false;                  // the decoded size is known (only needed where the stream ends)
-    uint64_t G = ~0ull, Gwords = ~0ull;
+    bool hdr = false;                  // the decoded size is known (only needed where the stream ends: read there, not kept)
+    auto total_groups = [&]() -> uint64_t { return *reinterpret_cast<const volatile uint64_t *>(&p.hdr->groups); };
     // Software pipeline over a warp's chunks -- nothing a tile needs is asked for when it is needed:
     //   chunk i + 2   its table entries are requested                      (fetch)
     //   chunk i + 1   the first word of each of its tiles is requested     (needs the entries)
@@ -824,7 +843,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     // The first EXPAND_STATIC_ROUNDS rounds of chunks are dealt round robin (known before the scan phase is over);
     // after that a warp draws a ticket three chunks ahead of the chunk it is for.
     static_assert(EXPAND_STATIC_ROUNDS >= 3, "the first three chunks of a warp are dealt statically");
-    uint64_t c0 = gw, c1 = gw + GW, c2 = gw + 2ull * GW;
+    uint32_t c0 = gw, c1 = gw + GW, c2 = gw + 2u * GW;
     uint64_t e0x, e0y, e1x, e1y, e2x, e2y;
     fetch(c0, e0x, e0y);
     fetch(c1, e1x, e1y);
@@ -847,14 +866,24 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         // ---- the chunk's entries must have been recorded by the scan -- or lie behind the end of the stream
         if (__any_sync(0xffffffffu, lane <= nt && e0x == 0ull)) {
             const bool had = e0x != 0ull;
+            const uint64_t end_g = __shfl_sync(0xffffffffu, my_g, nt);   // the group where the chunk ends
             for (;;) {
-                const bool missing = lane <= nt && e0x == 0ull && !(hdr && my_g >= G);
+                // A chunk inside one long fill: the scan records the entry of the chunk's first tile only (write_fill_entries).
+                // If the word that entry names covers the whole chunk, every tile of the chunk starts in it.
+                const uint64_t x0 = __shfl_sync(0xffffffffu, e0x, 0), y0 = __shfl_sync(0xffffffffu, e0y, 0);
+                if (x0 != 0ull) {
+                    const uint32_t f0 = ld_stream_u32(p.in + (x0 - 1ull));
+                    if (is_fill(f0) && y0 + fill_count(f0) > end_g) {
+                        e0x = x0;
+                        e0y = y0;
+                        break;
+                    }
+                }
+                const bool missing = lane <= nt && e0x == 0ull && !(hdr && my_g >= total_groups());
                 if (!__any_sync(0xffffffffu, missing)) break;
                 if (!hdr) {
                     if (*reinterpret_cast<const volatile uint32_t *>(&p.hdr->valid) == p.epoch) {
                         __threadfence();
-                        G = *reinterpret_cast<const volatile uint64_t *>(&p.hdr->groups);
-                        Gwords = *reinterpret_cast<const volatile uint64_t *>(&p.hdr->words);
                         hdr = true;
                         continue;
                     }
@@ -887,7 +916,8 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 const bool last = nxt == 0ull;   // the stream's last tile: it ends with the last compressed word
                 const uint64_t w_lo = (uint64_t)k * TW;   // word offset in the column / the stream
                 uint64_t total_words = p.out_cap;         // single stream: capacity; batch: words per column
-                if (last) {
+                if (last) {   // (the header is known: that is how the missing entry was told from a late one)
+                    const uint64_t G = total_groups(), Gwords = *reinterpret_cast<const volatile uint64_t *>(&p.hdr->words);
                     if (G - g_start < (uint64_t)tg) tg = (uint32_t)(G - g_start);
                     if (!batch && Gwords < total_words) total_words = Gwords;
                 }
@@ -988,8 +1018,8 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             //   (no word is shared between lanes).  The number of flags below the window is the rank of the word that
             //   covers its first group; walking the 32 flag bits, the lane steps to the next word wherever a flag is set
             //   and emits output word j = group j >> j | group j+1 << (31 - j) (mergeWords, kernels.cu:375) into the
-            //   tile image.  Straight-line code, the same 9 instructions per group whatever the mix of fills and
-            //   literals; if all 32 windows lie inside fills the constants are written without the walk.
+            //   tile image.  Straight-line code, the same five or six instructions per group whatever the mix of fills and
+            //   literals (walk_from); if all 32 windows lie inside fills the constants are written without the walk.
             // The image leaves through one TMA bulk store.
             const uint32_t skip = __shfl_sync(0xffffffffu, my_skip, s);
             const uint32_t w_beg = (uint32_t)ws_t & 3u;                   // words before ws are ignored
@@ -1033,88 +1063,88 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 }
             }
             if (!image_done) {
-            s_flag[lane] = 0;
-            if (lane == 0) s_flag[32] = 0;
-            __syncwarp();
-            // a tile of many words is literal dense: neighbouring lanes of the walk then read words about 32 ranks apart, and
-            // the words are parked in rows of 32 padded to 33 (cw_pos) to keep those reads on different banks
-            const bool pad = nw_t > 256u;   // (unpadded: 8 bytes per word, ranks 0 .. 259)
-            uint32_t running = 0;   // group offset (tile relative) of the round's first word
-            uint32_t rk_run = 0;    // words of earlier rounds that hold at least one group
-            if (nw_t <= 32u) {
-                // word `lane`: component lane & 3 of lane (lane >> 2)'s pack
-                uint32_t x[1];
-                const uint32_t a = __shfl_sync(0xffffffffu, xc[0], lane >> 2), b = __shfl_sync(0xffffffffu, xc[1], lane >> 2);
-                const uint32_t c = __shfl_sync(0xffffffffu, xc[2], lane >> 2), d = __shfl_sync(0xffffffffu, xc[3], lane >> 2);
-                x[0] = (lane & 2u) ? ((lane & 1u) ? d : c) : ((lane & 1u) ? b : a);
-                park_words<1, false>(x, lane, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
-            } else if (nw_t <= 64u) {
-                // words 2 lane, 2 lane + 1: a half of lane (lane >> 1)'s pack
-                uint32_t x[2];
-                const uint32_t a = __shfl_sync(0xffffffffu, xc[0], lane >> 1), b = __shfl_sync(0xffffffffu, xc[1], lane >> 1);
-                const uint32_t c = __shfl_sync(0xffffffffu, xc[2], lane >> 1), d = __shfl_sync(0xffffffffu, xc[3], lane >> 1);
-                x[0] = (lane & 1u) ? c : a;
-                x[1] = (lane & 1u) ? d : b;
-                park_words<2, false>(x, 2u * lane, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
-            } else {
-                const uint32_t *src = p.in + (ws_t & ~3ull);              // 16-byte aligned start
-                const uint64_t room = p.c_words - (ws_t & ~3ull);         // words from there to the end of the stream
-                uint32_t xn[4] = {BIT31, BIT31, BIT31, BIT31};
-#pragma unroll 1
-                for (uint32_t r0 = 4u * lane;; r0 += 128u) {   // my four consecutive words, relative to the aligned start
-                    const bool more = r0 - 4u * lane + 128u < nw_t;
-                    if (more && r0 + 128u < nw_t) load_words<4>(src, r0 + 128u, room, xn);   // the next round's words, a round ahead
-                    if (pad)
-                        park_words<4, true>(xc, r0, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
-                    else
-                        park_words<4, false>(xc, r0, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
-#pragma unroll
-                    for (int i = 0; i < 4; i++) xc[i] = xn[i];
-                    if (!more || running >= tg) break;   // uniform: the tile is covered
-                }
-            }
-            if (lane == 0) {
-                if (tg < TG) {
-                    // a short tile (the end of a column / of the stream): what lies behind it reads as a zero fill
-                    const uint32_t re = rk_run <= TG ? rk_run : TG + 1u;
-                    if (pad)
-                        s_cw[cw_pos(re)] = 0u;
-                    else
-                        reinterpret_cast<uint2 *>(s_cw)[re] = make_uint2(0u, 0u);
-                    atomicOr(s_flag + (tg >> 5), 1u << (tg & 31u));
-                }
-                bulk_wait_read<0>();   // the previous tile's bulk store has read the image
-            }
-            __syncwarp();   // words parked, flags set, image free
-
-            const uint32_t F = s_flag[lane];
-            const uint32_t pc = __popc(F);
-            uint32_t r = warp_incl_scan(pc) - pc + (F & 1u) - 1u;   // rank of the word that covers my first group
-            DCHK(r <= TG + 1u, 2, r);
-            uint32_t *o = s_stage + 31u * lane;
-            uint32_t v = pad ? s_cw[cw_pos(r)] : reinterpret_cast<const uint2 *>(s_cw)[r].y;
-            if (__any_sync(0xffffffffu, (F >> 1) != 0u)) {
-                if (!pad) {
-                    // (the words are parked as {bits << 1, bits}: the two forms in which a group enters the two output words it
-                    //  contributes to -- one 8-byte load per group, no shift; the address advances by predicate)
-                    const uint32_t a = (uint32_t)__cvta_generic_to_shared(s_cw) + 8u * r;
-                    walk_from<1>(a, F, v << 1, v << 1, v, o);
+                s_flag[lane] = 0;
+                if (lane == 0) s_flag[32] = 0;
+                __syncwarp();
+                // a tile of many words is literal dense: neighbouring lanes of the walk then read words about 32 ranks apart, and
+                // the words are parked in rows of 32 padded to 33 (cw_pos) to keep those reads on different banks
+                const bool pad = nw_t > 256u;   // (unpadded: 8 bytes per word, ranks 0 .. 259)
+                uint32_t running = 0;   // group offset (tile relative) of the round's first word
+                uint32_t rk_run = 0;    // words of earlier rounds that hold at least one group
+                if (nw_t <= 32u) {
+                    // word `lane`: component lane & 3 of lane (lane >> 2)'s pack
+                    uint32_t x[1];
+                    const uint32_t a = __shfl_sync(0xffffffffu, xc[0], lane >> 2), b = __shfl_sync(0xffffffffu, xc[1], lane >> 2);
+                    const uint32_t c = __shfl_sync(0xffffffffu, xc[2], lane >> 2), d = __shfl_sync(0xffffffffu, xc[3], lane >> 2);
+                    x[0] = (lane & 2u) ? ((lane & 1u) ? d : c) : ((lane & 1u) ? b : a);
+                    park_words<1, false>(x, lane, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
+                } else if (nw_t <= 64u) {
+                    // words 2 lane, 2 lane + 1: a half of lane (lane >> 1)'s pack
+                    uint32_t x[2];
+                    const uint32_t a = __shfl_sync(0xffffffffu, xc[0], lane >> 1), b = __shfl_sync(0xffffffffu, xc[1], lane >> 1);
+                    const uint32_t c = __shfl_sync(0xffffffffu, xc[2], lane >> 1), d = __shfl_sync(0xffffffffu, xc[3], lane >> 1);
+                    x[0] = (lane & 1u) ? c : a;
+                    x[1] = (lane & 1u) ? d : b;
+                    park_words<2, false>(x, 2u * lane, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
                 } else {
+                    const uint32_t *src = p.in + (ws_t & ~3ull);              // 16-byte aligned start
+                    const uint64_t room = p.c_words - (ws_t & ~3ull);         // words from there to the end of the stream
+                    uint32_t xn[4] = {BIT31, BIT31, BIT31, BIT31};
+#pragma unroll 1
+                    for (uint32_t r0 = 4u * lane;; r0 += 128u) {   // my four consecutive words, relative to the aligned start
+                        const bool more = r0 - 4u * lane + 128u < nw_t;
+                        if (more && r0 + 128u < nw_t) load_words<4>(src, r0 + 128u, room, xn);   // the next round's words, a round ahead
+                        if (pad)
+                            park_words<4, true>(xc, r0, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
+                        else
+                            park_words<4, false>(xc, r0, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
 #pragma unroll
-                    for (int jj = 1; jj < 32; jj++) {
-                        r += (F >> jj) & 1u;
-                        const uint32_t nv = s_cw[cw_pos(r)];
-                        o[jj - 1] = __funnelshift_r(v << 1, nv, jj);
-                        v = nv;
+                        for (int i = 0; i < 4; i++) xc[i] = xn[i];
+                        if (!more || running >= tg) break;   // uniform: the tile is covered
                     }
                 }
-            } else {
-                // every window lies inside one word (a fill, or the zeros behind a short tile)
-                const uint32_t v1 = v << 1;
+                if (lane == 0) {
+                    if (tg < TG) {
+                        // a short tile (the end of a column / of the stream): what lies behind it reads as a zero fill
+                        const uint32_t re = rk_run <= TG ? rk_run : TG + 1u;
+                        if (pad)
+                            s_cw[cw_pos(re)] = 0u;
+                        else
+                            reinterpret_cast<uint2 *>(s_cw)[re] = make_uint2(0u, 0u);
+                        atomicOr(s_flag + (tg >> 5), 1u << (tg & 31u));
+                    }
+                    bulk_wait_read<0>();   // the previous tile's bulk store has read the image
+                }
+                __syncwarp();   // words parked, flags set, image free
+
+                const uint32_t F = s_flag[lane];
+                const uint32_t pc = __popc(F);
+                uint32_t r = warp_incl_scan(pc) - pc + (F & 1u) - 1u;   // rank of the word that covers my first group
+                DCHK(r <= TG + 1u, 2, r);
+                uint32_t *o = s_stage + 31u * lane;
+                uint32_t v = pad ? s_cw[cw_pos(r)] : reinterpret_cast<const uint2 *>(s_cw)[r].y;
+                if (__any_sync(0xffffffffu, (F >> 1) != 0u)) {
+                    if (!pad) {
+                        // (the words are parked as {bits << 1, bits}: the two forms in which a group enters the two output words it
+                        //  contributes to -- one 8-byte load per group, no shift; the address advances by predicate)
+                        const uint32_t a = (uint32_t)__cvta_generic_to_shared(s_cw) + 8u * r;
+                        walk_from<1>(a, F, v << 1, v << 1, v, o);
+                    } else {
 #pragma unroll
-                for (int jj = 1; jj < 32; jj++) o[jj - 1] = __funnelshift_r(v1, v, jj);
+                        for (int jj = 1; jj < 32; jj++) {
+                            r += (F >> jj) & 1u;
+                            const uint32_t nv = s_cw[cw_pos(r)];
+                            o[jj - 1] = __funnelshift_r(v << 1, nv, jj);
+                            v = nv;
+                        }
+                    }
+                } else {
+                    // every window lies inside one word (a fill, or the zeros behind a short tile)
+                    const uint32_t v1 = v << 1;
+#pragma unroll
+                    for (int jj = 1; jj < 32; jj++) o[jj - 1] = __funnelshift_r(v1, v, jj);
+                }
             }
-            }   // (!image_done)
             if (nout == TW) {
                 fence_async_smem();   // my writes to the image, visible to the bulk copy engine
                 __syncwarp();
@@ -1138,8 +1168,9 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
         c1 = c2;
         e1x = e2x;
         e1y = e2y;
-        c2 = it + 3u < (uint32_t)EXPAND_STATIC_ROUNDS || !tickets ? gw + (uint64_t)(it + 3u) * GW
-                                                                  : (uint64_t)EXPAND_STATIC_ROUNDS * GW + __shfl_sync(0xffffffffu, tk, 0);
+        c2 = it + 3u < (uint32_t)EXPAND_STATIC_ROUNDS || !tickets ? gw + (it + 3u) * GW
+                                                                  : (uint32_t)EXPAND_STATIC_ROUNDS * GW + __shfl_sync(0xffffffffu, tk, 0);
+        if (c2 < c1) c2 = n_chunks;   // (wrapped: behind the last chunk)
     }
     if (lane == 0) bulk_wait_read<0>();   // shared memory must outlive the bulk stores that read it
     __syncthreads();
@@ -1313,6 +1344,7 @@ cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStre
         return v == 1 || v == 2 || v == 4 || v == 8 ? v : 0;
     }();
     if (forced) b.chunk_tiles = (uint32_t)forced;
+    a.chunk_tiles = b.chunk_tiles;   // (the scan phase records the entries of long fills at chunk starts only)
     void *args[] = {&a, &b};
     return launch_pdl((const void *)wah_decode_kernel, grid, EXPAND_THREADS, args, expand_smem_bytes(), stream);
 }

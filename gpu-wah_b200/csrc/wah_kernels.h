@@ -100,11 +100,12 @@ struct ScanParams {
     uint64_t max_out_tiles;  // output tiles per column the table has room for (single stream: from the capacity)
     uint64_t *out_info;      // nullptr or device u64[3] {words, groups, status}
     // bitmap-index batch: the stream is n_cols columns back to back, each decoding to col_groups groups; output tile
-    // (j, k) = tile k of column j has table index j * max_out_tiles + k and starts at group j * col_groups + k * 8192.
+    // (j, k) = tile k of column j has table index j * max_out_tiles + k and starts at group j * col_groups + k * 1024.
     // Single stream: n_cols = 1, col_groups = ~0.
     uint64_t col_groups;
     uint32_t n_cols;
     DecodeCounters *next_ctr;   // the slot the NEXT launch will use: zeroed by this launch's first CTA
+    uint32_t chunk_tiles;    // == ExpandParams::chunk_tiles (0 for a size query)
     uint64_t *trace;         // nullptr; -DWAH_TRACE builds only
 };
 
@@ -122,7 +123,6 @@ struct ExpandParams {
     uint32_t n_cols;         // 1 = single stream
     DecodeHeader *hdr_rw;    // == hdr (the expand phase reports a timeout through it)
     uint64_t *out_info;      // nullptr or device u64[3]: the last CTA to leave writes the status into [2]
-    uint32_t zero;           // 0 (opaque to the compiler, see the ticket draw in expand_body)
     uint32_t dynamic_tiles;  // 0: tiles are dealt round robin; else: by ticket after EXPAND_STATIC_ROUNDS rounds
     uint32_t chunk_tiles;    // tiles per chunk of work: 8, 4, 2 or 1 (set by launch_decode)
     DecodeCounters *ctr;     // zero at launch; the last CTA to leave zeroes it again

@@ -5,6 +5,7 @@ grep -q "failed\|error" gpurun_out/pytest_q.log && exit 1
 timeout 120 python scripts/fuzz_gpu.py 60 $RANDOM > gpurun_out/dbg_fuzz.log 2>&1; tail -3 gpurun_out/dbg_fuzz.log
 grep -q "fuzz ok" gpurun_out/dbg_fuzz.log || exit 1
 for d in 0.5 0.25 0.1 0.01 0.001 0.0001; do python scripts/prof_kernels.py --density $d --log2n 29 --reps 5 --which decode; done > gpurun_out/r2_new_c3.jsonl 2>gpurun_out/r2_new_c3.err
+python scripts/prof_kernels.py --density 0.0001 --mode 1 --log2n 29 --reps 5 --which decode >> gpurun_out/r2_new_c3.jsonl
 python scripts/prof_kernels.py --gen uniform --density 0.5 --log2n 25 --reps 7 --which decode >> gpurun_out/r2_new_c3.jsonl
 python scripts/prof_kernels.py --gen uniform --density 0.001 --log2n 25 --reps 7 --which decode >> gpurun_out/r2_new_c3.jsonl
 python scripts/prof_kernels.py --gen uniform --density 0.05 --log2n 27 --reps 5 --which decode >> gpurun_out/r2_new_c3.jsonl

@@ -520,11 +520,19 @@ def e2e_single(wah, np, torch, h_in, n_words, mode, steps, d_x):
     cap = wah.max_compressed_words(n_words)
     nbytes = 4.0 * n_words
 
+    moved = [0, 0]   # bytes the last round trip moved over PCIe, each way (the library's own count)
+    t_h2d, t_d2h = ctypes.c_uint64(), ctypes.c_uint64()
+
     def round_trip(src_ptr, check=False):
         rc = lib.wah_compress_host(src_ptr, n_words, mode, ctypes.byref(outp), ctypes.byref(outn), None, None, None)
         assert rc == 0, lib.wah_last_error_string()
+        lib.wah_host_last_transfer_bytes(ctypes.byref(t_h2d), ctypes.byref(t_d2h))
+        moved[0], moved[1] = t_h2d.value, t_d2h.value
         rc = lib.wah_decompress_host(outp.value, outn.value, ctypes.byref(decp), ctypes.byref(decn), None, None, None)
         assert rc == 0, lib.wah_last_error_string()
+        lib.wah_host_last_transfer_bytes(ctypes.byref(t_h2d), ctypes.byref(t_d2h))
+        moved[0] += t_h2d.value
+        moved[1] += t_d2h.value
         c, n = outn.value, decn.value
         if check:
             back = np.frombuffer((ctypes.c_uint32 * n_words).from_address(decp.value), dtype=np.uint32)
@@ -543,6 +551,7 @@ def e2e_single(wah, np, torch, h_in, n_words, mode, steps, d_x):
 
     round_trip(h_in.ctypes.data, check=True)
     dt, c_e2e, n_e2e = timed(lambda: round_trip(h_in.ctypes.data))
+    moved_e2e = tuple(moved)
     # the reference's three timers (ms): H2D / compute / D2H, one extra untimed step
     fl = [ctypes.c_float() for _ in range(6)]
     lib.wah_compress_host(h_in.ctypes.data, n_words, mode, ctypes.byref(outp), ctypes.byref(outn),
@@ -572,7 +581,9 @@ def e2e_single(wah, np, torch, h_in, n_words, mode, steps, d_x):
     assert torch.equal(h_dec[:n_words], h_pin), "host round trip failed"
     return {
         "value": 2 * nbytes * steps / dt / 1e9, "unit": UNIT,
-        "h2d_bytes_per_step": int(nbytes + 4 * c_e2e), "d2h_bytes_per_step": int(4 * c_e2e + 4 * n_e2e + 48),
+        "h2d_bytes_per_step": int(moved_e2e[0]), "d2h_bytes_per_step": int(moved_e2e[1] + 48),
+        "bytes_note": f"counted by the library: 4 KiB blocks that are all zero do not cross PCIe (the vector itself is {int(nbytes)} bytes each way; "
+                      "WAH_B200_SPARSE_COPY=0 moves every byte)",
         "steps": steps, "ms_per_step": dt / steps * 1e3, "segments_ms": segments,
         "api": "wah_compress_host + wah_decompress_host (= the reference's compress()/decompress()): PAGEABLE malloc()ed input "
                "(source.cpp:75,97-100), malloc()ed results freed by the caller",
@@ -776,14 +787,22 @@ def e2e_columns(wah, np, torch, dist, x_cols, mode, args, rank, world, dev):
     outp, outn = ctypes.c_void_p(), ctypes.c_uint64()
     decp, decn = ctypes.c_void_p(), ctypes.c_uint64()
     tot = [0, 0]
+    moved = [0, 0]   # bytes moved over PCIe each way (the library's own count: all-zero 4 KiB blocks stay where they are)
+    t_h2d, t_d2h = ctypes.c_uint64(), ctypes.c_uint64()
 
     def one_pass(check=False):
-        tot[0] = tot[1] = 0
+        tot[0] = tot[1] = moved[0] = moved[1] = 0
         for j in range(n_cols):
             rc = lib.wah_compress_host(h[j].ctypes.data, wpc, mode, ctypes.byref(outp), ctypes.byref(outn), None, None, None)
             assert rc == 0, lib.wah_last_error_string()
+            lib.wah_host_last_transfer_bytes(ctypes.byref(t_h2d), ctypes.byref(t_d2h))
+            moved[0] += t_h2d.value
+            moved[1] += t_d2h.value
             rc = lib.wah_decompress_host(outp.value, outn.value, ctypes.byref(decp), ctypes.byref(decn), None, None, None)
             assert rc == 0, lib.wah_last_error_string()
+            lib.wah_host_last_transfer_bytes(ctypes.byref(t_h2d), ctypes.byref(t_d2h))
+            moved[0] += t_h2d.value
+            moved[1] += t_d2h.value
             if check and j % 37 == 0:
                 back = np.frombuffer((ctypes.c_uint32 * wpc).from_address(decp.value), dtype=np.uint32)
                 assert np.array_equal(back, h[j]), "host round trip failed"
@@ -804,7 +823,7 @@ def e2e_columns(wah, np, torch, dist, x_cols, mode, args, rank, world, dev):
     dt = dt.item()
     nbytes = 4.0 * args.cols * wpc
     return {"value": 2 * nbytes * steps / dt / 1e9, "unit": UNIT,
-            "h2d_bytes_per_step": int(4 * (n_cols * wpc + tot[0])), "d2h_bytes_per_step": int(4 * (tot[0] + tot[1]) + 48 * n_cols),
+            "h2d_bytes_per_step": int(moved[0]), "d2h_bytes_per_step": int(moved[1] + 48 * n_cols),
             "steps": steps, "ms_per_step": dt / steps * 1e3, "bytes_are": "this rank's (every rank moves its own columns)",
             "api": "per column: wah_compress_host + wah_decompress_host (= the reference's compress()/decompress()), pageable input, malloc()ed results"}
 

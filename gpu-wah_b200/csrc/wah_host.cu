@@ -17,6 +17,7 @@
 #include <sys/mman.h>
 
 #include <algorithm>
+#include <chrono>
 #include <condition_variable>
 #include <cstdarg>
 #include <cstdio>
@@ -43,6 +44,14 @@ namespace {
 
 constexpr size_t CHUNK = 16u << 20;  // bytes per pinned bounce buffer
 constexpr int NSLOT = 4;             // bounce buffers in the ring
+// Sparse transfers: a bitvector worth compressing is mostly zero, and a block of zeros need not cross PCIe -- the input
+// buffer on the device is cleared and only the 4 KiB blocks that hold a set bit are sent (packed by the copy threads,
+// put in place by a small kernel); the decoded vector's non-zero blocks are packed on the device and only those come
+// back, into a result that calloc() handed out as zeros.  A chunk without a zero block moves as before.
+constexpr size_t XBLK = 4096;                        // bytes per block
+constexpr size_t BLKS = CHUNK / XBLK;                // blocks per chunk
+constexpr size_t SLOT = CHUNK + BLKS * 4;            // a bounce buffer: the chunk (or its packed blocks) + their block numbers
+constexpr size_t SPARSE_MIN = 8u << 20;              // smaller transfers are not worth the bookkeeping
 
 // ------------------------------------------------------------------ copy threads
 
@@ -191,7 +200,62 @@ class CopyPool {
         parallel(work);
     }
 
+    // Packs the blocks of src (len bytes) that hold a non-zero byte into `packed`, in order, and their numbers into
+    // `list`; returns how many.  The last block may be short: it is padded with zeros.
+    size_t pack_nonzero(char *packed, uint32_t *list, const char *src, size_t len)
+    {
+        const size_t nblk = (len + XBLK - 1) / XBLK;
+        const size_t per = (nblk + n_ - 1) / n_;
+        nz_.assign(nblk, 0);
+        cnt_.assign(n_ + 1, 0);
+        parallel([&](int i) {
+            const size_t b0 = std::min(nblk, per * i), b1 = std::min(nblk, per * (i + 1));
+            size_t c = 0;
+            for (size_t b = b0; b < b1; b++) {
+                const bool z = all_zero(src + b * XBLK, std::min(XBLK, len - b * XBLK));
+                nz_[b] = !z;
+                c += !z;
+            }
+            cnt_[i + 1] = c;
+        });
+        for (int i = 0; i < n_; i++) cnt_[i + 1] += cnt_[i];
+        parallel([&](int i) {
+            const size_t b0 = std::min(nblk, per * i), b1 = std::min(nblk, per * (i + 1));
+            size_t pos = cnt_[i];
+            for (size_t b = b0; b < b1; b++) {
+                if (!nz_[b]) continue;
+                const size_t n = std::min(XBLK, len - b * XBLK);
+                stream_copy(packed + pos * XBLK, src + b * XBLK, n);
+                if (n < XBLK) memset(packed + pos * XBLK + n, 0, XBLK - n);
+                list[pos++] = (uint32_t)b;
+            }
+        });
+        return cnt_[n_];
+    }
+
+    // the reverse on the way back: block list[i] of dst (dst_len bytes) = packed[i]
+    void scatter_blocks(char *dst, size_t dst_len, const char *packed, const uint32_t *list, size_t n)
+    {
+        // (a contiguous stretch of the list per thread: threads that fault in neighbouring pages of a fresh result
+        //  fight over the same page-table lock -- dealt round robin this was 2 us of copying and 6 us of waiting per block)
+        const size_t per = (n + n_ - 1) / n_;
+        auto work = [&](int i) {
+            const size_t k1 = std::min(n, per * (i + 1));
+            for (size_t k = std::min(n, per * i); k < k1; k++) {
+                const size_t off = (size_t)list[k] * XBLK;
+                if (off < dst_len) stream_copy(dst + off, packed + k * XBLK, std::min(XBLK, dst_len - off));
+            }
+        };
+        if (n < 64 || n_ == 1) {
+            for (int i = 0; i < n_; i++) work(i);
+            return;
+        }
+        parallel(work);
+    }
+
    private:
+    std::vector<uint8_t> nz_;
+    std::vector<size_t> cnt_;
     void loop(int i)
     {
         uint64_t seen = 0;
@@ -250,7 +314,9 @@ struct HostCtx {
     std::mutex mu;
     int device = -1;
     DevBuf a, b, ws, small;          // input, output, workspace, 64 B of scalars
-    char *pin = nullptr;             // NSLOT * CHUNK bytes, page locked
+    DevBuf stg, pack, flags, lists, counts;   // sparse transfers: staging slots; packed blocks, block flags, lists, counts
+    uint64_t h2d_bytes = 0, d2h_bytes = 0;    // bytes the last entry point moved over PCIe
+    char *pin = nullptr;             // NSLOT * SLOT bytes, page locked
     cudaStream_t stream = nullptr;   // everything is ordered on this stream
     cudaEvent_t slot_ev[NSLOT] = {};
     cudaEvent_t t0 = nullptr, t1 = nullptr;
@@ -263,7 +329,7 @@ struct HostCtx {
         if (device == dev && stream) return WAH_OK;
         release();
         CUDA_TRY(cudaStreamCreateWithFlags(&stream, cudaStreamNonBlocking));
-        CUDA_TRY(cudaHostAlloc((void **)&pin, NSLOT * CHUNK, cudaHostAllocDefault));
+        CUDA_TRY(cudaHostAlloc((void **)&pin, NSLOT * SLOT, cudaHostAllocDefault));
         for (int i = 0; i < NSLOT; i++) CUDA_TRY(cudaEventCreateWithFlags(&slot_ev[i], cudaEventDisableTiming));
         CUDA_TRY(cudaEventCreate(&t0));
         CUDA_TRY(cudaEventCreate(&t1));
@@ -282,6 +348,11 @@ struct HostCtx {
         b.release();
         ws.release();
         small.release();
+        stg.release();
+        pack.release();
+        flags.release();
+        lists.release();
+        counts.release();
         if (pin) cudaFreeHost(pin);
         pin = nullptr;
         for (auto &e : slot_ev) {
@@ -322,21 +393,49 @@ bool is_pinned(const void *p)
     return at.type == cudaMemoryTypeHost || at.type == cudaMemoryTypeManaged;
 }
 
+bool sparse_copy();
+int result_strategy();
+
 // host -> device, asynchronous on ctx.stream for pinned memory, pipelined through the ring otherwise
 int upload(HostCtx &c, void *d_dst, const void *h_src, size_t bytes)
 {
     if (bytes == 0) return WAH_OK;
     if (is_pinned(h_src)) {
         CUDA_TRY(cudaMemcpyAsync(d_dst, h_src, bytes, cudaMemcpyHostToDevice, c.stream));
+        c.h2d_bytes += bytes;
         return WAH_OK;
     }
     const size_t n = (bytes + CHUNK - 1) / CHUNK;
+    const bool sparse = sparse_copy() && bytes >= SPARSE_MIN;
+    if (sparse) {
+        CUDA_TRY(c.stg.reserve(NSLOT * SLOT));
+        CUDA_TRY(cudaMemsetAsync(d_dst, 0, (bytes + 15) & ~(size_t)15, c.stream));   // (the device buffers have 16 bytes of slack)
+    }
     for (size_t k = 0; k < n; k++) {
         const int s = (int)(k % NSLOT);
         const size_t off = k * CHUNK, len = std::min(CHUNK, bytes - off);
+        char *slot = c.pin + s * SLOT;
         if (k >= NSLOT) CUDA_TRY(cudaEventSynchronize(c.slot_ev[s]));   // the DMA out of this slot is done
-        c.pool->copy(c.pin + s * CHUNK, (const char *)h_src + off, len);
-        CUDA_TRY(cudaMemcpyAsync((char *)d_dst + off, c.pin + s * CHUNK, len, cudaMemcpyHostToDevice, c.stream));
+        if (!sparse) {
+            c.pool->copy(slot, (const char *)h_src + off, len);
+            CUDA_TRY(cudaMemcpyAsync((char *)d_dst + off, slot, len, cudaMemcpyHostToDevice, c.stream));
+            c.h2d_bytes += len;
+        } else {
+            uint32_t *list = reinterpret_cast<uint32_t *>(slot + CHUNK);
+            const size_t nblk = (len + XBLK - 1) / XBLK;
+            const size_t nnz = c.pool->pack_nonzero(slot, list, (const char *)h_src + off, len);
+            if (nnz == nblk) {   // no zero block in the chunk: straight into place
+                CUDA_TRY(cudaMemcpyAsync((char *)d_dst + off, slot, len, cudaMemcpyHostToDevice, c.stream));
+                c.h2d_bytes += len;
+            } else if (nnz != 0) {
+                char *d_slot = (char *)c.stg.p + s * SLOT;
+                CUDA_TRY(cudaMemcpyAsync(d_slot, slot, nnz * XBLK, cudaMemcpyHostToDevice, c.stream));
+                CUDA_TRY(cudaMemcpyAsync(d_slot + CHUNK, list, nnz * 4, cudaMemcpyHostToDevice, c.stream));
+                CUDA_TRY(launch_scatter_blocks((char *)d_dst + off, (len + 15) & ~(size_t)15, d_slot,
+                                               reinterpret_cast<const uint32_t *>(d_slot + CHUNK), (uint32_t)nnz, c.stream));
+                c.h2d_bytes += nnz * (XBLK + 4);
+            }
+        }
         CUDA_TRY(cudaEventRecord(c.slot_ev[s], c.stream));
     }
     return WAH_OK;
@@ -354,6 +453,91 @@ int result_strategy()
     return st;
 }
 
+bool sparse_copy()
+{
+    static const bool on = [] {
+        const char *e = getenv("WAH_B200_SPARSE_COPY");
+        return e ? e[0] != '0' : true;
+    }();
+    return on;
+}
+
+// device -> host into a fresh result the caller will free(): only the blocks with a set bit.  How the result is
+// handed out depends on how much of it is non-zero: mostly zeros -- calloc() and nothing else, the pages of the zero
+// blocks are never touched (never faulted in, never zeroed by the kernel); otherwise the pages are populated up front
+// by the copy threads, as huge pages where the kernel allows it (a fault per 4 KiB page of a 2 GiB result costs more
+// than the transfer: a 2 GiB round trip with nearly every block non-zero took 195 ms that way, 122 ms populated).
+int download_sparse(HostCtx &c, uint32_t **h_out, const void *d_src, size_t bytes)
+{
+    const size_t n_blocks = (bytes + XBLK - 1) / XBLK, n = (bytes + CHUNK - 1) / CHUNK;
+    CUDA_TRY(c.pack.reserve(n * CHUNK));
+    CUDA_TRY(c.flags.reserve(n_blocks));
+    CUDA_TRY(c.lists.reserve(n * BLKS * 4));
+    CUDA_TRY(c.counts.reserve(n * 4));
+    CUDA_TRY(launch_pack_nonzero_blocks(d_src, bytes, (uint32_t)BLKS, (uint8_t *)c.flags.p, (uint32_t *)c.lists.p, (uint32_t *)c.counts.p,
+                                        c.pack.p, c.stream));
+    static const bool trace = getenv("WAH_B200_HOST_TRACE") != nullptr;
+    const auto T0 = std::chrono::steady_clock::now();
+    double t_wait = 0, t_scatter = 0;
+    std::vector<uint32_t> cnt(n);
+    CUDA_TRY(cudaMemcpyAsync(cnt.data(), c.counts.p, n * 4, cudaMemcpyDeviceToHost, c.stream));
+    CUDA_TRY(cudaStreamSynchronize(c.stream));
+    const auto T1 = std::chrono::steady_clock::now();
+    std::vector<size_t> live;   // chunks that hold anything
+    size_t nnz = 0;
+    for (size_t k = 0; k < n; k++) {
+        if (cnt[k] != 0) live.push_back(k);
+        nnz += cnt[k];
+    }
+    char *h_dst = (char *)calloc(bytes, 1);
+    if (!h_dst) return wah_set_error(WAH_ERR_NOMEM, "calloc of %zu bytes failed", bytes);
+    *h_out = (uint32_t *)h_dst;
+    if (nnz * 2 >= n_blocks) {   // half of the blocks or more (measured: 0.29 of them is still 8 ms better left alone)
+        const uintptr_t lo = ((uintptr_t)h_dst + (2u << 20) - 1) & ~(uintptr_t)((2u << 20) - 1);
+        const uintptr_t hi = ((uintptr_t)h_dst + bytes) & ~(uintptr_t)((2u << 20) - 1);
+        if (hi > lo) madvise((void *)lo, hi - lo, MADV_HUGEPAGE);
+        c.pool->prefault(h_dst, bytes);
+    }
+    auto chunk_len = [&](size_t k) { return std::min(CHUNK, bytes - k * CHUNK); };
+    auto dense = [&](size_t k) { return cnt[k] == (chunk_len(k) + XBLK - 1) / XBLK; };
+    auto issue = [&](size_t i) -> cudaError_t {
+        const size_t k = live[i];
+        char *slot = c.pin + (i % NSLOT) * SLOT;
+        cudaError_t e;
+        if (dense(k)) {   // no zero block: straight from the decoded vector
+            e = cudaMemcpyAsync(slot, (const char *)d_src + k * CHUNK, chunk_len(k), cudaMemcpyDeviceToHost, c.stream);
+            c.d2h_bytes += chunk_len(k);
+        } else {
+            e = cudaMemcpyAsync(slot, (const char *)c.pack.p + k * CHUNK, (size_t)cnt[k] * XBLK, cudaMemcpyDeviceToHost, c.stream);
+            if (e == cudaSuccess)
+                e = cudaMemcpyAsync(slot + CHUNK, (const char *)c.lists.p + k * BLKS * 4, (size_t)cnt[k] * 4, cudaMemcpyDeviceToHost, c.stream);
+            c.d2h_bytes += (size_t)cnt[k] * (XBLK + 4);
+        }
+        if (e != cudaSuccess) return e;
+        return cudaEventRecord(c.slot_ev[i % NSLOT], c.stream);
+    };
+    for (size_t i = 0; i < live.size() && i < NSLOT; i++) CUDA_TRY(issue(i));
+    for (size_t i = 0; i < live.size(); i++) {
+        const size_t k = live[i];
+        const char *slot = c.pin + (i % NSLOT) * SLOT;
+        const auto a0 = std::chrono::steady_clock::now();
+        CUDA_TRY(cudaEventSynchronize(c.slot_ev[i % NSLOT]));
+        const auto a1 = std::chrono::steady_clock::now();
+        if (dense(k))
+            c.pool->copy((char *)h_dst + k * CHUNK, slot, chunk_len(k));
+        else
+            c.pool->scatter_blocks((char *)h_dst + k * CHUNK, chunk_len(k), slot, reinterpret_cast<const uint32_t *>(slot + CHUNK), cnt[k]);
+        const auto a2 = std::chrono::steady_clock::now();
+        t_wait += std::chrono::duration<double, std::milli>(a1 - a0).count();
+        t_scatter += std::chrono::duration<double, std::milli>(a2 - a1).count();
+        if (i + NSLOT < live.size()) CUDA_TRY(issue(i + NSLOT));
+    }
+    if (trace)
+        fprintf(stderr, "download_sparse: %zu chunks (%zu live), pack+sync %.2f ms, DMA waits %.2f ms, scatter %.2f ms\n", n, live.size(),
+                std::chrono::duration<double, std::milli>(T1 - T0).count(), t_wait, t_scatter);
+    return WAH_OK;
+}
+
 // device -> host; returns with the data in place
 int download(HostCtx &c, void *h_dst, const void *d_src, size_t bytes, bool zeroed)
 {
@@ -361,13 +545,15 @@ int download(HostCtx &c, void *h_dst, const void *d_src, size_t bytes, bool zero
     if (is_pinned(h_dst)) {
         CUDA_TRY(cudaMemcpyAsync(h_dst, d_src, bytes, cudaMemcpyDeviceToHost, c.stream));
         CUDA_TRY(cudaStreamSynchronize(c.stream));
+        c.d2h_bytes += bytes;
         return WAH_OK;
     }
     const size_t n = (bytes + CHUNK - 1) / CHUNK;
+    c.d2h_bytes += bytes;
     auto issue = [&](size_t k) -> cudaError_t {
         const int s = (int)(k % NSLOT);
         const size_t off = k * CHUNK, len = std::min(CHUNK, bytes - off);
-        cudaError_t e = cudaMemcpyAsync(c.pin + s * CHUNK, (const char *)d_src + off, len, cudaMemcpyDeviceToHost, c.stream);
+        cudaError_t e = cudaMemcpyAsync(c.pin + s * SLOT, (const char *)d_src + off, len, cudaMemcpyDeviceToHost, c.stream);
         if (e != cudaSuccess) return e;
         return cudaEventRecord(c.slot_ev[s], c.stream);
     };
@@ -380,9 +566,9 @@ int download(HostCtx &c, void *h_dst, const void *d_src, size_t bytes, bool zero
         const size_t off = k * CHUNK, len = std::min(CHUNK, bytes - off);
         CUDA_TRY(cudaEventSynchronize(c.slot_ev[s]));
         if (zeroed)
-            c.pool->copy_into_zeroed((char *)h_dst + off, c.pin + s * CHUNK, len);
+            c.pool->copy_into_zeroed((char *)h_dst + off, c.pin + s * SLOT, len);
         else
-            c.pool->copy((char *)h_dst + off, c.pin + s * CHUNK, len);
+            c.pool->copy((char *)h_dst + off, c.pin + s * SLOT, len);
         if (k + NSLOT < n) CUDA_TRY(issue(k + NSLOT));
     }
     return WAH_OK;
@@ -405,9 +591,38 @@ uint32_t *alloc_result(uint64_t words)
     return (uint32_t *)p;
 }
 
+// the malloc()ed result of compress() / decompress(), filled from the device
+int fetch_result(HostCtx &c, uint32_t **h_out, const void *d_src, uint64_t words)
+{
+    const size_t bytes = (size_t)words * 4;
+    if (sparse_copy() && bytes >= SPARSE_MIN) {
+        const int rc = download_sparse(c, h_out, d_src, bytes);
+        if (rc != WAH_OK && *h_out) {
+            free(*h_out);
+            *h_out = nullptr;
+        }
+        return rc;
+    }
+    uint32_t *host = alloc_result(words);
+    if (!host) return wah_set_error(WAH_ERR_NOMEM, "malloc of %llu words failed", (unsigned long long)words);
+    if (int rc = download(c, host, d_src, bytes, true)) {
+        free(host);
+        return rc;
+    }
+    *h_out = host;
+    return WAH_OK;
+}
+
 }  // namespace
 
 extern "C" void wah_free(void *p) { free(p); }
+
+extern "C" void wah_host_last_transfer_bytes(uint64_t *h2d_bytes, uint64_t *d2h_bytes)
+{
+    std::lock_guard<std::mutex> g(g_ctx.mu);
+    if (h2d_bytes) *h2d_bytes = g_ctx.h2d_bytes;
+    if (d2h_bytes) *d2h_bytes = g_ctx.d2h_bytes;
+}
 
 extern "C" void wah_host_release(void)
 {
@@ -425,6 +640,7 @@ extern "C" int wah_compress_host(const uint32_t *h_in, uint64_t n_words, int mod
     std::lock_guard<std::mutex> g(g_ctx.mu);
     HostCtx &c = g_ctx;
     if (int rc = c.init()) return rc;
+    c.h2d_bytes = c.d2h_bytes = 0;
     CUDA_TRY(cudaEventRecord(c.t0, c.stream));
     // -- segment 1: buffers (kept between calls) + H2D (compress.cu:57-120)
     const uint64_t cap = wah_max_compressed_words(n_words);
@@ -445,12 +661,8 @@ extern "C" int wah_compress_host(const uint32_t *h_in, uint64_t n_words, int mod
     if (cw == ~0ull)
         return wah_set_error(WAH_ERR_CUDA, "the compress kernel gave up waiting for part of its grid (is another context holding the GPU?)");
     // -- segment 3: D2H into a malloc()ed buffer (compress.cu:177-202)
-    uint32_t *host = alloc_result(cw);
-    if (!host) return wah_set_error(WAH_ERR_NOMEM, "malloc of %llu words failed", (unsigned long long)cw);
-    if (int rc = download(c, host, c.b.p, cw * 4, true)) {
-        free(host);
-        return rc;
-    }
+    uint32_t *host = nullptr;
+    if (int rc = fetch_result(c, &host, c.b.p, cw)) return rc;
     const float t_d2h = c.lap();
     *h_out = host;
     if (out_words) *out_words = cw;
@@ -515,6 +727,7 @@ extern "C" int wah_decompress_host(const uint32_t *h_in, uint64_t c_words, uint3
     std::lock_guard<std::mutex> g(g_ctx.mu);
     HostCtx &c = g_ctx;
     if (int rc = c.init()) return rc;
+    c.h2d_bytes = c.d2h_bytes = 0;
     CUDA_TRY(cudaEventRecord(c.t0, c.stream));
     // -- segment 1: buffers + H2D (decompress.cu:34-56)
     CUDA_TRY(c.a.reserve(c_words * 4 + 16));
@@ -527,12 +740,8 @@ extern "C" int wah_decompress_host(const uint32_t *h_in, uint64_t c_words, uint3
     }
     const float t_compute = c.lap();
     // -- segment 3: D2H into a malloc()ed buffer (decompress.cu:127-133)
-    uint32_t *host = alloc_result(words);
-    if (!host) return wah_set_error(WAH_ERR_NOMEM, "malloc of %llu words failed", (unsigned long long)words);
-    if (int rc = download(c, host, c.b.p, words * 4, true)) {
-        free(host);
-        return rc;
-    }
+    uint32_t *host = nullptr;
+    if (int rc = fetch_result(c, &host, c.b.p, words)) return rc;
     const float t_d2h = c.lap();
     *h_out = host;
     if (out_words) *out_words = words;
@@ -552,6 +761,7 @@ extern "C" int wah_compress_host_into(const uint32_t *h_in, uint64_t n_words, in
     std::lock_guard<std::mutex> g(g_ctx.mu);
     HostCtx &c = g_ctx;
     if (int rc = c.init()) return rc;
+    c.h2d_bytes = c.d2h_bytes = 0;
     const uint64_t cap = wah_max_compressed_words(n_words);
     const size_t ws_bytes = wah_compress_workspace_bytes(n_words);
     CUDA_TRY(c.a.reserve(n_words * 4 + 16));
@@ -582,6 +792,7 @@ extern "C" int wah_decompress_host_into(const uint32_t *h_in, uint64_t c_words, 
     std::lock_guard<std::mutex> g(g_ctx.mu);
     HostCtx &c = g_ctx;
     if (int rc = c.init()) return rc;
+    c.h2d_bytes = c.d2h_bytes = 0;
     CUDA_TRY(c.a.reserve(c_words * 4 + 16));
     if (int rc = upload(c, c.a.p, h_in, c_words * 4)) return rc;
     // the caller's capacity bounds the output, so one pass does both the size and the expansion

@@ -178,6 +178,11 @@ cudaError_t poison_counter_slots();
 
 cudaError_t launch_shard_probe(const uint32_t *d_shard, uint64_t words, uint64_t *d_result /*[5]*/,
                                cudaStream_t stream);
+// sparse host transfers (wah_host.cu): 4 KiB blocks, lists of block numbers
+cudaError_t launch_scatter_blocks(void *d_dst, uint64_t dst_bytes, const void *d_packed, const uint32_t *d_list, uint32_t n,
+                                  cudaStream_t stream);
+cudaError_t launch_pack_nonzero_blocks(const void *d_src, uint64_t bytes, uint32_t blocks_per_chunk, uint8_t *d_flags, uint32_t *d_lists,
+                                       uint32_t *d_counts, void *d_packed, cudaStream_t stream);
 cudaError_t launch_popcount(const uint32_t *d_in, uint64_t c_words, uint64_t *d_bits, cudaStream_t stream);
 cudaError_t launch_logical(int op, uint32_t *d_a, const uint32_t *d_b, uint64_t n_words, cudaStream_t stream);
 cudaError_t launch_gen_uniform(uint32_t *d_out, uint64_t n_words, double density, uint64_t seed,

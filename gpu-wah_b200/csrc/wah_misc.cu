@@ -118,6 +118,122 @@ __global__ void wah_logical_kernel(int op, uint4 *a, const uint4 *b, uint64_t n4
     }
 }
 
+// ---- sparse host transfers (wah_host.cu): bitvectors are mostly zero, so the host path moves only the 4 KiB blocks
+//      that hold a set bit.  Upload: the copy threads pack the non-zero blocks of a chunk and their block numbers; this
+//      kernel puts them in place in a buffer that was cleared.  Download: the non-zero blocks of the decoded vector are
+//      packed per 16 MiB chunk (block test, scan of the flags, copy) and only those cross PCIe.
+constexpr uint32_t XBLK = 4096;   // bytes per block
+
+// block list[i] of `dst` (dst_bytes long) = packed[i]; one CTA of 256 threads per block
+__global__ void __launch_bounds__(256) wah_scatter_blocks_kernel(char *dst, uint64_t dst_bytes, const char *packed, const uint32_t *list,
+                                                                 uint32_t n)
+{
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint64_t off = (uint64_t)list[i] * XBLK;
+        const uint4 v = reinterpret_cast<const uint4 *>(packed + (uint64_t)i * XBLK)[threadIdx.x];
+        if (off + (uint64_t)(threadIdx.x + 1u) * 16u <= dst_bytes) reinterpret_cast<uint4 *>(dst + off)[threadIdx.x] = v;
+    }
+}
+
+// flags[b] = block b of src holds a non-zero byte; one warp per block (src is 16-byte aligned, bytes a multiple of 4)
+__global__ void __launch_bounds__(256) wah_flag_blocks_kernel(const char *src, uint64_t bytes, uint8_t *flags, uint64_t n_blocks)
+{
+    const uint32_t lane = threadIdx.x & 31u;
+    for (uint64_t b = (uint64_t)blockIdx.x * 8u + (threadIdx.x >> 5); b < n_blocks; b += (uint64_t)gridDim.x * 8u) {
+        const uint64_t lo = b * XBLK;
+        uint32_t any = 0;
+        if (lo + XBLK <= bytes) {
+            const uint4 *q = reinterpret_cast<const uint4 *>(src + lo);
+#pragma unroll
+            for (int k = 0; k < 8; k++) {
+                const uint4 v = ld_stream_v4(q + lane + 32 * k);
+                any |= v.x | v.y | v.z | v.w;
+            }
+        } else {
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(src + lo);
+            for (uint64_t i = lane; lo + 4ull * i < bytes; i += 32) any |= q[i];
+        }
+        any = __any_sync(0xffffffffu, any != 0u);
+        if (lane == 0) flags[b] = (uint8_t)any;
+    }
+}
+
+// per chunk of `per_chunk` blocks (<= 4096): lists[chunk][i] = number (within the chunk) of its i-th non-zero block,
+// counts[chunk] = how many; one CTA of 1024 threads per chunk, four flags per thread
+__global__ void __launch_bounds__(1024) wah_list_blocks_kernel(const uint8_t *flags, uint64_t n_blocks, uint32_t per_chunk, uint32_t *lists,
+                                                               uint32_t *counts)
+{
+    __shared__ uint32_t s_w[32];
+    const uint64_t base = (uint64_t)blockIdx.x * per_chunk;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    uint32_t f[4], mine = 0;
+#pragma unroll
+    for (int i = 0; i < 4; i++) {
+        const uint32_t k = 4u * t + i;
+        f[i] = (k < per_chunk && base + k < n_blocks) ? flags[base + k] : 0u;
+        mine += f[i];
+    }
+    const uint32_t incl = warp_incl_scan(mine);
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint32_t before = incl - mine, total = 0;
+#pragma unroll
+    for (int k = 0; k < 32; k++) {
+        const uint32_t v = s_w[k];
+        if (k < (int)warp) before += v;
+        total += v;
+    }
+    uint32_t *list = lists + (uint64_t)blockIdx.x * per_chunk;
+#pragma unroll
+    for (int i = 0; i < 4; i++)
+        if (f[i]) list[before++] = 4u * t + i;
+    if (t == 0) counts[blockIdx.x] = total;
+}
+
+// packed[chunk][i] = block lists[chunk][i] of the chunk; grid.y = chunk, CTAs of 256 threads walk the list
+__global__ void __launch_bounds__(256) wah_pack_blocks_kernel(const char *src, uint64_t bytes, uint32_t per_chunk, const uint32_t *lists,
+                                                              const uint32_t *counts, char *packed)
+{
+    const uint32_t chunk = blockIdx.y, n = counts[chunk];
+    const uint32_t *list = lists + (uint64_t)chunk * per_chunk;
+    const uint64_t cbase = (uint64_t)chunk * per_chunk * XBLK;
+    for (uint32_t i = blockIdx.x; i < n; i += gridDim.x) {
+        const uint64_t off = cbase + (uint64_t)list[i] * XBLK + 16ull * threadIdx.x;
+        uint4 v = make_uint4(0u, 0u, 0u, 0u);
+        if (off + 16u <= bytes) {
+            v = ld_stream_v4(reinterpret_cast<const uint4 *>(src + off));
+        } else if (off < bytes) {   // the vector's last, partial 16 bytes (bytes is a multiple of 4)
+            const uint32_t *q = reinterpret_cast<const uint32_t *>(src + off);
+            v.x = q[0];
+            if (off + 8u <= bytes) v.y = q[1];
+            if (off + 12u <= bytes) v.z = q[2];
+        }
+        reinterpret_cast<uint4 *>(packed + cbase + (uint64_t)i * XBLK)[threadIdx.x] = v;
+    }
+}
+
+cudaError_t launch_scatter_blocks(void *d_dst, uint64_t dst_bytes, const void *d_packed, const uint32_t *d_list, uint32_t n,
+                                  cudaStream_t stream)
+{
+    if (n == 0) return cudaSuccess;
+    wah_scatter_blocks_kernel<<<n < 4096u ? n : 4096u, 256, 0, stream>>>((char *)d_dst, dst_bytes, (const char *)d_packed, d_list, n);
+    return cudaGetLastError();
+}
+
+cudaError_t launch_pack_nonzero_blocks(const void *d_src, uint64_t bytes, uint32_t blocks_per_chunk, uint8_t *d_flags, uint32_t *d_lists,
+                                       uint32_t *d_counts, void *d_packed, cudaStream_t stream)
+{
+    const uint64_t n_blocks = (bytes + XBLK - 1) / XBLK;
+    if (n_blocks == 0) return cudaSuccess;
+    if (blocks_per_chunk == 0 || blocks_per_chunk > 4096u) return cudaErrorInvalidValue;
+    const uint32_t n_chunks = (uint32_t)((n_blocks + blocks_per_chunk - 1) / blocks_per_chunk);
+    const uint64_t g = (n_blocks + 7) / 8;
+    wah_flag_blocks_kernel<<<(unsigned)(g < 148ull * 16 ? g : 148ull * 16), 256, 0, stream>>>((const char *)d_src, bytes, d_flags, n_blocks);
+    wah_list_blocks_kernel<<<n_chunks, 1024, 0, stream>>>(d_flags, n_blocks, blocks_per_chunk, d_lists, d_counts);
+    wah_pack_blocks_kernel<<<dim3(64, n_chunks), 256, 0, stream>>>((const char *)d_src, bytes, blocks_per_chunk, d_lists, d_counts, (char *)d_packed);
+    return cudaGetLastError();
+}
+
 cudaError_t launch_shard_probe(const uint32_t *d_shard, uint64_t words, uint64_t *d_result, cudaStream_t stream)
 {
     wah_shard_probe_kernel<<<1, 32, 0, stream>>>(d_shard, words, d_result);

@@ -100,6 +100,7 @@ _sig("wah_free", None, _vp)
 _sig("wah_compress_host_into", ctypes.c_int, _vp, _u64, ctypes.c_int, _vp, _u64, ctypes.POINTER(_u64))
 _sig("wah_decompress_host_into", ctypes.c_int, _vp, _u64, _vp, _u64, ctypes.POINTER(_u64))
 _sig("wah_host_release", None)
+_sig("wah_host_last_transfer_bytes", None, ctypes.POINTER(_u64), ctypes.POINTER(_u64))
 _sig("wah_shard_record_device", ctypes.c_int, _vp, _u64, _u64, ctypes.POINTER(ShardRecord), _vp)
 _sig("wah_stitch_plan", ctypes.c_int, ctypes.POINTER(ShardRecord), ctypes.c_int, ctypes.c_int,
      ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(_u64), ctypes.POINTER(ctypes.c_uint32),
@@ -158,6 +159,13 @@ def _host_u32(a) -> np.ndarray:
     return a
 
 
+def _moved():
+    """bytes the last host entry point moved over PCIe, each way (all-zero 4 KiB blocks do not travel)"""
+    a, b = _u64(), _u64()
+    lib.wah_host_last_transfer_bytes(ctypes.byref(a), ctypes.byref(b))
+    return {"h2d_bytes": a.value, "d2h_bytes": b.value}
+
+
 def compress(data, mode: int = WAH_BLOCK1024, timings: dict | None = None) -> np.ndarray:
     """WAH-compress a host array of 32-bit words (reference: compress(), compress.cu:41-209).
 
@@ -169,7 +177,7 @@ def compress(data, mode: int = WAH_BLOCK1024, timings: dict | None = None) -> np
     _check(lib.wah_compress_host(a.ctypes.data, a.size, mode, ctypes.byref(out), ctypes.byref(c),
                                  ctypes.byref(t[0]), ctypes.byref(t[1]), ctypes.byref(t[2])))
     if timings is not None:
-        timings.update(h2d_ms=t[0].value, compute_ms=t[1].value, d2h_ms=t[2].value)
+        timings.update(h2d_ms=t[0].value, compute_ms=t[1].value, d2h_ms=t[2].value, **_moved())
     return _wrap_malloced(out.value, c.value)
 
 
@@ -182,7 +190,7 @@ def decompress(data, timings: dict | None = None) -> np.ndarray:
     _check(lib.wah_decompress_host(a.ctypes.data, a.size, ctypes.byref(out), ctypes.byref(n),
                                    ctypes.byref(t[0]), ctypes.byref(t[1]), ctypes.byref(t[2])))
     if timings is not None:
-        timings.update(h2d_ms=t[0].value, compute_ms=t[1].value, d2h_ms=t[2].value)
+        timings.update(h2d_ms=t[0].value, compute_ms=t[1].value, d2h_ms=t[2].value, **_moved())
     return _wrap_malloced(out.value, n.value)
 
 

@@ -121,7 +121,10 @@ int wah_decoded_size_device(const uint32_t *d_in, uint64_t c_words, uint64_t *d_
  * H2D(+allocation) / compute / D2H(+release), like the reference's out-params
  * (compress.cu:205-207, decompress.cu:136-138).  Page-locked inputs are DMAed directly; pageable
  * memory moves through a ring of pinned bounce buffers filled by a few copy threads
- * (WAH_B200_COPY_THREADS, default min(16, cores)).  Calls are serialised by a process-wide lock. */
+ * (WAH_B200_COPY_THREADS, default min(16, cores)).  Transfers of 8 MiB and more are sparse: 4 KiB
+ * blocks that are all zero do not cross PCIe (the device input is cleared first, the malloc()ed
+ * result comes from calloc()); WAH_B200_SPARSE_COPY=0 moves every byte.  Calls are serialised by a
+ * process-wide lock.                                                                              */
 int wah_compress_host(const uint32_t *h_in, uint64_t n_words, int mode,
                       uint32_t **h_out, uint64_t *out_words,
                       float *ms_h2d, float *ms_compute, float *ms_d2h);
@@ -140,6 +143,8 @@ int wah_decompress_host_into(const uint32_t *h_in, uint64_t c_words,
 /* The host entry points keep their device buffers, pinned bounce buffers and copy threads between
  * calls (the reference allocates and frees everything per call); this releases them.            */
 void wah_host_release(void);
+/* bytes the last host entry point of this process moved over PCIe, each way */
+void wah_host_last_transfer_bytes(uint64_t *h2d_bytes, uint64_t *d2h_bytes);
 
 /* ---- range sharding of one vector across GPUs ------------------------ */
 

@@ -23,8 +23,8 @@ a = ap.parse_args()
 if not a.one:
     thp = open("/sys/kernel/mm/transparent_hugepage/enabled").read().strip() if os.path.exists("/sys/kernel/mm/transparent_hugepage/enabled") else "?"
     print("transparent_hugepage:", thp, " cores:", len(os.sched_getaffinity(0)), flush=True)
-    for st in ("0", "1", "2", "3"):
-        env = dict(os.environ, WAH_B200_RESULT=st)
+    for st, sp in (("0", "0"), ("1", "0"), ("2", "0"), ("2", "1")):
+        env = dict(os.environ, WAH_B200_RESULT=st, WAH_B200_SPARSE_COPY=sp)
         subprocess.run([sys.executable, __file__, "--one", "--log2n", str(a.log2n), "--density", str(a.density), "--steps", str(a.steps)], env=env, check=False)
     sys.exit(0)
 
@@ -64,6 +64,8 @@ for _ in range(a.steps):
     for i in range(6):
         seg[i] += fl[i].value
 dt = (time.perf_counter() - t0) / a.steps
-print(json.dumps({"strategy": os.environ.get("WAH_B200_RESULT"), "ms_per_step": round(dt * 1e3, 2), "gbs": round(8.0 * n / dt / 1e9, 2),
+mv_h, mv_d = ctypes.c_uint64(), ctypes.c_uint64()
+lib.wah_host_last_transfer_bytes(ctypes.byref(mv_h), ctypes.byref(mv_d))
+print(json.dumps({"strategy": os.environ.get("WAH_B200_RESULT"), "sparse_copy": os.environ.get("WAH_B200_SPARSE_COPY"), "last_d2h_mb": round(mv_d.value / 1e6, 1), "ms_per_step": round(dt * 1e3, 2), "gbs": round(8.0 * n / dt / 1e9, 2),
                   "c_h2d": round(seg[0] / a.steps, 2), "c_d2h": round(seg[2] / a.steps, 2), "d_h2d": round(seg[3] / a.steps, 2),
                   "d_compute": round(seg[4] / a.steps, 2), "d_d2h": round(seg[5] / a.steps, 2)}), flush=True)

@@ -272,16 +272,19 @@ struct DecodeJob {
     uint64_t out_cap;
     uint64_t n_cols, col_groups, col_stride;
     bool expand;
+    bool table_only = false;   // the scan phase alone, but with the output-tile table (out_cap sizes it): the logical operators
+    ScanParams *scan_out = nullptr;   // receives the launch's parameters (epoch, header, table)
 };
 
 static int decode_launch(const DecodeJob &job, uint64_t *d_out_info, void *d_workspace, size_t workspace_bytes,
                          cudaStream_t stream)
 {
     const bool batch = job.col_groups != ~0ull;
-    const uint64_t tpc = batch ? ceil_div(job.col_groups, EXPAND_TILE_GROUPS) : (job.expand ? max_out_tiles(job.out_cap) : 0);
+    const bool table = job.expand || job.table_only;
+    const uint64_t tpc = batch ? ceil_div(job.col_groups, EXPAND_TILE_GROUPS) : (table ? max_out_tiles(job.out_cap) : 0);
     if (tpc > 0xFFFFFFF0ull || job.n_cols > 0xFFFFFFF0ull || job.n_cols * tpc > 0xFFFFFFF0ull)
         return fail(WAH_ERR_INVALID, "too many output tiles for one launch");
-    const uint64_t entries = job.expand ? job.n_cols * tpc : 0;
+    const uint64_t entries = table ? job.n_cols * tpc : 0;
     const size_t need = decode_ws_bytes(job.c_words, entries);
     if (workspace_bytes < need) return fail(WAH_ERR_CAPACITY, "workspace too small: %zu < %zu", workspace_bytes, need);
     if (scan_tiles(job.c_words) > 0x7FFFFFFFull) return fail(WAH_ERR_INVALID, "compressed stream too long");
@@ -298,7 +301,7 @@ static int decode_launch(const DecodeJob &job, uint64_t *d_out_info, void *d_wor
     sp.desc = reinterpret_cast<ulonglong2 *>(ws + ws_desc_off());
     sp.excl = sp.desc + scan_tiles(job.c_words);
     sp.epoch = next_epoch();
-    sp.starts = job.expand ? reinterpret_cast<ulonglong2 *>(ws + ws_starts_off(job.c_words)) : nullptr;
+    sp.starts = table ? reinterpret_cast<ulonglong2 *>(ws + ws_starts_off(job.c_words)) : nullptr;
     sp.max_out_tiles = tpc;
     sp.out_info = d_out_info;
     sp.col_groups = job.col_groups;
@@ -308,6 +311,9 @@ static int decode_launch(const DecodeJob &job, uint64_t *d_out_info, void *d_wor
     CUDA_TRY(order.status());
     CUDA_TRY(order.counter_slots(&sp.ctr, &sp.next_ctr));
     if (!job.expand) {
+        sp.scan_only = 1;
+        sp.chunk_tiles = 1;   // (a table entry for every tile, long fills included)
+        if (job.scan_out) *job.scan_out = sp;
         CUDA_TRY(launch_scan(sp, stream));
         return WAH_OK;
     }
@@ -519,11 +525,100 @@ extern "C" int wah_popcount_device(const uint32_t *d_in, uint64_t c_words, uint6
 static size_t logical_operand_bytes(uint64_t n_words) { return (size_t)((n_words + 8 + 3) / 4 * 4) * 4; }
 static size_t align256(size_t v) { return (v + 255) & ~(size_t)255; }
 
+// workspace of the compressed-domain path: the two scans' workspaces (header, tile cells, a table entry per tile), the
+// tiles' word counts and offsets, a slot of 1024 words per tile
+struct LogicalLayout {
+    uint64_t n_tiles;
+    size_t ws_a, ws_b, off_b, off_counts, off_offsets, off_info, off_slots, total;
+};
+static LogicalLayout logical_layout(uint64_t n_words, uint64_t ca_words, uint64_t cb_words)
+{
+    LogicalLayout l;
+    l.n_tiles = ceil_div(wah_num_groups(n_words), EXPAND_TILE_GROUPS);
+    l.ws_a = align256(decode_ws_bytes(ca_words, l.n_tiles));
+    l.ws_b = align256(decode_ws_bytes(cb_words, l.n_tiles));
+    l.off_b = l.ws_a;
+    l.off_counts = l.off_b + l.ws_b;
+    l.off_offsets = l.off_counts + align256(l.n_tiles * 4);
+    l.off_info = l.off_offsets + align256(l.n_tiles * 8);
+    l.off_slots = l.off_info + 256;
+    l.total = l.off_slots + align256(l.n_tiles * (size_t)EXPAND_TILE_GROUPS * 4);
+    return l;
+}
+
+static bool logical_plain()
+{
+    static const bool v = [] {
+        const char *e = getenv("WAH_B200_LOGICAL_PLAIN");
+        return e && e[0] == '1';
+    }();
+    return v;
+}
+
 extern "C" size_t wah_logical_workspace_bytes(uint64_t n_words, uint64_t ca_words, uint64_t cb_words)
 {
     const uint64_t cmax = ca_words > cb_words ? ca_words : cb_words;
-    return 2 * align256(logical_operand_bytes(n_words)) + 256 + align256(wah_decompress_workspace_bytes(cmax, n_words + 8)) +
-           align256(wah_compress_workspace_bytes(n_words));
+    const size_t plain = 2 * align256(logical_operand_bytes(n_words)) + 256 + align256(wah_decompress_workspace_bytes(cmax, n_words + 8)) +
+                         align256(wah_compress_workspace_bytes(n_words));
+    const size_t compressed = logical_layout(n_words, ca_words, cb_words).total;
+    return plain > compressed ? plain : compressed;
+}
+
+// BLOCK1024 result straight from the two streams (wah_decompress.cu, wah_logical_tiles_kernel): neither operand is decoded
+// into HBM; cost proportional to the compressed sizes plus a few instructions per 1024-group tile
+static int logical_compressed(int op, const uint32_t *d_a, uint64_t ca_words, const uint32_t *d_b, uint64_t cb_words, uint64_t n_words,
+                              uint32_t *d_out, uint64_t out_capacity_words, uint64_t *d_out_words, char *ws, cudaStream_t stream)
+{
+    const LogicalLayout l = logical_layout(n_words, ca_words, cb_words);
+    if (l.n_tiles > 0xFFFFFFF0ull) return fail(WAH_ERR_INVALID, "too many tiles for one launch");
+    uint64_t *info = reinterpret_cast<uint64_t *>(ws + l.off_info);
+    ScanParams spa, spb;
+    memset(&spa, 0, sizeof(spa));
+    memset(&spb, 0, sizeof(spb));
+    const uint32_t *ins[2] = {d_a, d_b};
+    const uint64_t cs[2] = {ca_words, cb_words};
+    ScanParams *sps[2] = {&spa, &spb};
+    char *wss[2] = {ws, ws + l.off_b};
+    const size_t wsb[2] = {l.ws_a, l.ws_b};
+    for (int i = 0; i < 2; i++) {
+        if (cs[i] == 0) continue;   // an empty stream: zeros
+        if (!ins[i] || !aligned16(ins[i])) return fail(WAH_ERR_INVALID, "operands must be 16-byte aligned device buffers");
+        DecodeJob job;
+        job.d_in = ins[i];
+        job.c_words = cs[i];
+        job.skip_words = 0;
+        job.d_out = nullptr;
+        job.out_cap = l.n_tiles * (uint64_t)EXPAND_TILE_WORDS;
+        job.n_cols = 1;
+        job.col_groups = ~0ull;
+        job.col_stride = 0;
+        job.expand = false;
+        job.table_only = true;
+        job.scan_out = sps[i];
+        if (int rc = decode_launch(job, info + 4 * i, wss[i], wsb[i], stream)) return rc;
+    }
+    LogicalJob lj;
+    lj.a = d_a;
+    lj.b = d_b;
+    lj.ca = ca_words;
+    lj.cb = cb_words;
+    lj.starts_a = spa.starts;
+    lj.starts_b = spb.starts;
+    lj.hdr_a = spa.hdr;
+    lj.hdr_b = spb.hdr;
+    lj.epoch_a = spa.epoch;
+    lj.epoch_b = spb.epoch;
+    lj.groups = wah_num_groups(n_words);
+    lj.n_tiles = (uint32_t)l.n_tiles;
+    lj.op = op;
+    lj.slots = reinterpret_cast<uint32_t *>(ws + l.off_slots);
+    lj.counts = reinterpret_cast<uint32_t *>(ws + l.off_counts);
+    lj.offsets = reinterpret_cast<uint64_t *>(ws + l.off_offsets);
+    lj.out = d_out;
+    lj.out_cap = out_capacity_words;
+    lj.total = d_out_words;
+    CUDA_TRY(launch_logical_compressed(lj, stream));
+    return WAH_OK;
 }
 
 extern "C" int wah_logical_device(int op, const uint32_t *d_a, uint64_t ca_words, const uint32_t *d_b, uint64_t cb_words,
@@ -536,11 +631,13 @@ extern "C" int wah_logical_device(int op, const uint32_t *d_a, uint64_t ca_words
     if (!d_workspace || !aligned16(d_workspace)) return fail(WAH_ERR_INVALID, "workspace must be a 16-byte aligned device buffer");
     const size_t need = wah_logical_workspace_bytes(n_words, ca_words, cb_words);
     if (workspace_bytes < need) return fail(WAH_ERR_CAPACITY, "workspace too small: %zu < %zu", workspace_bytes, need);
-    // First version: both operands are expanded into scratch, combined word by word, and the result is compressed
-    // again -- three validated kernels and one trivial one, about 5 x 4n bytes of traffic.  Operating on the runs
-    // themselves (a merge of the two streams' group offsets; cost proportional to the compressed sizes) is the next
-    // step; this call's contract will not change with it.
     char *ws = static_cast<char *>(d_workspace);
+    if (mode == WAH_BLOCK1024 && !logical_plain()) {
+        if (!d_out_words || (out_capacity_words && !d_out)) return fail(WAH_ERR_INVALID, "null output");
+        return logical_compressed(op, d_a, ca_words, d_b, cb_words, n_words, d_out, out_capacity_words, d_out_words, ws, stream);
+    }
+    // CANONICAL results (and WAH_B200_LOGICAL_PLAIN=1): both operands are expanded into scratch, combined word by word,
+    // and the result is compressed again -- three validated kernels and one trivial one, about 6 x 4n bytes of traffic.
     const size_t ob = align256(logical_operand_bytes(n_words));
     uint32_t *buf_a = reinterpret_cast<uint32_t *>(ws), *buf_b = reinterpret_cast<uint32_t *>(ws + ob);
     uint64_t *info = reinterpret_cast<uint64_t *>(ws + 2 * ob);

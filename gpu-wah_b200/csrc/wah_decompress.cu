@@ -435,7 +435,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
                     // the last round: every CTA added its malformed-word count before it arrived for its last tile
                     const uint32_t bad = atomicAdd(&p.ctr->bad_acc, 0u);
                     p.hdr->bad_words = bad;
-                    if (p.starts == nullptr) {
+                    if (p.starts == nullptr || p.scan_only) {
                         // size query: nobody arrives any more; leave the counters zeroed for the next launch and
                         // report the status (a full decode does both when its last CTA leaves the expand phase)
                         p.ctr->agg_count = 0;
@@ -637,7 +637,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
         __syncthreads();   // partial sums and the heavy queue are rewritten by the next tile
     }
     // a size query that went wrong says so even if no aggregator of a last round ever gets to report
-    if (tid == 0 && p.starts == nullptr && p.out_info != nullptr && budget == 0u) p.out_info[2] = STATUS_TIMEOUT;
+    if (tid == 0 && (p.starts == nullptr || p.scan_only) && p.out_info != nullptr && budget == 0u) p.out_info[2] = STATUS_TIMEOUT;
 }
 
 __global__ void __launch_bounds__(SCAN_THREADS) wah_scan_kernel(const ScanParams p)
@@ -1197,6 +1197,270 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     }
 }
 
+// ---------------------------------------------------------------- logical operators on two compressed vectors
+//
+// result = compress(decode(a) op decode(b)) in BLOCK1024 mode without either vector ever being decoded into HBM
+// (the specification is wah_oracle_logical, oracle/wah_oracle.c).  Both streams are scanned (the scan
+// phase above, table entries for every tile); then a warp takes a tile of 1024 groups -- one block of the reference
+// encoder (kernels.cu:256,273-280) -- at a time: a tile that lies inside one fill of each operand becomes one fill word
+// without a group being looked at; otherwise the operands' tiles are expanded into two images in shared memory (the
+// window path of the expand phase), combined word by word, and encoded the way the compressor's warp encodes a block
+// (classify, run-end rule, warp scan, compaction: kernels.cu:79,93-141,244-248).  The words of tile t go to slot t of a
+// scratch array; a prefix sum over the tiles' word counts and a gather make the stream.  Traffic: the two streams, the
+// result twice.
+
+constexpr int LOG_IMG_WORDS = EXPAND_TILE_WORDS + 8;                             // an image + the word the last group's extraction touches
+constexpr int LOG_WARP_SMEM_WORDS = CW_WORDS + FLAG_WORDS + 2 * LOG_IMG_WORDS;   // 12.3 KB per warp
+constexpr uint32_t LOG_CONST0 = 1u, LOG_CONST1 = 2u;
+
+struct LogicalParams {
+    const uint32_t *a, *b;
+    uint64_t ca, cb;
+    const ulonglong2 *starts_a, *starts_b;   // one entry per tile (+ 1), written by the two scans
+    const DecodeHeader *hdr_a, *hdr_b;
+    uint32_t epoch_a, epoch_b;
+    uint64_t groups;                          // groups of the vectors the streams stand for
+    uint32_t n_tiles;
+    int op;
+    uint32_t *slots;                          // n_tiles x 1024 words
+    uint32_t *counts;                         // n_tiles
+    unsigned long long *partials;             // words of every 256 tiles (zero at launch)
+};
+
+// Expands the part of tile t (groups g_start .. g_start + tg) that stream `in` covers into `img`; what lies behind the
+// stream's end reads as zeros.  Returns LOG_CONST0 / LOG_CONST1 if the whole tile is zeros / ones without an image.
+__device__ __forceinline__ uint32_t expand_operand(const uint32_t *in, uint64_t c_words, const ulonglong2 *starts, uint32_t epoch,
+                                                   uint64_t G, uint32_t t, uint32_t tg_tile, uint32_t *s_cw, uint32_t *s_flag,
+                                                   uint32_t *img, uint32_t lane)
+{
+    constexpr uint32_t TG = (uint32_t)EXPAND_TILE_GROUPS;
+    const uint64_t g_start = (uint64_t)t << TG_SHIFT;
+    if (c_words == 0 || g_start >= G) return LOG_CONST0;
+    const uint32_t tg = G - g_start < (uint64_t)tg_tile ? (uint32_t)(G - g_start) : tg_tile;
+    uint64_t sx, sy, nx, ny;
+    load_entry(starts + t, epoch, sx, sy);
+    load_entry(starts + t + 1, epoch, nx, ny);
+    if (sx == 0ull) return LOG_CONST0;   // (cannot happen for g_start < G)
+    const bool last = nx == 0ull;        // the stream ends in this tile
+    const uint64_t ws = sx - 1ull, we = last ? c_words - 1ull : nx - 1ull;
+    const uint32_t skip = (uint32_t)(g_start - sy);
+    if (ws == we) {
+        const uint32_t first = in[ws];
+        if (is_fill(first)) {
+            if (!(first & BIT30)) return LOG_CONST0;
+            if (tg == tg_tile) return LOG_CONST1;
+        }
+    }
+    const uint64_t wa = ws & ~3ull;
+    const uint64_t span = we - wa + 1ull;
+    const uint32_t nw = span > 0xFFFFFFF0ull ? 0xFFFFFFF0u : (uint32_t)span;
+    const uint32_t w_beg = (uint32_t)ws & 3u, w_span = nw - 1u - w_beg;
+    const uint32_t *src = in + wa;
+    const uint64_t room = c_words - wa;
+    const bool pad = nw > 256u;
+    s_flag[lane] = 0;
+    if (lane == 0) s_flag[32] = 0;
+    __syncwarp();
+    uint32_t running = 0, rk_run = 0;
+    uint32_t xc[4], xn[4] = {BIT31, BIT31, BIT31, BIT31};
+    load_words<4>(src, 4u * lane, room, xc);
+#pragma unroll 1
+    for (uint32_t r0 = 4u * lane;; r0 += 128u) {
+        const bool more = r0 - 4u * lane + 128u < nw;
+        if (more) load_words<4>(src, r0 + 128u, room, xn);
+        if (pad)
+            park_words<4, true>(xc, r0, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
+        else
+            park_words<4, false>(xc, r0, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
+#pragma unroll
+        for (int i = 0; i < 4; i++) xc[i] = xn[i];
+        if (!more || running >= tg) break;
+    }
+    if (lane == 0 && tg < TG) {
+        const uint32_t re = rk_run <= TG ? rk_run : TG + 1u;
+        if (pad)
+            s_cw[cw_pos(re)] = 0u;
+        else
+            reinterpret_cast<uint2 *>(s_cw)[re] = make_uint2(0u, 0u);
+        atomicOr(s_flag + (tg >> 5), 1u << (tg & 31u));
+    }
+    __syncwarp();
+    const uint32_t F = s_flag[lane];
+    const uint32_t pc = __popc(F);
+    uint32_t r = warp_incl_scan(pc) - pc + (F & 1u) - 1u;
+    uint32_t *o = img + 31u * lane;
+    uint32_t v = pad ? s_cw[cw_pos(r)] : reinterpret_cast<const uint2 *>(s_cw)[r].y;
+    if (!pad) {
+        walk_from<1>((uint32_t)__cvta_generic_to_shared(s_cw) + 8u * r, F, v << 1, v << 1, v, o);
+    } else {
+#pragma unroll
+        for (int jj = 1; jj < 32; jj++) {
+            r += (F >> jj) & 1u;
+            const uint32_t nv = s_cw[cw_pos(r)];
+            o[jj - 1] = __funnelshift_r(v << 1, nv, jj);
+            v = nv;
+        }
+    }
+    __syncwarp();   // image complete; s_cw and the flag map are free again
+    return 0u;
+}
+
+__device__ __forceinline__ uint32_t apply_op(int op, uint32_t x, uint32_t y)
+{
+    return op == 0 ? (x & y) : (op == 1 ? (x | y) : (op == 2 ? (x ^ y) : (x & ~y)));
+}
+
+__global__ void __launch_bounds__(EXPAND_THREADS, 2) wah_logical_tiles_kernel(const LogicalParams p)
+{
+    constexpr uint32_t TG = (uint32_t)EXPAND_TILE_GROUPS, TW = (uint32_t)EXPAND_TILE_WORDS;
+    extern __shared__ __align__(16) uint32_t smem[];
+    const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
+    uint32_t *s_cw = smem + warp * LOG_WARP_SMEM_WORDS;
+    uint32_t *s_flag = s_cw + CW_WORDS;
+    uint32_t *img_a = s_flag + FLAG_WORDS;
+    uint32_t *img_b = img_a + LOG_IMG_WORDS;
+    const uint64_t Ga = p.ca ? p.hdr_a->groups : 0ull, Gb = p.cb ? p.hdr_b->groups : 0ull;
+    const uint32_t GW = gridDim.x * (EXPAND_THREADS / 32), gw = blockIdx.x * (EXPAND_THREADS / 32) + warp;
+    if (lane < 8u) {   // the word the extraction of a row's last group reads behind the image
+        img_a[TW + lane] = 0;
+        img_b[TW + lane] = 0;
+    }
+    for (uint32_t t = gw; t < p.n_tiles; t += GW) {
+        const uint64_t g_start = (uint64_t)t << TG_SHIFT;
+        const uint32_t tg = p.groups - g_start < (uint64_t)TG ? (uint32_t)(p.groups - g_start) : TG;
+        const uint32_t ka = expand_operand(p.a, p.ca, p.starts_a, p.epoch_a, Ga, t, tg, s_cw, s_flag, img_a, lane);
+        const uint32_t kb = expand_operand(p.b, p.cb, p.starts_b, p.epoch_b, Gb, t, tg, s_cw, s_flag, img_b, lane);
+        uint32_t *slot = p.slots + (uint64_t)t * TG;
+        if (ka != 0u && kb != 0u) {
+            // both operands constant over the tile: one fill word, no group looked at
+            const uint32_t r = apply_op(p.op, ka == LOG_CONST1 ? 1u : 0u, kb == LOG_CONST1 ? 1u : 0u) & 1u;
+            if (lane == 0) {
+                slot[0] = fill_word(r, tg);
+                p.counts[t] = 1u;
+                atomicAdd(p.partials + (t >> 8), 1ull);
+            }
+            continue;
+        }
+        // ---- combine, in place in image a
+        {
+            uint32_t *ra = img_a + 31u * lane;
+            const uint32_t *rb = img_b + 31u * lane;
+            const uint32_t fa = ka == LOG_CONST1 ? 0xFFFFFFFFu : 0u, fb = kb == LOG_CONST1 ? 0xFFFFFFFFu : 0u;
+#pragma unroll
+            for (int k = 0; k < 31; k++) ra[k] = apply_op(p.op, ka ? fa : ra[k], kb ? fb : rb[k]);
+        }
+        __syncwarp();
+        // ---- encode the block (the compressor's warp, BLOCK1024 mode)
+        const uint32_t *row = img_a + 31u * lane;
+        uint32_t nvalid = tg > 32u * lane ? tg - 32u * lane : 0u;
+        if (nvalid > 32u) nvalid = 32u;
+        const uint32_t vmask = nvalid == 32u ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);
+        uint32_t Z = 0, O = 0;
+#pragma unroll
+        for (int j = 0; j < 32; j++) {
+            const uint32_t g = extract_group(row, j);
+            Z |= (g == 0u ? 1u : 0u) << j;
+            O |= (g == ONES31 ? 1u : 0u) << j;
+        }
+        Z &= vmask;
+        O &= vmask;
+        const uint32_t F = Z | O;
+        // type of the group after my 32 (the next lane's first); the block's last group has no successor
+        const uint32_t nzb = __shfl_down_sync(0xffffffffu, Z & 1u, 1), nob = __shfl_down_sync(0xffffffffu, O & 1u, 1);
+        const uint32_t nz = (lane != 31u && nzb) ? BIT31 : 0u, no = (lane != 31u && nob) ? BIT31 : 0u;
+        // tail = literal, or fill whose successor differs (run-end rule, kernels.cu:126-141)
+        const uint32_t T = ((~F) & vmask) | (Z & ~((Z >> 1) | nz)) | (O & ~((O >> 1) | no));
+        const uint32_t cnt = __popc(T);
+        const uint32_t my_open = T ? (uint32_t)__clz(T) : 32u;   // groups after my last tail
+        const uint32_t incl = warp_incl_scan(cnt);
+        const uint32_t tb = __ballot_sync(0xffffffffu, T != 0u);
+        const uint32_t below = tb & lanemask_lt();
+        const uint32_t qb = below ? 31u - (uint32_t)__clz(below) : 0u;
+        const uint32_t open_q = __shfl_sync(0xffffffffu, my_open, qb);
+        const uint32_t prev_open = below ? open_q + 32u * (lane - qb - 1u) : 32u * lane;   // run open where my groups start
+        const uint32_t off = incl - cnt;
+        const uint32_t wcnt = __shfl_sync(0xffffffffu, incl, 31);
+        uint32_t m = T & ~F;   // literals: the group itself (kernels.cu:107-112,256)
+        while (m) {
+            const uint32_t j = 31u - (uint32_t)__clz(m);
+            m ^= 1u << j;
+            s_cw[off + __popc(T & ((1u << j) - 1u))] = extract_group(row, j);
+        }
+        m = T & F;             // fills: BIT31 | type << 30 | length (kernels.cu:244-248)
+        while (m) {
+            const uint32_t j = 31u - (uint32_t)__clz(m);
+            m ^= 1u << j;
+            const uint32_t lower = T & ((1u << j) - 1u);
+            const uint32_t len = lower ? j - (31u - (uint32_t)__clz(lower)) : j + 1u + prev_open;
+            s_cw[off + __popc(lower)] = fill_word((O >> j) & 1u, len);
+        }
+        __syncwarp();
+        for (uint32_t i = lane; i < wcnt; i += 32u) slot[i] = s_cw[i];
+        if (lane == 0) {
+            p.counts[t] = wcnt;
+            atomicAdd(p.partials + (t >> 8), (unsigned long long)wcnt);
+        }
+        __syncwarp();
+    }
+}
+
+// exclusive prefix over the words of every 256 tiles, in place (one CTA: a 16 Gbit vector has 2114 of them); total into *total
+__global__ void __launch_bounds__(1024) wah_logical_offsets_kernel(unsigned long long *partials, uint32_t n, uint64_t *total)
+{
+    __shared__ uint64_t s_w[32];
+    __shared__ uint64_t s_base;
+    const uint32_t t = threadIdx.x, lane = t & 31u, warp = t >> 5;
+    if (t == 0) s_base = 0;
+    __syncthreads();
+    for (uint32_t i0 = 0; i0 < n; i0 += 1024u) {
+        const uint64_t mine = i0 + t < n ? partials[i0 + t] : 0ull;
+        const uint64_t incl = warp_incl_scan_u64(mine);
+        if (lane == 31) s_w[warp] = incl;
+        __syncthreads();
+        uint64_t before = s_base + incl - mine, all = 0;
+#pragma unroll
+        for (int k = 0; k < 32; k++) {
+            const uint64_t v = s_w[k];
+            if (k < (int)warp) before += v;
+            all += v;
+        }
+        if (i0 + t < n) partials[i0 + t] = before;
+        __syncthreads();
+        if (t == 0) s_base += all;
+        __syncthreads();
+    }
+    if (t == 0) *total = s_base;
+}
+
+// the stream: CTA b takes tiles 256 b .. 256 b + 255 -- their offsets by a scan of their counts on top of the group's --
+// and copies tile t's words from slot t to their place, a warp per tile
+__global__ void __launch_bounds__(256) wah_logical_gather_kernel(const uint32_t *slots, const uint32_t *counts, const unsigned long long *partials,
+                                                                 uint32_t n_tiles, uint32_t *out, uint64_t out_cap)
+{
+    __shared__ uint32_t s_w[8];
+    __shared__ uint64_t s_off[256];
+    const uint32_t tid = threadIdx.x, lane = tid & 31u, warp = tid >> 5;
+    const uint32_t t0 = blockIdx.x * 256u;
+    const uint32_t mine = t0 + tid < n_tiles ? counts[t0 + tid] : 0u;
+    const uint32_t incl = warp_incl_scan(mine);
+    if (lane == 31) s_w[warp] = incl;
+    __syncthreads();
+    uint64_t before = partials[blockIdx.x] + (incl - mine);
+#pragma unroll
+    for (int k = 0; k < 8; k++)
+        if (k < (int)warp) before += s_w[k];
+    s_off[tid] = before;
+    __syncthreads();
+    // (blockIdx.y: which eighth of the group's tiles this CTA copies -- every CTA of a group does the group's scan)
+    for (uint32_t k = 32u * blockIdx.y + warp; k < 32u * blockIdx.y + 32u && t0 + k < n_tiles; k += 8u) {
+        const uint32_t c = counts[t0 + k];
+        const uint64_t o = s_off[k];
+        const uint32_t *s = slots + (uint64_t)(t0 + k) * EXPAND_TILE_GROUPS;
+        for (uint32_t i = lane; i < c; i += 32u)
+            if (o + i < out_cap) out[o + i] = s[i];
+    }
+}
+
 // Both phases in one persistent launch: every CTA first takes its share of the scan tiles, then its share of the
 // output tiles, each of which waits only for its own two `starts` entries.  Saves a launch, the idle tail / ramp
 // between two kernels, and the wait for the slowest scan tile.
@@ -1347,6 +1611,53 @@ cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStre
     a.chunk_tiles = b.chunk_tiles;   // (the scan phase records the entries of long fills at chunk starts only)
     void *args[] = {&a, &b};
     return launch_pdl((const void *)wah_decode_kernel, grid, EXPAND_THREADS, args, expand_smem_bytes(), stream);
+}
+
+cudaError_t launch_logical_compressed(const LogicalJob &job, cudaStream_t stream)
+{
+    constexpr size_t smem = (size_t)(EXPAND_THREADS / 32) * LOG_WARP_SMEM_WORDS * sizeof(uint32_t);
+    static int grid_of[MAX_DEVICES] = {};
+    int dev = 0;
+    cudaError_t e = current_device(&dev);
+    if (e != cudaSuccess) return e;
+    if (grid_of[dev] == 0) {
+        e = cudaFuncSetAttribute(wah_logical_tiles_kernel, cudaFuncAttributeMaxDynamicSharedMemorySize, (int)smem);
+        if (e != cudaSuccess) return e;
+        int sms = 0, per_sm = 0;
+        e = cudaDeviceGetAttribute(&sms, cudaDevAttrMultiProcessorCount, dev);
+        if (e != cudaSuccess) return e;
+        e = cudaOccupancyMaxActiveBlocksPerMultiprocessor(&per_sm, wah_logical_tiles_kernel, EXPAND_THREADS, smem);
+        if (e != cudaSuccess) return e;
+        if (per_sm < 1) return cudaErrorLaunchOutOfResources;
+        grid_of[dev] = sms * per_sm;
+    }
+    if (job.n_tiles == 0) return cudaMemsetAsync(job.total, 0, sizeof(uint64_t), stream);
+    LogicalParams p;
+    p.a = job.a;
+    p.b = job.b;
+    p.ca = job.ca;
+    p.cb = job.cb;
+    p.starts_a = job.starts_a;
+    p.starts_b = job.starts_b;
+    p.hdr_a = job.hdr_a;
+    p.hdr_b = job.hdr_b;
+    p.epoch_a = job.epoch_a;
+    p.epoch_b = job.epoch_b;
+    p.groups = job.groups;
+    p.n_tiles = job.n_tiles;
+    p.op = job.op;
+    p.slots = job.slots;
+    p.counts = job.counts;
+    p.partials = reinterpret_cast<unsigned long long *>(job.offsets);
+    const uint32_t n_groups = (job.n_tiles + 255u) / 256u;   // groups of 256 tiles
+    e = cudaMemsetAsync(job.offsets, 0, (size_t)n_groups * 8, stream);
+    if (e != cudaSuccess) return e;
+    const uint32_t want = (job.n_tiles + 7u) / 8u;
+    const int grid = (int)(want < (uint32_t)grid_of[dev] ? want : (uint32_t)grid_of[dev]);
+    wah_logical_tiles_kernel<<<grid, EXPAND_THREADS, smem, stream>>>(p);
+    wah_logical_offsets_kernel<<<1, 1024, 0, stream>>>(p.partials, n_groups, job.total);
+    wah_logical_gather_kernel<<<dim3(n_groups, 8), 256, 0, stream>>>(job.slots, job.counts, p.partials, job.n_tiles, job.out, job.out_cap);
+    return cudaGetLastError();
 }
 
 }  // namespace wahb200

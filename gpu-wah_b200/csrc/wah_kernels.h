@@ -106,6 +106,7 @@ struct ScanParams {
     uint32_t n_cols;
     DecodeCounters *next_ctr;   // the slot the NEXT launch will use: zeroed by this launch's first CTA
     uint32_t chunk_tiles;    // == ExpandParams::chunk_tiles (0 for a size query)
+    uint32_t scan_only;      // the scan phase alone (wah_scan_kernel): its last round leaves the counters zeroed and reports the status
     uint64_t *trace;         // nullptr; -DWAH_TRACE builds only
 };
 
@@ -135,6 +136,25 @@ size_t expand_smem_bytes();
 cudaError_t scan_tile_words(uint64_t c_words, uint32_t *tile_words);
 cudaError_t launch_scan(const ScanParams &p, cudaStream_t stream);
 cudaError_t launch_decode(const ScanParams &sp, const ExpandParams &ep, cudaStream_t stream);   // scan + expand, one launch
+
+// a op b on two compressed vectors, BLOCK1024 result (wah_decompress.cu); both streams scanned with a table entry per tile
+struct LogicalJob {
+    const uint32_t *a, *b;
+    uint64_t ca, cb;
+    const ulonglong2 *starts_a, *starts_b;
+    const DecodeHeader *hdr_a, *hdr_b;
+    uint32_t epoch_a, epoch_b;
+    uint64_t groups;
+    uint32_t n_tiles;
+    int op;
+    uint32_t *slots;       // n_tiles x 1024 words of scratch
+    uint32_t *counts;      // n_tiles
+    uint64_t *offsets;     // ceil(n_tiles / 256): words before every 256 tiles
+    uint32_t *out;
+    uint64_t out_cap;
+    uint64_t *total;       // device u64: words of the result
+};
+cudaError_t launch_logical_compressed(const LogicalJob &job, cudaStream_t stream);
 
 // launch with programmatic stream serialisation (see pdl_wait in wah_common.cuh)
 inline cudaError_t launch_pdl(const void *kernel, int grid, int threads, void **args, size_t smem, cudaStream_t stream)

@@ -698,3 +698,28 @@ def test_host_entry_points_move_only_nonzero_blocks(name, gen):
         assert td["d2h_bytes"] <= nonzero_blocks * 4100 + 64 and td["d2h_bytes"] >= nonzero_blocks * 4096 - 4096
         if nonzero_blocks < all_blocks // 2:
             assert tc["h2d_bytes"] < 4 * n // 2 and td["d2h_bytes"] < 4 * n // 2
+
+
+@pytest.mark.parametrize("mode", MODES)
+def test_logical_operator_zero_extends_a_short_operand(mode):
+    """An operand whose stream decodes to fewer groups than the vectors have counts as zero-extended (wah_oracle_logical,
+    oracle/wah_oracle.c: cur_next); so does an empty stream.  Tiles behind the short operand's end, the tile its end falls
+    into, and long fills that cover many tiles all go through the compressed-domain path in BLOCK1024 mode."""
+    n = 7 * TW + 333
+    a = np.concatenate([datagen.clustered(3 * TW, 0.3, 500, 51), np.full(2 * TW, 0xFFFFFFFF, dtype=np.uint32),
+                        datagen.uniform(2 * TW + 333, 0.02, 52)])
+    short = datagen.clustered(2 * TW + 100, 0.4, 300, 53)
+    b_full = np.concatenate([short, np.zeros(n - short.size, dtype=np.uint32)])
+    ca = orc.compress(a, mode)
+    cap = wah.max_compressed_words(n)
+    d_out = torch.full((cap,), -1, dtype=torch.int32, device="cuda")
+    d_cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
+    for cb in (orc.compress(short, mode), np.zeros(0, dtype=np.uint32)):
+        want_b = b_full if cb.size else np.zeros(n, dtype=np.uint32)
+        d_a, d_b = to_dev(ca), (to_dev(cb) if cb.size else torch.zeros(4, dtype=torch.int32, device="cuda"))
+        ws = wah.Workspace.for_logical(n, ca.size, cb.size)
+        for op, f in _NP_OPS.items():
+            wah.logical_device(op, d_a, ca.size, d_b, cb.size, n, d_out, cap, d_cnt, ws, mode)
+            c = int(d_cnt.item())
+            want = orc.compress(f(a, want_b), mode)
+            assert c == want.size and np.array_equal(to_host(d_out[:c]), want), (op, cb.size)

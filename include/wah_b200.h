@@ -188,7 +188,10 @@ int wah_popcount_device(const uint32_t *d_in, uint64_t c_words, uint64_t *d_bits
 #define WAH_OP_ANDNOT 3 /* a & ~b */
 /* out = compress(decompress(a) op decompress(b)) for two streams that stand for vectors of n_words words each (a
  * stream that decodes to fewer words counts as zero-extended), in either encoder mode; bit-identical to what
- * wah_compress_device produces for the combined vector.  This version expands both operands into the workspace;
+ * wah_compress_device produces for the combined vector.  A WAH_BLOCK1024 result is made from the two streams
+ * directly -- neither operand is decoded into HBM: tiles of 1024 groups that lie inside fills of both operands become
+ * one fill word each, the others are expanded, combined and encoded in shared memory; a WAH_CANONICAL result (or
+ * WAH_B200_LOGICAL_PLAIN=1) expands both operands into the workspace, combines them and compresses the result.
  * d_out / d_out_words / capacity as for wah_compress_device.  Asynchronous on `stream`.                       */
 size_t wah_logical_workspace_bytes(uint64_t n_words, uint64_t ca_words, uint64_t cb_words);
 int wah_logical_device(int op, const uint32_t *d_a, uint64_t ca_words, const uint32_t *d_b, uint64_t cb_words,

@@ -364,6 +364,9 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
         // its words: boundary k * 8192 falls on word (k * 8192 - excl) of the tile.  (Single stream only.)
         const bool unit_tile = !batch && w_last > w_first && tile_sum == w_last - w_first;
         const bool pre_scan = p.starts != nullptr && !unit_tile && nsub == 1u;
+        // a tile of several sub-tiles is read again in pass 2: its first sub-tile is requested now, while the offset is on its way
+        const bool refetch = p.starts != nullptr && !unit_tile && nsub > 1u;
+        if (refetch) fetch_sub(0);
 #ifdef WAH_TRACE
         if (p.trace && tid == 0 && first_tile) {
             p.trace[(uint64_t)blockIdx.x * 64u + 48u] = ((uint64_t)unit_tile << 63) | ((uint64_t)nsub << 48) | tile_sum;
@@ -526,7 +529,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
             ColumnCursor rcur;          // (uniform) the column that holds the row at hand
             rcur.base = 0;
             rcur.j = 0;
-            fetch_sub(0);
+            // (sub-tile 0 was requested before the offset exchange)
 #pragma unroll 1
             for (uint32_t sub = 0; sub < nsub; sub++) {
                 if (sub + 1u < nsub) {
@@ -538,11 +541,13 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
                 geometry(sub);
                 if (ragged) patch_sub(sub);
                 if (!skip_rows) {
-                    // (most rows hold a boundary: every row is scanned, 64-bit)
+                    // (most rows hold a boundary: every row is scanned -- in 32-bit arithmetic relative to the row unless
+                    //  the warp's eight rows hold 2^32 groups or more)
                     uint64_t lsub = 0;
 #pragma unroll 2
-                    for (uint32_t v = 0; v < nv; v++) lsub += pack_groups(*my_pack(sub & 1u, v));
+                    for (uint32_t v = 0; v < nv; v++) lsub += pack_groups32(*my_pack(sub & 1u, v));
                     const uint64_t wsub = warp_sum_u64(lsub);
+                    const bool narrow = wsub < (1ull << 32);
                     __syncthreads();   // s_wsum: the previous sub-tile's (or pass 1's) sums have been consumed
                     if (lane == 0) s_wsum[warp] = wsub;
                     __syncthreads();
@@ -556,16 +561,26 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
 #pragma unroll 1
                     for (uint32_t v = 0; v < nv; v++) {
                         const uint4 x = *my_pack(sub & 1u, v);
-                        const uint64_t sl = pack_groups(x);
-                        const uint64_t incl = warp_incl_scan_u64(sl);
-                        const uint64_t off = row_base + incl - sl;
+                        uint64_t sl, off, rsum;
+                        if (narrow) {
+                            const uint32_t s32 = pack_groups32(x);
+                            const uint32_t i32 = warp_incl_scan(s32);
+                            sl = s32;
+                            off = row_base + (uint64_t)(i32 - s32);
+                            rsum = __shfl_sync(0xffffffffu, i32, 31);
+                        } else {
+                            sl = pack_groups(x);
+                            const uint64_t incl = warp_incl_scan_u64(sl);
+                            off = row_base + incl - sl;
+                            rsum = __shfl_sync(0xffffffffu, incl, 31);
+                        }
                         col_seek(cur, off, geo.cg);
                         const uint64_t rel = off - cur.base;
                         const uint64_t kf = (rel + TGM) >> TG_SHIFT, ke = (rel + sl + TGM) >> TG_SHIFT;
                         if (kf != ke || rel + sl > geo.cg)   // a boundary in my 4 words
                             note_boundaries(p.starts, p.epoch, geo, cur, batch, kf, ke, seg_begin + (uint64_t)(v * 32u + lane) * 4u, off, x,
                                             s_heavy, &s_nheavy);
-                        row_base += __shfl_sync(0xffffffffu, incl, 31);
+                        row_base += rsum;
                     }
                     continue;
                 }

@@ -746,10 +746,7 @@ __device__ __forceinline__ void park_words(const uint32_t (&x)[W], uint32_t r0, 
         //  consecutive -- but reads as zeros: behind a short tile lies padding)
         if (c[i] != 0u && off <= tg) {
             const uint32_t gb = off < tg ? group_bits(x[i]) : 0u;
-            if (PAD)
-                s_cw[cw_pos(rk)] = gb;
-            else
-                reinterpret_cast<uint2 *>(s_cw)[rk] = make_uint2(gb << 1, gb);   // both operand forms of the repack, one 8-byte load in the walk
+            s_cw[PAD ? cw_pos(rk) : rk] = gb;
             atomicOr(s_flag + (off >> 5), 1u << (off & 31u));
         }
         rk += c[i] != 0u ? 1u : 0u;
@@ -757,29 +754,31 @@ __device__ __forceinline__ void park_words(const uint32_t (&x)[W], uint32_t r0, 
     }
 }
 
-// The walk of the window path over words parked 8 bytes apart as {bits << 1, bits}: group JJ of the lane's window.  Where
-// the flag map says a word starts, the address steps to it and one 8-byte load brings both operand forms -- both under
-// the flag's predicate: a lane inside a fill issues no load at all, so a shared-memory request serves the two or three
-// lanes that change word at this step instead of all 32 (measured: the unconditional load kept the shared-memory pipe
-// 70 % busy, two wavefronts per request plus bank conflicts).  One funnel shift makes output word
-// JJ - 1 = group JJ-1 >> (JJ-1) | group JJ << (32-JJ) (kernels.cu:375).
+// The walk of the window path: group JJ of the lane's window.  Where the flag map says a word starts, the address steps
+// to it and the word's group bits are loaded -- both under the flag's predicate (the flag bits go into predicate registers
+// seven at a time, R2P): a lane inside a fill issues no load at all, so a shared-memory request serves the two or three
+// lanes that change word at this step instead of all 32 (measured: unconditional loads kept the shared-memory pipe 70 %
+// busy).  One shift and one funnel shift make output word JJ - 1 = group JJ-1 >> (JJ-1) | group JJ << (32-JJ)
+// (kernels.cu:375).  Five instructions per group.  (Parking both operand forms, {bits << 1, bits}, and loading 8 bytes
+// saved the shift but cost two register moves per step: a predicated load of a register pair.)
 template <int JJ>
-__device__ __forceinline__ void walk_from(uint32_t a, uint32_t F, uint32_t lo, uint32_t cx, uint32_t cy, uint32_t *o)
+__device__ __forceinline__ void walk_from(uint32_t a, uint32_t F, uint32_t v, uint32_t *o)
 {
     if constexpr (JJ < 32) {
+        const uint32_t lo = v << 1;
         asm volatile(
             "{\n\t"
             ".reg .pred q;\n\t"
             ".reg .b32 t;\n\t"
-            "and.b32 t, %3, %4;\n\t"
+            "and.b32 t, %2, %3;\n\t"
             "setp.ne.u32 q, t, 0;\n\t"
-            "@q add.u32 %0, %0, 8;\n\t"
-            "@q ld.shared.v2.u32 {%1, %2}, [%0];\n\t"
+            "@q add.u32 %0, %0, 4;\n\t"
+            "@q ld.shared.u32 %1, [%0];\n\t"
             "}"
-            : "+r"(a), "+r"(cx), "+r"(cy)
+            : "+r"(a), "+r"(v)
             : "r"(F), "n"(1u << JJ));
-        o[JJ - 1] = __funnelshift_r(lo, cy, JJ);
-        walk_from<JJ + 1>(a, F, cx, cx, cy, o);
+        o[JJ - 1] = __funnelshift_r(lo, v, JJ);
+        walk_from<JJ + 1>(a, F, v, o);
     }
 }
 
@@ -1083,7 +1082,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 __syncwarp();
                 // a tile of many words is literal dense: neighbouring lanes of the walk then read words about 32 ranks apart, and
                 // the words are parked in rows of 32 padded to 33 (cw_pos) to keep those reads on different banks
-                const bool pad = nw_t > 256u;   // (unpadded: 8 bytes per word, ranks 0 .. 259)
+                const bool pad = nw_t > 256u;
                 uint32_t running = 0;   // group offset (tile relative) of the round's first word
                 uint32_t rk_run = 0;    // words of earlier rounds that hold at least one group
                 if (nw_t <= 32u) {
@@ -1122,10 +1121,7 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                     if (tg < TG) {
                         // a short tile (the end of a column / of the stream): what lies behind it reads as a zero fill
                         const uint32_t re = rk_run <= TG ? rk_run : TG + 1u;
-                        if (pad)
-                            s_cw[cw_pos(re)] = 0u;
-                        else
-                            reinterpret_cast<uint2 *>(s_cw)[re] = make_uint2(0u, 0u);
+                        s_cw[pad ? cw_pos(re) : re] = 0u;
                         atomicOr(s_flag + (tg >> 5), 1u << (tg & 31u));
                     }
                     bulk_wait_read<0>();   // the previous tile's bulk store has read the image
@@ -1137,13 +1133,10 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
                 uint32_t r = warp_incl_scan(pc) - pc + (F & 1u) - 1u;   // rank of the word that covers my first group
                 DCHK(r <= TG + 1u, 2, r);
                 uint32_t *o = s_stage + 31u * lane;
-                uint32_t v = pad ? s_cw[cw_pos(r)] : reinterpret_cast<const uint2 *>(s_cw)[r].y;
+                uint32_t v = s_cw[pad ? cw_pos(r) : r];
                 if (__any_sync(0xffffffffu, (F >> 1) != 0u)) {
                     if (!pad) {
-                        // (the words are parked as {bits << 1, bits}: the two forms in which a group enters the two output words it
-                        //  contributes to -- one 8-byte load per group, no shift; the address advances by predicate)
-                        const uint32_t a = (uint32_t)__cvta_generic_to_shared(s_cw) + 8u * r;
-                        walk_from<1>(a, F, v << 1, v << 1, v, o);
+                        walk_from<1>((uint32_t)__cvta_generic_to_shared(s_cw) + 4u * r, F, v, o);
                     } else {
 #pragma unroll
                         for (int jj = 1; jj < 32; jj++) {
@@ -1293,10 +1286,7 @@ __device__ __forceinline__ uint32_t expand_operand(const uint32_t *in, uint64_t 
     }
     if (lane == 0 && tg < TG) {
         const uint32_t re = rk_run <= TG ? rk_run : TG + 1u;
-        if (pad)
-            s_cw[cw_pos(re)] = 0u;
-        else
-            reinterpret_cast<uint2 *>(s_cw)[re] = make_uint2(0u, 0u);
+        s_cw[pad ? cw_pos(re) : re] = 0u;
         atomicOr(s_flag + (tg >> 5), 1u << (tg & 31u));
     }
     __syncwarp();
@@ -1304,9 +1294,9 @@ __device__ __forceinline__ uint32_t expand_operand(const uint32_t *in, uint64_t 
     const uint32_t pc = __popc(F);
     uint32_t r = warp_incl_scan(pc) - pc + (F & 1u) - 1u;
     uint32_t *o = img + 31u * lane;
-    uint32_t v = pad ? s_cw[cw_pos(r)] : reinterpret_cast<const uint2 *>(s_cw)[r].y;
+    uint32_t v = s_cw[pad ? cw_pos(r) : r];
     if (!pad) {
-        walk_from<1>((uint32_t)__cvta_generic_to_shared(s_cw) + 8u * r, F, v << 1, v << 1, v, o);
+        walk_from<1>((uint32_t)__cvta_generic_to_shared(s_cw) + 4u * r, F, v, o);
     } else {
 #pragma unroll
         for (int jj = 1; jj < 32; jj++) {

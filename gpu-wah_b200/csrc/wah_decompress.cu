@@ -1042,9 +1042,9 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
             if (nw_t <= 128u) {
                 // A tile of zero fills and literals only (uniformly sparse data): no walk.  The image is cleared and every
                 // literal ORs its 31 bits into the one or two output words they fall into; zero fills cost nothing.
-                bool one_fill = false;
-#pragma unroll
-                for (int i = 0; i < 4; i++) one_fill = one_fill || ((4u * lane + i - w_beg) <= w_span && (xc[i] >> 30) == 3u);
+                // (a one-fill among the up to three words of the first / last pack that belong to the neighbouring tiles
+                //  sends the tile down the window path for nothing: not worth a range check per word)
+                const bool one_fill = (xc[0] & xc[0] << 1 | xc[1] & xc[1] << 1 | xc[2] & xc[2] << 1 | xc[3] & xc[3] << 1) >> 31;
                 if (!__any_sync(0xffffffffu, one_fill)) {
                     if (lane == 0) bulk_wait_read<0>();   // the previous tile's bulk store has read the image
                     __syncwarp();

@@ -1,2 +1,2 @@
 export WAH_B200_LIB=$PWD/gpu-wah_b200/build_trace/lib/libwah_b200.so
-for a in "clustered 0.01 29"; do set -- $a; python scripts/trace_phases.py --gen $1 --density $2 --log2n $3; done 2>&1 | tee gpurun_out/r2_trace.log
+for m in 0 1; do echo "=== mode $m"; python scripts/trace_compress.py 0.01 $m clustered 27 2>&1 | grep -A10 "iteration 9\|per-CTA span\|re-polls"; done | tee gpurun_out/r2_trace_compress.log

@@ -4,8 +4,11 @@ import numpy as np, torch
 sys.path.insert(0, os.path.dirname(os.path.dirname(os.path.abspath(__file__))))
 import gpu_wah_b200 as wah
 
-n = 1 << 25
-d = wah.gen_uniform_device(n, float(sys.argv[1]) if len(sys.argv) > 1 else 0.001, 1337)
+# usage: trace_compress.py [density] [mode 0|1] [uniform|clustered] [log2n]
+dens = float(sys.argv[1]) if len(sys.argv) > 1 else 0.001
+MODE = int(sys.argv[2]) if len(sys.argv) > 2 else 0
+n = 1 << (int(sys.argv[4]) if len(sys.argv) > 4 else 25)
+d = wah.gen_clustered_device(n, dens, 1000.0, 1337) if len(sys.argv) > 3 and sys.argv[3] == "clustered" else wah.gen_uniform_device(n, dens, 1337)
 cap = wah.max_compressed_words(n)
 out = torch.empty(cap, dtype=torch.int32, device="cuda")
 cnt = torch.zeros(1, dtype=torch.int64, device="cuda")
@@ -16,7 +19,7 @@ wah.lib.wah_test_set_trace.argtypes = [ctypes.c_void_p]
 for it in range(3):
     trace.zero_()
     wah.lib.wah_test_set_trace(trace.data_ptr())
-    wah.compress_device(d, n, out, cap, cnt, ws, 0)
+    wah.compress_device(d, n, out, cap, cnt, ws, MODE)
     torch.cuda.synchronize()
 t = trace.cpu().numpy().reshape(NC, 64, 8).astype(np.int64)
 iters = 14

@@ -865,8 +865,20 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
     uint32_t first0 = first_word(e0x), first1;
     bool stop = false;
     for (uint32_t it = 0; !stop && c0 < n_chunks; it++) {
+        // Lane 0 draws a ticket.  (ptxas wraps an atom.add on a provably uniform address in its warp-aggregation idiom,
+        // whose shuffle waits for the result on the spot -- an L2 round trip per chunk, 7 % of the stall samples of a
+        // 1 Gbit decode: hence an address the compiler cannot prove uniform (p.zero is 0) and a predicated instruction.
+        // The result is first used at the end of the iteration.)
         uint32_t tk = 0;
-        if (tickets && it + 3u >= (uint32_t)EXPAND_STATIC_ROUNDS && lane == 0) tk = atomicAdd(&p.ctr->ticket, 1u);
+        asm volatile(
+            "{\n\t"
+            ".reg .pred q;\n\t"
+            "setp.ne.u32 q, %2, 0;\n\t"
+            "@q atom.relaxed.gpu.global.add.u32 %0, [%1], 1;\n\t"
+            "}"
+            : "+r"(tk)
+            : "l"(&p.ctr->ticket + (size_t)lane * p.zero), "r"((uint32_t)(tickets && it + 3u >= (uint32_t)EXPAND_STATIC_ROUNDS && lane == 0u))
+            : "memory");
         fetch(c2, e2x, e2y);
         first1 = first_word(e1x);
 

@@ -126,6 +126,7 @@ struct ExpandParams {
     uint64_t *out_info;      // nullptr or device u64[3]: the last CTA to leave writes the status into [2]
     uint32_t dynamic_tiles;  // 0: tiles are dealt round robin; else: by ticket after EXPAND_STATIC_ROUNDS rounds
     uint32_t chunk_tiles;    // tiles per chunk of work: 8, 4, 2 or 1 (set by launch_decode)
+    uint32_t zero;           // 0 (opaque to the compiler, see the ticket draw in expand_body)
     DecodeCounters *ctr;     // zero at launch; the last CTA to leave zeroes it again
     uint64_t *trace;         // nullptr; phase timestamps in -DWAH_TRACE builds (scripts/trace_decode.py)
 };

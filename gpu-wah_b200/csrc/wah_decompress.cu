@@ -761,7 +761,14 @@ __device__ __forceinline__ void park_words(const uint32_t (&x)[W], uint32_t r0, 
 // busy).  One shift and one funnel shift make output word JJ - 1 = group JJ-1 >> (JJ-1) | group JJ << (32-JJ)
 // (kernels.cu:375).  Five instructions per group.  (Parking both operand forms, {bits << 1, bits}, and loading 8 bytes
 // saved the shift but cost two register moves per step: a predicated load of a register pair.)
-template <int JJ>
+// OP < 0: the output word is stored; OP = 0..3 (AND, OR, XOR, ANDNOT): it is combined into the word already there
+// (the logical operators: the image holds the first operand's tile).
+template <int OP>
+__device__ __forceinline__ uint32_t combine(uint32_t x, uint32_t y)
+{
+    return OP == 0 ? (x & y) : (OP == 1 ? (x | y) : (OP == 2 ? (x ^ y) : (x & ~y)));
+}
+template <int JJ, int OP = -1>
 __device__ __forceinline__ void walk_from(uint32_t a, uint32_t F, uint32_t v, uint32_t *o)
 {
     if constexpr (JJ < 32) {
@@ -777,8 +784,11 @@ __device__ __forceinline__ void walk_from(uint32_t a, uint32_t F, uint32_t v, ui
             "}"
             : "+r"(a), "+r"(v)
             : "r"(F), "n"(1u << JJ));
-        o[JJ - 1] = __funnelshift_r(lo, v, JJ);
-        walk_from<JJ + 1>(a, F, v, o);
+        if constexpr (OP < 0)
+            o[JJ - 1] = __funnelshift_r(lo, v, JJ);
+        else
+            o[JJ - 1] = combine<OP>(o[JJ - 1], __funnelshift_r(lo, v, JJ));
+        walk_from<JJ + 1, OP>(a, F, v, o);
     }
 }
 
@@ -1229,8 +1239,8 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
 // scratch array; a prefix sum over the tiles' word counts and a gather make the stream.  Traffic: the two streams, the
 // result twice.
 
-constexpr int LOG_IMG_WORDS = EXPAND_TILE_WORDS + 8;                             // an image + the word the last group's extraction touches
-constexpr int LOG_WARP_SMEM_WORDS = CW_WORDS + FLAG_WORDS + 2 * LOG_IMG_WORDS;   // 12.3 KB per warp
+constexpr int LOG_IMG_WORDS = EXPAND_TILE_WORDS + 8;                         // the image + the word the last group's extraction touches
+constexpr int LOG_WARP_SMEM_WORDS = CW_WORDS + FLAG_WORDS + LOG_IMG_WORDS;   // 8.4 KB per warp
 constexpr uint32_t LOG_CONST0 = 1u, LOG_CONST1 = 2u;
 
 struct LogicalParams {
@@ -1249,6 +1259,7 @@ struct LogicalParams {
 
 // Expands the part of tile t (groups g_start .. g_start + tg) that stream `in` covers into `img`; what lies behind the
 // stream's end reads as zeros.  Returns LOG_CONST0 / LOG_CONST1 if the whole tile is zeros / ones without an image.
+template <int OP>
 __device__ __forceinline__ uint32_t expand_operand(const uint32_t *in, uint64_t c_words, const ulonglong2 *starts, uint32_t epoch,
                                                    uint64_t G, uint32_t t, uint32_t tg_tile, uint32_t *s_cw, uint32_t *s_flag,
                                                    uint32_t *img, uint32_t lane)
@@ -1282,19 +1293,29 @@ __device__ __forceinline__ uint32_t expand_operand(const uint32_t *in, uint64_t 
     if (lane == 0) s_flag[32] = 0;
     __syncwarp();
     uint32_t running = 0, rk_run = 0;
-    uint32_t xc[4], xn[4] = {BIT31, BIT31, BIT31, BIT31};
-    load_words<4>(src, 4u * lane, room, xc);
+    if (nw <= 32u) {
+        uint32_t x[1];
+        load_words<1>(src, lane, room, x);
+        park_words<1, false>(x, lane, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
+    } else if (nw <= 64u) {
+        uint32_t x[2];
+        load_words<2>(src, 2u * lane, room, x);
+        park_words<2, false>(x, 2u * lane, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
+    } else {
+        uint32_t xc[4], xn[4] = {BIT31, BIT31, BIT31, BIT31};
+        load_words<4>(src, 4u * lane, room, xc);
 #pragma unroll 1
-    for (uint32_t r0 = 4u * lane;; r0 += 128u) {
-        const bool more = r0 - 4u * lane + 128u < nw;
-        if (more) load_words<4>(src, r0 + 128u, room, xn);
-        if (pad)
-            park_words<4, true>(xc, r0, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
-        else
-            park_words<4, false>(xc, r0, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
+        for (uint32_t r0 = 4u * lane;; r0 += 128u) {
+            const bool more = r0 - 4u * lane + 128u < nw;
+            if (more) load_words<4>(src, r0 + 128u, room, xn);
+            if (pad)
+                park_words<4, true>(xc, r0, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
+            else
+                park_words<4, false>(xc, r0, w_beg, w_span, skip, tg, running, rk_run, s_cw, s_flag);
 #pragma unroll
-        for (int i = 0; i < 4; i++) xc[i] = xn[i];
-        if (!more || running >= tg) break;
+            for (int i = 0; i < 4; i++) xc[i] = xn[i];
+            if (!more || running >= tg) break;
+        }
     }
     if (lane == 0 && tg < TG) {
         const uint32_t re = rk_run <= TG ? rk_run : TG + 1u;
@@ -1308,13 +1329,17 @@ __device__ __forceinline__ uint32_t expand_operand(const uint32_t *in, uint64_t 
     uint32_t *o = img + 31u * lane;
     uint32_t v = s_cw[pad ? cw_pos(r) : r];
     if (!pad) {
-        walk_from<1>((uint32_t)__cvta_generic_to_shared(s_cw) + 4u * r, F, v, o);
+        walk_from<1, OP>((uint32_t)__cvta_generic_to_shared(s_cw) + 4u * r, F, v, o);
     } else {
 #pragma unroll
         for (int jj = 1; jj < 32; jj++) {
             r += (F >> jj) & 1u;
             const uint32_t nv = s_cw[cw_pos(r)];
-            o[jj - 1] = __funnelshift_r(v << 1, nv, jj);
+            const uint32_t w = __funnelshift_r(v << 1, nv, jj);
+            if constexpr (OP < 0)
+                o[jj - 1] = w;
+            else
+                o[jj - 1] = combine<OP>(o[jj - 1], w);
             v = nv;
         }
     }
@@ -1327,48 +1352,61 @@ __device__ __forceinline__ uint32_t apply_op(int op, uint32_t x, uint32_t y)
     return op == 0 ? (x & y) : (op == 1 ? (x | y) : (op == 2 ? (x ^ y) : (x & ~y)));
 }
 
-__global__ void __launch_bounds__(EXPAND_THREADS, 2) wah_logical_tiles_kernel(const LogicalParams p)
+__global__ void __launch_bounds__(EXPAND_THREADS, 3) wah_logical_tiles_kernel(const LogicalParams p)
 {
     constexpr uint32_t TG = (uint32_t)EXPAND_TILE_GROUPS, TW = (uint32_t)EXPAND_TILE_WORDS;
     extern __shared__ __align__(16) uint32_t smem[];
     const uint32_t lane = threadIdx.x & 31u, warp = threadIdx.x >> 5;
     uint32_t *s_cw = smem + warp * LOG_WARP_SMEM_WORDS;
     uint32_t *s_flag = s_cw + CW_WORDS;
-    uint32_t *img_a = s_flag + FLAG_WORDS;
-    uint32_t *img_b = img_a + LOG_IMG_WORDS;
+    uint32_t *img = s_flag + FLAG_WORDS;
     const uint64_t Ga = p.ca ? p.hdr_a->groups : 0ull, Gb = p.cb ? p.hdr_b->groups : 0ull;
     const uint32_t GW = gridDim.x * (EXPAND_THREADS / 32), gw = blockIdx.x * (EXPAND_THREADS / 32) + warp;
-    if (lane < 8u) {   // the word the extraction of a row's last group reads behind the image
-        img_a[TW + lane] = 0;
-        img_b[TW + lane] = 0;
-    }
+    if (lane < 8u) img[TW + lane] = 0;   // the word the extraction of a row's last group reads behind the image
     for (uint32_t t = gw; t < p.n_tiles; t += GW) {
         const uint64_t g_start = (uint64_t)t << TG_SHIFT;
         const uint32_t tg = p.groups - g_start < (uint64_t)TG ? (uint32_t)(p.groups - g_start) : TG;
-        const uint32_t ka = expand_operand(p.a, p.ca, p.starts_a, p.epoch_a, Ga, t, tg, s_cw, s_flag, img_a, lane);
-        const uint32_t kb = expand_operand(p.b, p.cb, p.starts_b, p.epoch_b, Gb, t, tg, s_cw, s_flag, img_b, lane);
         uint32_t *slot = p.slots + (uint64_t)t * TG;
-        if (ka != 0u && kb != 0u) {
-            // both operands constant over the tile: one fill word, no group looked at
-            const uint32_t r = apply_op(p.op, ka == LOG_CONST1 ? 1u : 0u, kb == LOG_CONST1 ? 1u : 0u) & 1u;
-            if (lane == 0) {
-                slot[0] = fill_word(r, tg);
-                p.counts[t] = 1u;
-                atomicAdd(p.partials + (t >> 8), 1ull);
+        uint32_t *row_rw = img + 31u * lane;
+        // ---- the first operand's tile into the image, the second combined into it by its walk (a constant operand by a
+        //      loop over the lane's 31 words, unless the operator leaves the other operand as it is)
+        const uint32_t ka = expand_operand<-1>(p.a, p.ca, p.starts_a, p.epoch_a, Ga, t, tg, s_cw, s_flag, img, lane);
+        if (ka != 0u) {
+            const uint32_t kb = expand_operand<-1>(p.b, p.cb, p.starts_b, p.epoch_b, Gb, t, tg, s_cw, s_flag, img, lane);
+            if (kb != 0u) {
+                // both operands constant over the tile: one fill word, no group looked at
+                const uint32_t r = apply_op(p.op, ka == LOG_CONST1 ? 1u : 0u, kb == LOG_CONST1 ? 1u : 0u) & 1u;
+                if (lane == 0) {
+                    slot[0] = fill_word(r, tg);
+                    p.counts[t] = 1u;
+                    atomicAdd(p.partials + (t >> 8), 1ull);
+                }
+                continue;
             }
-            continue;
-        }
-        // ---- combine, in place in image a
-        {
-            uint32_t *ra = img_a + 31u * lane;
-            const uint32_t *rb = img_b + 31u * lane;
-            const uint32_t fa = ka == LOG_CONST1 ? 0xFFFFFFFFu : 0u, fb = kb == LOG_CONST1 ? 0xFFFFFFFFu : 0u;
+            const uint32_t fa = ka == LOG_CONST1 ? 0xFFFFFFFFu : 0u;
 #pragma unroll
-            for (int k = 0; k < 31; k++) ra[k] = apply_op(p.op, ka ? fa : ra[k], kb ? fb : rb[k]);
+            for (int k = 0; k < 31; k++) row_rw[k] = apply_op(p.op, fa, row_rw[k]);
+        } else {
+            uint32_t kb;
+            switch (p.op) {
+            case 0: kb = expand_operand<0>(p.b, p.cb, p.starts_b, p.epoch_b, Gb, t, tg, s_cw, s_flag, img, lane); break;
+            case 1: kb = expand_operand<1>(p.b, p.cb, p.starts_b, p.epoch_b, Gb, t, tg, s_cw, s_flag, img, lane); break;
+            case 2: kb = expand_operand<2>(p.b, p.cb, p.starts_b, p.epoch_b, Gb, t, tg, s_cw, s_flag, img, lane); break;
+            default: kb = expand_operand<3>(p.b, p.cb, p.starts_b, p.epoch_b, Gb, t, tg, s_cw, s_flag, img, lane); break;
+            }
+            if (kb != 0u) {
+                const uint32_t fb = kb == LOG_CONST1 ? 0xFFFFFFFFu : 0u;
+                // (x op 0 = x for OR, XOR, ANDNOT; x AND ones = x)
+                const bool same = fb == 0u ? p.op != 0 : p.op == 0;
+                if (!same) {
+#pragma unroll
+                    for (int k = 0; k < 31; k++) row_rw[k] = apply_op(p.op, row_rw[k], fb);
+                }
+            }
         }
         __syncwarp();
         // ---- encode the block (the compressor's warp, BLOCK1024 mode)
-        const uint32_t *row = img_a + 31u * lane;
+        const uint32_t *row = img + 31u * lane;
         uint32_t nvalid = tg > 32u * lane ? tg - 32u * lane : 0u;
         if (nvalid > 32u) nvalid = 32u;
         const uint32_t vmask = nvalid == 32u ? 0xFFFFFFFFu : ((1u << nvalid) - 1u);

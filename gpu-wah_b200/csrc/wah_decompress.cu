@@ -1233,11 +1233,11 @@ __device__ __forceinline__ void expand_body(const ExpandParams &p)
 // (the specification is wah_oracle_logical, oracle/wah_oracle.c).  Both streams are scanned (the scan
 // phase above, table entries for every tile); then a warp takes a tile of 1024 groups -- one block of the reference
 // encoder (kernels.cu:256,273-280) -- at a time: a tile that lies inside one fill of each operand becomes one fill word
-// without a group being looked at; otherwise the operands' tiles are expanded into two images in shared memory (the
-// window path of the expand phase), combined word by word, and encoded the way the compressor's warp encodes a block
-// (classify, run-end rule, warp scan, compaction: kernels.cu:79,93-141,244-248).  The words of tile t go to slot t of a
-// scratch array; a prefix sum over the tiles' word counts and a gather make the stream.  Traffic: the two streams, the
-// result twice.
+// without a group being looked at; otherwise the first operand's tile is expanded into an image in shared memory (the
+// window path of the expand phase), the second operand's walk combines its output words into that image, and the image
+// is encoded the way the compressor's warp encodes a block (classify, run-end rule, warp scan, compaction:
+// kernels.cu:79,93-141,244-248).  The words of tile t go to slot t of a scratch array; a prefix sum over the tiles' word
+// counts and a gather make the stream.  Traffic: the two streams, the result twice.
 
 constexpr int LOG_IMG_WORDS = EXPAND_TILE_WORDS + 8;                         // the image + the word the last group's extraction touches
 constexpr int LOG_WARP_SMEM_WORDS = CW_WORDS + FLAG_WORDS + LOG_IMG_WORDS;   // 8.4 KB per warp

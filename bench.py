@@ -477,6 +477,10 @@ def run_single(args):
                         "sample": f"the whole {n_words}-word vector, {r['reps']} round trips",
                         "compress_gbs": r["compress_gbs"], "decompress_gbs": r["decompress_gbs"]}
 
+    ref_ctx = None
+    if not args.no_cpu_baseline and h_in is not None and n_words >= 33_554_400:
+        ref_ctx = reference_kernels_context(np, h_in, density)
+
     nbytes = 4.0 * n_words
     emit({
         "metric": METRIC, "value": 2 * nbytes / (ms_per_step * 1e-3) / 1e9, "unit": UNIT, "n_gpus": 1,
@@ -489,8 +493,40 @@ def run_single(args):
         "compress_gbs": head["compress"]["uncompressed_gbs"], "decompress_gbs": head["decompress"]["uncompressed_gbs"],
         "clocks": clocks, "e2e": e2e, "gpu_launches": 2 * args.steps,
         "gpu_launches_note": "per step: wah_compress_kernel, wah_decode_kernel (scan + expand fused); no memset, no other kernel",
-        "roofline": roofline, "sweep": sweep, **extras, "cpu_baseline": cpu_baseline, "parity_checked": True,
+        "roofline": roofline, "sweep": sweep, **extras, "cpu_baseline": cpu_baseline, "reference_kernels": ref_ctx, "parity_checked": True,
     })
+
+
+def reference_kernels_context(np, h_in, density):
+    """Context, not a target (north_star: "the reference's original CUDA kernels on the same B200"): the reference's own
+    compress() / decompress(), untouched, built for sm_100a with the three-macro shuffle shim (oracle/_ref/
+    libgpuwah_ref.so, made by oracle/Makefile from the sources where they lie), on the first 33 554 400 words of the
+    workload vector (the reference is defined for n % 992 == 0; its host path is pageable and serial), in a process of
+    its own (tests/ref_runner.py), medians of its own three timers over 10 repetitions like its benchmark loop
+    (source.cpp:70,83-126).  TEST INFRASTRUCTURE: nothing of it is on the measured path."""
+    import subprocess
+    import tempfile
+
+    lib = os.path.join(ROOT, "oracle", "_ref", "libgpuwah_ref.so")
+    if not os.path.exists(lib):
+        return {"unavailable": "oracle/_ref/libgpuwah_ref.so has not been built (python -c 'import __graft_entry__ as g; g.build()' where /root/reference is mounted)"}
+    n = 33_554_400
+    try:
+        with tempfile.TemporaryDirectory() as d:
+            fin, fout = os.path.join(d, "in.npy"), os.path.join(d, "out.npy")
+            np.save(fin, h_in[:n])
+            subprocess.run([sys.executable, os.path.join(ROOT, "tests", "ref_runner.py"), lib, "time", fin, fout], check=True, timeout=300,
+                           stdout=subprocess.DEVNULL, stderr=subprocess.DEVNULL)
+            t = np.load(fout)
+    except Exception as e:  # the reference is what it is: context only
+        return {"unavailable": f"{type(e).__name__}: {e}"[:200]}
+    nb = 4.0 * n
+    return {"words": n, "density": density, "sample": "the first 33 554 400 words of the workload vector (n % 992 == 0)",
+            "compress_ms": {"h2d": float(t[0][0]), "compute": float(t[0][1]), "d2h": float(t[0][2])},
+            "decompress_ms": {"h2d": float(t[1][0]), "compute": float(t[1][1]), "d2h": float(t[1][2])},
+            "compress_gbs_compute_timer": nb / float(t[0][1]) / 1e6, "decompress_gbs_compute_timer": nb / float(t[1][1]) / 1e6,
+            "e2e_gbs": 2 * nb / float(t[0].sum() + t[1].sum()) / 1e6, "unit": UNIT,
+            "note": "the reference's kernels recompiled with a shuffle shim, its own timers; reported for context"}
 
 
 def cpu_round_trips(orc, data, mode, budget_s, threads):

@@ -86,12 +86,18 @@ __device__ __forceinline__ uint32_t lanemask_lt()
 
 __device__ __forceinline__ uint32_t warp_incl_scan(uint32_t v)
 {
-    const uint32_t lane = lane_id();
+    // (the shuffle's own predicate says whether the source lane exists: two instructions per step instead of three)
 #pragma unroll
-    for (int d = 1; d < 32; d <<= 1) {
-        uint32_t o = __shfl_up_sync(0xffffffffu, v, d);
-        if (lane >= (uint32_t)d) v += o;
-    }
+    for (int d = 1; d < 32; d <<= 1)
+        asm volatile(
+            "{\n\t"
+            ".reg .u32 r;\n\t"
+            ".reg .pred p;\n\t"
+            "shfl.sync.up.b32 r|p, %0, %1, 0, 0xffffffff;\n\t"
+            "@p add.u32 %0, %0, r;\n\t"
+            "}"
+            : "+r"(v)
+            : "r"(d));
     return v;
 }
 

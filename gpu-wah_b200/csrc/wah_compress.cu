@@ -141,7 +141,7 @@ struct Geom {
     static constexpr int TILE_GROUPS = NWORK * 1024;
     static constexpr int PAD_FRONT = 4;                       // row[-1] of the tile's first thread
     static constexpr int STAGE_WORDS = TILE_WORDS + 8;        // + 4 in front, + look-ahead word (16 B) behind
-    static constexpr int THREADS = (NWORK + 3) * 32;
+    static constexpr int THREADS = (NWORK + 4) * 32;          // workers, two control warps, producer, writer
     static constexpr int RING_WORDS = NWORK * WARP_RING;      // power of two for NWORK = 4, 8
     static_assert((RING_WORDS & (RING_WORDS - 1)) == 0, "ring size must be a power of two");
     static_assert(TILE_GROUPS <= 8192, "descriptor fields are 14 bits");
@@ -176,6 +176,10 @@ struct TileMeta {
     int32_t lead_adjust;       // added to the launch's very first word (seam with an earlier launch)
     uint64_t dst;              // output word index of the tile's first word
     uint32_t wcarry[NWORK];    // groups of a run still open where the warp starts (CANONICAL)
+    // control warp of tile i -> control warp of tile i + 1 (the CTA's chain)
+    uint32_t cnt_end;          // words of this launch up to the end of the tile
+    uint32_t open_end;         // groups of the run still open at the end of the tile
+    uint32_t failed;           // a control warp of this CTA has given up waiting for descriptors
 };
 
 template <int NWORK, int STAGES>
@@ -188,6 +192,7 @@ struct Smem {
     StageInfo info[STAGES];
     uint64_t full[STAGES], empty[STAGES];              // input ring: producer <-> workers
     uint64_t agg[QDEPTH], pref[QDEPTH], done[QDEPTH];  // tile queue: workers <-> control
+    uint64_t chain[QDEPTH];                            // control warp of a tile -> control warp of the next tile
 };
 
 // literal group j (0..31) of the row that starts at `row`: stream bits [31 j, 31 j + 31), LSB first
@@ -220,7 +225,7 @@ __device__ __forceinline__ void classify_group(uint32_t u, uint32_t one, uint32_
 }
 
 template <int NWORK, int STAGES, bool BLOCK_MODE>
-__global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const CompressParams p)
+__global__ void __launch_bounds__((NWORK + 4) * 32, 2) wah_compress_kernel(const CompressParams p)
 {
     using G = Geom<NWORK, STAGES>;
     using SM = Smem<NWORK, STAGES>;
@@ -241,6 +246,7 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
             mbar_init(smem_u32(&sm.agg[q]), NWORK);
             mbar_init(smem_u32(&sm.pref[q]), 1);
             mbar_init(smem_u32(&sm.done[q]), 1);
+            mbar_init(smem_u32(&sm.chain[q]), 1);
         }
         asm volatile("fence.mbarrier_init.release.cluster;" ::: "memory");
     }
@@ -295,8 +301,14 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
                 if (lane == 0) mbar_arrive(bar);
             }
         }
-    } else if (warp == NWORK) {
-        // ============================================================ control warp
+    } else if (warp == NWORK || warp == NWORK + 3) {
+        // ============================================================ control warps
+        // Two of them, taking the CTA's tiles in turn.  (Phase trace of the single control warp: 1.5 us per tile in
+        // BLOCK1024 mode, 2.0 us in CANONICAL mode, with no descriptor missing -- the workers need 1.1 us and ran the
+        // full QDEPTH tiles ahead: that warp set the pace of the CTA.)  The sum over the other CTAs' descriptors, which
+        // is what takes the time, does not depend on this CTA's own running totals; those pass from the warp of tile i
+        // to the warp of tile i + 1 through shared memory (sm.chain), two additions per tile.
+        const uint32_t cw = warp == NWORK ? 0u : 1u;
         // Offsets by a chained sum instead of a status-polling look-back: this CTA owns tiles b, b + G,
         // b + 2G, ... (G = gridDim), so the words before tile k are the words before its previous tile
         // k - G, plus that tile's, plus the aggregates of the G - 1 tiles in between.  Those are published
@@ -310,8 +322,7 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
         // (WAH_ERR_CUDA at the host entry points) instead of hanging the GPU.
         uint32_t budget = COMPRESS_SPIN_LIMIT;
         bool failed = base == ~0ull;   // an earlier launch of a chained stream failed
-        uint32_t own_cnt = 0, own_open = 0;   // words of this launch up to / run open at the end of my previous tile
-        uint64_t d[LBN];                      // first window of the next tile, requested one tile ahead
+        uint64_t d[LBN];               // first window of my next tile, requested while the other warp's tile is at hand
         auto request = [&](int64_t hi, int64_t lo) {
 #pragma unroll
             for (int r = 0; r < LBN; r++) {
@@ -319,26 +330,27 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
                 d[r] = lk >= lo ? ld_relaxed_u64(p.desc + lk) : ~((uint64_t)p.epoch << 32);
             }
         };
-        if (n_my > 0) request((int64_t)blockIdx.x - 1, 0);
-        for (uint32_t i = 0; i < n_my; i++) {
+        if (cw == 0u && n_my > 0) request((int64_t)blockIdx.x - 1, 0);
+        if (cw == 1u && n_my > 1) request((int64_t)(blockIdx.x + stride) - 1, (int64_t)blockIdx.x + 1);
+        for (uint32_t i = cw; i < n_my; i += 2u) {
             const uint32_t q = i % QDEPTH, use = i / QDEPTH;
             const uint32_t tile = blockIdx.x + i * stride;
             const uint32_t col = tile / p.tiles_per_col;
             const uint32_t t = tile - col * p.tiles_per_col;
             TileMeta<NWORK> &mt = sm.meta[q];
 
+            // my own CTA's workers first: the other CTAs' run at the same pace, so their descriptors are (nearly
+            // always) there by now and the sum below does not poll the L2 for tiles that are still being classified
             mbar_wait(smem_u32(&sm.agg[q]), use & 1u);
             if (lane == 0) TRACE(i, 3, clock64());
 
-            // ---- tile aggregate (computed and published to the other CTAs by the workers)
-            const uint32_t tile_cnt = mt.tile_cnt, tile_open = mt.tile_open, tile_has = mt.tile_has;
-
             // ---- sum the aggregates of tiles [lo, hi], nearest first
-            uint32_t excl = own_cnt, carry = 0;
+            uint32_t between = 0, open_between = 0;   // words of / run open across the tiles between my CTA's previous tile and this one
+            bool open_done;
             {
                 const int64_t lo = i == 0 ? 0 : (int64_t)tile - (int64_t)stride + 1;
                 int64_t hi = (int64_t)tile - 1;
-                bool open_done = BLOCK_MODE || (t == 0u);   // BLOCK mode never carries; CANONICAL restarts per column
+                open_done = BLOCK_MODE || (t == 0u);   // BLOCK mode never carries; CANONICAL restarts per column
                 uint32_t csum = 0, osum = 0;
                 bool fresh = true;
 #ifdef WAH_TRACE
@@ -377,15 +389,36 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
 #ifdef WAH_TRACE
                 if (lane == 0) TRACE(i, 7, polls);
 #endif
-                // no run end between my previous tile and this one: the run open at its end goes on
-                if (!open_done && lane == 0) osum += own_open;
-                excl += warp_sum(csum);
-                if (!BLOCK_MODE) carry = warp_sum(osum);
-                if (BLOCK_MODE || t == 0u) carry = 0;
+                between = warp_sum(csum);
+                if (!BLOCK_MODE) open_between = warp_sum(osum);
             }
-            // my own running totals, for the next tile of this CTA
-            own_cnt = excl + tile_cnt;
-            own_open = tile_has ? tile_open : carry + tile_open;
+            // request my next tile's window now: it is in flight for the whole of the other warp's tile
+            if (i + 2u < n_my) request((int64_t)(tile + 2u * stride) - 1, (int64_t)(tile + stride) + 1);
+
+            // ---- the CTA's chain: where its previous tile ended (the other control warp's tile)
+            uint32_t own_cnt = 0, own_open = 0;
+            if (i > 0u) {
+                const uint32_t qp = (i - 1u) % QDEPTH;
+                mbar_wait(smem_u32(&sm.chain[qp]), ((i - 1u) / QDEPTH) & 1u);
+                own_cnt = sm.meta[qp].cnt_end;
+                own_open = sm.meta[qp].open_end;
+                failed = failed || sm.meta[qp].failed != 0u;
+            }
+            const uint32_t excl = own_cnt + between;
+            // no run end between my CTA's previous tile and this one: the run open at its end goes on
+            uint32_t carry = open_between + (open_done ? 0u : own_open);
+            if (BLOCK_MODE || t == 0u) carry = 0;
+
+            // ---- tile aggregate (computed and published to the other CTAs by the workers)
+            const uint32_t tile_cnt = mt.tile_cnt, tile_open = mt.tile_open, tile_has = mt.tile_has;
+            // the CTA's running totals, for its next tile
+            if (lane == 0) {
+                mt.cnt_end = excl + tile_cnt;
+                mt.open_end = tile_has ? tile_open : carry + tile_open;
+                mt.failed = failed ? 1u : 0u;
+            }
+            __syncwarp();
+            if (lane == 0) mbar_arrive(smem_u32(&sm.chain[q]));
 
             // ---- hand the offsets to the writer warp (and to the workers, if they write this tile themselves)
             const uint64_t dst0 = base + excl;
@@ -408,8 +441,6 @@ __global__ void __launch_bounds__((NWORK + 3) * 32, 2) wah_compress_kernel(const
                 mbar_arrive(smem_u32(&sm.pref[q]));
                 TRACE(i, 4, clock64());
             }
-            // request the next tile's first window now: it is in flight while the workers finish that tile
-            if (i + 1u < n_my) request((int64_t)(tile + stride) - 1, (int64_t)tile + 1);
             if (lane == 0) {
                 if (p.col_offsets && t == 0u) p.col_offsets[col] = dst0;
                 if (tile == p.n_tiles - 1u) {

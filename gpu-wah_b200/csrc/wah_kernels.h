@@ -2,6 +2,7 @@
 #pragma once
 
 #include <cuda_runtime.h>
+#include <stdlib.h>
 #include <stdint.h>
 
 namespace wahb200 {
@@ -85,6 +86,16 @@ struct DecodeCounters {
     uint64_t pad[2];
 };
 
+// L2 cache-policy hints of the decoder (launch_decode); WAH_B200_L2_HINTS=0 (experiments, read once) switches them off
+inline bool l2_hints()
+{
+    static const bool on = [] {
+        const char *e = getenv("WAH_B200_L2_HINTS");
+        return !(e && e[0] == '0');
+    }();
+    return on;
+}
+
 struct ScanParams {
     const uint32_t *in;
     uint64_t c_words;        // words from `in` to the end of the stream
@@ -107,6 +118,8 @@ struct ScanParams {
     DecodeCounters *next_ctr;   // the slot the NEXT launch will use: zeroed by this launch's first CTA
     uint32_t chunk_tiles;    // == ExpandParams::chunk_tiles (0 for a size query)
     uint32_t scan_only;      // the scan phase alone (wah_scan_kernel): its last round leaves the counters zeroed and reports the status
+    uint32_t l2_keep;        // 1: the scan's loads ask the L2 to keep the stream for the reads that follow (pass 2, the expand
+                             // phase); set by launch_decode
     uint64_t *trace;         // nullptr; -DWAH_TRACE builds only
 };
 
@@ -127,6 +140,7 @@ struct ExpandParams {
     uint32_t dynamic_tiles;  // 0: tiles are dealt round robin; else: by ticket after EXPAND_STATIC_ROUNDS rounds
     uint32_t chunk_tiles;    // tiles per chunk of work: 8, 4, 2 or 1 (set by launch_decode)
     uint32_t zero;           // 0 (opaque to the compiler, see the ticket draw in expand_body)
+    uint32_t l2_stream_out;  // 1: the output is stored with an L2 evict-first hint (it is never read again; the stream is)
     DecodeCounters *ctr;     // zero at launch; the last CTA to leave zeroes it again
     uint64_t *trace;         // nullptr; phase timestamps in -DWAH_TRACE builds (scripts/trace_decode.py)
 };

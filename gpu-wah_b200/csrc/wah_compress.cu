@@ -11,17 +11,21 @@
 //             (bit-exact to the reference: runs never cross a block, kernels.cu:256)
 //             no run state ever leaves a warp
 //   tile    = NWORK reference blocks, one per WORKER warp
-//   CTA     = persistent and warp specialised (cooperative launch: all CTAs co-resident):
-//               NWORK worker warps   classify a tile from shared memory, compact its words
-//                                    into a per-warp staging area and copy them out coalesced
-//               1 control warp       tile aggregate -> decoupled look-back over one 64-bit
-//                                    descriptor per tile -> hands the workers their offsets
-//               1 producer warp      cp.async.bulk (TMA) of tile blockIdx + k * gridDim into a
-//                                    ring of STAGES shared-memory buffers, mbarrier signalled
-//             The roles talk through mbarriers only; there is no __syncthreads in the loop.
-//             Workers are software pipelined: tile k+1 is classified and its aggregate handed
-//             to the control warp BEFORE tile k is emitted, so the look-back latency of tile k
-//             is covered by useful work.
+//   CTA     = persistent (every CTA of the grid resident: SMs x occupancy, or a cooperative launch) and warp
+//             specialised:
+//               NWORK worker warps   classify a tile from shared memory, publish its aggregate (one 64-bit
+//                                    descriptor per tile) to the other CTAs, compact its words into a ring
+//                                    in shared memory -- or, for a tile of more words than the ring takes,
+//                                    write them once the offset is known
+//               2 control warps      taking the CTA's tiles in turn: tile offset = the CTA's previous tile's
+//                                    end + the descriptors of the tiles in between (a chained sum: no warp
+//                                    ever waits for another CTA's control warp)
+//               1 writer warp        copies a tile's words from the ring to their place in the output
+//               1 producer warp      cp.async.bulk (TMA) of tile blockIdx + k * gridDim into a ring of
+//                                    STAGES shared-memory buffers, mbarrier signalled
+//             The roles talk through mbarriers only; there is no __syncthreads in the loop.  The workers run
+//             up to QDEPTH tiles ahead of the control warps and the writer, so the latency of a tile's offset
+//             is covered by the classification of the tiles behind it.
 //
 // A run is emitted where it ENDS ("tail"): group k is a tail if it is a literal,
 // or the next group has another type, or it is the last group of the stream /
@@ -168,7 +172,7 @@ struct WarpAgg {
     uint32_t whas[NWORK];      // warp has at least one tail
 };
 
-// one per tile in flight between the workers and the control warp (slot = CTA-local tile index % QDEPTH)
+// one per tile in flight between the workers and the control warps (slot = CTA-local tile index % QDEPTH)
 template <int NWORK>
 struct TileMeta {
     // workers -> control
@@ -670,7 +674,7 @@ __global__ void __launch_bounds__((NWORK + 4) * 32, 2) wah_compress_kernel(const
             };
 
             if (ring_mode) {
-                // ---- stage the tile's words back to back in the ring; the control warp copies them out
+                // ---- stage the tile's words back to back in the ring; the writer warp copies them out
                 //      once the tile's offset is known.  Wait until the ring has room for them.
                 while (jd < i && head - sm.meta[jd % QDEPTH].ring_base + tile_cnt > (uint32_t)G::RING_WORDS) {
                     mbar_wait(smem_u32(&sm.done[jd % QDEPTH]), (jd / QDEPTH) & 1u);

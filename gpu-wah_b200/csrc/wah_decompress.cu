@@ -221,6 +221,12 @@ __device__ __forceinline__ uint64_t l2_keep_policy()
     asm volatile("createpolicy.fractional.L2::evict_last.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+__device__ __forceinline__ uint64_t l2_normal_policy()
+{
+    uint64_t pol;
+    asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
+    return pol;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait()
@@ -228,6 +234,7 @@ __device__ __forceinline__ void cp_async_wait()
     asm volatile("cp.async.wait_group %0;" ::"n"(N) : "memory");
 }
 constexpr int SCAN_SUB_WORDS = SCAN_MAXV * 4 * SCAN_THREADS;   // 8192 words = 32 KB: one sub-tile
+constexpr int SCAN_SUBSUMS = 32;   // sub-tiles of a tile whose per-warp sums pass 1 keeps for pass 2 (a longer tile adds them up again)
 
 __device__ __forceinline__ uint64_t pack_groups(const uint4 x)
 {
@@ -238,6 +245,13 @@ __device__ __forceinline__ uint32_t pack_groups32(const uint4 x)   // (four coun
     return word_groups(x.x) + word_groups(x.y) + word_groups(x.z) + word_groups(x.w);
 }
 __device__ __forceinline__ uint32_t zero_fill(uint32_t x) { return (x & ~BIT30) == BIT31; }   // a fill of 0 groups
+// groups of a pack (below 2^32) and how many of its four words are fills of 0 groups (the only words that hold no group)
+__device__ __forceinline__ uint32_t pack_groups_zeros(const uint4 x, uint32_t &zeros)
+{
+    const uint32_t c0 = word_groups(x.x), c1 = word_groups(x.y), c2 = word_groups(x.z), c3 = word_groups(x.w);
+    zeros += 4u - (min(c0, 1u) + min(c1, 1u) + min(c2, 1u) + min(c3, 1u));
+    return c0 + c1 + c2 + c3;
+}
 
 // `smem`: 2 * SCAN_SUB_WORDS words (the expand phase's shared memory, not in use yet).
 __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
@@ -247,6 +261,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
     __shared__ uint64_t s_wsum[NW];
     __shared__ uint32_t s_wbad[NW];
     __shared__ uint64_t s_lb_sum[NW];
+    __shared__ uint64_t s_subsum[SCAN_SUBSUMS][NW];
     __shared__ ulonglong4 s_heavy[SCAN_HEAVY];
     __shared__ uint32_t s_nheavy;
     __shared__ uint32_t s_flag;
@@ -300,22 +315,23 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
             nv = rows - sub * SCAN_MAXV < (uint32_t)SCAN_MAXV ? rows - sub * SCAN_MAXV : (uint32_t)SCAN_MAXV;
             seg_begin = tile_begin + (uint64_t)sub * SCAN_SUB_WORDS + (uint64_t)warp * (nv * 128u);
         };
+        // (the scan is bound by its instruction count -- 24 warps per SM, about 450 instructions per thread and sub-tile in
+        //  pass 1 before this was trimmed, against 4.3 TB/s -- so a tile that lies inside the stream, i.e. every tile but the
+        //  first and the last, is fetched without the per-pack bounds arithmetic)
         auto fetch_sub = [&](uint32_t sub) {   // (leaves nv / seg_begin set for `sub`)
             geometry(sub);
-            if (p.l2_keep != 0u) {
-                const uint64_t pol = l2_keep_policy();
+            const uint64_t pol = p.l2_keep != 0u ? l2_keep_policy() : l2_normal_policy();
+            if (!ragged) {
+                const uint32_t *src = p.in + seg_begin + lane * 4u;
+                uint32_t dst = (uint32_t)__cvta_generic_to_shared(my_pack(sub & 1u, 0));
 #pragma unroll 1
-                for (uint32_t v = 0; v < nv; v++) {
-                    const uint64_t i0 = seg_begin + (uint64_t)(v * 32u + lane) * 4u;
-                    const uint32_t bytes = i0 + 4 <= p.c_words ? 16u : (i0 < p.c_words ? (uint32_t)(p.c_words - i0) * 4u : 0u);
-                    cp_async16_hint((uint32_t)__cvta_generic_to_shared(my_pack(sub & 1u, v)), p.in + (i0 < p.c_words ? i0 : 0), bytes, pol);
-                }
+                for (uint32_t v = 0; v < nv; v++, src += 128, dst += 512u) cp_async16_hint(dst, src, 16u, pol);
             } else {
 #pragma unroll 1
                 for (uint32_t v = 0; v < nv; v++) {
                     const uint64_t i0 = seg_begin + (uint64_t)(v * 32u + lane) * 4u;
                     const uint32_t bytes = i0 + 4 <= p.c_words ? 16u : (i0 < p.c_words ? (uint32_t)(p.c_words - i0) * 4u : 0u);
-                    cp_async16((uint32_t)__cvta_generic_to_shared(my_pack(sub & 1u, v)), p.in + (i0 < p.c_words ? i0 : 0), bytes);
+                    cp_async16_hint((uint32_t)__cvta_generic_to_shared(my_pack(sub & 1u, v)), p.in + (i0 < p.c_words ? i0 : 0), bytes, pol);
                 }
             }
             cp_async_commit();
@@ -340,6 +356,7 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
         };
 
         // ---- pass 1: groups in the tile (getCounts, kernels.cu:298-304)
+        const bool keep_subsums = p.starts != nullptr && nsub > 1u && nsub <= (uint32_t)SCAN_SUBSUMS;
         uint64_t lsum = 0;
         uint32_t zc = 0;   // fills of 0 groups among my words: malformed -- unless they are my own padding
         fetch_sub(0);
@@ -353,11 +370,13 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
             }
             geometry(sub);
             if (ragged) patch_sub(sub);
+            uint64_t lsub = 0;
 #pragma unroll 2
-            for (uint32_t v = 0; v < nv; v++) {
-                const uint4 x = *my_pack(sub & 1u, v);
-                lsum += pack_groups(x);
-                zc += zero_fill(x.x) + zero_fill(x.y) + zero_fill(x.z) + zero_fill(x.w);
+            for (uint32_t v = 0; v < nv; v++) lsub += pack_groups_zeros(*my_pack(sub & 1u, v), zc);
+            lsum += lsub;
+            if (keep_subsums) {   // my warp's share of this sub-tile, for pass 2
+                const uint64_t wsub = warp_sum_u64(lsub);
+                if (lane == 0) s_subsum[sub][warp] = wsub;
             }
         }
         const uint64_t wtotal = warp_sum_u64(lsum);
@@ -564,22 +583,46 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
                 geometry(sub);
                 if (ragged) patch_sub(sub);
                 if (!skip_rows) {
-                    // (most rows hold a boundary: every row is scanned -- in 32-bit arithmetic relative to the row unless
-                    //  the warp's eight rows hold 2^32 groups or more)
-                    uint64_t lsub = 0;
+                    // (most rows hold a boundary: every row is scanned -- in 32-bit arithmetic relative to the sub-tile unless
+                    //  the warp's eight rows hold 2^31 groups or more)
+                    uint64_t wsub;
+                    if (keep_subsums) {
+                        wsub = s_subsum[sub][warp];   // (pass 1 left them; the barrier behind pass 1 has been passed)
+                    } else {
+                        uint64_t lsub = 0;
 #pragma unroll 2
-                    for (uint32_t v = 0; v < nv; v++) lsub += pack_groups32(*my_pack(sub & 1u, v));
-                    const uint64_t wsub = warp_sum_u64(lsub);
-                    const bool narrow = wsub < (1ull << 32);
-                    __syncthreads();   // s_wsum: the previous sub-tile's (or pass 1's) sums have been consumed
-                    if (lane == 0) s_wsum[warp] = wsub;
-                    __syncthreads();
+                        for (uint32_t v = 0; v < nv; v++) lsub += pack_groups32(*my_pack(sub & 1u, v));
+                        wsub = warp_sum_u64(lsub);
+                        __syncthreads();   // s_wsum: the previous sub-tile's (or pass 1's) sums have been consumed
+                        if (lane == 0) s_wsum[warp] = wsub;
+                        __syncthreads();
+                    }
+                    const bool narrow = wsub < (1ull << 31);
                     uint64_t row_base = sub_base;   // group offset of the row's first word
 #pragma unroll
                     for (int k = 0; k < NW; k++) {
-                        const uint64_t sv = s_wsum[k];
+                        const uint64_t sv = keep_subsums ? s_subsum[sub][k] : s_wsum[k];
                         if (k < (int)warp) row_base += sv;
                         sub_base += sv;
+                    }
+                    if (narrow && !batch) {
+                        // a single stream, the warp's rows below 2^31 groups: offsets relative to the output-tile boundary
+                        // at or below the warp's first row, in 32 bits; 64 bits only for the pack that holds a boundary
+                        const uint64_t q0 = row_base & ~TGM;
+                        uint32_t rb = (uint32_t)(row_base - q0);
+#pragma unroll 1
+                        for (uint32_t v = 0; v < nv; v++) {
+                            const uint4 x = *my_pack(sub & 1u, v);
+                            const uint32_t s32 = pack_groups32(x);
+                            const uint32_t i32 = warp_incl_scan(s32);
+                            const uint32_t e = rb + (i32 - s32);
+                            const uint32_t kf = (e + (uint32_t)TGM) >> TG_SHIFT, ke = (e + s32 + (uint32_t)TGM) >> TG_SHIFT;
+                            if (kf != ke)   // a boundary in my 4 words
+                                note_boundaries(p.starts, p.epoch, geo, cur, false, (q0 >> TG_SHIFT) + kf, (q0 >> TG_SHIFT) + ke,
+                                                seg_begin + (uint64_t)(v * 32u + lane) * 4u, q0 + e, x, s_heavy, &s_nheavy);
+                            rb += __shfl_sync(0xffffffffu, i32, 31);
+                        }
+                        continue;
                     }
 #pragma unroll 1
                     for (uint32_t v = 0; v < nv; v++) {

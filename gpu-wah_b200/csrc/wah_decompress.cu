@@ -227,6 +227,14 @@ __device__ __forceinline__ uint64_t l2_normal_policy()
     asm volatile("createpolicy.fractional.L2::evict_normal.b64 %0, 1.0;" : "=l"(pol));
     return pol;
 }
+__device__ __forceinline__ uint4 ld_v4_hint(const uint4 *p, uint64_t pol)
+{
+    uint4 r;
+    asm volatile("ld.global.L1::no_allocate.L2::cache_hint.v4.u32 {%0,%1,%2,%3}, [%4], %5;"
+                 : "=r"(r.x), "=r"(r.y), "=r"(r.z), "=r"(r.w)
+                 : "l"(p), "l"(pol));
+    return r;
+}
 __device__ __forceinline__ void cp_async_commit() { asm volatile("cp.async.commit_group;" ::: "memory"); }
 template <int N>
 __device__ __forceinline__ void cp_async_wait()
@@ -359,24 +367,48 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
         const bool keep_subsums = p.starts != nullptr && nsub > 1u && nsub <= (uint32_t)SCAN_SUBSUMS;
         uint64_t lsum = 0;
         uint32_t zc = 0;   // fills of 0 groups among my words: malformed -- unless they are my own padding
-        fetch_sub(0);
+        if (nsub > 1u && !ragged) {
+            // A tile of several sub-tiles is read again in pass 2 anyway: pass 1 takes its words straight into registers,
+            // eight 16-byte loads per thread in flight.  (Through the two shared-memory buffers a CTA gets one sub-tile per
+            // memory latency: 3.4-4.4 TB/s on a 138 MB stream, where plain loads reach 7 -- scripts/micro/read_patterns.cu.)
+            const uint64_t pol = p.l2_keep != 0u ? l2_keep_policy() : l2_normal_policy();
 #pragma unroll 1
-        for (uint32_t sub = 0; sub < nsub; sub++) {
-            if (sub + 1u < nsub) {
-                fetch_sub(sub + 1u);   // into the other buffer (which this thread has finished reading)
-                cp_async_wait<1>();
-            } else {
-                cp_async_wait<0>();
+            for (uint32_t sub = 0; sub < nsub; sub++) {
+                geometry(sub);
+                const uint4 *src = reinterpret_cast<const uint4 *>(p.in + seg_begin) + lane;
+                uint4 x[SCAN_MAXV];
+#pragma unroll
+                for (int v = 0; v < SCAN_MAXV; v++) x[v] = ld_v4_hint(src + ((uint32_t)v < nv ? v * 32 : 0), pol);   // (all in registers)
+                uint64_t lsub = 0;
+#pragma unroll
+                for (int v = 0; v < SCAN_MAXV; v++)
+                    if ((uint32_t)v < nv) lsub += pack_groups_zeros(x[v], zc);
+                lsum += lsub;
+                if (keep_subsums) {   // my warp's share of this sub-tile, for pass 2
+                    const uint64_t wsub = warp_sum_u64(lsub);
+                    if (lane == 0) s_subsum[sub][warp] = wsub;
+                }
             }
-            geometry(sub);
-            if (ragged) patch_sub(sub);
-            uint64_t lsub = 0;
+        } else {
+            fetch_sub(0);
+#pragma unroll 1
+            for (uint32_t sub = 0; sub < nsub; sub++) {
+                if (sub + 1u < nsub) {
+                    fetch_sub(sub + 1u);   // into the other buffer (which this thread has finished reading)
+                    cp_async_wait<1>();
+                } else {
+                    cp_async_wait<0>();
+                }
+                geometry(sub);
+                if (ragged) patch_sub(sub);
+                uint64_t lsub = 0;
 #pragma unroll 2
-            for (uint32_t v = 0; v < nv; v++) lsub += pack_groups_zeros(*my_pack(sub & 1u, v), zc);
-            lsum += lsub;
-            if (keep_subsums) {   // my warp's share of this sub-tile, for pass 2
-                const uint64_t wsub = warp_sum_u64(lsub);
-                if (lane == 0) s_subsum[sub][warp] = wsub;
+                for (uint32_t v = 0; v < nv; v++) lsub += pack_groups_zeros(*my_pack(sub & 1u, v), zc);
+                lsum += lsub;
+                if (keep_subsums) {   // my warp's share of this sub-tile, for pass 2
+                    const uint64_t wsub = warp_sum_u64(lsub);
+                    if (lane == 0) s_subsum[sub][warp] = wsub;
+                }
             }
         }
         const uint64_t wtotal = warp_sum_u64(lsum);

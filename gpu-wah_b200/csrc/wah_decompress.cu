@@ -369,8 +369,9 @@ __device__ __forceinline__ void scan_body(const ScanParams &p, uint32_t *smem)
         uint32_t zc = 0;   // fills of 0 groups among my words: malformed -- unless they are my own padding
         if (nsub > 1u && !ragged) {
             // A tile of several sub-tiles is read again in pass 2 anyway: pass 1 takes its words straight into registers,
-            // eight 16-byte loads per thread in flight.  (Through the two shared-memory buffers a CTA gets one sub-tile per
-            // memory latency: 3.4-4.4 TB/s on a 138 MB stream, where plain loads reach 7 -- scripts/micro/read_patterns.cu.)
+            // eight 16-byte loads per thread in flight.  (Measured on a 138 MB stream, pass 1 published by the slowest CTA
+            // after: 41 us through the two shared-memory buffers, one sub-tile in flight; 36 us this way; slower again with
+            // two sub-tiles in flight through the buffers, the packs copied to registers before the next request.)
             const uint64_t pol = p.l2_keep != 0u ? l2_keep_policy() : l2_normal_policy();
 #pragma unroll 1
             for (uint32_t sub = 0; sub < nsub; sub++) {

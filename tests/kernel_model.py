@@ -9,7 +9,6 @@ output-tile boundary bookkeeping, the word-centric expansion -- is restated here
 """
 from __future__ import annotations
 
-import random
 
 ONES31 = 0x7FFFFFFF
 BIT31 = 0x80000000
@@ -52,49 +51,54 @@ def word_groups(w):
 
 # ------------------------------------------------------------------ compress model
 
-ST_EMPTY, ST_AGG, ST_INCL = 0, 1, 2
+LBN = 10   # descriptors per lane and round of the control warps' window (wah_compress.cu)
 
 
-def lookback(desc, tile, block_mode, t_in_col, rng, threads=256):
-    """Mirror of the CTA-wide look-back: every warp reduces its own 32-tile window, the partials are
-    combined in warp order.  ``desc[i]`` = (aggregate form, inclusive form); to exercise the AGGREGATE
-    path, predecessors are randomly presented in their aggregate form."""
-    NW = threads // 32
-    excl, carry = 0, 0
-    open_done = block_mode or t_in_col == 0
-    look0 = tile - 1
-    while True:
-        parts = []
-        for warp in range(NW):
-            lanes = []
-            for lane in range(32):
-                look = look0 - (32 * warp + lane)
-                if look < 0:
-                    lanes.append((ST_INCL, 0, 0, 0))
-                else:
-                    agg, incl = desc[look]
-                    lanes.append(agg if (agg is not None and rng.random() < 0.6 and look > 0) else incl)
-            first_incl = next((i for i, d in enumerate(lanes) if d[0] == ST_INCL), 32)
-            part = [lane <= first_incl for lane in range(32)]
-            csum = sum(d[3] for lane, d in enumerate(lanes) if part[lane])
-            osum, flags = 0, (1 if first_incl < 32 else 0)
-            if not block_mode:
-                first_term = next((i for i, d in enumerate(lanes) if part[i] and (d[0] == ST_INCL or not d[1])), 32)
-                osum = sum(d[2] for lane, d in enumerate(lanes) if part[lane] and lane <= first_term)
-                flags |= 2 if first_term < 32 else 0
-            parts.append((csum, osum, flags))
-        done = False
-        for csum, osum, flags in parts:
-            if not done:
-                excl += csum
-                if not open_done:
-                    carry += osum
-                    open_done = bool(flags & 2)
-                done = bool(flags & 1)
-        if done:
-            break
-        look0 -= threads
-    return excl, carry
+def chained_offsets(aggs, grid, tiles_per_col, block_mode):
+    """Mirror of the control warps of wah_compress_kernel: the chained sum that gives every tile the number of words
+    the launch emits before it (excl) and the length of the run still open where it starts (carry).
+
+    aggs[k] = (tile_cnt, tile_open, tile_has) as the workers publish them: words the tile emits, groups behind its
+    last run end (the whole tile if it has none), whether it holds a run end.  CTA b of `grid` owns tiles b, b + grid,
+    ...; its two control warps take them in turn, the warp of tile i handing (cnt_end, open_end) to the warp of tile
+    i + 1 (sm.chain).  A warp sums the descriptors of the tiles between the CTA's previous tile and this one, nearest
+    first, 32 lanes x LBN descriptors per round; towards older tiles the open groups add up until a tile with a run
+    end is met."""
+    n_tiles = len(aggs)
+    out = [None] * n_tiles
+    for b in range(min(grid, n_tiles)):
+        chain = None   # (cnt_end, open_end) of the CTA's previous tile, written by the OTHER control warp
+        for i, tile in enumerate(range(b, n_tiles, grid)):
+            t = tile % tiles_per_col
+            lo = 0 if i == 0 else tile - grid + 1
+            hi = tile - 1
+            open_done = block_mode or t == 0
+            lane_csum, lane_osum = [0] * 32, [0] * 32
+            while hi >= lo:
+                for r in range(LBN):
+                    lk = [hi - lane - 32 * r for lane in range(32)]
+                    inside = [k >= lo for k in lk]
+                    for lane in range(32):
+                        if inside[lane]:
+                            lane_csum[lane] += aggs[lk[lane]][0]
+                    if not open_done:
+                        term = [inside[lane] and aggs[lk[lane]][2] for lane in range(32)]
+                        first_term = next((lane for lane in range(32) if term[lane]), 32)
+                        for lane in range(32):
+                            if inside[lane] and lane <= first_term:
+                                lane_osum[lane] += aggs[lk[lane]][1]
+                        open_done = first_term < 32
+                hi -= 32 * LBN
+            between, open_between = sum(lane_csum), sum(lane_osum)
+            own_cnt, own_open = chain if chain is not None else (0, 0)
+            excl = own_cnt + between
+            carry = open_between + (0 if open_done else own_open)
+            if block_mode or t == 0:
+                carry = 0
+            tile_cnt, tile_open, tile_has = aggs[tile]
+            chain = (excl + tile_cnt, tile_open if tile_has else carry + tile_open)
+            out[tile] = (excl, carry)
+    return out
 
 
 def seam_model(seg, groups, out):
@@ -124,11 +128,10 @@ def seam_model(seg, groups, out):
     return adj
 
 
-def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0):
+def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0, grid=3):
     """cols: list of equally long word lists (one launch).  mode 0 = BLOCK1024, 1 = CANONICAL.
     merge_prev_words: output of the earlier launches of the same stream (chained launches).
     Returns (out, col_offsets)."""
-    rng = random.Random(seed)
     block_mode = mode == 0
     NW = threads // 32
     TW, TG = threads * 31, threads * 32
@@ -139,7 +142,7 @@ def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0):
     out = list(merge_prev_words) if merge_prev_words else []
     lead_adjust = seam_model(cols[0], groups, out) if (merge_prev_words is not None and mode == 1) else 0
     base = len(out)
-    desc = [None] * n_tiles
+    aggs, classified = [], []
     col_offsets = [0] * (len(cols) + 1)
 
     for tile in range(n_tiles):
@@ -149,7 +152,6 @@ def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0):
         left = n_words - w0
         nload = TW + 1 if left > TW else left
         s_in = [src[w0 + i] if i < nload else 0 for i in range(TW + 4)]
-        s_out = [None] * TG
         th = []
         for tid in range(threads):
             lane = tid & 31
@@ -204,7 +206,7 @@ def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0):
             s_wcnt[warp] = incl
             s_whas[warp] = 1 if tb else 0
             s_wopen[warp] = lanes[qlast]["my_open"] + 32 * (31 - qlast) if tb else 1024
-        # warp 0: aggregate + look-back
+        # warp 0: the tile's aggregate, published to the other CTAs as soon as the tile is classified
         tile_cnt = tile_open = tile_has = 0
         for w in range(NW):
             tile_cnt += s_wcnt[w]
@@ -212,17 +214,20 @@ def compress_model(cols, mode, threads=256, merge_prev_words=None, seed=0):
                 tile_has, tile_open = 1, s_wopen[w]
             else:
                 tile_open += s_wopen[w]
-        if t == tiles_per_col - 1:
+        if block_mode or t == tiles_per_col - 1:   # the end of a column (and of every block) is always a run end
             tile_open, tile_has = 0, 1
-        excl = carry = 0
-        if tile == 0:
-            desc[0] = (None, (ST_INCL, 0, tile_open, tile_cnt))
-        else:
-            agg = (ST_AGG, tile_has ^ 1, tile_open, tile_cnt)
-            excl, carry = lookback(desc, tile, block_mode, t, rng, threads)
-            incl_open = tile_open if tile_has else carry + tile_open
-            desc[tile] = (agg, (ST_INCL, 0, incl_open, excl + tile_cnt))
-        s_excl = excl
+        aggs.append((tile_cnt, tile_open, tile_has))
+        classified.append((s_in, th, s_wcnt, s_wopen, s_whas))
+
+    # control warps: every tile's offset and open run from the chained sum over the published aggregates
+    offsets = chained_offsets(aggs, grid, tiles_per_col, block_mode)
+
+    for tile in range(n_tiles):
+        col, t = divmod(tile, tiles_per_col)
+        s_in, th, s_wcnt, s_wopen, s_whas = classified[tile]
+        tile_cnt = aggs[tile][0]
+        s_out = [None] * TG
+        s_excl, carry = offsets[tile]
         s_carry = 0 if (block_mode or t == 0) else carry
         # emission
         for warp in range(NW):

@@ -47,6 +47,41 @@ def test_compress_model_batch(mode):
     assert got_offs == offs.tolist()
 
 
+@pytest.mark.parametrize("block_mode", [True, False])
+@pytest.mark.parametrize("grid,n_tiles,tiles_per_col,p_tail", [
+    (1, 40, 40, 0.5), (2, 9, 9, 0.0), (3, 100, 25, 0.3), (7, 1000, 1000, 0.02), (296, 2500, 2500, 0.01),
+    (296, 1200, 37, 0.1), (321, 1500, 1500, 0.001), (700, 3000, 500, 0.005), (1000, 999, 999, 0.0),
+])
+def test_chained_offsets_model_is_a_prefix_sum_with_run_carry(grid, n_tiles, tiles_per_col, p_tail, block_mode):
+    """The control warps' chained sum (windows of 320 descriptors, nearest first, two warps handing the CTA's running
+    totals to each other) against the plain left-to-right definition of what it computes."""
+    rng = np.random.default_rng(grid * 7919 + n_tiles)
+    aggs = []
+    for k in range(n_tiles):
+        has = int(rng.random() < p_tail)
+        cnt = int(rng.integers(0, 8193)) if has else 0
+        opn = int(rng.integers(0, 8192)) if has else 8192
+        if block_mode or k % tiles_per_col == tiles_per_col - 1:
+            has, opn = 1, 0
+        aggs.append((cnt, opn, has))
+    got = km.chained_offsets(aggs, grid, tiles_per_col, block_mode)
+    excl = run = 0
+    for k, (cnt, opn, has) in enumerate(aggs):
+        if block_mode or k % tiles_per_col == 0:
+            run = 0
+        assert got[k] == (excl, run), (k, got[k], excl, run)
+        excl += cnt
+        run = opn if has else run + opn
+
+
+def test_compress_model_is_the_same_for_every_grid():
+    data = datagen.clustered(6 * TW + 123, 0.05, 3000, 21)
+    want = orc.compress(data, 1)
+    for grid in (1, 2, 5, 296):
+        got, _ = km.compress_model([data.tolist()], 1, grid=grid)
+        assert np.array_equal(np.array(got, dtype=np.uint32), want), grid
+
+
 def test_compress_model_append_merges_seam():
     # CANONICAL stream compressed as two launches: the second one's leading run joins the last word (launch_seam)
     a = np.zeros(992 * 3, dtype=np.uint32)

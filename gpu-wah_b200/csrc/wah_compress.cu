@@ -651,6 +651,8 @@ __global__ void __launch_bounds__((NWORK + 4) * 32, 2) wah_compress_kernel(const
             // compaction of my words into the ring at `origin`: those with warp-relative index in
             // [lo, lo + WARP_RING) when `windowed`, else all of them
             auto compact = [&](uint32_t origin, uint32_t lo, bool windowed) {
+                // (a round of the windowed form concerns the threads whose words [off, off + cnt) reach into it)
+                if (windowed && (off + cnt <= lo || off >= lo + (uint32_t)WARP_RING)) return;
                 // literals: the group itself (kernels.cu:107-112,256)
                 uint32_t m = T & ~F;
                 while (m) {

@@ -423,6 +423,117 @@ def scan_geometry_model(cw, skip_words=0, grid=444):
     return out
 
 
+TGM = TG - 1
+SCAN_SUBSUMS = 32
+
+
+def _note_boundaries(starts, required, k_lim, ct, kf, ke, wi, off, pack):
+    """note_boundaries / record_boundaries / write_fill_entries for a single stream: the pack's four words, the first at
+    word index wi and group offset off, record the output-tile boundaries kf .. ke - 1 that fall into them.  `required`
+    collects the table indices the expand phase will ask for (a long fill writes only its first and last nine entries and
+    the chunk starts in between)."""
+    c = [word_groups(w) for w in pack]
+    if ke - kf == 1:                       # the inline case: one boundary in the pack
+        if kf < k_lim:
+            d = ((kf << 10) - off) & M32
+            s1, s2 = (c[0] + c[1]) & M32, (c[0] + c[1] + c[2]) & M32
+            jj = (c[0] <= d) + (s1 <= d) + (s2 <= d)
+            before = (0, c[0], s1, s2)[jj]
+            assert kf not in starts
+            starts[kf] = (wi + jj, off + before)
+            required.add(kf)
+        return
+    for j in range(4):
+        if c[j]:
+            k_first, k_end = (off + TGM) >> 10, min((off + c[j] + TGM) >> 10, k_lim)
+            if k_first < k_end:
+                ks = range(k_first, k_end)
+                if k_end - k_first > 4:    # a long fill: sparse entries
+                    head_end = min(k_first + 9, k_end)
+                    tail_begin = k_end - 9 if k_end > head_end + 9 else head_end
+                    k_mid = (head_end + ct - 1) // ct * ct
+                    ks = list(range(k_first, head_end)) + list(range(tail_begin, k_end)) + list(range(k_mid, tail_begin, ct))
+                for k in ks:
+                    assert k not in starts or starts[k] == (wi + j, off)
+                    starts[k] = (wi + j, off)
+                    required.add(k)
+        off += c[j]
+
+
+def scan_pass2_model(cw, grid=444, max_out_tiles=1 << 40, chunk_tiles=8, routes=None):
+    """Mirror of scan_body's pass 2 for a single stream (after pass 1 and the offset exchange): which compressed word
+    covers every output-tile boundary k * 1024.  Follows the kernel's three methods -- boundaries by arithmetic for a
+    literal-dense tile; every row scanned, in 32-bit arithmetic relative to the output-tile boundary below the warp's
+    first row (the per-warp sub-tile sums kept from pass 1); row sums first and boundary-free rows skipped -- and its
+    geometry (tiles, sub-tiles of 8 rows per warp, lanes of four words).  Returns (starts, required); `routes` (a dict)
+    counts the rows that went each way."""
+    c = len(cw)
+    NW = SCAN_THREADS // 32
+    tw = scan_tile_words_model(c, grid)
+    n_tiles = (c + tw - 1) // tw
+    k_lim = max_out_tiles + 1
+    word = lambda i: int(cw[i]) if i < c else BIT31   # (behind the stream: fills of 0 groups)
+    starts, required = {}, set()
+    routes = {} if routes is None else routes
+    count = lambda key: routes.__setitem__(key, routes.get(key, 0) + 1)
+    excl = 0
+    for tile in range(n_tiles):
+        tile_begin, w_last = tile * tw, min(tile * tw + tw, c)
+        rows = (w_last - tile_begin + 4 * SCAN_THREADS - 1) // (4 * SCAN_THREADS) if w_last - tile_begin < tw else tw // (4 * SCAN_THREADS)
+        nsub = (rows + SCAN_MAXV - 1) // SCAN_MAXV
+        tile_sum = sum(word_groups(word(i)) for i in range(tile_begin, tile_begin + rows * 4 * SCAN_THREADS))
+        n_words_tile = w_last - tile_begin
+        if tile_sum == n_words_tile and n_words_tile > 0:          # unit tile: no second look at the words
+            for k in range((excl + TGM) >> 10, min((excl + tile_sum + TGM) >> 10, k_lim)):
+                starts[k] = (tile_begin + (k << 10) - excl, k << 10)
+                required.add(k)
+            excl += tile_sum
+            count("unit_tile")
+            continue
+        skip_rows = tile_sum < 8 * n_words_tile
+        sub_base = excl
+        for sub in range(nsub):
+            nv = min(SCAN_MAXV, rows - sub * SCAN_MAXV)
+            seg = [tile_begin + sub * SCAN_SUB_WORDS + warp * nv * 128 for warp in range(NW)]
+            wsub = [sum(word_groups(word(i)) for i in range(seg[w], seg[w] + nv * 128)) for w in range(NW)]
+            for warp in range(NW):
+                row_base = sub_base + sum(wsub[:warp])
+                narrow = wsub[warp] < (1 << 31)
+                q0 = row_base & ~TGM
+                rb = row_base - q0
+                for v in range(nv):
+                    packs = [[word(seg[warp] + (v * 32 + lane) * 4 + j) for j in range(4)] for lane in range(32)]
+                    s = [sum(word_groups(w) for w in pk) for pk in packs]
+                    rsum = sum(s)
+                    if skip_rows and nsub > 1:
+                        # (a tile of one sub-tile takes the pre-scanned route, which looks at every pack like the wide form below)
+                        if ((row_base + TGM) >> 10) == ((row_base + rsum + TGM) >> 10):
+                            row_base += rsum
+                            count("row_skipped")
+                            continue
+                    e64 = row_base
+                    count("row_32bit" if (narrow and not skip_rows and nsub > 1) else "row_64bit")
+                    for lane in range(32):
+                        wi = seg[warp] + (v * 32 + lane) * 4
+                        if narrow and not skip_rows and nsub > 1:
+                            e = (rb + (e64 - row_base)) & M32
+                            assert e == rb + (e64 - row_base), "32-bit offset wrapped"
+                            kf, ke = ((e + TGM) & M32) >> 10, ((e + s[lane] + TGM) & M32) >> 10
+                            assert e + s[lane] + TGM <= M32, "32-bit boundary arithmetic wrapped"
+                            if kf != ke:
+                                _note_boundaries(starts, required, k_lim, chunk_tiles, (q0 >> 10) + kf, (q0 >> 10) + ke, wi, q0 + e, packs[lane])
+                        else:
+                            kf, ke = (e64 + TGM) >> 10, (e64 + s[lane] + TGM) >> 10
+                            if kf != ke:
+                                _note_boundaries(starts, required, k_lim, chunk_tiles, kf, ke, wi, e64, packs[lane])
+                        e64 += s[lane]
+                    row_base += rsum
+                    rb += rsum
+            sub_base += sum(wsub)
+        excl += tile_sum
+    return starts, required
+
+
 # ---------------------------------------------------------------- window path of the expand phase (wah_decompress.cu)
 
 RANK_SHIFT = 20

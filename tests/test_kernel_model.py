@@ -186,6 +186,59 @@ def test_scan_geometry_covers_the_stream_once_and_counts_padding_out(c_words, sk
     assert all(t[1] >= 0 for t in tiles)
 
 
+def _scan_streams():
+    """(name, stream, grid, the routes of pass 2 the stream must reach)"""
+    rng = np.random.default_rng(77)
+    lit = lambda: int(rng.integers(1, 0x7FFFFFFF))
+    fill = lambda lo, hi: km.fill_word(int(rng.integers(0, 2)), int(rng.integers(lo, hi)))
+    # 16 groups per word on average, three sub-tiles per tile: every row scanned in 32-bit arithmetic
+    yield "short_fills", [fill(1, 64) if rng.random() < 0.5 else lit() for _ in range(41000)], 2, {"row_32bit"}
+    # literals with a fill now and then (3 groups per word): row sums first, most rows skipped
+    yield "mostly_literals", [fill(2, 60) if rng.random() < 0.07 else lit() for _ in range(20000)], 1, {"row_skipped", "row_64bit"}
+    # fills of up to 2^30 - 1 groups: a warp's rows beyond 2^31 groups take the wide form; long fills write sparse entries
+    huge = [fill(1, 3000) if rng.random() < 0.5 else lit() for _ in range(18000)]
+    for i in (700, 710, 720, 9000, 9001, 17990):   # (three in one warp's rows, two adjacent ones, one near the end)
+        huge[i] = km.fill_word(1, km.MAX_FILL)
+    yield "huge_fills", huge, 1, {"row_64bit", "row_32bit"}
+    # a few long fills only (one sub-tile: offsets pre-scanned, every pack looked at)
+    yield "long_fills_one_subtile", [fill(100000, 400000) if i % 3 else lit() for i in range(300)], 4, {"row_64bit"}
+    # every word one group: boundaries by arithmetic; the last tile is ragged
+    yield "incompressible", [lit() for _ in range(12288 + 77)], 3, {"unit_tile"}
+    # compressed by the oracle, both modes
+    yield "oracle_block1024", orc.compress(datagen.clustered(60 * 992, 0.3, 300, 1), 0).tolist(), 2, set()
+    yield "oracle_canonical", orc.compress(datagen.clustered(200 * 992, 0.001, 5000, 3), 1).tolist(), 1, set()
+
+
+@pytest.mark.parametrize("name,cw,grid,must_reach", list(_scan_streams()), ids=[c[0] for c in _scan_streams()])
+def test_scan_pass2_model_records_every_boundary_the_expand_phase_asks_for(name, cw, grid, must_reach):
+    """Pass 2 of the decoder's scan (tiles / sub-tiles / rows / packs, the 32-bit row arithmetic, the inline
+    single-boundary case, sparse entries for long fills) against the definition of the table: entry k names the word
+    that holds group 1024 k, and that word's group offset."""
+    import bisect
+    cw = [int(w) for w in cw]
+    cnt = [km.word_groups(w) for w in cw]
+    off = [0]
+    for c_ in cnt:
+        off.append(off[-1] + c_)
+    for ct in ((8,) if name == "huge_fills" else (1, 8)):   # (a table entry per tile of a 2^30-group fill is a million entries)
+        routes = {}
+        got, _ = km.scan_pass2_model(cw, grid=grid, chunk_tiles=ct, routes=routes)
+        assert must_reach <= set(routes), routes
+        for k, (wi, woff) in got.items():
+            i = bisect.bisect_right(off, 1024 * k) - 1          # the last word that starts at or before the boundary
+            assert i < len(cw) and (wi, woff) == (i, off[i]) and off[i] <= 1024 * k < off[i + 1], (k, wi, woff, i)
+        # what must be there: every boundary of a word that holds up to four; of a longer fill the nine at either end and
+        # the chunk starts in between
+        for i, c_ in enumerate(cnt):
+            k_first, k_end = (off[i] + 1023) >> 10, (off[i] + c_ + 1023) >> 10
+            if k_end - k_first <= 4:
+                need = range(k_first, k_end)
+            else:
+                need = list(range(k_first, k_first + 9)) + list(range(k_end - 9, k_end)) + list(range((k_first + ct - 1) // ct * ct, k_end, ct))
+            for k in need:
+                assert k in got, (i, k, k_first, k_end)
+
+
 def test_scan_geometry_recognises_unit_tiles():
     cw = np.arange(1, 5000, dtype=np.uint32)          # literals only
     assert all(t[2] for t in km.scan_geometry_model(cw))

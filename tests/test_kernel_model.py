@@ -237,6 +237,19 @@ def test_scan_pass2_model_records_every_boundary_the_expand_phase_asks_for(name,
                 need = list(range(k_first, k_first + 9)) + list(range(k_end - 9, k_end)) + list(range((k_first + ct - 1) // ct * ct, k_end, ct))
             for k in need:
                 assert k in got, (i, k, k_first, k_end)
+        # ... and that is all the expand phase asks for (expand_body, "the chunk's entries must have been recorded"): per
+        # chunk of ct tiles the entry of its first tile and, unless the fill word that entry names reaches behind the
+        # chunk's end, the entries of its other tiles and of the tile behind it -- as far as they lie inside the stream
+        G = off[-1]
+        out_tiles = (G + 1023) >> 10
+        for k0 in range(0, out_tiles, ct):
+            nt = min(ct, out_tiles - k0)
+            assert k0 in got, k0
+            wi, woff = got[k0]
+            if (cw[wi] & km.BIT31) and woff + cnt[wi] > ((k0 + nt) << 10):
+                continue
+            for k in range(k0, k0 + nt + 1):
+                assert k in got or (k << 10) >= G, (k0, k, wi, woff, cnt[wi])
 
 
 def test_scan_geometry_recognises_unit_tiles():
